@@ -1,0 +1,177 @@
+/*
+ * slas_cuda.h -- C ABI of libslas_cuda.so, the B200 (sm_100a) compute backend that
+ * stands behind `slas_backend::Cuda`.
+ *
+ * This is the drop-in boundary: every op entry point takes exactly the arguments
+ * the matching method of the reference's backend-operation traits takes
+ * (/root/reference/src/backends.rs:121-183), with `impl StaticVec<T, LEN>`
+ * lowered to (len, pointer) -- the only thing a StaticVec gives a backend is
+ * `as_ptr()/as_mut_ptr()` to LEN contiguous elements (src/static_vec.rs:121-134).
+ * Each declaration cites the reference function it replaces; INTEGRATION.md holds
+ * the `extern "C"` block and trait impls a slas maintainer adds on the Rust side.
+ *
+ * Conventions
+ *  - Prefix s = f32, d = f64, c = Complex<f32>, z = Complex<f64> (interleaved re,im).
+ *  - Every function returns an int status (0 = SLAS_OK); the reference's ops are
+ *    infallible by type, so the Rust shim panics with slas_cuda_last_error().
+ *  - Sizes are size_t, never int: the reference's `LEN as i32` (src/backends/blas.rs:21)
+ *    truncates at 2^31 elements, this ABI does not.
+ *  - Data pointers may be DEVICE pointers (the fast, device-resident path) or HOST
+ *    pointers (staged through pinned buffers, copies overlapped with the kernels);
+ *    all data operands of one call must live on the same side.  Scalar results
+ *    (`out`) may independently be host or device pointers.
+ *  - Ops are enqueued on the context's stream (slas_cuda_set_stream); a call
+ *    returns after enqueueing unless it has to hand a scalar or host data back.
+ *  - There is no CPU fallback: without a CUDA device every op fails with
+ *    SLAS_ERR_CUDA.
+ */
+#ifndef SLAS_CUDA_H
+#define SLAS_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    SLAS_OK = 0,
+    SLAS_ERR_INVALID = 1,     /* bad argument (null pointer, shape mismatch, mixed host/device operands) */
+    SLAS_ERR_CUDA = 2,        /* CUDA runtime error, or no device */
+    SLAS_ERR_NCCL = 3,        /* NCCL missing or a collective failed */
+    SLAS_ERR_UNSUPPORTED = 4  /* valid in the reference but not built here */
+};
+
+/* ---- context -------------------------------------------------------------------
+ * A reference backend is a zero-sized type made by `B::default()` at every call
+ * site (src/backends/rust.rs:2-3, src/static_vec.rs:76,219), so it can hold no
+ * state: device, stream and scratch live in a process-global, lazily initialised
+ * context per device.  Calls are thread-safe (libtest runs tests concurrently). */
+int slas_cuda_init(int device);              /* device < 0: keep the current device */
+int slas_cuda_shutdown(void);
+const char *slas_cuda_last_error(void);      /* thread-local message of the last failure */
+int slas_cuda_device_count(int *count);
+int slas_cuda_device_info(int *sm_count, size_t *l2_bytes, size_t *hbm_bytes, int *cc_major, int *cc_minor);
+int slas_cuda_set_stream(void *cuda_stream); /* a cudaStream_t; NULL restores the library's own stream */
+int slas_cuda_synchronize(void);
+/* Number of kernels this library launched on the calling process so far (bench.py's gpu_launches). */
+uint64_t slas_cuda_launch_count(void);
+
+/* ---- device-resident storage (what `CudaVec<T, LEN>` / `CudaBatch` own) --------- */
+int slas_cuda_malloc(void **dptr, size_t bytes);
+int slas_cuda_free(void *dptr);
+int slas_cuda_malloc_host(void **hptr, size_t bytes);   /* pinned */
+int slas_cuda_free_host(void *hptr);
+int slas_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int slas_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
+int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes);
+int slas_cuda_memset(void *dst, int byte, size_t bytes);
+/* 1 if p is a device pointer, 0 if host. */
+int slas_cuda_is_device_ptr(const void *p, int *is_device);
+/* Counter-based synthetic data straight into HBM (bench/test plumbing for vectors that
+ * cannot be staged through the host): x[i] = lo + (hi-lo)*u(seed, offset+i). */
+int slas_cuda_sfill_uniform(size_t len, float *x, uint64_t seed, uint64_t offset, float lo, float hi);
+int slas_cuda_dfill_uniform(size_t len, double *x, uint64_t seed, uint64_t offset, double lo, double hi);
+
+/* ---- DotProduct::dot  (src/backends.rs:122-126; Rust: src/backends/rust.rs:20-41;
+ *      Blas: src/backends/blas.rs:15-23, complex dotu :31-52) ---------------------- */
+int slas_cuda_sdot(size_t len, const float *a, const float *b, float *out);
+int slas_cuda_ddot(size_t len, const double *a, const double *b, double *out);
+int slas_cuda_cdotu(size_t len, const float *a, const float *b, float *out /* [re, im] */);
+int slas_cuda_zdotu(size_t len, const double *a, const double *b, double *out /* [re, im] */);
+
+/* ---- Normalize::{norm, normalize}  (src/backends.rs:128-130; Rust real: rust.rs:116-127,
+ *      complex: rust.rs:129-147; Blas: blas.rs:156-170).  NormOutput is the real type. --- */
+int slas_cuda_snrm2(size_t len, const float *a, float *out);
+int slas_cuda_dnrm2(size_t len, const double *a, double *out);
+int slas_cuda_scnrm2(size_t len, const float *a, float *out);
+int slas_cuda_dznrm2(size_t len, const double *a, double *out);
+int slas_cuda_snormalize(size_t len, float *a);    /* a[i] /= norm (true division, rust.rs:125) */
+int slas_cuda_dnormalize(size_t len, double *a);
+int slas_cuda_cnormalize(size_t len, float *a);    /* len complex elements */
+int slas_cuda_znormalize(size_t len, double *a);
+
+/* ---- Addition/Subtraction/Multiplication/Divition  (src/backends.rs:156-182;
+ *      Rust: src/backends/rust.rs:45-73).  c[i] = a[i] op b[i], one IEEE op, bit-exact. --- */
+int slas_cuda_sadd(size_t len, const float *a, const float *b, float *c);
+int slas_cuda_ssub(size_t len, const float *a, const float *b, float *c);
+int slas_cuda_smul(size_t len, const float *a, const float *b, float *c);
+int slas_cuda_sdiv(size_t len, const float *a, const float *b, float *c);
+int slas_cuda_dadd(size_t len, const double *a, const double *b, double *c);
+int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c);
+int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c);
+int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c);
+
+/* ---- Transpose::{transpose, transpose_inplace}  (src/backends.rs:152-154;
+ *      Rust: src/backends/rust.rs:151-177).  buffer[columns*row + column] =
+ *      a[(len/columns)*column + row]; `columns` is the column count of the OUTPUT.
+ *      Generic over any Copy element: elem_size in {4, 8, 16} bytes.  Bit-exact. -------- */
+int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns);
+int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns);
+
+/* ---- MatrixMul::matrix_mul  (src/backends.rs:132-141; Blas: src/backends/blas.rs:67-111)
+ *      C[m x n] = op(A) . op(B), row-major, alpha = 1, beta = 0, exactly the
+ *      cblas_{s,d}gemm(RowMajor, opA, opB, m, n, k, 1, A, lda, B, ldb, 0, C, ldc) call. ---- */
+int slas_cuda_sgemm(const float *a, const float *b, float *c, size_t m, size_t n, size_t k,
+                    size_t lda, size_t ldb, size_t ldc, int a_trans, int b_trans);
+int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
+                    size_t lda, size_t ldb, size_t ldc, int a_trans, int b_trans);
+/* Which kernel a large f32 product runs on: 0 = FFMA (reference-faithful f32, the default),
+ * 1 = tcgen05/TMEM 3xTF32 for dense contractions whose m, n, k are multiples of the tile. */
+int slas_cuda_set_sgemm_path(int path);
+int slas_cuda_get_sgemm_path(int *path);
+
+/* ---- MatrixMul::matrix_vector_mul  (src/backends.rs:142-150; Blas: blas.rs:114-151)
+ *      TRAIT meaning of the arguments: m = underlying width (columns), n = underlying
+ *      height (rows), lda = width; y = op(A) . x, i.e. cblas_gemv(RowMajor, op, M=n, N=m, ...). */
+int slas_cuda_sgemv(const float *a, const float *x, float *y, size_t m, size_t n, size_t lda, int a_trans);
+int slas_cuda_dgemv(const double *a, const double *x, double *y, size_t m, size_t n, size_t lda, int a_trans);
+
+/* ---- batched views: `batch` same-shape objects, contiguous [[T; LEN]; batch] ------------
+ * (north_star: "batched views over many same-shape objects, so compile-time shapes become
+ * template parameters of the kernels").  Semantics = the single-object op applied to every
+ * object; matrices are dense (lda = a_trans ? m : k, ldb = b_trans ? k : n, ldc = n as
+ * Matrix::matrix_mul_buffer derives them, src/tensor.rs:376-382). */
+int slas_cuda_sgemm_batched(size_t batch, const float *a, const float *b, float *c, size_t m, size_t n,
+                            size_t k, int a_trans, int b_trans);
+int slas_cuda_dgemm_batched(size_t batch, const double *a, const double *b, double *c, size_t m, size_t n,
+                            size_t k, int a_trans, int b_trans);
+int slas_cuda_sgemv_batched(size_t batch, const float *a, const float *x, float *y, size_t m, size_t n,
+                            int a_trans);
+int slas_cuda_dgemv_batched(size_t batch, const double *a, const double *x, double *y, size_t m, size_t n,
+                            int a_trans);
+int slas_cuda_transpose_batched(size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
+                                size_t columns);
+int slas_cuda_sdot_batched(size_t batch, size_t len, const float *a, const float *b, float *out);
+int slas_cuda_ddot_batched(size_t batch, size_t len, const double *a, const double *b, double *out);
+int slas_cuda_snrm2_batched(size_t batch, size_t len, const float *a, float *out);
+int slas_cuda_dnrm2_batched(size_t batch, size_t len, const double *a, double *out);
+int slas_cuda_snormalize_batched(size_t batch, size_t len, float *a);
+int slas_cuda_dnormalize_batched(size_t batch, size_t len, double *a);
+
+/* ---- multi-GPU: one process per GPU, this rank owns one contiguous slice -----------------
+ * Batched ops shard by batch index and need no collective (call the *_batched entry on the
+ * local slice).  A single huge dot / norm / normalize shards by vector slice: local
+ * deterministic partial on this rank's slice, then ONE ncclAllReduce(sum) of the f64
+ * partial on the context's stream. */
+int slas_cuda_nccl_unique_id(void *id128);                      /* rank 0: 128-byte ncclUniqueId */
+int slas_cuda_comm_init(int nranks, int rank, const void *id128);
+int slas_cuda_comm_destroy(void);
+int slas_cuda_comm_info(int *nranks, int *rank);                /* nranks = 1 when no communicator */
+/* Slice [begin, end) of a len-element vector owned by `rank` of `nranks`; boundaries are
+ * multiples of 16 bytes' worth of elements (elem_size <= 16). */
+int slas_cuda_shard_range(size_t len, size_t elem_size, int nranks, int rank, size_t *begin, size_t *end);
+int slas_cuda_sdot_sharded(size_t local_len, const float *a, const float *b, float *out);
+int slas_cuda_ddot_sharded(size_t local_len, const double *a, const double *b, double *out);
+int slas_cuda_snrm2_sharded(size_t local_len, const float *a, float *out);
+int slas_cuda_dnrm2_sharded(size_t local_len, const double *a, double *out);
+int slas_cuda_snormalize_sharded(size_t local_len, float *a);
+int slas_cuda_dnormalize_sharded(size_t local_len, double *a);
+/* Local f64 partial sums (sum a[i]*b[i]) without the collective: what the sharded ops reduce. */
+int slas_cuda_sdot_partial(size_t len, const float *a, const float *b, double *partial);
+int slas_cuda_ddot_partial(size_t len, const double *a, const double *b, double *partial);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAS_CUDA_H */

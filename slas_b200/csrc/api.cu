@@ -1,0 +1,531 @@
+// api.cu -- the op entry points of the C ABI (include/slas_cuda.h): argument checks that mirror
+// the reference's asserts, host/device pointer dispatch, kernel selection.
+//
+// Device pointers: the op is enqueued on the context's stream and the call returns.
+// Host pointers (the reference's own calling convention: StaticVec::as_ptr() is host memory,
+// src/static_vec.rs:126): operands are staged into HBM.  Unit-parallel ops (element-wise and
+// every *_batched entry) run a 3-slot pipeline -- H2D copy, kernel, D2H copy of consecutive
+// chunks on three streams -- so that both PCIe directions and the SMs overlap; everything
+// else stages whole operands.  There is no CPU arithmetic path.
+#include <string.h>
+
+#include <algorithm>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+static int g_sgemm_path = 0;  // 0 FFMA, 1 tcgen05 3xTF32
+
+// ---- host staging ----------------------------------------------------------------------------
+enum Dir { IN = 1, OUT = 2, INOUT = 3 };
+struct Operand {
+    const void *host;
+    size_t unit_bytes;  // bytes per unit (element / object)
+    int dir;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Whole-operand staging: sizes[i] bytes each.  Fills dev[i]; caller runs the op on ctx->stream and
+// then calls stage_all_finish.
+static int stage_all_begin(Context *ctx, const Operand *ops, const size_t *sizes, int n, void **dev) {
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += align_up(sizes[i], 256);
+    void *base = nullptr;
+    SLAS_TRY(ensure_staging(ctx, total ? total : 256, &base));
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        dev[i] = (char *)base + off;
+        off += align_up(sizes[i], 256);
+        if ((ops[i].dir & IN) && sizes[i])
+            SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], ops[i].host, sizes[i], cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return SLAS_OK;
+}
+static int stage_all_finish(Context *ctx, const Operand *ops, const size_t *sizes, int n, void *const *dev) {
+    for (int i = 0; i < n; ++i)
+        if ((ops[i].dir & OUT) && sizes[i])
+            SLAS_CUDA_TRY(cudaMemcpyAsync(const_cast<void *>(ops[i].host), dev[i], sizes[i], cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+    SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return SLAS_OK;
+}
+
+// Chunked 3-slot pipeline over `units` independent units.  `granule`: chunk sizes are multiples of
+// it (keeps every chunk's device pointers 16-byte aligned and whole objects together).
+template <typename F>
+static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand *ops, int n, F launch) {
+    if (units == 0) return SLAS_OK;
+    size_t unit_total = 0;
+    for (int i = 0; i < n; ++i) unit_total += ops[i].unit_bytes;
+    constexpr size_t kSlotBytes = (size_t)96 << 20;
+    size_t chunk = kSlotBytes / (unit_total ? unit_total : 1);
+    chunk = chunk / granule * granule;
+    if (chunk == 0) chunk = granule;
+    if (chunk > units) chunk = align_up(units, granule);
+    size_t slot_bytes = 0;
+    for (int i = 0; i < n; ++i) slot_bytes += align_up(chunk * ops[i].unit_bytes, 256);
+    const int nslots = units > chunk ? 3 : 1;
+    void *base = nullptr;
+    SLAS_TRY(ensure_staging(ctx, slot_bytes * nslots, &base));
+    // the copy streams must not overtake work already queued on the op stream
+    SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    size_t done = 0;
+    for (size_t ci = 0; done < units; ++ci) {
+        const int slot = (int)(ci % nslots);
+        cudaStream_t st = ctx->copy_streams[slot];
+        const size_t cnt = std::min(chunk, units - done);
+        void *dev[8];
+        size_t off = 0;
+        for (int i = 0; i < n; ++i) {
+            dev[i] = (char *)base + (size_t)slot * slot_bytes + off;
+            off += align_up(chunk * ops[i].unit_bytes, 256);
+            if (ops[i].dir & IN)
+                SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], (const char *)ops[i].host + done * ops[i].unit_bytes,
+                                              cnt * ops[i].unit_bytes, cudaMemcpyHostToDevice, st));
+        }
+        SLAS_TRY(launch(dev, cnt, st));
+        for (int i = 0; i < n; ++i)
+            if (ops[i].dir & OUT)
+                SLAS_CUDA_TRY(cudaMemcpyAsync((char *)const_cast<void *>(ops[i].host) + done * ops[i].unit_bytes, dev[i],
+                                              cnt * ops[i].unit_bytes, cudaMemcpyDeviceToHost, st));
+        done += cnt;
+    }
+    for (int s = 0; s < nslots; ++s) SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_streams[s]));
+    return SLAS_OK;
+}
+
+// ---- element-wise ----------------------------------------------------------------------------
+template <typename T>
+static int api_ewise(int op, size_t len, const T *a, const T *b, T *c) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (len == 0) return SLAS_OK;
+    const void *ptrs[3] = {a, b, c};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 3, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (dev) return launch_ewise<T>(ctx, ctx->stream, op, len, a, b, c);
+    const Operand ops[3] = {{a, sizeof(T), IN}, {b, sizeof(T), IN}, {c, sizeof(T), OUT}};
+    return run_chunked(ctx, len, 4096, ops, 3, [&](void **d, size_t cnt, cudaStream_t st) {
+        return launch_ewise<T>(ctx, st, op, cnt, (const T *)d[0], (const T *)d[1], (T *)d[2]);
+    });
+}
+
+// ---- reductions -------------------------------------------------------------------------------
+// kind: 0 dot, 1 squared norm, 2 complex dotu; `len` counts real scalars.  mode 1 = sqrt.
+// sharded: allreduce the f64 partial over the communicator before the typed result is formed.
+template <typename T>
+static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T *out, bool sharded,
+                      double *partial_out) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    SLAS_REQUIRE(out || partial_out, "null result pointer");
+    const int nres = kind == 2 ? 2 : 1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    double *res = ctx->scalars;                        // [0..1] f64 sums
+    T *typed = reinterpret_cast<T *>(ctx->scalars + 4);  // typed result(s)
+    const T *da = a, *db = b;
+    bool dev = true;
+    if (len > 0) {
+        const void *ptrs[2] = {a, kind == 1 ? a : b};
+        SLAS_TRY(operands_side(ptrs, 2, &dev));
+    }
+    if (len > 0 && !dev) {
+        const Operand ops[2] = {{a, sizeof(T), IN}, {b, sizeof(T), IN}};
+        const size_t sizes[2] = {len * sizeof(T), kind == 1 ? 0 : len * sizeof(T)};
+        void *d[2];
+        SLAS_TRY(stage_all_begin(ctx, ops, sizes, 2, d));
+        da = (const T *)d[0];
+        db = kind == 1 ? da : (const T *)d[1];
+    }
+    const bool need_collective = sharded && comm_nranks() > 1;
+    if (len == 0) {
+        // the reference returns the empty sum: 0 (and sqrt(0) = 0)
+        SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
+    } else {
+        SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0));
+    }
+    if (need_collective) {
+        SLAS_TRY(comm_allreduce_f64(res, nres, ctx->stream));
+        SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, mode));
+        if (nres == 2) SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res + 1, typed + 1, mode));
+    }
+    if (partial_out) SLAS_TRY(deliver_scalar(ctx, res, partial_out, sizeof(double) * nres));
+    if (out) SLAS_TRY(deliver_scalar(ctx, typed, out, sizeof(T) * nres));
+    return SLAS_OK;
+}
+
+template <typename T>
+static int api_normalize(size_t len, T *a, bool sharded) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (len == 0 && !(sharded && comm_nranks() > 1)) return SLAS_OK;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    double *res = ctx->scalars;
+    T *typed = reinterpret_cast<T *>(ctx->scalars + 4);
+    bool dev = true;
+    if (len > 0) SLAS_TRY(pointer_is_device(a, &dev));
+    T *da = a;
+    const Operand ops[1] = {{a, sizeof(T), INOUT}};
+    const size_t sizes[1] = {len * sizeof(T)};
+    void *d[1];
+    if (!dev) {
+        SLAS_TRY(stage_all_begin(ctx, ops, sizes, 1, d));
+        da = (T *)d[0];
+    }
+    const bool need_collective = sharded && comm_nranks() > 1;
+    if (len == 0) SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
+    else SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, 1, len, da, da, res, need_collective ? nullptr : typed, 1, 0));
+    if (need_collective) {
+        SLAS_TRY(comm_allreduce_f64(res, 1, ctx->stream));
+        SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, 1));
+    }
+    SLAS_TRY(launch_scale_div<T>(ctx, ctx->stream, len, da, typed));
+    if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
+    return SLAS_OK;
+}
+
+// ---- transpose ---------------------------------------------------------------------------------
+static int api_transpose(size_t batch, size_t len, size_t elem, const void *a, void *buffer, size_t columns,
+                         bool inplace) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, src/backends/rust.rs:169)");
+    SLAS_REQUIRE(elem == 4 || elem == 8 || elem == 16, "transpose: element size %zu (supported: 4, 8, 16)", elem);
+    if (len == 0 || batch == 0) return SLAS_OK;
+    const void *ptrs[2] = {a, inplace ? a : buffer};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 2, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t bytes = batch * len * elem;
+    if (inplace) {
+        // rust.rs:152-160: transpose into a zeroed temporary, then copy the temporary back
+        void *tmp = nullptr;
+        void *target = const_cast<void *>(a);
+        const Operand ops[1] = {{a, len * elem, INOUT}};
+        const size_t sizes[1] = {bytes};
+        void *d[1];
+        if (!dev) {
+            SLAS_TRY(stage_all_begin(ctx, ops, sizes, 1, d));
+            target = d[0];
+        }
+        SLAS_TRY(ensure_workspace(ctx, bytes, &tmp));
+        SLAS_CUDA_TRY(cudaMemsetAsync(tmp, 0, bytes, ctx->stream));
+        SLAS_TRY(launch_transpose(ctx, ctx->stream, batch, len, elem, target, tmp, columns));
+        SLAS_CUDA_TRY(cudaMemcpyAsync(target, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
+        return SLAS_OK;
+    }
+    if (dev) return launch_transpose(ctx, ctx->stream, batch, len, elem, a, buffer, columns);
+    if (batch > 1) {
+        // elements the reference never writes (len % columns != 0) must keep the caller's bytes: INOUT
+        const int out_dir = (len % columns) ? INOUT : OUT;
+        const Operand ops[2] = {{a, len * elem, IN}, {buffer, len * elem, out_dir}};
+        return run_chunked(ctx, batch, 1, ops, 2, [&](void **d, size_t cnt, cudaStream_t st) {
+            return launch_transpose(ctx, st, cnt, len, elem, d[0], d[1], columns);
+        });
+    }
+    const Operand ops[2] = {{a, len * elem, IN}, {buffer, len * elem, (len % columns) ? INOUT : OUT}};
+    const size_t sizes[2] = {bytes, bytes};
+    void *d[2];
+    SLAS_TRY(stage_all_begin(ctx, ops, sizes, 2, d));
+    SLAS_TRY(launch_transpose(ctx, ctx->stream, 1, len, elem, d[0], d[1], columns));
+    return stage_all_finish(ctx, ops, sizes, 2, d);
+}
+
+// ---- matrix_mul ---------------------------------------------------------------------------------
+template <typename T>
+static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                       size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, bool dense) {
+    if (dense) {
+        const int r = launch_gemm_small_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+        if (r != SLAS_ERR_UNSUPPORTED) return r;
+    }
+    if (batch == 1 && m * n >= 64 * 64 && k >= 8) {
+        if (sizeof(T) == 4 && g_sgemm_path == 1) {
+            const int r = launch_sgemm_3xtf32(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb,
+                                              ldc, ta, tb);
+            if (r != SLAS_ERR_UNSUPPORTED) return r;
+        }
+        return launch_gemm_large<T>(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
+    }
+    return launch_gemm_generic<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);
+}
+
+template <typename T>
+static int api_gemm(const T *a, const T *b, T *c, size_t m, size_t n, size_t k, size_t lda, size_t ldb, size_t ldc,
+                    int ta, int tb) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (m == 0 || n == 0) return SLAS_OK;
+    // what cblas_?gemm(RowMajor) requires of the leading dimensions (the reference passes them through)
+    const size_t a_rows = ta ? k : m, a_cols = ta ? m : k, b_rows = tb ? n : k, b_cols = tb ? k : n;
+    SLAS_REQUIRE(lda >= std::max<size_t>(a_cols, 1), "matrix_mul: lda %zu < %zu", lda, a_cols);
+    SLAS_REQUIRE(ldb >= std::max<size_t>(b_cols, 1), "matrix_mul: ldb %zu < %zu", ldb, b_cols);
+    SLAS_REQUIRE(ldc >= n, "matrix_mul: ldc %zu < n %zu", ldc, n);
+    const bool dense = lda == a_cols && ldb == b_cols && ldc == n;
+    const void *ptrs[3] = {c, k ? (const void *)a : (const void *)c, k ? (const void *)b : (const void *)c};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 3, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (dev) return gemm_device<T>(ctx, ctx->stream, 1, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, dense);
+    const size_t ea = a_rows && a_cols ? (a_rows - 1) * lda + a_cols : 0;
+    const size_t eb = b_rows && b_cols ? (b_rows - 1) * ldb + b_cols : 0;
+    const size_t ec = (m - 1) * ldc + n;
+    // C is INOUT when ldc > n: the gaps between rows keep the caller's bytes (beta = 0 only covers m x n)
+    const Operand ops[3] = {{a, sizeof(T), IN}, {b, sizeof(T), IN}, {c, sizeof(T), ldc > n ? INOUT : OUT}};
+    const size_t sizes[3] = {ea * sizeof(T), eb * sizeof(T), ec * sizeof(T)};
+    void *d[3];
+    SLAS_TRY(stage_all_begin(ctx, ops, sizes, 3, d));
+    SLAS_TRY(gemm_device<T>(ctx, ctx->stream, 1, (const T *)d[0], (const T *)d[1], (T *)d[2], m, n, k, lda, ldb, ldc, ta,
+                            tb, dense));
+    return stage_all_finish(ctx, ops, sizes, 3, d);
+}
+
+template <typename T>
+static int api_gemm_batched(size_t batch, const T *a, const T *b, T *c, size_t m, size_t n, size_t k, int ta, int tb) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (batch == 0 || m == 0 || n == 0) return SLAS_OK;
+    const size_t lda = ta ? m : k, ldb = tb ? k : n, ldc = n;  // src/tensor.rs:376-382 on dense objects
+    const void *ptrs[3] = {c, k ? (const void *)a : (const void *)c, k ? (const void *)b : (const void *)c};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 3, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (dev) return gemm_device<T>(ctx, ctx->stream, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, true);
+    const Operand ops[3] = {{a, m * k * sizeof(T), IN}, {b, k * n * sizeof(T), IN}, {c, m * n * sizeof(T), OUT}};
+    // granule: keep chunk starts 16-byte aligned for every operand
+    size_t granule = 1;
+    while ((granule * m * k * sizeof(T)) % 16 || (granule * k * n * sizeof(T)) % 16 || (granule * m * n * sizeof(T)) % 16)
+        granule *= 2;
+    return run_chunked(ctx, batch, granule, ops, 3, [&](void **d, size_t cnt, cudaStream_t st) {
+        return gemm_device<T>(ctx, st, cnt, (const T *)d[0], (const T *)d[1], (T *)d[2], m, n, k, lda, ldb, ldc, ta, tb,
+                              true);
+    });
+}
+
+// ---- matrix_vector_mul ---------------------------------------------------------------------------
+template <typename T>
+static int api_gemv(size_t batch, const T *a, const T *x, T *y, size_t m, size_t n, size_t lda, int ta, bool batched) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    const size_t xlen = ta ? n : m, ylen = ta ? m : n;
+    if (batch == 0 || ylen == 0) return SLAS_OK;
+    SLAS_REQUIRE(lda >= std::max<size_t>(m, 1), "matrix_vector_mul: lda %zu < width %zu", lda, m);
+    const void *ptrs[3] = {y, xlen ? (const void *)a : (const void *)y, xlen ? (const void *)x : (const void *)y};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 3, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const size_t ea = n ? (n - 1) * lda + m : 0;
+    const size_t sa = batched ? n * m : 0;
+    if (dev) return launch_gemv<T>(ctx, ctx->stream, batch, a, x, y, m, n, lda, ta, sa, xlen, ylen);
+    if (batched) {
+        const Operand ops[3] = {{a, n * m * sizeof(T), IN}, {x, xlen * sizeof(T), IN}, {y, ylen * sizeof(T), OUT}};
+        return run_chunked(ctx, batch, 1, ops, 3, [&](void **d, size_t cnt, cudaStream_t st) {
+            return launch_gemv<T>(ctx, st, cnt, (const T *)d[0], (const T *)d[1], (T *)d[2], m, n, lda, ta, sa, xlen, ylen);
+        });
+    }
+    const Operand ops[3] = {{a, sizeof(T), IN}, {x, sizeof(T), IN}, {y, sizeof(T), OUT}};
+    const size_t sizes[3] = {ea * sizeof(T), xlen * sizeof(T), ylen * sizeof(T)};
+    void *d[3];
+    SLAS_TRY(stage_all_begin(ctx, ops, sizes, 3, d));
+    SLAS_TRY(launch_gemv<T>(ctx, ctx->stream, 1, (const T *)d[0], (const T *)d[1], (T *)d[2], m, n, lda, ta, 0, 0, 0));
+    return stage_all_finish(ctx, ops, sizes, 3, d);
+}
+
+// ---- batched reductions -----------------------------------------------------------------------------
+template <typename T>
+static int api_batched_reduce(int mode, size_t batch, size_t len, const T *a, const T *b, T *out, T *a_mut) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (batch == 0) return SLAS_OK;
+    if (mode == 2 && len == 0) return SLAS_OK;
+    const T *base = mode == 2 ? a_mut : a;
+    const void *anchor = mode == 2 ? (const void *)a_mut : (const void *)out;
+    const void *ptrs[3] = {anchor, len ? (const void *)base : anchor, (mode == 0 && len) ? (const void *)b : anchor};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 3, &dev));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (dev) return launch_batched_reduce<T>(ctx, ctx->stream, mode, batch, len, a, b, out, a_mut);
+    // granule 4: out chunks (4 bytes x 4 = 16) stay aligned
+    const size_t granule = 4;
+    if (mode == 0) {
+        const Operand ops[3] = {{a, len * sizeof(T), IN}, {b, len * sizeof(T), IN}, {out, sizeof(T), OUT}};
+        return run_chunked(ctx, batch, granule, ops, 3, [&](void **d, size_t cnt, cudaStream_t st) {
+            return launch_batched_reduce<T>(ctx, st, 0, cnt, len, (const T *)d[0], (const T *)d[1], (T *)d[2], nullptr);
+        });
+    }
+    if (mode == 1) {
+        const Operand ops[2] = {{a, len * sizeof(T), IN}, {out, sizeof(T), OUT}};
+        return run_chunked(ctx, batch, granule, ops, 2, [&](void **d, size_t cnt, cudaStream_t st) {
+            return launch_batched_reduce<T>(ctx, st, 1, cnt, len, (const T *)d[0], nullptr, (T *)d[1], nullptr);
+        });
+    }
+    const Operand ops[1] = {{a_mut, len * sizeof(T), INOUT}};
+    size_t g2 = 1;
+    while ((g2 * len * sizeof(T)) % 16) g2 *= 2;
+    return run_chunked(ctx, batch, g2, ops, 1, [&](void **d, size_t cnt, cudaStream_t st) {
+        return launch_batched_reduce<T>(ctx, st, 2, cnt, len, nullptr, nullptr, nullptr, (T *)d[0]);
+    });
+}
+
+template <typename T>
+static int api_fill(size_t len, T *x, uint64_t seed, uint64_t offset, T lo, T hi) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (len == 0) return SLAS_OK;
+    bool dev = false;
+    SLAS_TRY(pointer_is_device(x, &dev));
+    SLAS_REQUIRE(dev, "fill_uniform writes device memory only");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return launch_fill_uniform<T>(ctx, ctx->stream, len, x, seed, offset, lo, hi);
+}
+
+}  // namespace slas
+
+using namespace slas;
+
+extern "C" {
+
+int slas_cuda_sfill_uniform(size_t len, float *x, uint64_t seed, uint64_t offset, float lo, float hi) {
+    return api_fill<float>(len, x, seed, offset, lo, hi);
+}
+int slas_cuda_dfill_uniform(size_t len, double *x, uint64_t seed, uint64_t offset, double lo, double hi) {
+    return api_fill<double>(len, x, seed, offset, lo, hi);
+}
+
+// DotProduct
+int slas_cuda_sdot(size_t len, const float *a, const float *b, float *out) {
+    return api_reduce<float>(0, 0, len, a, b, out, false, nullptr);
+}
+int slas_cuda_ddot(size_t len, const double *a, const double *b, double *out) {
+    return api_reduce<double>(0, 0, len, a, b, out, false, nullptr);
+}
+int slas_cuda_cdotu(size_t len, const float *a, const float *b, float *out) {
+    return api_reduce<float>(2, 0, 2 * len, a, b, out, false, nullptr);
+}
+int slas_cuda_zdotu(size_t len, const double *a, const double *b, double *out) {
+    return api_reduce<double>(2, 0, 2 * len, a, b, out, false, nullptr);
+}
+
+// Normalize
+int slas_cuda_snrm2(size_t len, const float *a, float *out) { return api_reduce<float>(1, 1, len, a, a, out, false, nullptr); }
+int slas_cuda_dnrm2(size_t len, const double *a, double *out) { return api_reduce<double>(1, 1, len, a, a, out, false, nullptr); }
+int slas_cuda_scnrm2(size_t len, const float *a, float *out) { return api_reduce<float>(1, 1, 2 * len, a, a, out, false, nullptr); }
+int slas_cuda_dznrm2(size_t len, const double *a, double *out) { return api_reduce<double>(1, 1, 2 * len, a, a, out, false, nullptr); }
+int slas_cuda_snormalize(size_t len, float *a) { return api_normalize<float>(len, a, false); }
+int slas_cuda_dnormalize(size_t len, double *a) { return api_normalize<double>(len, a, false); }
+int slas_cuda_cnormalize(size_t len, float *a) { return api_normalize<float>(2 * len, a, false); }
+int slas_cuda_znormalize(size_t len, double *a) { return api_normalize<double>(2 * len, a, false); }
+
+// Addition / Subtraction / Multiplication / Divition
+int slas_cuda_sadd(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(0, len, a, b, c); }
+int slas_cuda_ssub(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(1, len, a, b, c); }
+int slas_cuda_smul(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(2, len, a, b, c); }
+int slas_cuda_sdiv(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(3, len, a, b, c); }
+int slas_cuda_dadd(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(0, len, a, b, c); }
+int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(1, len, a, b, c); }
+int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(2, len, a, b, c); }
+int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(3, len, a, b, c); }
+
+// Transpose
+int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns) {
+    return api_transpose(1, len, elem_size, a, buffer, columns, false);
+}
+int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns) {
+    return api_transpose(1, len, elem_size, a, nullptr, columns, true);
+}
+int slas_cuda_transpose_batched(size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
+                                size_t columns) {
+    return api_transpose(batch, len, elem_size, a, buffer, columns, false);
+}
+
+// MatrixMul
+int slas_cuda_sgemm(const float *a, const float *b, float *c, size_t m, size_t n, size_t k, size_t lda, size_t ldb,
+                    size_t ldc, int a_trans, int b_trans) {
+    return api_gemm<float>(a, b, c, m, n, k, lda, ldb, ldc, a_trans, b_trans);
+}
+int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_t n, size_t k, size_t lda, size_t ldb,
+                    size_t ldc, int a_trans, int b_trans) {
+    return api_gemm<double>(a, b, c, m, n, k, lda, ldb, ldc, a_trans, b_trans);
+}
+int slas_cuda_set_sgemm_path(int path) {
+    SLAS_REQUIRE(path == 0 || path == 1, "sgemm path must be 0 (FFMA) or 1 (tcgen05 3xTF32)");
+    g_sgemm_path = path;
+    return SLAS_OK;
+}
+int slas_cuda_get_sgemm_path(int *path) {
+    SLAS_REQUIRE(path, "null path");
+    *path = g_sgemm_path;
+    return SLAS_OK;
+}
+int slas_cuda_sgemm_batched(size_t batch, const float *a, const float *b, float *c, size_t m, size_t n, size_t k,
+                            int a_trans, int b_trans) {
+    return api_gemm_batched<float>(batch, a, b, c, m, n, k, a_trans, b_trans);
+}
+int slas_cuda_dgemm_batched(size_t batch, const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
+                            int a_trans, int b_trans) {
+    return api_gemm_batched<double>(batch, a, b, c, m, n, k, a_trans, b_trans);
+}
+
+// matrix_vector_mul
+int slas_cuda_sgemv(const float *a, const float *x, float *y, size_t m, size_t n, size_t lda, int a_trans) {
+    return api_gemv<float>(1, a, x, y, m, n, lda, a_trans, false);
+}
+int slas_cuda_dgemv(const double *a, const double *x, double *y, size_t m, size_t n, size_t lda, int a_trans) {
+    return api_gemv<double>(1, a, x, y, m, n, lda, a_trans, false);
+}
+int slas_cuda_sgemv_batched(size_t batch, const float *a, const float *x, float *y, size_t m, size_t n, int a_trans) {
+    return api_gemv<float>(batch, a, x, y, m, n, m, a_trans, true);
+}
+int slas_cuda_dgemv_batched(size_t batch, const double *a, const double *x, double *y, size_t m, size_t n, int a_trans) {
+    return api_gemv<double>(batch, a, x, y, m, n, m, a_trans, true);
+}
+
+// batched dot / norm / normalize
+int slas_cuda_sdot_batched(size_t batch, size_t len, const float *a, const float *b, float *out) {
+    return api_batched_reduce<float>(0, batch, len, a, b, out, nullptr);
+}
+int slas_cuda_ddot_batched(size_t batch, size_t len, const double *a, const double *b, double *out) {
+    return api_batched_reduce<double>(0, batch, len, a, b, out, nullptr);
+}
+int slas_cuda_snrm2_batched(size_t batch, size_t len, const float *a, float *out) {
+    return api_batched_reduce<float>(1, batch, len, a, nullptr, out, nullptr);
+}
+int slas_cuda_dnrm2_batched(size_t batch, size_t len, const double *a, double *out) {
+    return api_batched_reduce<double>(1, batch, len, a, nullptr, out, nullptr);
+}
+int slas_cuda_snormalize_batched(size_t batch, size_t len, float *a) {
+    return api_batched_reduce<float>(2, batch, len, nullptr, nullptr, nullptr, a);
+}
+int slas_cuda_dnormalize_batched(size_t batch, size_t len, double *a) {
+    return api_batched_reduce<double>(2, batch, len, nullptr, nullptr, nullptr, a);
+}
+
+// sharded (one slice per rank + one allreduce)
+int slas_cuda_sdot_sharded(size_t local_len, const float *a, const float *b, float *out) {
+    return api_reduce<float>(0, 0, local_len, a, b, out, true, nullptr);
+}
+int slas_cuda_ddot_sharded(size_t local_len, const double *a, const double *b, double *out) {
+    return api_reduce<double>(0, 0, local_len, a, b, out, true, nullptr);
+}
+int slas_cuda_snrm2_sharded(size_t local_len, const float *a, float *out) {
+    return api_reduce<float>(1, 1, local_len, a, a, out, true, nullptr);
+}
+int slas_cuda_dnrm2_sharded(size_t local_len, const double *a, double *out) {
+    return api_reduce<double>(1, 1, local_len, a, a, out, true, nullptr);
+}
+int slas_cuda_snormalize_sharded(size_t local_len, float *a) { return api_normalize<float>(local_len, a, true); }
+int slas_cuda_dnormalize_sharded(size_t local_len, double *a) { return api_normalize<double>(local_len, a, true); }
+int slas_cuda_sdot_partial(size_t len, const float *a, const float *b, double *partial) {
+    return api_reduce<float>(0, 0, len, a, b, nullptr, false, partial);
+}
+int slas_cuda_ddot_partial(size_t len, const double *a, const double *b, double *partial) {
+    return api_reduce<double>(0, 0, len, a, b, nullptr, false, partial);
+}
+
+}  // extern "C"

@@ -1,0 +1,10 @@
+// comm.cuh -- internal face of comm.cu
+#pragma once
+#include "common.cuh"
+
+namespace slas {
+int comm_nranks();
+// In-place sum-allreduce of `count` f64 values at dev_inout over all ranks, on stream st.
+// A no-op when no communicator (or a 1-rank one) is active.
+int comm_allreduce_f64(double *dev_inout, size_t count, cudaStream_t st);
+}  // namespace slas

@@ -1,0 +1,122 @@
+// common.cuh -- shared plumbing of libslas_cuda: status/error handling, the
+// per-process context (device, stream, scratch), pointer classification and small
+// device helpers.  No reference code here: the reference has no device side at all.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <mutex>
+
+#include "../../include/slas_cuda.h"
+
+namespace slas {
+
+// ---- errors ------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define SLAS_CUDA_TRY(expr)                                                                 \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return ::slas::fail(SLAS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);                \
+    } while (0)
+
+#define SLAS_TRY(expr)                  \
+    do {                                \
+        int _s = (expr);                \
+        if (_s != SLAS_OK) return _s;   \
+    } while (0)
+
+#define SLAS_REQUIRE(cond, ...)                                        \
+    do {                                                               \
+        if (!(cond)) return ::slas::fail(SLAS_ERR_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ---- context -------------------------------------------------------------------
+struct Context {
+    int device = -1;
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    size_t hbm_bytes = 0;
+    int cc_major = 0, cc_minor = 0;
+    cudaStream_t own_stream = nullptr;   // created non-blocking at init
+    cudaStream_t stream = nullptr;       // the stream ops are enqueued on
+    // Reduction scratch: partial sums + self-resetting ticket + device scalars.
+    double *partials = nullptr;          // [kMaxPartials * 2]
+    unsigned int *ticket = nullptr;      // [4]
+    double *scalars = nullptr;           // [16] device scalars (norm, sharded partial, ...)
+    // Grow-only device workspace (transpose_inplace temp, tcgen05 hi/lo split, host staging).
+    void *workspace = nullptr;
+    size_t workspace_bytes = 0;
+    // Host-pointer path: staging area in HBM, copy streams + events, pinned bounce scalars.
+    void *staging = nullptr;
+    size_t staging_bytes = 0;
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};
+    double *pinned_scalars = nullptr;    // [16]
+    std::mutex mu;                       // serialises enqueue + scratch use
+};
+
+constexpr int kMaxPartials = 148 * 16;
+
+// Returns the context of the current device, initialising it on first use.
+int get_context(Context **out);
+int ensure_workspace(Context *ctx, size_t bytes, void **out);
+int ensure_staging(Context *ctx, size_t bytes, void **out);
+
+// Counts every kernel launch of this library (slas_cuda_launch_count).
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define SLAS_LAUNCH_CHECK()                                                                 \
+    do {                                                                                    \
+        ::slas::count_launch();                                                             \
+        cudaError_t _e = cudaPeekAtLastError();                                             \
+        if (_e != cudaSuccess) {                                                            \
+            cudaGetLastError();                                                             \
+            return ::slas::fail(SLAS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",          \
+                                cudaGetErrorString(_e), __FILE__, __LINE__);                \
+        }                                                                                   \
+    } while (0)
+
+// Pointer side: 1 device, 0 host (pageable or pinned).
+int pointer_is_device(const void *p, bool *is_dev);
+// Classify all data operands of a call; fails on a mix.
+int operands_side(const void *const *ptrs, int n, bool *is_dev);
+
+// Write a device scalar (value computed on ctx->stream) to `out`, which may be a host or a
+// device pointer.  Host: copies through the pinned bounce buffer and synchronises the stream.
+int deliver_scalar(Context *ctx, const void *dev_src, void *out, size_t bytes);
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device helpers ----------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum in a fixed order (warp butterflies, then warp 0 over the per-warp sums):
+// the same launch geometry always adds in the same order => deterministic.
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v, double *smem /* [THREADS/32] */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (warp == 0) {
+        r = lane < THREADS / 32 ? smem[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;  // valid in warp 0
+}
+#endif
+
+}  // namespace slas

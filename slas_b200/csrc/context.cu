@@ -1,0 +1,302 @@
+// context.cu -- process-global context, error reporting and the device-resident storage
+// entry points of the C ABI (include/slas_cuda.h).  A reference backend is a stateless ZST
+// (src/backends/rust.rs:2-3), so all device state lives here.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace slas {
+
+static thread_local char t_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+constexpr int kMaxDevices = 32;
+static Context g_ctx[kMaxDevices];
+static std::mutex g_init_mu;
+
+static int init_context(Context *c, int dev) {
+    cudaDeviceProp prop;
+    SLAS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(SLAS_ERR_CUDA, "device %d is sm_%d%d; libslas_cuda is built for sm_100a only", dev,
+                    prop.major, prop.minor);
+    c->sm_count = prop.multiProcessorCount;
+    c->l2_bytes = (size_t)prop.l2CacheSize;
+    c->hbm_bytes = prop.totalGlobalMem;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    SLAS_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    SLAS_CUDA_TRY(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials * 2));
+    SLAS_CUDA_TRY(cudaMalloc(&c->ticket, sizeof(unsigned int) * 4));
+    SLAS_CUDA_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned int) * 4));
+    SLAS_CUDA_TRY(cudaMalloc(&c->scalars, sizeof(double) * 16));
+    SLAS_CUDA_TRY(cudaMemset(c->scalars, 0, sizeof(double) * 16));
+    SLAS_CUDA_TRY(cudaMallocHost(&c->pinned_scalars, sizeof(double) * 16));
+    for (int i = 0; i < 3; ++i) {
+        SLAS_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking));
+        SLAS_CUDA_TRY(cudaEventCreateWithFlags(&c->copy_events[i], cudaEventDisableTiming));
+    }
+    c->device = dev;
+    return SLAS_OK;
+}
+
+int get_context(Context **out) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SLAS_ERR_CUDA, "no CUDA device: %s (libslas_cuda has no CPU fallback)",
+                    cudaGetErrorString(e));
+    }
+    if (dev < 0 || dev >= kMaxDevices) return fail(SLAS_ERR_CUDA, "device index %d out of range", dev);
+    Context *c = &g_ctx[dev];
+    if (c->device != dev) {
+        std::lock_guard<std::mutex> lk(g_init_mu);
+        if (c->device != dev) SLAS_TRY(init_context(c, dev));
+    }
+    *out = c;
+    return SLAS_OK;
+}
+
+int ensure_workspace(Context *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->workspace_bytes) {
+        if (ctx->workspace) {
+            SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            SLAS_CUDA_TRY(cudaFree(ctx->workspace));
+            ctx->workspace = nullptr;
+            ctx->workspace_bytes = 0;
+        }
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        SLAS_CUDA_TRY(cudaMalloc(&ctx->workspace, want));
+        ctx->workspace_bytes = want;
+    }
+    *out = ctx->workspace;
+    return SLAS_OK;
+}
+
+int ensure_staging(Context *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->staging_bytes) {
+        if (ctx->staging) {
+            SLAS_CUDA_TRY(cudaDeviceSynchronize());
+            SLAS_CUDA_TRY(cudaFree(ctx->staging));
+            ctx->staging = nullptr;
+            ctx->staging_bytes = 0;
+        }
+        size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        SLAS_CUDA_TRY(cudaMalloc(&ctx->staging, want));
+        ctx->staging_bytes = want;
+    }
+    *out = ctx->staging;
+    return SLAS_OK;
+}
+
+int pointer_is_device(const void *p, bool *is_dev) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(SLAS_ERR_CUDA, "cudaPointerGetAttributes: %s", cudaGetErrorString(e));
+    }
+    *is_dev = (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+    return SLAS_OK;
+}
+
+int operands_side(const void *const *ptrs, int n, bool *is_dev) {
+    bool first = false;
+    for (int i = 0; i < n; ++i) {
+        if (!ptrs[i]) return fail(SLAS_ERR_INVALID, "null data pointer (operand %d)", i);
+        bool d = false;
+        SLAS_TRY(pointer_is_device(ptrs[i], &d));
+        if (i == 0) first = d;
+        else if (d != first)
+            return fail(SLAS_ERR_INVALID, "operands mix host and device pointers (operand %d)", i);
+    }
+    *is_dev = first;
+    return SLAS_OK;
+}
+
+int deliver_scalar(Context *ctx, const void *dev_src, void *out, size_t bytes) {
+    if (!out) return fail(SLAS_ERR_INVALID, "null result pointer");
+    bool d = false;
+    SLAS_TRY(pointer_is_device(out, &d));
+    if (d) {
+        SLAS_CUDA_TRY(cudaMemcpyAsync(out, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return SLAS_OK;
+    }
+    SLAS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned_scalars, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->pinned_scalars, bytes);
+    return SLAS_OK;
+}
+
+}  // namespace slas
+
+using namespace slas;
+
+extern "C" {
+
+int slas_cuda_init(int device) {
+    if (device >= 0) SLAS_CUDA_TRY(cudaSetDevice(device));
+    Context *c;
+    return get_context(&c);
+}
+
+int slas_cuda_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        Context *c = &g_ctx[d];
+        if (c->device != d) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        cudaFree(c->partials);
+        cudaFree(c->ticket);
+        cudaFree(c->scalars);
+        cudaFree(c->workspace);
+        cudaFree(c->staging);
+        cudaFreeHost(c->pinned_scalars);
+        for (int i = 0; i < 3; ++i) {
+            if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
+            if (c->copy_events[i]) cudaEventDestroy(c->copy_events[i]);
+        }
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        c->device = -1;
+        c->own_stream = c->stream = nullptr;
+        c->partials = nullptr; c->ticket = nullptr; c->scalars = nullptr;
+        c->workspace = nullptr; c->workspace_bytes = 0; c->pinned_scalars = nullptr;
+        c->staging = nullptr; c->staging_bytes = 0;
+        for (int i = 0; i < 3; ++i) { c->copy_streams[i] = nullptr; c->copy_events[i] = nullptr; }
+    }
+    if (cur >= 0) cudaSetDevice(cur);
+    return SLAS_OK;
+}
+
+const char *slas_cuda_last_error(void) { return t_error; }
+
+int slas_cuda_device_count(int *count) {
+    SLAS_REQUIRE(count, "null count");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *count = 0;
+        return fail(SLAS_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    return SLAS_OK;
+}
+
+int slas_cuda_device_info(int *sm_count, size_t *l2_bytes, size_t *hbm_bytes, int *cc_major, int *cc_minor) {
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    if (sm_count) *sm_count = c->sm_count;
+    if (l2_bytes) *l2_bytes = c->l2_bytes;
+    if (hbm_bytes) *hbm_bytes = c->hbm_bytes;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    return SLAS_OK;
+}
+
+int slas_cuda_set_stream(void *cuda_stream) {
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return SLAS_OK;
+}
+
+int slas_cuda_synchronize(void) {
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SLAS_OK;
+}
+
+uint64_t slas_cuda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int slas_cuda_malloc(void **dptr, size_t bytes) {
+    SLAS_REQUIRE(dptr, "null dptr");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaMalloc(dptr, bytes ? bytes : 16));
+    return SLAS_OK;
+}
+
+int slas_cuda_free(void *dptr) {
+    if (!dptr) return SLAS_OK;
+    SLAS_CUDA_TRY(cudaFree(dptr));
+    return SLAS_OK;
+}
+
+int slas_cuda_malloc_host(void **hptr, size_t bytes) {
+    SLAS_REQUIRE(hptr, "null hptr");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaMallocHost(hptr, bytes ? bytes : 16));
+    return SLAS_OK;
+}
+
+int slas_cuda_free_host(void *hptr) {
+    if (!hptr) return SLAS_OK;
+    SLAS_CUDA_TRY(cudaFreeHost(hptr));
+    return SLAS_OK;
+}
+
+static int copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    if (bytes == 0) return SLAS_OK;
+    SLAS_REQUIRE(dst && src, "null pointer in memcpy");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
+    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return SLAS_OK;
+}
+
+int slas_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes) {
+    return copy_sync(dst, src, bytes, cudaMemcpyHostToDevice);
+}
+int slas_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes) {
+    return copy_sync(dst, src, bytes, cudaMemcpyDeviceToHost);
+}
+int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return SLAS_OK;
+    SLAS_REQUIRE(dst && src, "null pointer in memcpy");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return SLAS_OK;
+}
+int slas_cuda_memset(void *dst, int byte, size_t bytes) {
+    if (bytes == 0) return SLAS_OK;
+    SLAS_REQUIRE(dst, "null pointer in memset");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaMemsetAsync(dst, byte, bytes, c->stream));
+    return SLAS_OK;
+}
+
+int slas_cuda_is_device_ptr(const void *p, int *is_device) {
+    SLAS_REQUIRE(p && is_device, "null pointer");
+    bool d = false;
+    SLAS_TRY(pointer_is_device(p, &d));
+    *is_device = d ? 1 : 0;
+    return SLAS_OK;
+}
+
+}  // extern "C"

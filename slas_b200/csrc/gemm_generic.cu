@@ -1,0 +1,138 @@
+// gemm_generic.cu -- shape-agnostic MatrixMul kernels: the fallback for every product that has
+// no shape-specialised kernel (odd sizes, leading dimensions wider than the matrix, tiny
+// golden-test shapes), and matrix_vector_mul.
+//
+// Argument convention = the reference's call into cblas (src/backends/blas.rs:94-109, 136-149):
+//   gemm: C[m x n] = op(A) . op(B), row-major, alpha 1, beta 0,
+//         op(A)[i][p] = a_trans ? a[p*lda + i] : a[i*lda + p]
+//         op(B)[p][j] = b_trans ? b[j*ldb + p] : b[p*ldb + j]
+//   gemv: trait arguments m = underlying width, n = underlying height (src/tensor.rs:428-437);
+//         y = op(A) . x with A stored n rows x m columns, lda = m.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+// One thread per output element; consecutive threads walk along a row of C so that B (and C)
+// accesses coalesce.  Serves tiny shapes where launch latency dominates anyway.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_naive_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t total, unsigned m,
+                  unsigned n, unsigned k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t sa, size_t sb,
+                  size_t sc) {
+    const size_t per = (size_t)m * n;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (size_t)gridDim.x * 256) {
+        const size_t obj = t / per;
+        const unsigned e = (unsigned)(t - obj * per);
+        const unsigned i = e / n, j = e % n;
+        const T *pa = a + obj * sa;
+        const T *pb = b + obj * sb;
+        T acc = T(0);
+        for (unsigned p = 0; p < k; ++p) {
+            const T av = ta ? pa[(size_t)p * lda + i] : pa[(size_t)i * lda + p];
+            const T bv = tb ? pb[(size_t)j * ldb + p] : pb[(size_t)p * ldb + j];
+            acc = fma(av, bv, acc);
+        }
+        c[obj * sc + (size_t)i * ldc + j] = acc;
+    }
+}
+
+template <typename T>
+int launch_gemm_generic(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m,
+                        size_t n, size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a,
+                        size_t stride_b, size_t stride_c) {
+    if (batch == 0 || m == 0 || n == 0) return SLAS_OK;
+    SLAS_REQUIRE(m <= 0xffffffffu && n <= 0xffffffffu && k <= 0xffffffffu && m * n <= 0xffffffffu,
+                 "gemm: dimension too large for the generic kernel");
+    const size_t total = batch * m * n;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    gemm_naive_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a, b, c, total, (unsigned)m, (unsigned)n, (unsigned)k, lda,
+                                                           ldb, ldc, ta, tb, stride_a, stride_b, stride_c);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_gemm_generic<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *,
+                                        size_t, size_t, size_t, size_t, size_t, size_t, int, int, size_t, size_t,
+                                        size_t);
+template int launch_gemm_generic<double>(Context *, cudaStream_t, size_t, const double *, const double *, double *,
+                                         size_t, size_t, size_t, size_t, size_t, size_t, int, int, size_t, size_t,
+                                         size_t);
+
+// ---- gemv ------------------------------------------------------------------------------------
+// not transposed: y[i] = sum_j a[i*lda + j] * x[j]   (i < n rows, j < m columns): a warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemv_n_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, size_t total_rows, unsigned m,
+              unsigned n, size_t lda, size_t sa, size_t sx, size_t sy) {
+    const unsigned lane = threadIdx.x & 31;
+    const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * 8;
+    for (size_t row = warp; row < total_rows; row += nwarps) {
+        const size_t obj = row / n;
+        const unsigned i = (unsigned)(row - obj * n);
+        const T *pa = a + obj * sa + (size_t)i * lda;
+        const T *px = x + obj * sx;
+        T acc = T(0);
+        for (unsigned j = lane; j < m; j += 32) acc = fma(pa[j], px[j], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) y[obj * sy + i] = acc;
+    }
+}
+
+// transposed: y[j] = sum_i a[i*lda + j] * x[i]   (j < m, i < n): 32 columns x 8 row slices per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, unsigned m, unsigned n,
+              size_t lda, size_t sa, size_t sx, size_t sy, unsigned col_tiles) {
+    __shared__ T red[8][33];
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t obj = blockIdx.x / col_tiles;
+    const unsigned j = (blockIdx.x % col_tiles) * 32 + tx;
+    const T *pa = a + obj * sa;
+    const T *px = x + obj * sx;
+    T acc = T(0);
+    if (j < m)
+        for (unsigned i = ty; i < n; i += 8) acc = fma(pa[(size_t)i * lda + j], px[i], acc);
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < m) {
+        T s = red[0][tx];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) s += red[r][tx];
+        y[obj * sy + j] = s;
+    }
+}
+
+template <typename T>
+int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *x, T *y, size_t m, size_t n,
+                size_t lda, int ta, size_t stride_a, size_t stride_x, size_t stride_y) {
+    if (batch == 0) return SLAS_OK;
+    SLAS_REQUIRE(m <= 0xffffffffu && n <= 0xffffffffu, "gemv: dimension too large");
+    if (!ta) {
+        if (n == 0) return SLAS_OK;
+        const size_t rows = batch * n;
+        size_t blocks = (rows + 7) / 8;
+        const size_t cap = (size_t)ctx->sm_count * 16;
+        if (blocks > cap) blocks = cap;
+        gemv_n_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows, (unsigned)m, (unsigned)n, lda, stride_a,
+                                                           stride_x, stride_y);
+    } else {
+        if (m == 0) return SLAS_OK;
+        const size_t col_tiles = (m + 31) / 32;
+        const size_t blocks = batch * col_tiles;
+        SLAS_REQUIRE(blocks <= 0x7fffffffu, "gemv: too many tiles");
+        gemv_t_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, (unsigned)m, (unsigned)n, lda, stride_a, stride_x,
+                                                           stride_y, (unsigned)col_tiles);
+    }
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_gemv<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *, size_t,
+                                size_t, size_t, int, size_t, size_t, size_t);
+template int launch_gemv<double>(Context *, cudaStream_t, size_t, const double *, const double *, double *, size_t,
+                                 size_t, size_t, int, size_t, size_t, size_t);
+
+}  // namespace slas

@@ -1,0 +1,174 @@
+// gemm_large.cu -- one big MatrixMul::matrix_mul (replaces the cblas_{s,d}gemm call of
+// src/backends/blas.rs:94-109 for products too large for the batched static-shape kernels,
+// e.g. the single 4096 x 4096 f32 contraction of BASELINE config 4).
+//
+// This is the REFERENCE-FAITHFUL path: fp32 (fp64) multiply-add on the FMA pipe, every C element
+// accumulated in T in ascending k order inside one thread.  Classic register-tiled design:
+//   CTA tile (16*TMICRO)^2 x 8, 256 threads, each thread a TMICRO x TMICRO block of C held as
+//   2 x 2 sub-blocks one 16-byte vector wide (f32: 8x8, f64: 4x4) so every shared-memory
+//   read is a conflict-free 128-bit load; A and B tiles are staged k-major in padded shared
+//   memory, double buffered, with the next tile's global loads in flight during the FMAs.
+// Any m, n, k, leading dimensions and op(A)/op(B) are accepted: interior tiles use 128-bit
+// loads, edge tiles fall back to guarded scalar loads with zero fill.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+template <typename T> struct LargeCfg;
+template <> struct LargeCfg<float> {
+    static constexpr int VW = 4, TMICRO = 8, BM = 128, BN = 128, BK = 8, PAD = 4;
+    using V = float4;
+};
+template <> struct LargeCfg<double> {
+    static constexpr int VW = 2, TMICRO = 4, BM = 64, BN = 64, BK = 8, PAD = 2;
+    using V = double2;
+};
+
+// Fetch this thread's one vector of a (BM|BN) x BK operand tile into registers.
+// KCONTIG: the source is contiguous along k (A not transposed / B transposed); otherwise it is
+// contiguous along the m (or n) index.
+template <typename T, bool KCONTIG>
+__device__ __forceinline__ void tile_fetch(T (&reg)[LargeCfg<T>::VW], const T *__restrict__ src, size_t ld,
+                                           size_t row0, size_t rows, size_t k0, size_t kdim, bool vec_ok) {
+    using C = LargeCfg<T>;
+    constexpr int VW = C::VW;
+    const int t = threadIdx.x;
+    if (KCONTIG) {
+        constexpr int VPR = C::BK / VW;  // vectors per row
+        const size_t row = row0 + t / VPR, kk = k0 + (size_t)(t % VPR) * VW;
+        if (vec_ok && row < rows && kk + VW <= kdim) {
+            *reinterpret_cast<typename C::V *>(reg) = *reinterpret_cast<const typename C::V *>(src + row * ld + kk);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VW; ++i) reg[i] = (row < rows && kk + i < kdim) ? src[row * ld + kk + i] : T(0);
+        }
+    } else {
+        constexpr int VPK = C::BM / VW;  // vectors per k row (BM == BN)
+        const size_t kk = k0 + t / VPK, row = row0 + (size_t)(t % VPK) * VW;
+        if (vec_ok && kk < kdim && row + VW <= rows) {
+            *reinterpret_cast<typename C::V *>(reg) = *reinterpret_cast<const typename C::V *>(src + kk * ld + row);
+        } else {
+#pragma unroll
+            for (int i = 0; i < VW; ++i) reg[i] = (kk < kdim && row + i < rows) ? src[kk * ld + row + i] : T(0);
+        }
+    }
+}
+
+// Store the fetched vector k-major into shared memory: S[k][row].
+template <typename T, bool KCONTIG>
+__device__ __forceinline__ void tile_stash(T (*S)[LargeCfg<T>::BM + LargeCfg<T>::PAD], const T (&reg)[LargeCfg<T>::VW]) {
+    using C = LargeCfg<T>;
+    constexpr int VW = C::VW;
+    const int t = threadIdx.x;
+    if (KCONTIG) {
+        constexpr int VPR = C::BK / VW;
+        const int row = t / VPR, kq = (t % VPR) * VW;
+#pragma unroll
+        for (int i = 0; i < VW; ++i) S[kq + i][row] = reg[i];
+    } else {
+        constexpr int VPK = C::BM / VW;
+        const int kk = t / VPK, row = (t % VPK) * VW;
+        *reinterpret_cast<typename C::V *>(&S[kk][row]) = *reinterpret_cast<const typename C::V *>(reg);
+    }
+}
+
+template <typename T, bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+gemm_large_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t m, size_t n, size_t k,
+                  size_t lda, size_t ldb, size_t ldc, int vec_a, int vec_b, int vec_c) {
+    using C = LargeCfg<T>;
+    constexpr int VW = C::VW, BM = C::BM, BN = C::BN, BK = C::BK, PAD = C::PAD;
+    __shared__ __align__(16) T As[2][BK][BM + PAD];
+    __shared__ __align__(16) T Bs[2][BK][BN + PAD];
+    const size_t m0 = (size_t)blockIdx.y * BM, n0 = (size_t)blockIdx.x * BN;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+
+    T acc[2 * VW][2 * VW];
+#pragma unroll
+    for (int i = 0; i < 2 * VW; ++i)
+#pragma unroll
+        for (int j = 0; j < 2 * VW; ++j) acc[i][j] = T(0);
+
+    T ra[VW], rb[VW];
+    // op(A)[i][p]: !TA -> a[i*lda + p] (k contiguous); TA -> a[p*lda + i] (m contiguous)
+    tile_fetch<T, !TA>(ra, a, lda, m0, m, 0, k, vec_a);
+    // op(B)[p][j]: !TB -> b[p*ldb + j] (n contiguous); TB -> b[j*ldb + p] (k contiguous)
+    tile_fetch<T, TB>(rb, b, ldb, n0, n, 0, k, vec_b);
+    tile_stash<T, !TA>(As[0], ra);
+    tile_stash<T, TB>(Bs[0], rb);
+    __syncthreads();
+
+    const size_t ktiles = (k + BK - 1) / BK;
+    for (size_t kt = 0; kt < ktiles; ++kt) {
+        const int cur = (int)(kt & 1);
+        if (kt + 1 < ktiles) {
+            tile_fetch<T, !TA>(ra, a, lda, m0, m, (kt + 1) * BK, k, vec_a);
+            tile_fetch<T, TB>(rb, b, ldb, n0, n, (kt + 1) * BK, k, vec_b);
+        }
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T av[2 * VW], bv[2 * VW];
+            *reinterpret_cast<typename C::V *>(&av[0]) = *reinterpret_cast<const typename C::V *>(&As[cur][kk][ty * VW]);
+            *reinterpret_cast<typename C::V *>(&av[VW]) = *reinterpret_cast<const typename C::V *>(&As[cur][kk][BM / 2 + ty * VW]);
+            *reinterpret_cast<typename C::V *>(&bv[0]) = *reinterpret_cast<const typename C::V *>(&Bs[cur][kk][tx * VW]);
+            *reinterpret_cast<typename C::V *>(&bv[VW]) = *reinterpret_cast<const typename C::V *>(&Bs[cur][kk][BN / 2 + tx * VW]);
+#pragma unroll
+            for (int i = 0; i < 2 * VW; ++i)
+#pragma unroll
+                for (int j = 0; j < 2 * VW; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+        }
+        if (kt + 1 < ktiles) {
+            tile_stash<T, !TA>(As[cur ^ 1], ra);
+            tile_stash<T, TB>(Bs[cur ^ 1], rb);
+        }
+        __syncthreads();
+    }
+
+    // C rows: ty*VW + i (i < VW) and BM/2 + ty*VW + i; columns likewise with tx
+#pragma unroll
+    for (int hi = 0; hi < 2; ++hi)
+#pragma unroll
+        for (int i = 0; i < VW; ++i) {
+            const size_t row = m0 + hi * (BM / 2) + ty * VW + i;
+            if (row >= m) continue;
+#pragma unroll
+            for (int hj = 0; hj < 2; ++hj) {
+                const size_t col = n0 + hj * (BN / 2) + tx * VW;
+                T *dst = c + row * ldc + col;
+                if (vec_c && col + VW <= n) {
+                    *reinterpret_cast<typename C::V *>(dst) = *reinterpret_cast<const typename C::V *>(&acc[hi * VW + i][hj * VW]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < VW; ++j)
+                        if (col + j < n) dst[j] = acc[hi * VW + i][hj * VW + j];
+                }
+            }
+        }
+}
+
+template <typename T>
+int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *c, size_t m, size_t n, size_t k,
+                      size_t lda, size_t ldb, size_t ldc, int ta, int tb) {
+    using C = LargeCfg<T>;
+    (void)ctx;
+    if (m == 0 || n == 0) return SLAS_OK;
+    const size_t gx = (n + C::BN - 1) / C::BN, gy = (m + C::BM - 1) / C::BM;
+    SLAS_REQUIRE(gx <= 0x7fffffffu && gy <= 65535, "gemm: grid too large (%zu x %zu tiles)", gx, gy);
+    const int vec_a = aligned16(a) && (lda * sizeof(T)) % 16 == 0;
+    const int vec_b = aligned16(b) && (ldb * sizeof(T)) % 16 == 0;
+    const int vec_c = aligned16(c) && (ldc * sizeof(T)) % 16 == 0;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    if (!ta && !tb) gemm_large_kernel<T, false, false><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
+    else if (ta && !tb) gemm_large_kernel<T, true, false><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
+    else if (!ta && tb) gemm_large_kernel<T, false, true><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
+    else gemm_large_kernel<T, true, true><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_gemm_large<float>(Context *, cudaStream_t, const float *, const float *, float *, size_t, size_t,
+                                      size_t, size_t, size_t, size_t, int, int);
+template int launch_gemm_large<double>(Context *, cudaStream_t, const double *, const double *, double *, size_t,
+                                       size_t, size_t, size_t, size_t, size_t, int, int);
+
+}  // namespace slas

@@ -1,0 +1,302 @@
+// gemm_small.cu -- batched static-shape matrix_mul: C_i = op(A_i) . op(B_i) for `batch` dense
+// row-major objects laid out [[T; M*K]; batch], [[T; K*N]; batch] -> [[T; M*N]; batch].
+// Replaces a loop of Matrix::matrix_mul calls (src/tensor.rs:441-454), each of which is one
+// cblas_{s,d}gemm(RowMajor, opA, opB, m, n, k, 1, A, lda, B, ldb, 0, C, n)
+// (src/backends/blas.rs:94-109).  The reference's compile-time shapes (MatrixShape<M, K>,
+// src/tensor.rs:108-115) become template parameters here.
+//
+// These products are HBM-bound up to 32x32 (4x4 f32: 0.67 flop/byte), so the kernel is built
+// around the memory system, not the FMA pipe:
+//   * persistent CTAs, one producer warp + 8 consumer warps;
+//   * the producer streams CHUNKS of G consecutive matrices of A and of B into a ring of
+//     shared-memory stages with 1-D bulk TMA copies (cp.async.bulk -> UBLKCP) that complete on
+//     an mbarrier -- a batch of static matrices is one contiguous byte range, so no tensor
+//     map is needed and every HBM request is a full, aligned burst;
+//   * consumers wait on the stage's "full" barrier, compute register-tiled TM x TN blocks of
+//     C with FFMA/DFMA (fp32 products accumulate in fp32: the reference-faithful path) straight
+//     out of shared memory, store C with 128-bit coalesced stores, and release the stage
+//     through its "empty" barrier.
+// Deterministic: every C element is one thread's fixed-order sum over k.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// A wait that can never be satisfied (a byte-count bug) must fail loudly, not hang the GPU:
+// after 4 s of spinning the CTA traps and the launch reports an error.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---- register-tile helpers -----------------------------------------------------------------------
+template <typename T> struct KV { static constexpr int N = 16 / (int)sizeof(T); };  // elements per 16-byte vector
+
+// load CNT contiguous elements (CNT * sizeof(T) a multiple of 16, 16-byte aligned) from shared memory
+template <typename T, int CNT>
+__device__ __forceinline__ void lds_vec(T (&dst)[CNT], const T *p) {
+    static_assert((CNT * sizeof(T)) % 16 == 0, "vector loads move whole 16-byte words");
+    constexpr int NV = CNT * (int)sizeof(T) / 16;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p);
+    uint4 *d = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) d[i] = src[i];
+}
+template <typename T, int CNT>
+__device__ __forceinline__ void stg_vec(T *p, const T (&src)[CNT]) {
+    constexpr int NV = CNT * (int)sizeof(T) / 16;
+    const uint4 *s = reinterpret_cast<const uint4 *>(src);
+    uint4 *d = reinterpret_cast<uint4 *>(p);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) __stcs(d + i, s[i]);
+}
+
+template <typename T, int M_, int N_, int K_, int TM_, int TN_, int CONS_, int G_, int STAGES_>
+struct SmallCfg {
+    static constexpr int M = M_, N = N_, K = K_, TM = TM_, TN = TN_;
+    static constexpr int CONSUMERS = CONS_;           // consumer threads
+    static constexpr int G = G_;                      // matrices per stage
+    static constexpr int STAGES = STAGES_;
+    static constexpr int TPM = (M / TM) * (N / TN);   // threads per matrix
+    static constexpr int MPP = CONSUMERS / TPM;       // matrices per pass
+    static constexpr int PASSES = G / MPP;
+    static constexpr int A_ELEMS = M * K, B_ELEMS = K * N, C_ELEMS = M * N;
+    static constexpr size_t STAGE_BYTES = (size_t)G * (A_ELEMS + B_ELEMS) * sizeof(T);
+    static constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t);
+    static_assert(M % TM == 0 && N % TN == 0, "tile must divide the matrix");
+    static_assert(CONSUMERS % TPM == 0 && G % MPP == 0, "chunk must be whole passes");
+    static_assert((A_ELEMS * sizeof(T)) % 16 == 0 && (B_ELEMS * sizeof(T)) % 16 == 0, "bulk copies move 16-byte words");
+    static_assert((TN * sizeof(T)) % 16 == 0, "C rows are stored with 128-bit stores");
+};
+
+template <typename T, typename Cfg, bool TA, bool TB>
+__global__ void __launch_bounds__(Cfg::CONSUMERS + 32)
+gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t batch, size_t nchunks) {
+    constexpr int M = Cfg::M, N = Cfg::N, K = Cfg::K, TM = Cfg::TM, TN = Cfg::TN;
+    constexpr int G = Cfg::G, STAGES = Cfg::STAGES, TPM = Cfg::TPM, MPP = Cfg::MPP, PASSES = Cfg::PASSES;
+    constexpr int KVN = KV<T>::N;
+    constexpr int NCHUNK = K / KVN;
+    static_assert(K % KVN == 0, "K must be a whole number of 16-byte vectors");
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    T *stage_base = reinterpret_cast<T *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, Cfg::CONSUMERS / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == Cfg::CONSUMERS / 32) {
+        // ===== producer warp: one elected lane issues the bulk copies =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+                const uint32_t s = it % STAGES, use = it / STAGES;
+                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                const size_t first = ch * G;
+                const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+                T *sa = stage_base + (size_t)s * (Cfg::STAGE_BYTES / sizeof(T));
+                T *sb = sa + (size_t)G * Cfg::A_ELEMS;
+                const uint32_t bytes_a = cnt * Cfg::A_ELEMS * (uint32_t)sizeof(T);
+                const uint32_t bytes_b = cnt * Cfg::B_ELEMS * (uint32_t)sizeof(T);
+                mbar_expect_tx(full + s, bytes_a + bytes_b);
+                bulk_g2s(sa, a + first * Cfg::A_ELEMS, bytes_a, full + s);
+                bulk_g2s(sb, b + first * Cfg::B_ELEMS, bytes_b, full + s);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int t = threadIdx.x % TPM;          // thread within its matrix
+    const int slot = threadIdx.x / TPM;       // matrix within the pass
+    constexpr int TJ = N / TN, TI = M / TM;
+    const int tj = t % TJ, ti = t / TJ;
+    // row s of this thread's tile: interleaved for row-major A (conflict-free 128-bit smem reads
+    // across ti), contiguous for transposed A (its TM rows are one vector of A^T's storage)
+    auto row_of = [&](int s) { return TA ? ti * TM + s : ti + s * TI; };
+    const int j0 = tj * TN;
+    const int rot = TB ? tj : 0;  // k-chunk rotation: spreads transposed-B reads over the banks
+
+    uint32_t it = 0;
+    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+        const uint32_t s = it % STAGES, use = it / STAGES;
+        const size_t first = ch * G;
+        const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+        const T *sa = stage_base + (size_t)s * (Cfg::STAGE_BYTES / sizeof(T));
+        const T *sb = sa + (size_t)G * Cfg::A_ELEMS;
+        mbar_wait(full + s, use & 1);
+#pragma unroll 1
+        for (int p = 0; p < PASSES; ++p) {
+            const uint32_t mat = p * MPP + slot;
+            if (mat >= cnt) break;
+            const T *ma = sa + (size_t)mat * Cfg::A_ELEMS;
+            const T *mb = sb + (size_t)mat * Cfg::B_ELEMS;
+            T acc[TM][TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = T(0);
+#pragma unroll
+            for (int kc = 0; kc < NCHUNK; ++kc) {
+                const int k0 = ((kc + rot) % NCHUNK) * KVN;
+                T ablk[TM][KVN], bblk[KVN][TN];
+                if (!TA) {
+#pragma unroll
+                    for (int i = 0; i < TM; ++i) lds_vec<T, KVN>(ablk[i], ma + row_of(i) * K + k0);
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < KVN; ++kk) {
+                        if constexpr ((TM * sizeof(T)) % 16 == 0) {
+                            T col[TM];
+                            lds_vec<T, TM>(col, ma + (k0 + kk) * M + ti * TM);
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) ablk[i][kk] = col[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < TM; ++i) ablk[i][kk] = ma[(k0 + kk) * M + row_of(i)];
+                        }
+                    }
+                }
+                if (!TB) {
+#pragma unroll
+                    for (int kk = 0; kk < KVN; ++kk) lds_vec<T, TN>(bblk[kk], mb + (k0 + kk) * N + j0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        T row[KVN];
+                        lds_vec<T, KVN>(row, mb + (j0 + j) * K + k0);
+#pragma unroll
+                        for (int kk = 0; kk < KVN; ++kk) bblk[kk][j] = row[kk];
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < KVN; ++kk)
+#pragma unroll
+                    for (int i = 0; i < TM; ++i)
+#pragma unroll
+                        for (int j = 0; j < TN; ++j) acc[i][j] = fma(ablk[i][kk], bblk[kk][j], acc[i][j]);
+            }
+            T *mc = c + (first + mat) * Cfg::C_ELEMS;
+#pragma unroll
+            for (int i = 0; i < TM; ++i) stg_vec<T, TN>(mc + row_of(i) * N + j0, acc[i]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+template <typename T, typename Cfg>
+static int launch_cfg(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, int ta, int tb) {
+    const size_t nchunks = (batch + Cfg::G - 1) / Cfg::G;
+    const size_t smem = Cfg::SMEM_BYTES;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    size_t grid = (size_t)ctx->sm_count * per_sm;
+    if (grid > nchunks) grid = nchunks;
+    const unsigned threads = Cfg::CONSUMERS + 32;
+#define SLAS_SMALL_LAUNCH(TA_, TB_)                                                                              \
+    do {                                                                                                         \
+        auto kern = gemm_small_kernel<T, Cfg, TA_, TB_>;                                                         \
+        SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        kern<<<(unsigned)grid, threads, smem, st>>>(a, b, c, batch, nchunks);                                    \
+    } while (0)
+    if (!ta && !tb) SLAS_SMALL_LAUNCH(false, false);
+    else if (ta && !tb) SLAS_SMALL_LAUNCH(true, false);
+    else if (!ta && tb) SLAS_SMALL_LAUNCH(false, true);
+    else SLAS_SMALL_LAUNCH(true, true);
+#undef SLAS_SMALL_LAUNCH
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+//                         T       M   N   K  TM TN CONS   G  STAGES
+using CfgS4 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 128, 4>;
+using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3>;
+using CfgS16 = SmallCfg<float, 16, 16, 16, 4, 4, 256, 16, 3>;
+using CfgS32 = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 3>;
+using CfgD4 = SmallCfg<double, 4, 4, 4, 1, 4, 256, 128, 4>;
+using CfgD8 = SmallCfg<double, 8, 8, 8, 2, 4, 256, 32, 3>;
+using CfgD16 = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 3>;
+using CfgD32 = SmallCfg<double, 32, 32, 32, 8, 4, 128, 4, 3>;
+
+template <>
+int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch, const float *a, const float *b,
+                                     float *c, size_t m, size_t n, size_t k, int ta, int tb) {
+    if (batch == 0) return SLAS_OK;
+    if (!(aligned16(a) && aligned16(b) && aligned16(c)) || m != n || n != k) return SLAS_ERR_UNSUPPORTED;
+    switch (m) {
+    case 4: return launch_cfg<float, CfgS4>(ctx, st, batch, a, b, c, ta, tb);
+    case 8: return launch_cfg<float, CfgS8>(ctx, st, batch, a, b, c, ta, tb);
+    case 16: return launch_cfg<float, CfgS16>(ctx, st, batch, a, b, c, ta, tb);
+    case 32: return launch_cfg<float, CfgS32>(ctx, st, batch, a, b, c, ta, tb);
+    }
+    return SLAS_ERR_UNSUPPORTED;
+}
+
+template <>
+int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batch, const double *a, const double *b,
+                                      double *c, size_t m, size_t n, size_t k, int ta, int tb) {
+    if (batch == 0) return SLAS_OK;
+    if (!(aligned16(a) && aligned16(b) && aligned16(c)) || m != n || n != k) return SLAS_ERR_UNSUPPORTED;
+    switch (m) {
+    case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
+    case 8: return launch_cfg<double, CfgD8>(ctx, st, batch, a, b, c, ta, tb);
+    case 16: return launch_cfg<double, CfgD16>(ctx, st, batch, a, b, c, ta, tb);
+    case 32: return launch_cfg<double, CfgD32>(ctx, st, batch, a, b, c, ta, tb);
+    }
+    return SLAS_ERR_UNSUPPORTED;
+}
+
+}  // namespace slas

@@ -1,0 +1,53 @@
+// kernels.cuh -- internal launchers.  Every launcher enqueues on the stream it is given and
+// works on DEVICE pointers; api.cu adds the host-pointer staging and the C ABI on top.
+#pragma once
+#include "common.cuh"
+
+namespace slas {
+
+// vector_ops.cu
+template <typename T>
+int launch_ewise(Context *ctx, cudaStream_t st, int op, size_t len, const T *a, const T *b, T *c);
+// kind 0 dot, 1 squared-norm, 2 complex dotu (len counts REAL scalars); mode 0 cast, 1 sqrt
+template <typename T>
+int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
+                  T *typed_out, int mode, int accumulate);
+template <typename T> int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode);
+template <typename T> int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, T *a, const T *norm_dev);
+// mode 0 dot, 1 norm, 2 normalize in place
+template <typename T>
+int launch_batched_reduce(Context *ctx, cudaStream_t st, int mode, size_t batch, size_t len, const T *a,
+                          const T *b, T *out, T *a_mut);
+template <typename T>
+int launch_fill_uniform(Context *ctx, cudaStream_t st, size_t len, T *x, uint64_t seed, uint64_t offset, T lo, T hi);
+
+// transpose.cu -- batch objects of `len` elements each
+int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a,
+                     void *buffer, size_t columns);
+
+// gemm_small.cu -- batched dense small GEMM; returns SLAS_ERR_UNSUPPORTED when no
+// shape-specialised kernel exists (caller falls back to the generic kernel).
+template <typename T>
+int launch_gemm_small_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c,
+                              size_t m, size_t n, size_t k, int ta, int tb);
+
+// gemm_generic.cu -- any shape / leading dimensions, optional batch with element strides
+template <typename T>
+int launch_gemm_generic(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m,
+                        size_t n, size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a,
+                        size_t stride_b, size_t stride_c);
+template <typename T>
+int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *x, T *y, size_t m, size_t n,
+                size_t lda, int ta, size_t stride_a, size_t stride_x, size_t stride_y);
+
+// gemm_large.cu -- FFMA/DFMA tiled kernel for big single products
+template <typename T>
+int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *c, size_t m, size_t n, size_t k,
+                      size_t lda, size_t ldb, size_t ldc, int ta, int tb);
+
+// gemm_tcgen05.cu -- 3xTF32 on the 5th-gen tensor cores (TMA + TMEM); SLAS_ERR_UNSUPPORTED
+// when the shape does not fit its tiles.
+int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m,
+                        size_t n, size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb);
+
+}  // namespace slas

@@ -1,0 +1,183 @@
+// transpose.cu -- Transpose::{transpose, transpose_inplace} (replaces src/backends/rust.rs:151-177)
+// for single objects and for batches [[T; len]; batch].
+//
+// Reference semantics, per object:   rows = len / columns
+//     buffer[columns*row + column] = a[rows*column + row]   column in [0,columns), row in [0,rows)
+// i.e. the input is read as `columns` x `rows` row-major and written `rows` x `columns`
+// row-major; `columns` is the column count of the OUTPUT.  Elements past rows*columns (when
+// columns does not divide len) are never written, exactly like the reference's loop.
+// Pure data movement on opaque 4/8/16-byte elements => bit-exact for any Copy type.
+//
+// Kernels: (1) big matrices: 32x32 element tiles through padded shared memory, both sides
+// coalesced; (2) many small objects: one warp per object, coalesced read into a padded
+// per-warp shared tile, coalesced write of the transposed order; (3) square n x n with n a
+// multiple of the 16-byte vector width: 128-bit loads, register micro-transpose, 128-bit
+// stores, no shared memory.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+struct alignas(16) Elem16 { uint64_t lo, hi; };
+
+// ---- (1) tiled ---------------------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256)
+transpose_tiled_kernel(const E *__restrict__ in, E *__restrict__ out, size_t len, unsigned rows, unsigned columns,
+                       unsigned tiles_r, unsigned tiles_c) {
+    __shared__ E tile[32][33];
+    // blockIdx.x enumerates (object, tile_c, tile_r) with tile_r fastest
+    size_t bid = blockIdx.x;
+    const unsigned tr = (unsigned)(bid % tiles_r); bid /= tiles_r;
+    const unsigned tc = (unsigned)(bid % tiles_c); bid /= tiles_c;
+    const size_t obj = bid;
+    const E *src = in + obj * len;
+    E *dst = out + obj * len;
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    // input: `columns` rows of `rows` elements.  tile covers input rows [tc*32, +32), cols [tr*32, +32)
+#pragma unroll
+    for (unsigned j = 0; j < 32; j += 8) {
+        const unsigned c = tc * 32 + ty + j, r = tr * 32 + tx;
+        if (c < columns && r < rows) tile[ty + j][tx] = src[(size_t)c * rows + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (unsigned j = 0; j < 32; j += 8) {
+        const unsigned r = tr * 32 + ty + j, c = tc * 32 + tx;
+        if (r < rows && c < columns) dst[(size_t)r * columns + c] = tile[tx][ty + j];
+    }
+}
+
+// ---- (2) warp per small object ---------------------------------------------------------------
+template <typename E>
+__global__ void __launch_bounds__(256)
+transpose_small_kernel(const E *__restrict__ in, E *__restrict__ out, size_t batch, unsigned len, unsigned rows,
+                       unsigned columns, unsigned warp_elems /* smem elements per warp */) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    E *smem = reinterpret_cast<E *>(smem_raw) + (size_t)(threadIdx.x >> 5) * warp_elems;
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned pitch = rows + 1;
+    const unsigned live = rows * columns;
+    const size_t warp_global = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const size_t nwarps = (size_t)gridDim.x * 8;
+    // per-step increments of (quotient, remainder) when the linear index advances by 32
+    const unsigned qi = 32 / rows, ri = 32 % rows;
+    const unsigned qo = 32 / columns, ro = 32 % columns;
+    for (size_t obj = warp_global; obj < batch; obj += nwarps) {
+        const E *src = in + obj * len;
+        E *dst = out + obj * len;
+        unsigned c = lane / rows, r = lane % rows;
+        for (unsigned e = lane; e < live; e += 32) {
+            smem[c * pitch + r] = src[e];
+            c += qi; r += ri;
+            if (r >= rows) { r -= rows; ++c; }
+        }
+        __syncwarp();
+        unsigned orow = lane / columns, ocol = lane % columns;
+        for (unsigned o = lane; o < live; o += 32) {
+            dst[o] = smem[ocol * pitch + orow];
+            orow += qo; ocol += ro;
+            if (ocol >= columns) { ocol -= columns; ++orow; }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- (3) square n x n, 128-bit both sides, register micro-transpose ---------------------------
+// VW = elements per 16-byte vector (4 for 4-byte, 2 for 8-byte elements).  One thread owns a
+// VW x VW block: loads VW vectors from VW consecutive input rows, transposes in registers,
+// stores VW vectors to VW consecutive output rows.  Threads are ordered with the input
+// column block fastest, so loads are contiguous along input rows and the stores of the
+// threads sharing an output row land in the same instruction (full 32-byte sectors).
+// __ldcs overloads do not exist for arbitrary structs: route through uint4
+template <typename V> __device__ __forceinline__ V ld16(const V *p) {
+    uint4 r = __ldcs(reinterpret_cast<const uint4 *>(p));
+    return *reinterpret_cast<V *>(&r);
+}
+
+template <typename E, int VW>
+__global__ void __launch_bounds__(256)
+transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nblocks_total, unsigned n,
+                             unsigned blocks_per_row) {
+    struct alignas(16) V { E v[VW]; };
+    const unsigned blocks_per_obj = blocks_per_row * blocks_per_row;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < nblocks_total; t += (size_t)gridDim.x * 256) {
+        const size_t obj = t / blocks_per_obj;
+        const unsigned w = (unsigned)(t - obj * blocks_per_obj);
+        const unsigned bi = w / blocks_per_row, bj = w % blocks_per_row;
+        const E *src = in + obj * (size_t)n * n + (size_t)(bi * VW) * n + bj * VW;
+        E *dst = out + obj * (size_t)n * n + (size_t)(bj * VW) * n + bi * VW;
+        V x[VW];
+#pragma unroll
+        for (int s = 0; s < VW; ++s) x[s] = ld16(reinterpret_cast<const V *>(src + (size_t)s * n));
+#pragma unroll
+        for (int s = 0; s < VW; ++s) {
+            V y;
+#pragma unroll
+            for (int q = 0; q < VW; ++q) y.v[q] = x[q].v[s];
+            __stcs(reinterpret_cast<uint4 *>(dst + (size_t)s * n), *reinterpret_cast<uint4 *>(&y));
+        }
+    }
+}
+
+template <typename E>
+static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, size_t len, const E *a, E *buffer,
+                                  size_t columns) {
+    const size_t rows = len / columns;
+    if (rows == 0 || batch == 0) return SLAS_OK;
+    constexpr int VW = 16 / (int)sizeof(E);
+    // (3) square, vector-aligned
+    if constexpr (VW > 1) {
+      if (rows == columns && len == rows * columns && rows % VW == 0 && rows <= 64 && aligned16(a) &&
+          aligned16(buffer)) {
+        const unsigned bpr = (unsigned)(rows / VW);
+        const size_t total = batch * (size_t)bpr * bpr;
+        size_t blocks = (total + 255) / 256;
+        const size_t cap = (size_t)ctx->sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        transpose_square_vec_kernel<E, VW><<<(unsigned)blocks, 256, 0, st>>>(a, buffer, total, (unsigned)rows, bpr);
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+      }
+    }
+    // (2) small objects: padded tile must fit the per-warp shared slice
+    const size_t padded = columns * (rows + 1);
+    constexpr size_t kWarpBytes = 12 * 1024;
+    if (padded * sizeof(E) <= kWarpBytes && len <= 0xffffffffu) {
+        const size_t smem = 8 * padded * sizeof(E);
+        if (smem > 48 * 1024)
+            SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(8 * kWarpBytes)));
+        size_t blocks = (batch + 7) / 8;
+        const size_t cap = (size_t)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        transpose_small_kernel<E><<<(unsigned)blocks, 256, smem, st>>>(a, buffer, batch, (unsigned)len,
+                                                                       (unsigned)rows, (unsigned)columns,
+                                                                       (unsigned)padded);
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+    }
+    // (1) tiled
+    SLAS_REQUIRE(rows <= 0xffffffffu && columns <= 0xffffffffu, "transpose: dimension too large");
+    const size_t tiles_r = (rows + 31) / 32, tiles_c = (columns + 31) / 32;
+    const size_t blocks = batch * tiles_r * tiles_c;
+    SLAS_REQUIRE(blocks <= 0x7fffffffu, "transpose: too many tiles (%zu)", blocks);
+    transpose_tiled_kernel<E><<<(unsigned)blocks, 256, 0, st>>>(a, buffer, len, (unsigned)rows, (unsigned)columns,
+                                                                (unsigned)tiles_r, (unsigned)tiles_c);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a,
+                     void *buffer, size_t columns) {
+    SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, rust.rs:169)");
+    SLAS_REQUIRE(a != buffer, "transpose: input and buffer alias (use transpose_inplace)");
+    switch (elem_size) {
+    case 4: return launch_transpose_typed<uint32_t>(ctx, st, batch, len, (const uint32_t *)a, (uint32_t *)buffer, columns);
+    case 8: return launch_transpose_typed<uint64_t>(ctx, st, batch, len, (const uint64_t *)a, (uint64_t *)buffer, columns);
+    case 16: return launch_transpose_typed<Elem16>(ctx, st, batch, len, (const Elem16 *)a, (Elem16 *)buffer, columns);
+    }
+    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 4, 8, 16)", elem_size);
+}
+
+}  // namespace slas

@@ -1,0 +1,516 @@
+// vector_ops.cu -- the bandwidth-bound vector half of the hot path:
+//   element-wise add/sub/mul/div   (replaces src/backends/rust.rs:45-73)
+//   dot / complex dotu             (replaces src/backends/rust.rs:20-41, src/backends/blas.rs:15-52)
+//   norm / normalize               (replaces src/backends/rust.rs:116-147, src/backends/blas.rs:156-170)
+// plus their batched forms over [[T; LEN]; batch].
+//
+// Design (B200): 128-bit coalesced streaming loads (ld.global.cs), several independent
+// loads in flight per thread, fp32/fp64 register accumulators flushed into f64, warp-shuffle
+// + block reduction, and a deterministic single-launch grid reduction: every block writes
+// its partial to partials[blockIdx], the last block to finish (self-resetting ticket) adds
+// the partials in index order.  No float atomics anywhere => same input, same launch
+// geometry, same bits.  Element-wise ops and the normalize divide are single IEEE
+// operations (no fast-math, true division) => bit-exact against the reference.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+// ---------------------------------------------------------------------------------------
+// vector types: 16 bytes per load
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
+template <typename V> __device__ __forceinline__ void st_stream(V *p, V v) { __stcs(p, v); }
+
+template <int OP, typename T> __device__ __forceinline__ T apply_op(T a, T b) {
+    if (OP == 0) return a + b;
+    if (OP == 1) return a - b;
+    if (OP == 2) return a * b;
+    return a / b;  // IEEE div.rn (no --use_fast_math): rust.rs:45-73 divides, it does not multiply by 1/b
+}
+template <int OP> __device__ __forceinline__ float4 apply_vec(float4 a, float4 b) {
+    return make_float4(apply_op<OP>(a.x, b.x), apply_op<OP>(a.y, b.y), apply_op<OP>(a.z, b.z),
+                       apply_op<OP>(a.w, b.w));
+}
+template <int OP> __device__ __forceinline__ double2 apply_vec(double2 a, double2 b) {
+    return make_double2(apply_op<OP>(a.x, b.x), apply_op<OP>(a.y, b.y));
+}
+
+// ---- element-wise ------------------------------------------------------------------------
+constexpr int kEwThreads = 256;
+
+template <typename T, int OP, int UNROLL>
+__global__ void __launch_bounds__(kEwThreads)
+ewise_vec_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t nvec, size_t len) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const V *av = reinterpret_cast<const V *>(a);
+    const V *bv = reinterpret_cast<const V *>(b);
+    V *cv = reinterpret_cast<V *>(c);
+    const size_t base = (size_t)blockIdx.x * (kEwThreads * UNROLL) + threadIdx.x;
+    V ra[UNROLL], rb[UNROLL];
+    if (base + (size_t)(UNROLL - 1) * kEwThreads < nvec) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) ra[u] = ld_stream(av + base + (size_t)u * kEwThreads);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) rb[u] = ld_stream(bv + base + (size_t)u * kEwThreads);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) st_stream(cv + base + (size_t)u * kEwThreads, apply_vec<OP>(ra[u], rb[u]));
+    } else {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const size_t i = base + (size_t)u * kEwThreads;
+            if (i < nvec) st_stream(cv + i, apply_vec<OP>(ld_stream(av + i), ld_stream(bv + i)));
+        }
+    }
+    // scalar tail (len % N elements), done by the first threads of block 0
+    if (blockIdx.x == 0) {
+        const size_t i = nvec * N + threadIdx.x;
+        if (i < len) c[i] = apply_op<OP>(a[i], b[i]);
+    }
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kEwThreads)
+ewise_scalar_kernel(const T *a, const T *b, T *c, size_t len) {
+    for (size_t i = (size_t)blockIdx.x * kEwThreads + threadIdx.x; i < len; i += (size_t)gridDim.x * kEwThreads)
+        c[i] = apply_op<OP>(a[i], b[i]);
+}
+
+template <typename T, int OP>
+static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b, T *c) {
+    constexpr int N = Vec16<T>::N;
+    constexpr int UNROLL = 4;
+    if (len == 0) return SLAS_OK;
+    if (aligned16(a) && aligned16(b) && aligned16(c)) {
+        const size_t nvec = len / N;
+        size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
+        if (blocks == 0) blocks = 1;
+        SLAS_REQUIRE(blocks <= 0x7fffffffu, "ewise: vector too long (%zu elements)", len);
+        ewise_vec_kernel<T, OP, UNROLL><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, b, c, nvec, len);
+    } else {
+        size_t blocks = (len + kEwThreads - 1) / kEwThreads;
+        const size_t cap = (size_t)ctx->sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        ewise_scalar_kernel<T, OP><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, b, c, len);
+    }
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+template <typename T>
+int launch_ewise(Context *ctx, cudaStream_t st, int op, size_t len, const T *a, const T *b, T *c) {
+    switch (op) {
+    case 0: return launch_ewise_op<T, 0>(ctx, st, len, a, b, c);
+    case 1: return launch_ewise_op<T, 1>(ctx, st, len, a, b, c);
+    case 2: return launch_ewise_op<T, 2>(ctx, st, len, a, b, c);
+    case 3: return launch_ewise_op<T, 3>(ctx, st, len, a, b, c);
+    }
+    return fail(SLAS_ERR_INVALID, "unknown element-wise op %d", op);
+}
+template int launch_ewise<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, float *);
+template int launch_ewise<double>(Context *, cudaStream_t, int, size_t, const double *, const double *, double *);
+
+// ---- reductions --------------------------------------------------------------------------
+// KIND: 0 = dot (sum a*b), 1 = squared norm (sum a*a, one stream), 2 = complex dotu
+// (two sums: re, im over interleaved pairs).
+constexpr int kRedThreads = 256;
+constexpr int kRedUnroll = 4;
+constexpr int kFlushEvery = 16;  // outer iterations between flushes of the fp accumulators into f64
+
+template <typename T> struct Acc2 { T re, im; };
+
+template <typename T, int KIND>
+struct Reducer {
+    T acc[kRedUnroll];
+    T acc_im[kRedUnroll];
+    double sum = 0.0, sum_im = 0.0;
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int u = 0; u < kRedUnroll; ++u) { acc[u] = T(0); acc_im[u] = T(0); }
+    }
+    __device__ __forceinline__ void flush() {
+        T s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        sum += (double)s;
+        if (KIND == 2) {
+            T t = (acc_im[0] + acc_im[1]) + (acc_im[2] + acc_im[3]);
+            sum_im += (double)t;
+        }
+        clear();
+    }
+    // one 16-byte vector from each operand
+    __device__ __forceinline__ void add(int u, float4 x, float4 y) {
+        if (KIND == 2) {
+            acc[u] = fmaf(x.x, y.x, acc[u]); acc[u] = fmaf(-x.y, y.y, acc[u]);
+            acc[u] = fmaf(x.z, y.z, acc[u]); acc[u] = fmaf(-x.w, y.w, acc[u]);
+            acc_im[u] = fmaf(x.x, y.y, acc_im[u]); acc_im[u] = fmaf(x.y, y.x, acc_im[u]);
+            acc_im[u] = fmaf(x.z, y.w, acc_im[u]); acc_im[u] = fmaf(x.w, y.z, acc_im[u]);
+        } else {
+            acc[u] = fmaf(x.x, y.x, acc[u]); acc[u] = fmaf(x.y, y.y, acc[u]);
+            acc[u] = fmaf(x.z, y.z, acc[u]); acc[u] = fmaf(x.w, y.w, acc[u]);
+        }
+    }
+    __device__ __forceinline__ void add(int u, double2 x, double2 y) {
+        if (KIND == 2) {
+            acc[u] = fma(x.x, y.x, acc[u]); acc[u] = fma(-x.y, y.y, acc[u]);
+            acc_im[u] = fma(x.x, y.y, acc_im[u]); acc_im[u] = fma(x.y, y.x, acc_im[u]);
+        } else {
+            acc[u] = fma(x.x, y.x, acc[u]); acc[u] = fma(x.y, y.y, acc[u]);
+        }
+    }
+    __device__ __forceinline__ void add_scalar(T x, T y) { sum += (double)x * (double)y; }
+};
+
+// result[0] (and result[1] for KIND 2) receive the f64 sums; typed_out (may be null) receives
+// mode 0: (T)sum [, (T)sum_im]   mode 1: (T)sqrt(sum).  If accumulate != 0 the previous
+// content of result[] is added first (chunked host vectors).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kRedThreads)
+reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised,
+              double *__restrict__ partials, unsigned int *__restrict__ ticket, double *__restrict__ result,
+              T *__restrict__ typed_out, int mode, int accumulate) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    __shared__ double red[kRedThreads / 32];
+    __shared__ bool is_last;
+    Reducer<T, KIND> r;
+    r.clear();
+    const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * kRedThreads;
+    if (vectorised) {
+        const V *av = reinterpret_cast<const V *>(a);
+        const V *bv = reinterpret_cast<const V *>(b);
+        const size_t stride = nthreads * kRedUnroll;
+        size_t i = (size_t)blockIdx.x * (kRedThreads * kRedUnroll) + threadIdx.x;
+        int since_flush = 0;
+        // full tiles: every thread of the block has all kRedUnroll vectors in range
+        for (; i + (size_t)(kRedUnroll - 1) * kRedThreads < nvec; i += stride) {
+            V x[kRedUnroll], y[kRedUnroll];
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) x[u] = ld_stream(av + i + (size_t)u * kRedThreads);
+            if (KIND != 1) {
+#pragma unroll
+                for (int u = 0; u < kRedUnroll; ++u) y[u] = ld_stream(bv + i + (size_t)u * kRedThreads);
+            }
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
+            if (++since_flush == kFlushEvery) { r.flush(); since_flush = 0; }
+        }
+        // ragged remainder of this thread's last tile
+#pragma unroll
+        for (int u = 0; u < kRedUnroll; ++u) {
+            const size_t j = i + (size_t)u * kRedThreads;
+            if (j < nvec) {
+                V x = ld_stream(av + j);
+                V y = KIND == 1 ? x : ld_stream(bv + j);
+                r.add(u, x, y);
+            }
+        }
+        r.flush();
+        // scalar tail: len % N elements (never splits a complex pair: N is even)
+        if (KIND != 2) {
+            const size_t j = nvec * N + tid;
+            if (j < len) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+        }
+    } else {
+        // unaligned operands: scalar grid-stride loop, f64 accumulation
+        if (KIND == 2) {
+            for (size_t j = tid; j < len / 2; j += nthreads) {
+                const double ar = a[2 * j], ai = a[2 * j + 1], br = b[2 * j], bi = b[2 * j + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
+        } else {
+            for (size_t j = tid; j < len; j += nthreads) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+        }
+    }
+    double s = block_sum<kRedThreads>(r.sum, red);
+    double s_im = 0.0;
+    if (KIND == 2) s_im = block_sum<kRedThreads>(r.sum_im, red);
+    if (threadIdx.x == 0) {
+        partials[blockIdx.x] = s;
+        if (KIND == 2) partials[kMaxPartials + blockIdx.x] = s_im;
+        __threadfence();
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0 after the last block
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block: add the partials in index order (fixed stride pattern => deterministic)
+    double p = 0.0, p_im = 0.0;
+    for (unsigned int j = threadIdx.x; j < gridDim.x; j += kRedThreads) {
+        p += __ldcg(partials + j);
+        if (KIND == 2) p_im += __ldcg(partials + kMaxPartials + j);
+    }
+    p = block_sum<kRedThreads>(p, red);
+    if (KIND == 2) p_im = block_sum<kRedThreads>(p_im, red);
+    if (threadIdx.x == 0) {
+        if (accumulate) { p += result[0]; if (KIND == 2) p_im += result[1]; }
+        result[0] = p;
+        if (KIND == 2) result[1] = p_im;
+        if (typed_out) {
+            if (mode == 1) typed_out[0] = (T)sqrt(p);
+            else {
+                typed_out[0] = (T)p;
+                if (KIND == 2) typed_out[1] = (T)p_im;
+            }
+        }
+    }
+}
+
+template <typename T, int KIND>
+static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b,
+                              double *result, T *typed_out, int mode, int accumulate) {
+    constexpr int N = Vec16<T>::N;
+    const bool vec = aligned16(a) && (KIND == 1 || aligned16(b));
+    const size_t nvec = vec ? len / N : 0;
+    const size_t work = vec ? nvec : len;
+    size_t blocks = (work + (size_t)kRedThreads * kRedUnroll - 1) / ((size_t)kRedThreads * kRedUnroll);
+    const size_t cap = (size_t)ctx->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks > (size_t)kMaxPartials) blocks = kMaxPartials;
+    if (blocks == 0) blocks = 1;
+    reduce_kernel<T, KIND><<<(unsigned)blocks, kRedThreads, 0, st>>>(
+        a, KIND == 1 ? a : b, len, nvec, vec ? 1 : 0, ctx->partials, ctx->ticket, result, typed_out, mode,
+        accumulate);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+template <typename T>
+int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
+                  T *typed_out, int mode, int accumulate) {
+    switch (kind) {
+    case 0: return launch_reduce_kind<T, 0>(ctx, st, len, a, b, result, typed_out, mode, accumulate);
+    case 1: return launch_reduce_kind<T, 1>(ctx, st, len, a, a, result, typed_out, mode, accumulate);
+    case 2: return launch_reduce_kind<T, 2>(ctx, st, len, a, b, result, typed_out, mode, accumulate);
+    }
+    return fail(SLAS_ERR_INVALID, "unknown reduction kind %d", kind);
+}
+template int launch_reduce<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, double *,
+                                  float *, int, int);
+template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const double *, const double *,
+                                   double *, double *, int, int);
+
+// f64 sum -> typed scalar (used after the NCCL allreduce of the sharded ops)
+template <typename T>
+__global__ void finish_scalar_kernel(const double *in, T *out, int mode) {
+    out[0] = mode == 1 ? (T)sqrt(in[0]) : (T)in[0];
+}
+template <typename T>
+int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode) {
+    finish_scalar_kernel<T><<<1, 1, 0, st>>>(in, out, mode);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_finish_scalar<float>(cudaStream_t, const double *, float *, int);
+template int launch_finish_scalar<double>(cudaStream_t, const double *, double *, int);
+
+// ---- normalize scale pass: a[i] = a[i] / *norm (true division, rust.rs:125) --------------------
+template <typename T, int UNROLL>
+__global__ void __launch_bounds__(kEwThreads)
+scale_div_vec_kernel(T *__restrict__ a, size_t nvec, size_t len, const T *__restrict__ norm_ptr) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const T nrm = *norm_ptr;
+    V *av = reinterpret_cast<V *>(a);
+    const size_t base = (size_t)blockIdx.x * (kEwThreads * UNROLL) + threadIdx.x;
+    V r[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = base + (size_t)u * kEwThreads;
+        if (i < nvec) r[u] = av[i];  // second touch of the vector: let it hit L2
+    }
+    const V dv = [&] { V d; T *p = reinterpret_cast<T *>(&d); for (int j = 0; j < N; ++j) p[j] = nrm; return d; }();
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+        const size_t i = base + (size_t)u * kEwThreads;
+        if (i < nvec) st_stream(av + i, apply_vec<3>(r[u], dv));
+    }
+    if (blockIdx.x == 0) {
+        const size_t i = nvec * N + threadIdx.x;
+        if (i < len) a[i] = a[i] / nrm;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(kEwThreads) scale_div_scalar_kernel(T *a, size_t len, const T *norm_ptr) {
+    const T nrm = *norm_ptr;
+    for (size_t i = (size_t)blockIdx.x * kEwThreads + threadIdx.x; i < len; i += (size_t)gridDim.x * kEwThreads)
+        a[i] = a[i] / nrm;
+}
+
+template <typename T>
+int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, T *a, const T *norm_dev) {
+    constexpr int N = Vec16<T>::N;
+    constexpr int UNROLL = 4;
+    if (len == 0) return SLAS_OK;
+    if (aligned16(a)) {
+        const size_t nvec = len / N;
+        size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
+        if (blocks == 0) blocks = 1;
+        SLAS_REQUIRE(blocks <= 0x7fffffffu, "normalize: vector too long (%zu elements)", len);
+        scale_div_vec_kernel<T, UNROLL><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, nvec, len, norm_dev);
+    } else {
+        size_t blocks = (len + kEwThreads - 1) / kEwThreads;
+        const size_t cap = (size_t)ctx->sm_count * 32;
+        if (blocks > cap) blocks = cap;
+        scale_div_scalar_kernel<T><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, len, norm_dev);
+    }
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_scale_div<float>(Context *, cudaStream_t, size_t, float *, const float *);
+template int launch_scale_div<double>(Context *, cudaStream_t, size_t, double *, const double *);
+
+// ---- batched dot / norm / normalize over [[T; len]; batch] -----------------------------------
+// One group of GROUP threads per vector (GROUP = 32: a warp per vector, several vectors per
+// CTA; GROUP = 256: a CTA per vector).  MODE 0: out[v] = dot(a_v, b_v); 1: out[v] = norm(a_v);
+// 2: a_v /= norm(a_v) in place (second pass re-reads the vector from L1/L2, so HBM sees one
+// read and one write).
+template <typename T, int GROUP, int MODE>
+__global__ void __launch_bounds__(256)
+batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, T *__restrict__ a_mut,
+                      size_t batch, size_t len, int vectorised) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    constexpr int GROUPS_PER_CTA = 256 / GROUP;
+    __shared__ double red[8];
+    const int g = threadIdx.x / GROUP, t = threadIdx.x % GROUP;
+    for (size_t v0 = (size_t)blockIdx.x * GROUPS_PER_CTA; v0 < batch; v0 += (size_t)gridDim.x * GROUPS_PER_CTA) {
+        const size_t v = v0 + g;
+        const bool live = v < batch;
+        const T *pa = (MODE == 2 ? a_mut : a) + (live ? v : 0) * len;
+        const T *pb = MODE == 0 ? b + (live ? v : 0) * len : pa;
+        double s = 0.0;
+        if (live) {
+            if (vectorised) {
+                const V *av = reinterpret_cast<const V *>(pa);
+                const V *bv = reinterpret_cast<const V *>(pb);
+                const size_t nvec = len / N;
+                T acc0 = T(0), acc1 = T(0);
+                size_t i = t;
+                for (; i + GROUP < nvec; i += 2 * GROUP) {
+                    V x0 = av[i], x1 = av[i + GROUP];
+                    V y0 = MODE == 0 ? bv[i] : x0, y1 = MODE == 0 ? bv[i + GROUP] : x1;
+                    const T *px0 = reinterpret_cast<const T *>(&x0), *py0 = reinterpret_cast<const T *>(&y0);
+                    const T *px1 = reinterpret_cast<const T *>(&x1), *py1 = reinterpret_cast<const T *>(&y1);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) { acc0 += px0[j] * py0[j]; acc1 += px1[j] * py1[j]; }
+                }
+                if (i < nvec) {
+                    V x0 = av[i];
+                    V y0 = MODE == 0 ? bv[i] : x0;
+                    const T *px0 = reinterpret_cast<const T *>(&x0), *py0 = reinterpret_cast<const T *>(&y0);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) acc0 += px0[j] * py0[j];
+                }
+                s = (double)acc0 + (double)acc1;
+                for (size_t j = nvec * N + t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
+            } else {
+                for (size_t j = t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
+            }
+        }
+        if (GROUP == 32) {
+            s = warp_sum(s);
+        } else {
+            s = block_sum<256>(s, red);
+            if (threadIdx.x == 0) red[0] = s;
+            __syncthreads();
+            s = red[0];
+            __syncthreads();
+        }
+        if (!live) continue;
+        if (MODE == 0) {
+            if (t == 0) out[v] = (T)s;
+        } else if (MODE == 1) {
+            if (t == 0) out[v] = (T)sqrt(s);
+        } else {
+            const T nrm = (T)sqrt(s);
+            T *pm = a_mut + v * len;
+            if (vectorised) {
+                V *mv = reinterpret_cast<V *>(pm);
+                const size_t nvec = len / N;
+                for (size_t i = t; i < nvec; i += GROUP) {
+                    V x = mv[i];
+                    T *px = reinterpret_cast<T *>(&x);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                    st_stream(mv + i, x);
+                }
+                for (size_t j = nvec * N + t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
+            } else {
+                for (size_t j = t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
+            }
+        }
+    }
+}
+
+template <typename T, int MODE>
+static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batch, size_t len, const T *a,
+                                      const T *b, T *out, T *a_mut) {
+    if (batch == 0) return SLAS_OK;
+    const T *base = MODE == 2 ? a_mut : a;
+    const bool vec = aligned16(base) && (MODE != 0 || aligned16(b)) && (len * sizeof(T)) % 16 == 0;
+    const size_t cap = (size_t)ctx->sm_count * 8;
+    if (len <= 2048) {
+        size_t blocks = (batch + 7) / 8;
+        if (blocks > cap) blocks = cap;
+        batched_reduce_kernel<T, 32, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vec);
+    } else {
+        size_t blocks = batch;
+        if (blocks > cap) blocks = cap;
+        batched_reduce_kernel<T, 256, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vec);
+    }
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+template <typename T>
+int launch_batched_reduce(Context *ctx, cudaStream_t st, int mode, size_t batch, size_t len, const T *a,
+                          const T *b, T *out, T *a_mut) {
+    switch (mode) {
+    case 0: return launch_batched_reduce_mode<T, 0>(ctx, st, batch, len, a, b, out, a_mut);
+    case 1: return launch_batched_reduce_mode<T, 1>(ctx, st, batch, len, a, b, out, a_mut);
+    case 2: return launch_batched_reduce_mode<T, 2>(ctx, st, batch, len, a, b, out, a_mut);
+    }
+    return fail(SLAS_ERR_INVALID, "unknown batched reduction mode %d", mode);
+}
+template int launch_batched_reduce<float>(Context *, cudaStream_t, int, size_t, size_t, const float *,
+                                          const float *, float *, float *);
+template int launch_batched_reduce<double>(Context *, cudaStream_t, int, size_t, size_t, const double *,
+                                           const double *, double *, double *);
+
+// ---- synthetic fill (counter-based; bench/test plumbing for vectors too big to stage) ------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) fill_uniform_kernel(T *x, size_t len, uint64_t seed, uint64_t offset, T lo, T hi) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < len; i += (size_t)gridDim.x * 256) {
+        const uint64_t h = splitmix64(seed * 0xD1342543DE82EF95ull + offset + i);
+        const T u = sizeof(T) == 4 ? (T)((float)(h >> 40) * (1.0f / 16777216.0f))
+                                   : (T)((double)(h >> 11) * (1.0 / 9007199254740992.0));
+        x[i] = lo + (hi - lo) * u;
+    }
+}
+template <typename T>
+int launch_fill_uniform(Context *ctx, cudaStream_t st, size_t len, T *x, uint64_t seed, uint64_t offset, T lo, T hi) {
+    if (len == 0) return SLAS_OK;
+    size_t blocks = (len + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    fill_uniform_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(x, len, seed, offset, lo, hi);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_fill_uniform<float>(Context *, cudaStream_t, size_t, float *, uint64_t, uint64_t, float, float);
+template int launch_fill_uniform<double>(Context *, cudaStream_t, size_t, double *, uint64_t, uint64_t, double, double);
+
+}  // namespace slas

@@ -1,0 +1,407 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every op is called through the C ABI
+(slas_b200.backends.Cuda -> libslas_cuda.so) and compared with the CPU oracle on the same seeded
+inputs, against the reference's golden vectors, and -- at BASELINE.json's full sizes -- through
+sampled objects plus size-independent properties.
+
+Bars (BASELINE.json north_star): bit-exact for element-wise ops, transposes and anything that is
+index/shape work; floating-point reductions within  f32: 1e-5 * sqrt(K),  f64: 1e-13 * sqrt(K)
+relative (K = reduction length), taken relative to sum|a_i*b_i| so that cancelling inputs are
+judged on the same scale the rounding errors live on."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from slas_b200 import tensor as T
+from slas_b200.backends import Cuda, device_count, launch_count
+from slas_b200.static_vec import CudaBatch, CudaVec, moo
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": np.float32, "f64": np.float64, "c64": np.complex64}
+TOL = {np.dtype(np.float32): 1e-5, np.dtype(np.float64): 1e-13}
+cuda = Cuda()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert device_count() > 0, "the gpu-marked tests need a CUDA device (there is no CPU fallback)"
+    before = launch_count()
+    yield
+    assert launch_count() > before, "no kernel of libslas_cuda was launched"
+
+
+def _cplx(pairs, dt):
+    return np.array([complex(r, i) for r, i in pairs], dtype=dt)
+
+
+def _rand(rng, n, dt, lo=-1.0, hi=1.0):
+    return (rng.random(n) * (hi - lo) + lo).astype(dt)
+
+
+def _both(x):
+    """The same operand as a host vector and as a device-resident CudaVec."""
+    return [np.array(x, copy=True), CudaVec.from_host(x)]
+
+
+def _host(x):
+    return x.to_host() if isinstance(x, CudaVec) else x
+
+
+# ---- golden vectors of the reference's own tests, through the reference-shaped API ---------------
+def test_dot_golden(golden):
+    for g in golden["dot"]:
+        dt = DT[g["dtype"]]
+        for a, b in zip(_both(np.array(g["a"], dt)), _both(np.array(g["b"], dt))):
+            r = moo(dt, g["a"], on=Cuda).dot(moo(dt, g["b"], on=Cuda)) if isinstance(a, np.ndarray) else cuda.dot(a, b)
+            if "abs_tol" in g:
+                assert abs(float(r) - g["expect"]) < g["abs_tol"], g["cite"]
+            else:
+                assert float(r) == g["expect"], g["cite"]
+
+
+def test_complex_golden(golden):
+    for g in golden["dotu"]:
+        a, b = _cplx(g["a"], np.complex64), _cplx(g["b"], np.complex64)
+        assert complex(cuda.dot(a, b)) == complex(*g["expect"]), g["cite"]
+        assert complex(cuda.dot(CudaVec.from_host(a), CudaVec.from_host(b))) == complex(*g["expect"])
+    for g in golden["norm"]:
+        a = _cplx(g["a"], np.complex64)
+        assert cuda.norm(a) == np.float32(g["expect"]), g["cite"]
+        assert cuda.norm(a.astype(np.complex128)) == pytest.approx(g["expect"], rel=1e-7)
+
+
+def test_ewise_golden(golden):
+    for g in golden["ewise"]:
+        dt = DT[g["dtype"]]
+        a, b = np.array(g["a"], dt), np.array(g["b"], dt)
+        want = oracle.ewise(g["op"], a, b)
+        c = np.zeros_like(a)
+        getattr(cuda, g["op"])(a, b, c)
+        assert np.array_equal(c, want), g["cite"]
+        dc = CudaVec(a.size, dt)
+        getattr(cuda, g["op"])(CudaVec.from_host(a), CudaVec.from_host(b), dc)
+        assert np.array_equal(dc.to_host(), want), g["cite"]
+
+
+def test_transpose_golden(golden):
+    for g in golden["transpose"]:
+        for dt in (np.float32, np.float64, np.complex128):
+            a = np.array(g["a"], dtype=dt)
+            want = np.array(g["expect"], dtype=dt)
+            buf = np.zeros_like(a)
+            cuda.transpose(a, buf, g["columns"])
+            assert np.array_equal(buf, want), g["cite"]
+            d = CudaVec.from_host(a)
+            cuda.transpose_inplace(d, g["columns"])
+            assert np.array_equal(d.to_host(), want), g["cite"]
+    g = [t for t in golden["transpose"] if "debug" in t][0]
+    m = T.Matrix(T.Tensor(np.array(g["a"], np.float32), [3, 2], cuda), True)
+    t = m.deref_mut()  # materialise the lazy transpose on the GPU
+    assert list(t.data.data) == g["expect"] and t.shape.slice() == [2, 3]
+
+
+def test_matmul_golden(golden):
+    for g in golden["matmul"]:
+        for dt in (np.float32, np.float64):
+            a, b = g["a"], g["b"]
+            for da, db in zip(_both(np.array(a["data"], dt)), _both(np.array(b["data"], dt))):
+                A = T.Matrix(T.Tensor(da, a["shape"], cuda), a["trans"])
+                B = T.Matrix(T.Tensor(db, b["shape"], cuda), b["trans"])
+                got = _host(A.matrix_mul(B))
+                assert np.array_equal(got, np.array(g["expect"], dt)), g["cite"]
+
+
+def test_gemv_golden(golden):
+    for g in golden["gemv"]:
+        for dt in (np.float32, np.float64):
+            a = g["a"]
+            for da, dx in zip(_both(np.array(a["data"], dt)), _both(np.array(g["x"], dt))):
+                A = T.Matrix(T.Tensor(da, a["shape"], cuda), a["trans"])
+                assert np.array_equal(_host(A.vector_mul(dx)), np.array(g["expect"], dt)), g["cite"]
+    # gemv == gemm with n = 1 (tests/src/main.rs:355-394)
+    a = np.arange(2, 14, dtype=np.float32)
+    x = np.array([2, 3, 4, 5], np.float32)
+    A = T.matrix(a, 4, 3, cuda).transpose()
+    assert np.array_equal(A.vector_mul(x), A.matrix_mul(T.matrix(x, 4, 1, cuda)))
+
+
+# ---- element-wise: bit-exact, host and device operands, ragged lengths, unaligned views ------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 12, 1000, 4097, (1 << 20) + 3])
+def test_ewise_bit_exact(dt, n):
+    rng = np.random.default_rng(n)
+    a, b = _rand(rng, n, dt, -4, 4), _rand(rng, n, dt, 0.25, 4)
+    da, db, dc = CudaVec.from_host(a), CudaVec.from_host(b), CudaVec(n, dt)
+    for op in ("add", "sub", "mul", "div"):
+        want = oracle.ewise(op, a, b)
+        getattr(cuda, op)(da, db, dc)
+        assert np.array_equal(dc.to_host(), want), op
+        c = np.empty_like(a)
+        getattr(cuda, op)(a, b, c)
+        assert np.array_equal(c, want), op
+    if n > 8:  # device pointers that are not 16-byte aligned take the scalar kernel
+        cuda.div(da.view(1, n - 1), db.view(1, n - 1), dc.view(1, n - 1))
+        assert np.array_equal(dc.to_host()[1:], oracle.ewise("div", a[1:], b[1:]))
+
+
+def test_ewise_special_values_bit_exact():
+    a = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, 3.4e38, 1.0, 5e-324, 1.0], np.float32)
+    b = np.array([0.0, 0.0, np.inf, 1.0, 1.0, 3.0, 3.4e38, 3.0, 2.0, 0.0], np.float32)
+    with np.errstate(all="ignore"):
+        for op in ("add", "sub", "mul", "div"):
+            c = np.empty_like(a)
+            getattr(cuda, op)(a, b, c)
+            assert c.tobytes() == oracle.ewise(op, a, b).tobytes(), op  # incl. denormals and signed zeros
+
+
+def test_empty_vectors():
+    e = np.zeros(0, np.float32)
+    cuda.add(e, e, np.zeros(0, np.float32))
+    assert cuda.dot(e, e) == 0.0 and cuda.norm(e) == 0.0  # the reference's empty sum
+    cuda.normalize(np.zeros(0, np.float64))
+
+
+# ---- dot / norm / normalize ------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 100, 750, 4097, 65536 + 5, 1 << 20])
+def test_dot_within_tolerance(dt, n):
+    rng = np.random.default_rng(n + 1)
+    a, b = _rand(rng, n, dt, 0, 1), _rand(rng, n, dt)
+    truth = float(np.dot(a.astype(np.longdouble), b.astype(np.longdouble)))
+    scale = float(np.sum(np.abs(a.astype(np.float64) * b.astype(np.float64)))) + 1e-300
+    bound = TOL[np.dtype(dt)] * np.sqrt(n) * scale
+    got_h = cuda.dot(a, b)
+    got_d = cuda.dot(CudaVec.from_host(a), CudaVec.from_host(b))
+    assert got_h == got_d  # deterministic: same bits from the host-staged and the device-resident path
+    assert abs(float(got_d) - truth) <= bound
+    for lanes in (oracle.default_lanes(dt), oracle.default_lanes(dt, avx=True)):  # the reference's two builds
+        assert abs(float(got_d) - float(oracle.dot(a, b, lanes=lanes))) <= 2 * bound
+    if n > 8:
+        d = CudaVec.from_host(a)
+        assert abs(float(cuda.dot(d.view(1, n - 1), CudaVec.from_host(b[1:]))) -
+                   float(np.dot(a[1:].astype(np.float64), b[1:].astype(np.float64)))) <= bound
+
+
+def test_dot_is_deterministic_run_to_run():
+    rng = np.random.default_rng(5)
+    a, b = CudaVec.from_host(_rand(rng, (1 << 22) + 17, np.float32)), CudaVec.from_host(_rand(rng, (1 << 22) + 17, np.float32))
+    assert len({cuda.dot(a, b).tobytes() for _ in range(8)}) == 1
+
+
+@pytest.mark.parametrize("dt", [np.complex64, np.complex128])
+def test_complex_dotu_and_norm(dt):
+    rng = np.random.default_rng(9)
+    rdt = np.float32 if dt == np.complex64 else np.float64
+    for n in (1, 5, 1000, 4099):
+        a = (_rand(rng, n, rdt) + 1j * _rand(rng, n, rdt)).astype(dt)
+        b = (_rand(rng, n, rdt) + 1j * _rand(rng, n, rdt)).astype(dt)
+        truth = np.sum(a.astype(np.complex128) * b.astype(np.complex128))  # UNconjugated
+        tol = TOL[np.dtype(rdt)] * np.sqrt(2 * n) * float(np.sum(np.abs(a) * np.abs(b)))
+        got = cuda.dot(CudaVec.from_host(a), CudaVec.from_host(b))
+        assert abs(complex(got) - complex(truth)) <= tol
+        assert abs(complex(got) - complex(oracle.dotu(a, b))) <= 2 * tol
+        nrm = cuda.norm(a)
+        assert nrm.dtype == rdt  # NormOutput is the real type (src/backends/rust.rs:130)
+        assert abs(float(nrm) - float(oracle.norm(a))) <= TOL[np.dtype(rdt)] * np.sqrt(2 * n) * float(nrm)
+        h = a.copy()
+        cuda.normalize(h)
+        want = oracle.normalize(a)
+        assert np.max(np.abs(h - want)) <= 4 * np.finfo(rdt).eps * np.max(np.abs(want))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 1000, 4097, (1 << 20) + 1])
+def test_norm_and_normalize(dt, n):
+    rng = np.random.default_rng(n + 2)
+    a = _rand(rng, n, dt)
+    truth = float(np.sqrt(np.sum(a.astype(np.longdouble) ** 2)))
+    rel = TOL[np.dtype(dt)] * np.sqrt(n)
+    nrm = cuda.norm(CudaVec.from_host(a))
+    assert abs(float(nrm) - truth) <= rel * truth
+    assert abs(float(nrm) - float(oracle.norm(a))) <= 2 * rel * truth
+    d = CudaVec.from_host(a)
+    cuda.normalize(d)
+    got = d.to_host()
+    assert np.array_equal(got, a / nrm)  # normalize is a TRUE division by the backend's own norm: bit-exact
+    want = oracle.normalize(a)
+    assert np.max(np.abs(got - want)) <= (2 * rel + 2 * np.finfo(dt).eps) * np.max(np.abs(want))
+    h = a.copy()
+    cuda.normalize(h)  # in place through a host pointer
+    assert np.array_equal(h, got)
+
+
+# ---- transpose: bit-exact for any Copy element --------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48)])
+def test_transpose_bit_exact(dt, rows, cols):
+    a = np.arange(rows * cols).astype(dt)
+    if dt == np.int32:
+        a = a.view(np.float32)  # opaque 4-byte payloads, NaN patterns included
+    want = oracle.transpose(a, cols)
+    buf = CudaVec(a.size, a.dtype).zero_()
+    cuda.transpose(CudaVec.from_host(a), buf, cols)
+    assert buf.to_host().tobytes() == want.tobytes()
+    h = np.zeros_like(a)
+    cuda.transpose(a, h, cols)
+    assert h.tobytes() == want.tobytes()
+    d = CudaVec.from_host(a)
+    cuda.transpose_inplace(d, cols)
+    assert d.to_host().tobytes() == want.tobytes()
+
+
+def test_transpose_ragged_len_leaves_tail_untouched():
+    a = np.arange(11, dtype=np.float32)  # columns = 3 -> rows = 3, elements 9, 10 never written (rust.rs:168-175)
+    buf = np.full(11, -7.0, np.float32)
+    cuda.transpose(a, buf, 3)
+    want = np.full(11, -7.0, np.float32)
+    want[:] = oracle.transpose(a, 3) if False else want
+    ref = np.full(11, -7.0, np.float32)
+    for column in range(3):
+        for row in range(3):
+            ref[3 * row + column] = a[3 * column + row]
+    assert np.array_equal(buf, ref)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,cols,batch", [(4, 4, 1000), (16, 16, 257), (32, 32, 65), (3, 5, 77), (8, 2, 1), (64, 64, 9)])
+def test_transpose_batched_bit_exact(dt, rows, cols, batch):
+    rng = np.random.default_rng(rows * cols + batch)
+    a = _rand(rng, batch * rows * cols, dt)
+    want = np.concatenate([oracle.transpose(a[i * rows * cols:(i + 1) * rows * cols], cols) for i in range(batch)])
+    buf = CudaBatch(batch, rows * cols, dt)
+    cuda.transpose_batched(CudaVec.from_host(a), buf, rows * cols, cols)
+    assert buf.to_host().ravel().tobytes() == want.tobytes()
+    h = np.zeros_like(a)
+    cuda.transpose_batched(a, h, rows * cols, cols)
+    assert h.tobytes() == want.tobytes()
+
+
+# ---- matrix_mul ---------------------------------------------------------------------------------------
+def _gemm_truth(A, B, m, n, k, ta, tb):
+    Am = A.reshape(k, m).T if ta else A.reshape(m, k)
+    Bm = B.reshape(n, k).T if tb else B.reshape(k, n)
+    ref = Am.astype(np.float64) @ Bm.astype(np.float64)
+    mag = np.abs(Am).astype(np.float64) @ np.abs(Bm).astype(np.float64)
+    return ref.ravel(), mag.ravel()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("size", [4, 8, 16, 32])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_batched_small_gemm_vs_oracle(dt, size, ta, tb):
+    m = n = k = size
+    for batch in (1, 3, 1000 if size <= 16 else 300):
+        rng = np.random.default_rng(size * 7 + batch)
+        A, B = _rand(rng, batch * m * k, dt), _rand(rng, batch * k * n, dt)
+        want = oracle.gemm_batched(A, B, batch, m, n, k, ta, tb)
+        dc = CudaBatch(batch, m * n, dt)
+        cuda.matrix_mul_batched(CudaVec.from_host(A), CudaVec.from_host(B), dc, m, n, k, ta, tb)
+        got = dc.to_host().ravel()
+        tol = TOL[np.dtype(dt)] * np.sqrt(k)
+        for i in range(0, batch, max(1, batch // 16)):
+            sl = slice(i * m * n, (i + 1) * m * n)
+            ref, mag = _gemm_truth(A[i * m * k:(i + 1) * m * k], B[i * k * n:(i + 1) * k * n], m, n, k, ta, tb)
+            assert np.all(np.abs(got[sl] - ref) <= tol * mag + 1e-300)
+        assert np.max(np.abs(got - want)) <= 2 * tol * k  # |entries| <= 1 so every |C| <= k
+        h = np.zeros(batch * m * n, dt)
+        cuda.matrix_mul_batched(A, B, h, m, n, k, ta, tb)  # host pointers: chunked H2D / kernel / D2H pipeline
+        assert np.array_equal(h, got)
+
+
+def test_batched_view_api_and_integer_exactness():
+    # small-integer entries: every product and sum is exact in f32, so == numpy exactly
+    rng = np.random.default_rng(3)
+    batch = 513
+    for size in (4, 16, 32):
+        A = rng.integers(-4, 5, batch * size * size).astype(np.float32)
+        B = rng.integers(-4, 5, batch * size * size).astype(np.float32)
+        a3, b3 = A.reshape(batch, size, size), B.reshape(batch, size, size)
+        va = T.BatchedMatrix(CudaVec.from_host(A), size, size, cuda)
+        vb = T.BatchedMatrix(CudaVec.from_host(B), size, size, cuda)
+        assert np.array_equal(va.matrix_mul(vb).to_host().reshape(batch, size, size), a3 @ b3)
+        assert np.array_equal(va.transpose().matrix_mul(vb).to_host().reshape(batch, size, size), a3.transpose(0, 2, 1) @ b3)
+        assert np.array_equal(va.matrix_mul(vb.transpose()).to_host().reshape(batch, size, size), a3 @ b3.transpose(0, 2, 1))
+        assert np.array_equal(va.transpose().matrix_mul(vb.transpose()).to_host().reshape(batch, size, size),
+                              a3.transpose(0, 2, 1) @ b3.transpose(0, 2, 1))
+        out = CudaBatch(batch, size * size, np.float32)
+        va.materialize_transpose(out)
+        assert np.array_equal(out.to_host().reshape(batch, size, size), a3.transpose(0, 2, 1))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (2, 2, 3), (5, 7, 3), (1, 9, 2), (17, 33, 65), (64, 64, 64), (100, 130, 70), (128, 128, 8), (257, 129, 31)])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_single_gemm_any_shape(dt, m, n, k, ta, tb):
+    rng = np.random.default_rng(m * n + k)
+    pad = 3  # leading dimensions wider than the matrix: C keeps its bytes between rows (beta = 0 covers m x n only)
+    lda, ldb, ldc = (m if ta else k) + pad, (k if tb else n) + pad, n + pad
+    a_rows, b_rows = (k if ta else m), (n if tb else k)
+    A, B = _rand(rng, a_rows * lda, dt), _rand(rng, b_rows * ldb, dt)
+    C0 = np.full(m * ldc, 9.0, dt)
+    want = oracle.gemm(A, B, m, n, k, lda, ldb, ldc, ta, tb, f64acc=(dt == np.float32))
+    for dev in (False, True):
+        c = CudaVec.from_host(C0) if dev else C0.copy()
+        cuda.matrix_mul(CudaVec.from_host(A) if dev else A, CudaVec.from_host(B) if dev else B, c, m, n, k, lda, ldb, ldc, ta, tb)
+        got = _host(c).reshape(m, ldc)
+        assert np.all(got[:, n:] == 9.0)
+        Av = A.reshape(a_rows, lda)[:, : (m if ta else k)]
+        Bv = B.reshape(b_rows, ldb)[:, : (k if tb else n)]
+        ref, mag = _gemm_truth(np.ascontiguousarray(Av).ravel(), np.ascontiguousarray(Bv).ravel(), m, n, k, ta, tb)
+        assert np.all(np.abs(got[:, :n].ravel() - ref) <= TOL[np.dtype(dt)] * np.sqrt(k) * mag + 1e-300)
+        assert np.max(np.abs(got[:, :n] - want.reshape(m, ldc)[:, :n])) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
+
+
+def test_large_gemm_ffma_path():
+    rng = np.random.default_rng(12)
+    m = n = k = 512
+    A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
+    c = CudaVec(m * n, np.float32)
+    cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, k, n, n, False, False)
+    ref, mag = _gemm_truth(A, B, m, n, k, False, False)
+    assert np.all(np.abs(c.to_host() - ref) <= 1e-5 * np.sqrt(k) * mag)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64)])
+@pytest.mark.parametrize("ta", [False, True])
+def test_gemv_vs_oracle(dt, rows, cols, ta):
+    rng = np.random.default_rng(rows + cols)
+    A, x = _rand(rng, rows * cols, dt), _rand(rng, rows if ta else cols, dt)
+    want = oracle.gemv(A, x, cols, rows, cols, ta)  # trait: m = width, n = height
+    tol = 2 * TOL[np.dtype(dt)] * np.sqrt(len(x)) * len(x)
+    for dev in (False, True):
+        y = CudaVec(want.size, dt) if dev else np.zeros(want.size, dt)
+        cuda.matrix_vector_mul(CudaVec.from_host(A) if dev else A, CudaVec.from_host(x) if dev else x, y, cols, rows, cols, ta)
+        assert np.max(np.abs(_host(y) - want)) <= tol
+    batch = 37
+    Ab, xb = _rand(rng, batch * rows * cols, dt), _rand(rng, batch * len(x), dt)
+    yb = CudaBatch(batch, want.size, dt)
+    cuda.matrix_vector_mul_batched(CudaVec.from_host(Ab), CudaVec.from_host(xb), yb, cols, rows, ta)
+    got = yb.to_host()
+    for i in range(batch):
+        w = oracle.gemv(Ab[i * rows * cols:(i + 1) * rows * cols], xb[i * len(x):(i + 1) * len(x)], cols, rows, cols, ta)
+        assert np.max(np.abs(got[i] - w)) <= tol
+
+
+# ---- batched dot / norm / normalize --------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5)])
+def test_batched_reductions(dt, length, batch):
+    rng = np.random.default_rng(length + batch)
+    a, b = _rand(rng, batch * length, dt), _rand(rng, batch * length, dt)
+    a2, b2 = a.reshape(batch, length).astype(np.float64), b.reshape(batch, length).astype(np.float64)
+    rel = TOL[np.dtype(dt)] * np.sqrt(length)
+    out = CudaVec(batch, dt)
+    cuda.dot_batched(CudaVec.from_host(a), CudaVec.from_host(b), out, length)
+    assert np.all(np.abs(out.to_host() - np.sum(a2 * b2, axis=1)) <= rel * np.sum(np.abs(a2 * b2), axis=1) + 1e-300)
+    h = np.zeros(batch, dt)
+    cuda.dot_batched(a, b, h, length)
+    assert np.array_equal(h, out.to_host())
+    cuda.norm_batched(CudaVec.from_host(a), out, length)
+    norms = out.to_host()
+    assert np.all(np.abs(norms - np.sqrt(np.sum(a2 * a2, axis=1))) <= rel * np.sqrt(np.sum(a2 * a2, axis=1)))
+    d = CudaBatch.from_host(a, length)
+    cuda.normalize_batched(d, length)
+    assert np.array_equal(d.to_host(), a.reshape(batch, length) / norms[:, None])  # true division, bit-exact
