@@ -1,0 +1,77 @@
+"""One launch (after one warm-up) of each hot-path kernel at its BASELINE size, for ncu.
+Usage:  python profiles/prof_targets.py [names...]     (default: all)
+Never a source of bench numbers: anything timed under a profiler is not a measurement."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from slas_b200 import _lib  # noqa: E402
+from slas_b200.backends import Cuda, set_sgemm_path, synchronize  # noqa: E402
+from slas_b200.static_vec import CudaVec  # noqa: E402
+
+cuda = Cuda()
+
+
+def uniform(n, dt, seed, lo=-1.0, hi=1.0):
+    v = CudaVec(n, dt)
+    _lib.call("slas_cuda_sfill_uniform" if dt == np.float32 else "slas_cuda_dfill_uniform", n, v.as_ptr(), seed, 0, lo, hi)
+    return v
+
+
+def gemm_batched(size, dt, log2):
+    b = 1 << log2
+    a, bb, c = uniform(b * size * size, dt, 1), uniform(b * size * size, dt, 2), CudaVec(b * size * size, dt)
+    for _ in range(2):
+        cuda.matrix_mul_batched(a, bb, c, size, size, size)
+    synchronize()
+
+
+def transpose_batched(size, dt, log2):
+    b = 1 << log2
+    a, c = uniform(b * size * size, dt, 1), CudaVec(b * size * size, dt)
+    for _ in range(2):
+        cuda.transpose_batched(a, c, size * size, size)
+    synchronize()
+
+
+def vector_ops():
+    n = 1 << 28
+    a, b, c = uniform(n, np.float32, 3, 0, 1), uniform(n, np.float32, 4, 0, 1), CudaVec(n, np.float32)
+    out = CudaVec(4, np.float32)
+    for _ in range(2):
+        _lib.call("slas_cuda_sdot", n, a.as_ptr(), b.as_ptr(), out.as_ptr())
+        cuda.add(a, b, c)
+        cuda.normalize(c)
+    synchronize()
+
+
+def gemm_large(path):
+    n = 4096
+    a, b, c = uniform(n * n, np.float32, 5), uniform(n * n, np.float32, 6), CudaVec(n * n, np.float32)
+    set_sgemm_path(path)
+    for _ in range(2):
+        cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False)
+    synchronize()
+    set_sgemm_path("ffma")
+
+
+TARGETS = {
+    "gemm4_f32": lambda: gemm_batched(4, np.float32, 24),
+    "gemm16_f32": lambda: gemm_batched(16, np.float32, 20),
+    "gemm32_f32": lambda: gemm_batched(32, np.float32, 20),
+    "gemm16_f64": lambda: gemm_batched(16, np.float64, 20),
+    "gemm32_f64": lambda: gemm_batched(32, np.float64, 20),
+    "tr16_f32": lambda: transpose_batched(16, np.float32, 20),
+    "tr32_f32": lambda: transpose_batched(32, np.float32, 20),
+    "tr32_f64": lambda: transpose_batched(32, np.float64, 20),
+    "vector": vector_ops,
+    "gemm4096_ffma": lambda: gemm_large("ffma"),
+    "gemm4096_tc": lambda: gemm_large("tcgen05"),
+}
+
+if __name__ == "__main__":
+    for name in (sys.argv[1:] or list(TARGETS)):
+        TARGETS[name]()
+        print("ran", name, flush=True)

@@ -210,10 +210,18 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
             }
         }
         r.flush();
-        // scalar tail: len % N elements (never splits a complex pair: N is even)
+        // scalar tail: the len % N elements past the last whole vector (N is even, so a complex
+        // pair is never split: the complex tail is whole (re, im) pairs)
         if (KIND != 2) {
             const size_t j = nvec * N + tid;
             if (j < len) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+        } else {
+            const size_t j = nvec * N + 2 * tid;
+            if (j + 1 < len) {
+                const double ar = a[j], ai = a[j + 1], br = b[j], bi = b[j + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
         }
     } else {
         // unaligned operands: scalar grid-stride loop, f64 accumulation

@@ -151,7 +151,14 @@ def test_ewise_special_values_bit_exact():
         for op in ("add", "sub", "mul", "div"):
             c = np.empty_like(a)
             getattr(cuda, op)(a, b, c)
-            assert c.tobytes() == oracle.ewise(op, a, b).tobytes(), op  # incl. denormals and signed zeros
+            want = oracle.ewise(op, a, b)
+            # every non-NaN result is bit-identical (denormals, signed zeros, infinities included); a NaN
+            # result is a NaN in the same place.  NaN PAYLOADS are not part of the contract: the
+            # reference's own payload depends on the host ISA and on operand order after codegen (x86 SSE
+            # propagates the first operand's payload, the SM's FADD/FMUL return the canonical 0x7fffffff).
+            nan = np.isnan(want)
+            assert np.array_equal(np.isnan(c), nan), op
+            assert c[~nan].tobytes() == want[~nan].tobytes(), op
 
 
 def test_empty_vectors():
