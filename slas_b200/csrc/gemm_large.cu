@@ -74,7 +74,7 @@ __device__ __forceinline__ void tile_stash(T (*S)[LargeCfg<T>::BM + LargeCfg<T>:
 }
 
 template <typename T, bool TA, bool TB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 gemm_large_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t m, size_t n, size_t k,
                   size_t lda, size_t ldb, size_t ldc, int vec_a, int vec_b, int vec_c) {
     using C = LargeCfg<T>;

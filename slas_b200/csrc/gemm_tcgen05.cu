@@ -1,10 +1,333 @@
-// gemm_tcgen05.cu -- placeholder until the 3xTF32 tcgen05/TMEM kernel lands.
+// gemm_tcgen05.cu -- the tensor-core path for ONE large dense f32 MatrixMul::matrix_mul
+// (the cblas_sgemm call of src/backends/blas.rs:94-109 at BASELINE config 4, 4096^3):
+// 3xTF32 on the 5th-generation tensor cores.  Selected with slas_cuda_set_sgemm_path(1); the
+// default for f32 stays the reference-faithful FFMA kernel (gemm_large.cu).
+//
+// Numerics.  Every f32 operand x is split as x = hi + lo + e with hi = rna_tf32(x),
+// lo = rna_tf32(x - hi), |e| <= 2^-22 |x|, and
+//     a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi        (dropped: a_lo*b_lo <= 2^-22 |a||b|)
+// All three products accumulate into the same fp32 accumulator in TMEM.  Per-product relative
+// error ~3 * 2^-22, far inside the 1e-5 * sqrt(K) budget of north_star.
+//
+// Structure (one CTA per SM, persistent over 128 x 256 output tiles):
+//   split pass   one streaming kernel writes hi/lo copies of op(A) as [M][K] and of op(B) as
+//                [N][K] (both K-major, so the a_trans/b_trans flags are absorbed here).
+//   warp 0       TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A_hi, A_lo,
+//                B_hi, B_lo for one 32-wide k-block into a 2-stage shared-memory ring.
+//   warp 1       MMA issuer: one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8),
+//                12 per k-block, accumulating in TMEM; tcgen05.commit releases the stage and,
+//                after the last k-block, publishes the accumulator.
+//   warp 2       TMEM allocator (512 columns = two 128x256 fp32 accumulators, so the epilogue of
+//                tile i overlaps the MMAs of tile i+1).
+//   warps 4-7    epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> registers -> C.
+#include <cuda.h>
+
+#include "async.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace slas {
-int launch_sgemm_3xtf32(Context *, cudaStream_t, const float *, const float *, float *, size_t, size_t, size_t, size_t,
-                        size_t, size_t, int, int) {
-    return SLAS_ERR_UNSUPPORTED;
+
+namespace tc {
+constexpr int BM = 128, BN = 256, BK = 32;  // BK floats = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                   // tf32: 32 bytes of K per instruction
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int B_TILE_BYTES = BN * BK * 4;   // 32 KB
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi + lo of each
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /* 1024-byte alignment slack */ + 256 /* barriers */;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+}  // namespace tc
+
+// ---- tcgen05 / TMA PTX ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *dst_smem, const CUtensorMap *map, int crd_inner, int crd_outer,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(map), "r"(smem_u32(bar)), "r"(crd_inner), "r"(crd_outer)
+        : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all MMAs issued so far by this thread arrive on `bar` when they have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major tile with 128-byte swizzle: rows of 128 bytes, 8-row
+// groups 1024 bytes apart (SBO), version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor: D = f32, A = B = tf32, both K-major, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- split pass ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split1(float x, float &hi, float &lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
+}
+
+// src is [rows][cols] (ld) and already K-major: hi/lo are dense [rows][cols]
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float *__restrict__ src, size_t ld, float *__restrict__ hi, float *__restrict__ lo, size_t rows,
+                  size_t cols) {
+    const size_t total = rows * (cols / 4);
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (size_t)gridDim.x * 256) {
+        const size_t r = t / (cols / 4), c = (t % (cols / 4)) * 4;
+        const float4 x = *reinterpret_cast<const float4 *>(src + r * ld + c);
+        float4 h, l;
+        split1(x.x, h.x, l.x); split1(x.y, h.y, l.y); split1(x.z, h.z, l.z); split1(x.w, h.w, l.w);
+        *reinterpret_cast<float4 *>(hi + r * cols + c) = h;
+        *reinterpret_cast<float4 *>(lo + r * cols + c) = l;
+    }
+}
+// src is [k][rows_out] (ld): transpose while splitting, hi/lo are dense [rows_out][k]
+__global__ void __launch_bounds__(256)
+split_tf32_transpose_kernel(const float *__restrict__ src, size_t ld, float *__restrict__ hi, float *__restrict__ lo,
+                            size_t rows_out, size_t k) {
+    __shared__ float tile[32][33];
+    const size_t r0 = (size_t)blockIdx.x * 32, k0 = (size_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) tile[ty + j][tx] = src[(k0 + ty + j) * ld + r0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        float h, l;
+        split1(tile[tx][ty + j], h, l);
+        hi[(r0 + ty + j) * k + k0 + tx] = h;
+        lo[(r0 + ty + j) * k + k0 + tx] = l;
+    }
+}
+
+// ---- the GEMM -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(tc::THREADS, 1)
+sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                    float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t n_blocks, uint32_t k_blocks) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    // 128-byte swizzle atoms need 1024-byte aligned tiles
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *acc_full = bars + 2 * STAGES, *acc_empty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t num_tiles = m_blocks * n_blocks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 4); }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                    unsigned char *st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(full + s, STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, kb * BK, mb * BM, full + s);
+                    tma_load_2d(st + A_TILE_BYTES, &map_a_lo, kb * BK, mb * BM, full + s);
+                    tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, kb * BK, nb * BN, full + s);
+                    tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, kb * BK, nb * BN, full + s);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+            uint32_t it = 0, tile_it = 0;
+            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+                const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
+                if (buf_use > 0) mbar_wait(acc_empty + buf, (buf_use - 1) & 1);  // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    mbar_wait(full + s, use & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);  // +32 bytes of K inside the swizzle row
+                        umma_tf32(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        umma_tf32(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    umma_commit(empty + s);                        // stage reusable once these MMAs retire
+                    if (kb + 1 == k_blocks) umma_commit(acc_full + buf);  // accumulator complete
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q + 32) = tile rows =====
+        const uint32_t q = warp & 3;
+        uint32_t tile_it = 0;
+        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+            const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+            const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
+            mbar_wait(acc_full + buf, buf_use & 1);
+            tc_fence_after();
+            float *crow = c + (size_t)(mb * BM + q * 32 + lane) * ldc + (size_t)nb * BN;
+#pragma unroll 1
+            for (uint32_t cc = 0; cc < BN / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((q * 32) << 16) + buf * BN + cc * 32, v);
+                tmem_ld_wait();
+                float4 *dst = reinterpret_cast<float4 *>(crow + cc * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encode_fn(EncodeTiledFn *out) {
+    static EncodeTiledFn cached = nullptr;
+    if (!cached) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        SLAS_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn)
+            return fail(SLAS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        cached = (EncodeTiledFn)fn;
+    }
+    *out = cached;
+    return SLAS_OK;
+}
+
+// 2-D f32 tensor [rows][k] (dense, k contiguous), box = 32 x box_rows, 128-byte swizzle
+static int make_map(EncodeTiledFn enc, CUtensorMap *map, const float *base, size_t rows, size_t k, uint32_t box_rows) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)k * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, box_rows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SLAS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SLAS_OK;
+}
+
+int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m, size_t n,
+                        size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb) {
+    using namespace tc;
+    // whole tiles only; everything else runs on the FFMA kernel
+    if (m % BM || n % BN || k % BK || m == 0 || n == 0 || k == 0) return SLAS_ERR_UNSUPPORTED;
+    if (!aligned16(a) || !aligned16(b) || !aligned16(c) || lda % 4 || ldb % 4 || ldc % 4) return SLAS_ERR_UNSUPPORTED;
+    if (m > 0x7fffffffu || n > 0x7fffffffu || k > 0x7fffffffu) return SLAS_ERR_UNSUPPORTED;
+    EncodeTiledFn enc;
+    SLAS_TRY(get_encode_fn(&enc));
+    void *ws = nullptr;
+    const size_t a_elems = m * k, b_elems = n * k;
+    SLAS_TRY(ensure_workspace(ctx, 2 * (a_elems + b_elems) * sizeof(float), &ws));
+    float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_hi = a_lo + a_elems, *b_lo = b_hi + b_elems;
+    const unsigned cap = (unsigned)ctx->sm_count * 8;
+    // op(A) as [m][k]
+    if (!ta) split_tf32_kernel<<<cap, 256, 0, st>>>(a, lda, a_hi, a_lo, m, k);
+    else split_tf32_transpose_kernel<<<dim3((unsigned)(m / 32), (unsigned)(k / 32)), 256, 0, st>>>(a, lda, a_hi, a_lo, m, k);
+    SLAS_LAUNCH_CHECK();
+    // op(B)^T as [n][k]
+    if (tb) split_tf32_kernel<<<cap, 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k);
+    else split_tf32_transpose_kernel<<<dim3((unsigned)(n / 32), (unsigned)(k / 32)), 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k);
+    SLAS_LAUNCH_CHECK();
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, BM));
+    SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, BM));
+    SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, BN));
+    SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, BN));
+    SLAS_CUDA_TRY(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    const uint32_t m_blocks = (uint32_t)(m / BM), n_blocks = (uint32_t)(n / BN), k_blocks = (uint32_t)(k / BK);
+    unsigned grid = (unsigned)ctx->sm_count;
+    if (grid > m_blocks * n_blocks) grid = m_blocks * n_blocks;
+    sgemm_3xtf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks, n_blocks,
+                                                           k_blocks);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
 }  // namespace slas

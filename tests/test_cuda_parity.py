@@ -412,3 +412,26 @@ def test_batched_reductions(dt, length, batch):
     d = CudaBatch.from_host(a, length)
     cuda.normalize_batched(d, length)
     assert np.array_equal(d.to_host(), a.reshape(batch, length) / norms[:, None])  # true division, bit-exact
+
+
+# ---- the tensor-core path for one large f32 product: 3xTF32 on tcgen05 / TMEM -----------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 256, 32), (128, 256, 64), (256, 512, 96), (384, 256, 1024), (1024, 1024, 512)])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_sgemm_3xtf32_tcgen05(m, n, k, ta, tb):
+    from slas_b200.backends import set_sgemm_path
+    rng = np.random.default_rng(m + n + k)
+    A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
+    c = CudaVec(m * n, np.float32).zero_()
+    set_sgemm_path("tcgen05")
+    try:
+        n0 = launch_count()
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
+        assert launch_count() - n0 == 3, "expected split(A), split(B) and the tcgen05 kernel"
+    finally:
+        set_sgemm_path("ffma")
+    ref, mag = _gemm_truth(A, B, m, n, k, ta, tb)
+    err = np.abs(c.to_host() - ref)
+    assert np.all(err <= 1e-5 * np.sqrt(k) * mag), f"max err/mag {np.max(err / mag):.3e}"
+    # 3xTF32 is an fp32-class result: far tighter than plain TF32 (2^-11 per operand)
+    assert np.max(err / mag) < 2e-6
