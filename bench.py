@@ -160,6 +160,8 @@ def run_reference(args):
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------
 def run_cuda(args):
+    # stdout carries exactly one JSON line: NCCL's version/debug banner goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
 
@@ -337,18 +339,13 @@ def run_cuda(args):
         torch.cuda.empty_cache()
         # config 5 (vector half): dot / normalize over 2^32 f32 elements IN TOTAL, sharded by contiguous slice,
         # each rank's slice resident in its own HBM, ONE NCCL allreduce of the f64 partial per op
+        from slas_b200 import sharding
         if world > 1:
-            ident = [None]
-            if rank == 0:
-                buf = (C.c_char * 128)()
-                _lib.call("slas_cuda_nccl_unique_id", buf)
-                ident = [bytes(buf.raw)]
-            dist.broadcast_object_list(ident, src=0)
-            _lib.call("slas_cuda_comm_init", world, rank, ident[0])
+            sharding.init_comm(dist)
         total = 1 << 32
-        lo, hi = C.c_size_t(), C.c_size_t()
-        _lib.call("slas_cuda_shard_range", total, 4, world, rank, C.byref(lo), C.byref(hi))
-        local = hi.value - lo.value
+        lo_, hi_ = sharding.shard_range(total, 4, world, rank)
+        lo, hi = C.c_size_t(lo_), C.c_size_t(hi_)
+        local = hi_ - lo_
         a = torch.empty(local, device=dev, dtype=torch.float32)
         b = torch.empty(local, device=dev, dtype=torch.float32)
         _lib.call("slas_cuda_sfill_uniform", local, a.data_ptr(), 4, lo.value, 0.0, 1.0)
