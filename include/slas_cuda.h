@@ -57,6 +57,11 @@ int slas_cuda_synchronize(void);
 /* Number of kernels this library launched on the calling process so far (bench.py's gpu_launches). */
 uint64_t slas_cuda_launch_count(void);
 
+/* Kernel-selection knobs for benchmarking and profiling (not part of the reference interface): a
+ * named integer, e.g. "transpose_variant", "gemm32d_variant".  Unknown names are rejected. */
+int slas_cuda_set_tunable(const char *name, long value);
+int slas_cuda_get_tunable(const char *name, long *value);
+
 /* ---- device-resident storage (what `CudaVec<T, LEN>` / `CudaBatch` own) --------- */
 int slas_cuda_malloc(void **dptr, size_t bytes);
 int slas_cuda_free(void *dptr);

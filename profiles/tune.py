@@ -1,0 +1,106 @@
+"""Variant sweep for the benchmark knobs (slas_cuda_set_tunable): CUDA-event timings on one B200.
+Usage: python profiles/tune.py [group ...]   groups: transpose gemm32d gemm32s gemm16s large tc"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import slas_b200 as sl  # noqa: E402
+from slas_b200 import _lib  # noqa: E402
+from slas_b200.backends import set_tunable  # noqa: E402
+from slas_b200.static_vec import CudaVec  # noqa: E402
+
+PEAK = 6539.5
+dev = torch.device("cuda", 0)
+stream = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(stream)
+sl.set_stream(stream.cuda_stream)
+cuda = sl.Cuda()
+
+
+def uniform(n, dt, seed):
+    t = torch.empty(n, device=dev, dtype=torch.float32 if dt == np.float32 else torch.float64)
+    _lib.call("slas_cuda_sfill_uniform" if dt == np.float32 else "slas_cuda_dfill_uniform", n, t.data_ptr(), seed, 0, -1.0, 1.0)
+    return t, CudaVec(n, dt, _ptr=t.data_ptr(), _owner=t)
+
+
+def timed(fn, steps=20, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def report(name, ms, nbytes=None, flop=None):
+    row = {"name": name, "ms": round(ms, 4)}
+    if nbytes:
+        row["gbs"] = round(nbytes / ms / 1e6, 1)
+        row["hbm_frac"] = round(nbytes / ms / 1e6 / PEAK, 4)
+    if flop:
+        row["tflops"] = round(flop / ms / 1e9, 2)
+    print(json.dumps(row), flush=True)
+
+
+def g_transpose():
+    for size, dt in ((32, np.float64), (32, np.float32), (16, np.float64), (16, np.float32), (64, np.float32), (8, np.float32)):
+        b = 1 << 20
+        e = size * size
+        (_, a), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
+        for v in range(6):
+            set_tunable("transpose_variant", v)
+            report(f"transpose {size}x{size} {np.dtype(dt).name} variant {v}", timed(lambda: cuda.transpose_batched(a, c, e, size)),
+                   nbytes=2.0 * b * e * np.dtype(dt).itemsize)
+        set_tunable("transpose_variant", 0)
+    # 4x4 f32 (thread per matrix)
+    b, e = 1 << 24, 16
+    (_, a), (_, c) = uniform(b * e, np.float32, 1), uniform(b * e, np.float32, 2)
+    for v in (0, 1):
+        set_tunable("transpose_variant", v)
+        report(f"transpose 4x4 float32 2^24 variant {v}", timed(lambda: cuda.transpose_batched(a, c, e, 4)), nbytes=2.0 * b * e * 4)
+    set_tunable("transpose_variant", 0)
+
+
+def g_gemm(knob, size, dt, variants):
+    b = 1 << 20
+    e = size * size
+    (_, a), (_, bb), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2), uniform(b * e, dt, 3)
+    for v in variants:
+        set_tunable(knob, v)
+        report(f"gemm {size}^3 {np.dtype(dt).name} {knob}={v}", timed(lambda: cuda.matrix_mul_batched(a, bb, c, size, size, size)),
+               nbytes=3.0 * b * e * np.dtype(dt).itemsize, flop=2.0 * size ** 3 * b)
+    set_tunable(knob, 0)
+
+
+def g_large(path, knob, variants):
+    n = 4096
+    (_, a), (_, b), (_, c) = uniform(n * n, np.float32, 5), uniform(n * n, np.float32, 6), uniform(n * n, np.float32, 7)
+    sl.set_sgemm_path(path)
+    for v in variants:
+        set_tunable(knob, v)
+        report(f"sgemm 4096^3 {path} {knob}={v}", timed(lambda: cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False), 10, 3),
+               flop=2.0 * n ** 3)
+    set_tunable(knob, 0)
+    sl.set_sgemm_path("ffma")
+
+
+GROUPS = {
+    "transpose": g_transpose,
+    "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
+    "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),
+    "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2)),
+    "large": lambda: g_large("ffma", "gemm_large_variant", (0, 1, 2, 3)),
+    "tc": lambda: g_large("tcgen05", "tc_variant", (0, 1, 2, 3)),
+}
+
+if __name__ == "__main__":
+    for g in (sys.argv[1:] or list(GROUPS)):
+        GROUPS[g]()

@@ -49,6 +49,8 @@ SIGNATURES = {
     "slas_cuda_set_stream": [_vp],
     "slas_cuda_synchronize": [],
     "slas_cuda_launch_count": [],
+    "slas_cuda_set_tunable": [C.c_char_p, C.c_long],
+    "slas_cuda_get_tunable": [C.c_char_p, C.POINTER(C.c_long)],
     "slas_cuda_malloc": [C.POINTER(_vp), _sz],
     "slas_cuda_free": [_vp],
     "slas_cuda_malloc_host": [C.POINTER(_vp), _sz],

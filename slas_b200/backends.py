@@ -250,6 +250,11 @@ def launch_count() -> int:
     return int(_lib.lib().slas_cuda_launch_count())
 
 
+def set_tunable(name: str, value: int) -> None:
+    """Benchmark knob (kernel variant selection); 0 is always the shipped default."""
+    _lib.call("slas_cuda_set_tunable", name.encode(), int(value))
+
+
 def set_sgemm_path(path: str) -> None:
     """'ffma' (reference-faithful fp32, default) or 'tcgen05' (3xTF32 on the tensor cores)."""
     _lib.call("slas_cuda_set_sgemm_path", {"ffma": 0, "tcgen05": 1}[path])

@@ -91,6 +91,9 @@ int operands_side(const void *const *ptrs, int n, bool *is_dev);
 // device pointer.  Host: copies through the pinned bounce buffer and synchronises the stream.
 int deliver_scalar(Context *ctx, const void *dev_src, void *out, size_t bytes);
 
+// Benchmark knobs (slas_cuda_set_tunable); every knob defaults to 0 = the shipped choice.
+long tunable(const char *name);
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---- device helpers ----------------------------------------------------------

@@ -26,6 +26,16 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+struct Tunable { const char *name; long value; };
+static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0}, {"gemm32s_variant", 0},
+                               {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
+                               {"tc_variant", 0}};
+long tunable(const char *name) {
+    for (auto &t : g_tunables)
+        if (strcmp(t.name, name) == 0) return t.value;
+    return 0;
+}
+
 constexpr int kMaxDevices = 32;
 static Context g_ctx[kMaxDevices];
 static std::mutex g_init_mu;
@@ -156,6 +166,19 @@ int slas_cuda_init(int device) {
     if (device >= 0) SLAS_CUDA_TRY(cudaSetDevice(device));
     Context *c;
     return get_context(&c);
+}
+
+int slas_cuda_set_tunable(const char *name, long value) {
+    SLAS_REQUIRE(name, "null tunable name");
+    for (auto &t : g_tunables)
+        if (strcmp(t.name, name) == 0) { t.value = value; return SLAS_OK; }
+    return fail(SLAS_ERR_INVALID, "unknown tunable '%s'", name);
+}
+int slas_cuda_get_tunable(const char *name, long *value) {
+    SLAS_REQUIRE(name && value, "null argument");
+    for (auto &t : g_tunables)
+        if (strcmp(t.name, name) == 0) { *value = t.value; return SLAS_OK; }
+    return fail(SLAS_ERR_INVALID, "unknown tunable '%s'", name);
 }
 
 int slas_cuda_shutdown(void) {

@@ -117,7 +117,12 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
     // row s of this thread's tile: interleaved for row-major A (conflict-free 128-bit smem reads
     // across ti), contiguous for transposed A (its TM rows are one vector of A^T's storage)
     auto row_of = [&](int s) { return TA ? ti * TM + s : ti + s * TI; };
-    const int j0 = tj * TN;
+    // columns of this thread's tile: NG groups of one 16-byte vector each, group g at
+    // g * (N / NG) + tj * KVN -- so the lanes of a matrix read (and store) CONTIGUOUS 16-byte pieces of
+    // a row in every instruction (a 32-byte-per-lane footprint would 2-way bank-conflict for f64)
+    constexpr int NG = TN / KVN;
+    static_assert(TN % KVN == 0, "TN must be whole 16-byte vectors");
+    auto col_of = [&](int j) { return (j / KVN) * (N / NG) + tj * KVN + (j % KVN); };
     const int rot = TB ? tj : 0;  // k-chunk rotation: spreads transposed-B reads over the banks
 
     uint32_t it = 0;
@@ -162,12 +167,15 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
                 }
                 if (!TB) {
 #pragma unroll
-                    for (int kk = 0; kk < KVN; ++kk) lds_vec<T, TN>(bblk[kk], mb + (k0 + kk) * N + j0);
+                    for (int kk = 0; kk < KVN; ++kk)
+#pragma unroll
+                        for (int g = 0; g < NG; ++g)
+                            lds_vec<T, KVN>(*reinterpret_cast<T(*)[KVN]>(&bblk[kk][g * KVN]), mb + (k0 + kk) * N + col_of(g * KVN));
                 } else {
 #pragma unroll
                     for (int j = 0; j < TN; ++j) {
                         T row[KVN];
-                        lds_vec<T, KVN>(row, mb + (j0 + j) * K + k0);
+                        lds_vec<T, KVN>(row, mb + col_of(j) * K + k0);
 #pragma unroll
                         for (int kk = 0; kk < KVN; ++kk) bblk[kk][j] = row[kk];
                     }
@@ -181,7 +189,10 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
             }
             T *mc = c + (first + mat) * Cfg::C_ELEMS;
 #pragma unroll
-            for (int i = 0; i < TM; ++i) stg_vec<T, TN>(mc + row_of(i) * N + j0, acc[i]);
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    stg_vec<T, KVN>(mc + row_of(i) * N + col_of(g * KVN), *reinterpret_cast<const T(*)[KVN]>(&acc[i][g * KVN]));
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -222,6 +233,11 @@ using CfgD4 = SmallCfg<double, 4, 4, 4, 1, 4, 256, 128, 4>;
 using CfgD8 = SmallCfg<double, 8, 8, 8, 2, 4, 256, 32, 3>;
 using CfgD16 = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgD32 = SmallCfg<double, 32, 32, 32, 8, 4, 128, 4, 3>;
+// benchmark variants (slas_cuda_set_tunable)
+using CfgD32b = SmallCfg<double, 32, 32, 32, 4, 4, 256, 4, 3>;
+using CfgS32b = SmallCfg<float, 32, 32, 32, 8, 8, 128, 8, 3>;
+using CfgS16b = SmallCfg<float, 16, 16, 16, 4, 4, 256, 32, 3>;
+using CfgS16c = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 3>;
 
 template <>
 int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch, const float *a, const float *b,
@@ -231,8 +247,14 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
     switch (m) {
     case 4: return launch_cfg<float, CfgS4>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<float, CfgS8>(ctx, st, batch, a, b, c, ta, tb);
-    case 16: return launch_cfg<float, CfgS16>(ctx, st, batch, a, b, c, ta, tb);
-    case 32: return launch_cfg<float, CfgS32>(ctx, st, batch, a, b, c, ta, tb);
+    case 16:
+        // measured on B200 (profiles/r1b_tune.log): 8x4 tiles, 32 matrices per stage = 0.96 of HBM peak
+        if (tunable("gemm16s_variant") == 1) return launch_cfg<float, CfgS16b>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm16s_variant") == 2) return launch_cfg<float, CfgS16>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<float, CfgS16c>(ctx, st, batch, a, b, c, ta, tb);
+    case 32:
+        if (tunable("gemm32s_variant") == 1) return launch_cfg<float, CfgS32b>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<float, CfgS32>(ctx, st, batch, a, b, c, ta, tb);
     }
     return SLAS_ERR_UNSUPPORTED;
 }
@@ -246,7 +268,9 @@ int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batc
     case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<double, CfgD8>(ctx, st, batch, a, b, c, ta, tb);
     case 16: return launch_cfg<double, CfgD16>(ctx, st, batch, a, b, c, ta, tb);
-    case 32: return launch_cfg<double, CfgD32>(ctx, st, batch, a, b, c, ta, tb);
+    case 32:
+        if (tunable("gemm32d_variant") == 1) return launch_cfg<double, CfgD32b>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<double, CfgD32>(ctx, st, batch, a, b, c, ta, tb);
     }
     return SLAS_ERR_UNSUPPORTED;
 }

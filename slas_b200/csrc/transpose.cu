@@ -95,29 +95,50 @@ template <typename V> __device__ __forceinline__ V ld16(const V *p) {
     return *reinterpret_cast<V *>(&r);
 }
 
-template <typename E, int VW>
+// One thread owns a BR x VW block of the input (BR = MULT * VW rows, one 16-byte vector per row): BR
+// 128-bit loads, a register transpose, then VW output rows of BR contiguous elements each (MULT
+// 128-bit stores per row).  OUT_MAJOR orders the threads of an object with the input ROW block
+// fastest, so that consecutive lanes store consecutive pieces of the same output row (full 128-byte
+// lines per instruction); otherwise the input COLUMN block is fastest (contiguous loads).
+template <typename E, int VW, int MULT, bool OUT_MAJOR>
 __global__ void __launch_bounds__(256)
-transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nblocks_total, unsigned n,
-                             unsigned blocks_per_row) {
+transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nblocks_total, unsigned n) {
     struct alignas(16) V { E v[VW]; };
-    const unsigned blocks_per_obj = blocks_per_row * blocks_per_row;
+    constexpr int BR = MULT * VW;
+    const unsigned row_blocks = n / BR, col_blocks = n / VW;
+    const unsigned blocks_per_obj = row_blocks * col_blocks;
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < nblocks_total; t += (size_t)gridDim.x * 256) {
         const size_t obj = t / blocks_per_obj;
         const unsigned w = (unsigned)(t - obj * blocks_per_obj);
-        const unsigned bi = w / blocks_per_row, bj = w % blocks_per_row;
-        const E *src = in + obj * (size_t)n * n + (size_t)(bi * VW) * n + bj * VW;
-        E *dst = out + obj * (size_t)n * n + (size_t)(bj * VW) * n + bi * VW;
-        V x[VW];
+        const unsigned bi = OUT_MAJOR ? w % row_blocks : w / col_blocks;  // input row block
+        const unsigned bj = OUT_MAJOR ? w / row_blocks : w % col_blocks;  // input column block
+        const E *src = in + obj * (size_t)n * n + (size_t)(bi * BR) * n + bj * VW;
+        E *dst = out + obj * (size_t)n * n + (size_t)(bj * VW) * n + bi * BR;
+        V x[BR];
 #pragma unroll
-        for (int s = 0; s < VW; ++s) x[s] = ld16(reinterpret_cast<const V *>(src + (size_t)s * n));
+        for (int s = 0; s < BR; ++s) x[s] = ld16(reinterpret_cast<const V *>(src + (size_t)s * n));
 #pragma unroll
         for (int s = 0; s < VW; ++s) {
-            V y;
 #pragma unroll
-            for (int q = 0; q < VW; ++q) y.v[q] = x[q].v[s];
-            __stcs(reinterpret_cast<uint4 *>(dst + (size_t)s * n), *reinterpret_cast<uint4 *>(&y));
+            for (int m = 0; m < MULT; ++m) {
+                V y;
+#pragma unroll
+                for (int q = 0; q < VW; ++q) y.v[q] = x[m * VW + q].v[s];
+                __stcs(reinterpret_cast<uint4 *>(dst + (size_t)s * n + m * VW), *reinterpret_cast<uint4 *>(&y));
+            }
         }
     }
+}
+
+template <typename E, int VW, int MULT, bool OUT_MAJOR>
+static int launch_square_vec(Context *ctx, cudaStream_t st, size_t batch, unsigned n, const E *a, E *buffer) {
+    const size_t total = batch * (size_t)(n / (MULT * VW)) * (n / VW);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)ctx->sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    transpose_square_vec_kernel<E, VW, MULT, OUT_MAJOR><<<(unsigned)blocks, 256, 0, st>>>(a, buffer, total, n);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
 }
 
 template <typename E>
@@ -130,14 +151,16 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
     if constexpr (VW > 1) {
       if (rows == columns && len == rows * columns && rows % VW == 0 && rows <= 64 && aligned16(a) &&
           aligned16(buffer)) {
-        const unsigned bpr = (unsigned)(rows / VW);
-        const size_t total = batch * (size_t)bpr * bpr;
-        size_t blocks = (total + 255) / 256;
-        const size_t cap = (size_t)ctx->sm_count * 32;
-        if (blocks > cap) blocks = cap;
-        transpose_square_vec_kernel<E, VW><<<(unsigned)blocks, 256, 0, st>>>(a, buffer, total, (unsigned)rows, bpr);
-        SLAS_LAUNCH_CHECK();
-        return SLAS_OK;
+        const unsigned n = (unsigned)rows;
+        const long variant = tunable("transpose_variant");
+        // default = out-major lanes (full-line stores): measured best or equal for every n, f32 and f64
+        // (profiles/r1b_tune.log); variant 1 = the in-major ordering
+        if (variant == 1) return launch_square_vec<E, VW, 1, false>(ctx, st, batch, n, a, buffer);
+        if (variant == 2 && n % (2 * VW) == 0) return launch_square_vec<E, VW, 2, true>(ctx, st, batch, n, a, buffer);
+        if (variant == 3 && n % (4 * VW) == 0) return launch_square_vec<E, VW, 4, true>(ctx, st, batch, n, a, buffer);
+        if (variant == 4 && n % (2 * VW) == 0) return launch_square_vec<E, VW, 2, false>(ctx, st, batch, n, a, buffer);
+        if (variant == 5 && n % (4 * VW) == 0) return launch_square_vec<E, VW, 4, false>(ctx, st, batch, n, a, buffer);
+        return launch_square_vec<E, VW, 1, true>(ctx, st, batch, n, a, buffer);
       }
     }
     // (2) small objects: padded tile must fit the per-warp shared slice
