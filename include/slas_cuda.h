@@ -61,6 +61,9 @@ uint64_t slas_cuda_launch_count(void);
  * named integer, e.g. "transpose_variant", "gemm32d_variant".  Unknown names are rejected. */
 int slas_cuda_set_tunable(const char *name, long value);
 int slas_cuda_get_tunable(const char *name, long *value);
+/* Roofline denominator measured on the box: sustained FMA TFLOP/s of a register-only 8x8
+ * outer-product loop (the GEMM kernels' instruction mix), f32 (is_double = 0) or f64. */
+int slas_cuda_bench_fma_peak(int is_double, double *tflops);
 
 /* ---- device-resident storage (what `CudaVec<T, LEN>` / `CudaBatch` own) --------- */
 int slas_cuda_malloc(void **dptr, size_t bytes);

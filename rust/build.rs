@@ -34,7 +34,7 @@ fn main() {
         assert_eq!(arch, "sm_100a", "slas_backend::Cuda is written for sm_100a (B200) only");
         let csrc = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("cuda/csrc");
         let sources = ["context.cu", "api.cu", "vector_ops.cu", "transpose.cu", "gemm_small.cu", "gemm_generic.cu",
-                       "gemm_large.cu", "gemm_tcgen05.cu", "comm.cu"];
+                       "gemm_large.cu", "gemm_ffma.cu", "gemm_tcgen05.cu", "comm.cu"];
         let lib = Path::new(&out_dir).join("libslas_cuda.so");
         let mut cmd = Command::new(Path::new(&cuda_home).join("bin/nvcc"));
         cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -51,6 +51,7 @@ SIGNATURES = {
     "slas_cuda_launch_count": [],
     "slas_cuda_set_tunable": [C.c_char_p, C.c_long],
     "slas_cuda_get_tunable": [C.c_char_p, C.POINTER(C.c_long)],
+    "slas_cuda_bench_fma_peak": [_i, C.POINTER(C.c_double)],
     "slas_cuda_malloc": [C.POINTER(_vp), _sz],
     "slas_cuda_free": [_vp],
     "slas_cuda_malloc_host": [C.POINTER(_vp), _sz],

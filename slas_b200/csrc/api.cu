@@ -251,6 +251,12 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
                                               ldc, ta, tb);
             if (r != SLAS_ERR_UNSUPPORTED) return r;
         }
+        // measured on B200 (profiles/r1b_tune.log): the register-staged kernel of gemm_large.cu holds 43.4
+        // TFLOP/s at 4096^3, the cp.async ring of gemm_ffma.cu 41.8 -- the latter stays a benchmark variant
+        if (sizeof(T) == 4 && tunable("gemm_large_variant") == 1) {
+            const int r = launch_sgemm_ffma(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb, ldc, ta, tb);
+            if (r != SLAS_ERR_UNSUPPORTED) return r;
+        }
         return launch_gemm_large<T>(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
     }
     return launch_gemm_generic<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);

@@ -147,10 +147,22 @@ split_tf32_transpose_kernel(const float *__restrict__ src, size_t ld, float *__r
 }
 
 // ---- the GEMM -----------------------------------------------------------------------------------------
+// Work items of the static persistent schedule.  Items [0, full_tiles) are whole 128 x 256 tiles (as
+// many as fill complete rounds of the grid); the tiles of the last, partial round are each cut into
+// two 128 x 128 halves so that the tail keeps (almost) every SM busy instead of under half of them
+// (4096^2: 512 tiles on 148 SMs = 3 full rounds + 68 tiles -> 136 half tiles).
+struct WorkItem { uint32_t mb, nb, n_off, n_cols; };
+__device__ __forceinline__ WorkItem decode_item(uint32_t item, uint32_t m_blocks, uint32_t full_tiles) {
+    if (item < full_tiles) return {item % m_blocks, item / m_blocks, 0u, (uint32_t)tc::BN};
+    const uint32_t t = item - full_tiles, tile = full_tiles + (t >> 1);
+    return {tile % m_blocks, tile / m_blocks, (t & 1u) * (tc::BN / 2), (uint32_t)tc::BN / 2};
+}
+
 __global__ void __launch_bounds__(tc::THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                    float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t n_blocks, uint32_t k_blocks) {
+                    float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t k_blocks, uint32_t num_items,
+                    uint32_t full_tiles) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     // 128-byte swizzle atoms need 1024-byte aligned tiles
@@ -160,7 +172,6 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t num_tiles = m_blocks * n_blocks;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
@@ -181,17 +192,23 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+            for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x) {
+                const WorkItem w = decode_item(item, m_blocks, full_tiles);
+                const uint32_t b_row = w.nb * BN + w.n_off;
                 for (uint32_t kb = 0; kb < k_blocks; ++kb, ++it) {
                     const uint32_t s = it % STAGES, use = it / STAGES;
                     if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
                     unsigned char *st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(full + s, STAGE_BYTES);
-                    tma_load_2d(st, &map_a_hi, kb * BK, mb * BM, full + s);
-                    tma_load_2d(st + A_TILE_BYTES, &map_a_lo, kb * BK, mb * BM, full + s);
-                    tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, kb * BK, nb * BN, full + s);
-                    tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, kb * BK, nb * BN, full + s);
+                    mbar_expect_tx(full + s, 2 * A_TILE_BYTES + 2 * w.n_cols * BK * 4);
+                    tma_load_2d(st, &map_a_hi, kb * BK, w.mb * BM, full + s);
+                    tma_load_2d(st + A_TILE_BYTES, &map_a_lo, kb * BK, w.mb * BM, full + s);
+                    // B tiles arrive as 128-row boxes: two per operand for a full tile, one for a half tile
+                    tma_load_2d(st + 2 * A_TILE_BYTES, &map_b_hi, kb * BK, b_row, full + s);
+                    tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, kb * BK, b_row, full + s);
+                    if (w.n_cols == BN) {
+                        tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES / 2, &map_b_hi, kb * BK, b_row + BN / 2, full + s);
+                        tma_load_2d(st + 2 * A_TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &map_b_lo, kb * BK, b_row + BN / 2, full + s);
+                    }
                 }
             }
         }
@@ -199,9 +216,10 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
             uint32_t it = 0, tile_it = 0;
-            for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
+            for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++tile_it) {
+                const WorkItem w = decode_item(item, m_blocks, full_tiles);
+                const uint32_t idesc = w.n_cols == BN ? umma_idesc_tf32(BM, BN) : umma_idesc_tf32(BM, BN / 2);
                 const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
                 if (buf_use > 0) mbar_wait(acc_empty + buf, (buf_use - 1) & 1);  // epilogue drained this accumulator
                 tc_fence_after();
@@ -231,14 +249,14 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         // ===== epilogue: warp q = warp % 4 owns TMEM lanes [32q, 32q + 32) = tile rows =====
         const uint32_t q = warp & 3;
         uint32_t tile_it = 0;
-        for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tile_it) {
-            const uint32_t mb = tile % m_blocks, nb = tile / m_blocks;
+        for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++tile_it) {
+            const WorkItem w = decode_item(item, m_blocks, full_tiles);
             const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
             mbar_wait(acc_full + buf, buf_use & 1);
             tc_fence_after();
-            float *crow = c + (size_t)(mb * BM + q * 32 + lane) * ldc + (size_t)nb * BN;
+            float *crow = c + (size_t)(w.mb * BM + q * 32 + lane) * ldc + (size_t)w.nb * BN + w.n_off;
 #pragma unroll 1
-            for (uint32_t cc = 0; cc < BN / 32; ++cc) {
+            for (uint32_t cc = 0; cc < w.n_cols / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((q * 32) << 16) + buf * BN + cc * 32, v);
                 tmem_ld_wait();
@@ -318,14 +336,19 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, BM));
     SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, BM));
-    SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, BN));
-    SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, BN));
+    SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, BN / 2));
+    SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, BN / 2));
     SLAS_CUDA_TRY(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     const uint32_t m_blocks = (uint32_t)(m / BM), n_blocks = (uint32_t)(n / BN), k_blocks = (uint32_t)(k / BK);
-    unsigned grid = (unsigned)ctx->sm_count;
-    if (grid > m_blocks * n_blocks) grid = m_blocks * n_blocks;
-    sgemm_3xtf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks, n_blocks,
-                                                           k_blocks);
+    const uint32_t sms = (uint32_t)ctx->sm_count, num_tiles = m_blocks * n_blocks;
+    uint32_t full_tiles = num_tiles / sms * sms;
+    const uint32_t tail = num_tiles - full_tiles;
+    if (2 * tail > sms || tunable("tc_variant") == 1) full_tiles = num_tiles;  // halving the tail would not save a round
+    const uint32_t num_items = full_tiles + 2 * (num_tiles - full_tiles);
+    const unsigned grid = num_items < sms ? num_items : sms;
+    (void)n_blocks;
+    sgemm_3xtf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks, k_blocks,
+                                                           num_items, full_tiles);
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;
 }
