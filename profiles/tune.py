@@ -92,7 +92,34 @@ def g_large(path, knob, variants):
     sl.set_sgemm_path("ffma")
 
 
+def g_gemv():
+    for size, dt, log2 in ((4, np.float32, 24), (16, np.float32, 20), (32, np.float32, 20), (16, np.float64, 20), (32, np.float64, 20),
+                           (64, np.float32, 18)):
+        b = 1 << log2
+        es = np.dtype(dt).itemsize
+        (_, a), (_, x), (_, y) = uniform(b * size * size, dt, 1), uniform(b * size, dt, 2), uniform(b * size, dt, 3)
+        for ta in (False, True):
+            report(f"gemv {size}x{size} {np.dtype(dt).name} batch 2^{log2} trans={ta}",
+                   timed(lambda: cuda.matrix_vector_mul_batched(a, x, y, size, size, ta)), nbytes=float(b) * (size * size + 2 * size) * es)
+
+
+def g_bdot():
+    for length, log2, dt in ((1 << 20, 8, np.float32), (1 << 16, 12, np.float32), (4096, 16, np.float32), (256, 20, np.float32),
+                             (16, 24, np.float32), (1 << 20, 7, np.float64)):
+        b = 1 << log2
+        es = np.dtype(dt).itemsize
+        (_, a), (_, bb), (_, o) = uniform(b * length, dt, 1), uniform(b * length, dt, 2), uniform(b, dt, 3)
+        report(f"dot_batched len {length} x 2^{log2} {np.dtype(dt).name}", timed(lambda: cuda.dot_batched(a, bb, o, length)),
+               nbytes=2.0 * b * length * es)
+        report(f"norm_batched len {length} x 2^{log2} {np.dtype(dt).name}", timed(lambda: cuda.norm_batched(a, o, length)),
+               nbytes=1.0 * b * length * es)
+        report(f"normalize_batched len {length} x 2^{log2} {np.dtype(dt).name}", timed(lambda: cuda.normalize_batched(a, length)),
+               nbytes=2.0 * b * length * es)
+
+
 GROUPS = {
+    "gemv": g_gemv,
+    "bdot": g_bdot,
     "transpose": g_transpose,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
     "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),

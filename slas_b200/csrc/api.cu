@@ -143,6 +143,10 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
         db = kind == 1 ? da : (const T *)d[1];
     }
     const bool need_collective = sharded && comm_nranks() > 1;
+    // a device-resident result pointer is written by the kernel itself: one launch, no copy, no sync
+    bool out_dev = false;
+    if (out) SLAS_TRY(pointer_is_device(out, &out_dev));
+    if (out_dev && len > 0) typed = out;
     if (len == 0) {
         // the reference returns the empty sum: 0 (and sqrt(0) = 0)
         SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
@@ -155,7 +159,7 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
         if (nres == 2) SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res + 1, typed + 1, mode));
     }
     if (partial_out) SLAS_TRY(deliver_scalar(ctx, res, partial_out, sizeof(double) * nres));
-    if (out) SLAS_TRY(deliver_scalar(ctx, typed, out, sizeof(T) * nres));
+    if (out && typed != out) SLAS_TRY(deliver_scalar(ctx, typed, out, sizeof(T) * nres));
     return SLAS_OK;
 }
 

@@ -106,11 +106,104 @@ gemv_t_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ 
     }
 }
 
+// Batched dense gemv for power-of-two shapes: the batch is one contiguous stream of rows, so a warp
+// reads 512 consecutive bytes of A per load (LPR = m / VW lanes per row, R = 32 / LPR rows per load),
+// multiplies in registers and reduces with shuffles -- over the lanes of a row for y = A x, over the
+// lanes of a column for y = A^T x.  HBM traffic = A + x + y, every request fully coalesced.
+template <typename T, bool TRANS>
+__global__ void __launch_bounds__(256)
+gemv_small_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, size_t batch, unsigned m, unsigned n) {
+    constexpr int VW = 16 / (int)sizeof(T);
+    struct alignas(16) V { T v[VW]; };
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned lpr = m / VW, rpl = 32 / lpr;     // lanes per row, rows per warp-load
+    const unsigned q = lane % lpr, rl = lane / lpr;  // column vector of this lane, row within the load
+    const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
+    const size_t xlen = TRANS ? n : m, ylen = TRANS ? m : n;
+    if (n >= rpl) {
+        // one object per warp iteration, n / rpl loads
+        for (size_t obj = warp; obj < batch; obj += nwarps) {
+            const T *pa = a + obj * (size_t)m * n;
+            const T *px = x + obj * xlen;
+            T *py = y + obj * ylen;
+            V xv, acc;
+            if (!TRANS) xv = *reinterpret_cast<const V *>(px + q * VW);
+#pragma unroll
+            for (int j = 0; j < VW; ++j) acc.v[j] = T(0);
+            for (unsigned r0 = 0; r0 < n; r0 += rpl) {
+                const unsigned i = r0 + rl;
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4 *>(pa + (size_t)i * m + q * VW));
+                const V av = *reinterpret_cast<const V *>(&raw);
+                if (!TRANS) {
+                    T p = T(0);
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) p = fma(av.v[j], xv.v[j], p);
+                    for (unsigned o = 1; o < lpr; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+                    if (q == 0) py[i] = p;
+                } else {
+                    const T xi = px[i];
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) acc.v[j] = fma(av.v[j], xi, acc.v[j]);
+                }
+            }
+            if (TRANS) {
+                for (unsigned o = lpr; o < 32; o <<= 1)
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) acc.v[j] += __shfl_xor_sync(0xffffffffu, acc.v[j], o);
+                if (rl == 0) *reinterpret_cast<V *>(py + q * VW) = acc;
+            }
+        }
+    } else {
+        // several whole objects per warp-load
+        const unsigned opw = rpl / n, ol = rl / n, i = rl % n;
+        for (size_t obj0 = warp * opw; obj0 < batch; obj0 += nwarps * opw) {
+            const size_t obj = obj0 + ol;
+            const bool live = obj < batch;
+            const size_t o = live ? obj : batch - 1;
+            const uint4 raw = __ldcs(reinterpret_cast<const uint4 *>(a + o * (size_t)m * n + (size_t)i * m + q * VW));
+            const V av = *reinterpret_cast<const V *>(&raw);
+            if (!TRANS) {
+                const V xv = *reinterpret_cast<const V *>(x + o * xlen + q * VW);
+                T p = T(0);
+#pragma unroll
+                for (int j = 0; j < VW; ++j) p = fma(av.v[j], xv.v[j], p);
+                for (unsigned s = 1; s < lpr; s <<= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+                if (q == 0 && live) y[o * ylen + i] = p;
+            } else {
+                const T xi = x[o * xlen + i];
+                V acc;
+#pragma unroll
+                for (int j = 0; j < VW; ++j) acc.v[j] = av.v[j] * xi;
+                for (unsigned s = lpr; s < lpr * n; s <<= 1)
+#pragma unroll
+                    for (int j = 0; j < VW; ++j) acc.v[j] += __shfl_xor_sync(0xffffffffu, acc.v[j], s);
+                if (i == 0 && live) *reinterpret_cast<V *>(y + o * ylen + q * VW) = acc;
+            }
+        }
+    }
+}
+
 template <typename T>
 int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *x, T *y, size_t m, size_t n,
                 size_t lda, int ta, size_t stride_a, size_t stride_x, size_t stride_y) {
     if (batch == 0) return SLAS_OK;
     SLAS_REQUIRE(m <= 0xffffffffu && n <= 0xffffffffu, "gemv: dimension too large");
+    {
+        // batched dense power-of-two shapes: the coalesced streaming kernel
+        constexpr size_t VW = 16 / sizeof(T);
+        const bool pow2 = m && n && !(m & (m - 1)) && !(n & (n - 1));
+        const size_t xlen = ta ? n : m, ylen = ta ? m : n;
+        if (batch > 1 && pow2 && lda == m && m >= VW && m <= 32 * VW && n <= 4096 && stride_a == m * n &&
+            stride_x == xlen && stride_y == ylen && aligned16(a) && aligned16(x) && aligned16(y)) {
+            size_t blocks = (batch + 7) / 8;
+            const size_t cap = (size_t)ctx->sm_count * 8;
+            if (blocks > cap) blocks = cap;
+            if (!ta) gemv_small_kernel<T, false><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, batch, (unsigned)m, (unsigned)n);
+            else gemv_small_kernel<T, true><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, batch, (unsigned)m, (unsigned)n);
+            SLAS_LAUNCH_CHECK();
+            return SLAS_OK;
+        }
+    }
     if (!ta) {
         if (n == 0) return SLAS_OK;
         const size_t rows = batch * n;

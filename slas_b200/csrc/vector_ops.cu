@@ -457,6 +457,194 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
     }
 }
 
+// Tiny vectors (at most PER 16-byte pieces per lane): LPV lanes per vector, 32 / LPV vectors per warp
+// instruction, so a warp still reads 512 consecutive bytes per load; U such groups are in flight per
+// warp iteration (PER * U = 8 independent 16-byte loads per operand per lane).  The vector stays in
+// registers, so normalize is one read and one write.  Reduction = log2(LPV) shuffles.
+template <typename T, int MODE, int PER, int U>
+__global__ void __launch_bounds__(256)
+batched_reduce_subwarp_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out,
+                              T *__restrict__ a_mut, size_t batch, unsigned len, unsigned lpv) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    const unsigned lane = threadIdx.x & 31, vpw = 32 / lpv;  // vectors per warp instruction
+    const unsigned t = lane % lpv, vl = lane / lpv;
+    const unsigned nvec = len / N;                           // 16-byte pieces per vector (<= PER * lpv)
+    const size_t warp = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (size_t)gridDim.x * 8;
+    const T *abase = MODE == 2 ? a_mut : a;
+    for (size_t v0 = warp * vpw * U; v0 < batch; v0 += nwarps * vpw * U) {
+        V x[U][PER], y[U][PER];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + (size_t)u * vpw + vl;
+            live[u] = v < batch;
+            const size_t vv = live[u] ? v : batch - 1;
+            const V *av = reinterpret_cast<const V *>(abase + vv * len);
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                const unsigned i = t + p * lpv;
+                if (i < nvec) x[u][p] = ld_stream(av + i);
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t v = v0 + (size_t)u * vpw + vl;
+                const V *bv = reinterpret_cast<const V *>(b + (live[u] ? v : batch - 1) * len);
+#pragma unroll
+                for (int p = 0; p < PER; ++p) {
+                    const unsigned i = t + p * lpv;
+                    if (i < nvec) y[u][p] = ld_stream(bv + i);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            T acc = T(0);
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                const unsigned i = t + p * lpv;
+                if (i < nvec) {
+                    const T *px = reinterpret_cast<const T *>(&x[u][p]);
+                    const T *py = MODE == 0 ? reinterpret_cast<const T *>(&y[u][p]) : px;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) acc = fma(px[j], py[j], acc);
+                }
+            }
+            double s = (double)acc;
+            for (unsigned o = 1; o < lpv; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const size_t v = v0 + (size_t)u * vpw + vl;
+            if (!live[u]) continue;
+            if (MODE == 0) {
+                if (t == 0) out[v] = (T)s;
+            } else if (MODE == 1) {
+                if (t == 0) out[v] = (T)sqrt(s);
+            } else {
+                const T nrm = (T)sqrt(s);
+                V *mv = reinterpret_cast<V *>(a_mut + v * len);
+#pragma unroll
+                for (int p = 0; p < PER; ++p) {
+                    const unsigned i = t + p * lpv;
+                    if (i < nvec) {
+                        T *px = reinterpret_cast<T *>(&x[u][p]);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                        st_stream(mv + i, x[u][p]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Long vectors: every vector is cut into segments of kSegElems elements, one CTA per segment, so the
+// grid fills the chip even for a handful of vectors.  partial[v][s] (f64) -> batched_finish_kernel adds
+// the segments of a vector in index order (deterministic) -> out / norms.
+constexpr size_t kSegBytes = 256 * 1024;
+
+template <typename T, int MODE /* 0 dot, 1 squared norm */>
+__global__ void __launch_bounds__(256)
+batched_segment_kernel(const T *__restrict__ a, const T *__restrict__ b, double *__restrict__ partial, size_t len,
+                       unsigned segs, size_t seg_elems) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    __shared__ double red[8];
+    const size_t v = blockIdx.x / segs;
+    const unsigned sg = blockIdx.x % segs;
+    const size_t lo = (size_t)sg * seg_elems, hi = lo + seg_elems < len ? lo + seg_elems : len;
+    const V *av = reinterpret_cast<const V *>(a + v * len + lo);
+    const V *bv = reinterpret_cast<const V *>((MODE == 0 ? b : a) + v * len + lo);
+    const size_t nvec = (hi - lo) / N;
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    size_t i = threadIdx.x;
+    for (; i + 3 * 256 < nvec; i += 4 * 256) {
+        V x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) x[u] = ld_stream(av + i + u * 256);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y[u] = MODE == 0 ? ld_stream(bv + i + u * 256) : x[u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const T *px = reinterpret_cast<const T *>(&x[u]), *py = reinterpret_cast<const T *>(&y[u]);
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[u] = fma(px[j], py[j], acc[u]);
+        }
+    }
+    for (; i < nvec; i += 256) {
+        const V x = ld_stream(av + i);
+        const V y = MODE == 0 ? ld_stream(bv + i) : x;
+        const T *px = reinterpret_cast<const T *>(&x), *py = reinterpret_cast<const T *>(&y);
+#pragma unroll
+        for (int j = 0; j < N; ++j) acc[0] = fma(px[j], py[j], acc[0]);
+    }
+    double s = ((double)acc[0] + (double)acc[1]) + ((double)acc[2] + (double)acc[3]);
+    // ragged end of the vector (len % N elements) belongs to the last segment
+    if (sg == segs - 1) {
+        const T *pa = a + v * len, *pb = (MODE == 0 ? b : a) + v * len;
+        for (size_t j = lo + nvec * N + threadIdx.x; j < len; j += 256) s += (double)pa[j] * (double)pb[j];
+    }
+    s = block_sum<256>(s, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+batched_finish_kernel(const double *__restrict__ partial, T *__restrict__ out, size_t batch, unsigned segs, int take_sqrt) {
+    for (size_t v = (size_t)blockIdx.x * 256 + threadIdx.x; v < batch; v += (size_t)gridDim.x * 256) {
+        double s = 0.0;
+        for (unsigned j = 0; j < segs; ++j) s += partial[v * segs + j];
+        out[v] = take_sqrt ? (T)sqrt(s) : (T)s;
+    }
+}
+
+// a[v][i] /= norms[v] over the whole batch (true division)
+template <typename T>
+__global__ void __launch_bounds__(256)
+batched_scale_kernel(T *__restrict__ a, const T *__restrict__ norms, size_t len, size_t nvec_per, size_t total_vec) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * 256) {
+        const size_t v = i / nvec_per, w = i - v * nvec_per;
+        V *p = reinterpret_cast<V *>(a + v * len) + w;
+        V x = *p;
+        const T nrm = norms[v];
+        T *px = reinterpret_cast<T *>(&x);
+#pragma unroll
+        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+        st_stream(p, x);
+    }
+}
+
+template <typename T, int MODE>
+static int launch_batched_segmented(Context *ctx, cudaStream_t st, size_t batch, size_t len, const T *a, const T *b,
+                                    T *out, T *a_mut) {
+    constexpr int N = Vec16<T>::N;
+    const size_t seg_elems = kSegBytes / sizeof(T);
+    const size_t segs = (len + seg_elems - 1) / seg_elems;
+    SLAS_REQUIRE(batch * segs <= 0x7fffffffu && segs <= 0xffffffffu, "batched reduction: too many segments");
+    void *ws = nullptr;
+    SLAS_TRY(ensure_workspace(ctx, batch * segs * sizeof(double) + batch * sizeof(T) + 256, &ws));
+    double *partial = (double *)ws;
+    T *norms = (T *)((char *)ws + ((batch * segs * sizeof(double) + 255) & ~(size_t)255));
+    const T *src = MODE == 2 ? a_mut : a;
+    if (MODE == 0) batched_segment_kernel<T, 0><<<(unsigned)(batch * segs), 256, 0, st>>>(src, b, partial, len, (unsigned)segs, seg_elems);
+    else batched_segment_kernel<T, 1><<<(unsigned)(batch * segs), 256, 0, st>>>(src, src, partial, len, (unsigned)segs, seg_elems);
+    SLAS_LAUNCH_CHECK();
+    size_t fb = (batch + 255) / 256;
+    if (fb > (size_t)ctx->sm_count * 8) fb = (size_t)ctx->sm_count * 8;
+    batched_finish_kernel<T><<<(unsigned)fb, 256, 0, st>>>(partial, MODE == 2 ? norms : out, batch, (unsigned)segs, MODE != 0);
+    SLAS_LAUNCH_CHECK();
+    if (MODE == 2) {
+        const size_t nvec_per = len / N, total = batch * nvec_per;
+        size_t sb = (total + 255) / 256;
+        if (sb > (size_t)ctx->sm_count * 32) sb = (size_t)ctx->sm_count * 32;
+        batched_scale_kernel<T><<<(unsigned)sb, 256, 0, st>>>(a_mut, norms, len, nvec_per, total);
+        SLAS_LAUNCH_CHECK();
+    }
+    return SLAS_OK;
+}
+
 template <typename T, int MODE>
 static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batch, size_t len, const T *a,
                                       const T *b, T *out, T *a_mut) {
@@ -464,6 +652,26 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
     const T *base = MODE == 2 ? a_mut : a;
     const bool vec = aligned16(base) && (MODE != 0 || aligned16(b)) && (len * sizeof(T)) % 16 == 0;
     const size_t cap = (size_t)ctx->sm_count * 8;
+    constexpr int N = Vec16<T>::N;
+    if (vec && len >= (size_t)N && len / N <= 32 * 8) {
+        // tiny: sub-warp groups, registers only
+        const size_t pieces = len / N;
+        unsigned lpv = 1;
+        while (lpv < 32 && (size_t)lpv * 2 <= pieces) lpv *= 2;  // largest power of two <= pieces: every lane has work
+        const size_t per = (pieces + lpv - 1) / lpv;             // 1 .. PER
+        const size_t vec_per_cta = (size_t)8 * (32 / lpv);
+        auto blocks_for = [&](int u) {
+            size_t blocks = (batch + vec_per_cta * u - 1) / (vec_per_cta * u);
+            return (unsigned)(blocks > cap ? cap : blocks);
+        };
+        if (per <= 1) batched_reduce_subwarp_kernel<T, MODE, 1, 8><<<blocks_for(8), 256, 0, st>>>(a, b, out, a_mut, batch, (unsigned)len, lpv);
+        else if (per <= 2) batched_reduce_subwarp_kernel<T, MODE, 2, 4><<<blocks_for(4), 256, 0, st>>>(a, b, out, a_mut, batch, (unsigned)len, lpv);
+        else if (per <= 4) batched_reduce_subwarp_kernel<T, MODE, 4, 2><<<blocks_for(2), 256, 0, st>>>(a, b, out, a_mut, batch, (unsigned)len, lpv);
+        else batched_reduce_subwarp_kernel<T, MODE, 8, 1><<<blocks_for(1), 256, 0, st>>>(a, b, out, a_mut, batch, (unsigned)len, lpv);
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+    }
+    if (vec && len * sizeof(T) >= 2 * kSegBytes) return launch_batched_segmented<T, MODE>(ctx, st, batch, len, a, b, out, a_mut);
     if (len <= 2048) {
         size_t blocks = (batch + 7) / 8;
         if (blocks > cap) blocks = cap;

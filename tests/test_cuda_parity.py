@@ -371,7 +371,8 @@ def test_large_gemm_ffma_path():
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64)])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64), (4, 4), (32, 32), (64, 16),
+                                       (2, 128), (128, 8), (1, 4), (256, 64)])
 @pytest.mark.parametrize("ta", [False, True])
 def test_gemv_vs_oracle(dt, rows, cols, ta):
     rng = np.random.default_rng(rows + cols)
