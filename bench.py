@@ -340,30 +340,37 @@ def run_cuda(args):
         # config 5 (vector half): dot / normalize over 2^32 f32 elements IN TOTAL, sharded by contiguous slice,
         # each rank's slice resident in its own HBM, ONE NCCL allreduce of the f64 partial per op
         from slas_b200 import sharding
-        if world > 1:
-            sharding.init_comm(dist)
         total = 1 << 32
         lo_, hi_ = sharding.shard_range(total, 4, world, rank)
-        lo, hi = C.c_size_t(lo_), C.c_size_t(hi_)
         local = hi_ - lo_
         a = torch.empty(local, device=dev, dtype=torch.float32)
         b = torch.empty(local, device=dev, dtype=torch.float32)
-        _lib.call("slas_cuda_sfill_uniform", local, a.data_ptr(), 4, lo.value, 0.0, 1.0)
-        _lib.call("slas_cuda_sfill_uniform", local, b.data_ptr(), 5, lo.value, 0.0, 1.0)
         res = np.zeros(1, np.float32)
-        ms_, _ = timed(lambda: L.slas_cuda_sdot_sharded(local, a.data_ptr(), b.data_ptr(), res.ctypes.data), 5, 2)
-        # E[u*v] = 1/4 for independent U[0,1): the analytic check SURVEY 8d asks for at this size
-        assert abs(float(res[0]) / total - 0.25) < 1e-3, f"sharded dot {res[0]} is not ~ 2^32/4"
-        record(f"sharded dot f32, 2^32 elements over {world} GPU(s), one allreduce, scalar returned to host", ms_,
-               flop=2.0 * total, bytes_=8.0 * total, bound="hbm-aggregate",
-               extra={"aggregate_hbm_frac": 8.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world), "result": float(res[0])})
-        ms_, _ = timed(lambda: L.slas_cuda_snormalize_sharded(local, a.data_ptr()), 5, 2)
-        record(f"sharded normalize f32, 2^32 elements over {world} GPU(s), one allreduce", ms_, bytes_=12.0 * total,
-               bound="hbm-aggregate", extra={"aggregate_hbm_frac": 12.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world)})
-        L.slas_cuda_snrm2_sharded(local, a.data_ptr(), res.ctypes.data)
-        assert abs(float(res[0]) - 1.0) < 1e-3, f"norm after sharded normalize is {res[0]}"
-        if world > 1:
-            _lib.call("slas_cuda_comm_destroy")
+        dres = torch.zeros(4, device=dev, dtype=torch.float32)
+        # the collective two ways: fused into the reduction kernel over NVLink peer memory (p2p, the default)
+        # and as a separate ncclAllReduce behind it
+        for fused in ((True, False) if world > 1 else (True,)):
+            how = sharding.init_comm(dist, fused=fused) if world > 1 else "single"
+            _lib.call("slas_cuda_sfill_uniform", local, a.data_ptr(), 4, lo_, 0.0, 1.0)
+            _lib.call("slas_cuda_sfill_uniform", local, b.data_ptr(), 5, lo_, 0.0, 1.0)
+            ms_, _ = timed(lambda: L.slas_cuda_sdot_sharded(local, a.data_ptr(), b.data_ptr(), res.ctypes.data), 5, 2)
+            # E[u*v] = 1/4 for independent U[0,1): the analytic check SURVEY 8d asks for at this size
+            assert abs(float(res[0]) / total - 0.25) < 1e-3, f"sharded dot {res[0]} is not ~ 2^32/4"
+            record(f"sharded dot f32, 2^32 elements over {world} GPU(s), collective: {how}, scalar returned to host", ms_,
+                   flop=2.0 * total, bytes_=8.0 * total, bound="hbm-aggregate",
+                   extra={"aggregate_hbm_frac": 8.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world), "result": float(res[0])})
+            ms_, _ = timed(lambda: L.slas_cuda_sdot_sharded(local, a.data_ptr(), b.data_ptr(), dres.data_ptr()), 5, 2)
+            record(f"sharded dot f32, 2^32 elements over {world} GPU(s), collective: {how}, result left in HBM", ms_,
+                   flop=2.0 * total, bytes_=8.0 * total, bound="hbm-aggregate",
+                   extra={"aggregate_hbm_frac": 8.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world)})
+            ms_, _ = timed(lambda: L.slas_cuda_snormalize_sharded(local, a.data_ptr()), 5, 2)
+            record(f"sharded normalize f32, 2^32 elements over {world} GPU(s), collective: {how}", ms_, bytes_=12.0 * total,
+                   bound="hbm-aggregate", extra={"aggregate_hbm_frac": 12.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world)})
+            L.slas_cuda_snrm2_sharded(local, a.data_ptr(), res.ctypes.data)
+            assert abs(float(res[0]) - 1.0) < 1e-3, f"norm after sharded normalize is {res[0]}"
+            if world > 1:
+                sharding.destroy_comm(dist)
+        del dres
         del a, b
         torch.cuda.empty_cache()
         # config 4: single 4096^2 f32 product, FFMA path (and tcgen05 3xTF32 when built)

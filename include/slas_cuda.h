@@ -166,6 +166,14 @@ int slas_cuda_nccl_unique_id(void *id128);                      /* rank 0: 128-b
 int slas_cuda_comm_init(int nranks, int rank, const void *id128);
 int slas_cuda_comm_destroy(void);
 int slas_cuda_comm_info(int *nranks, int *rank);                /* nranks = 1 when no communicator */
+/* Peer-memory exchange: the fused form of the collective.  Every rank exports a small mailbox
+ * (slas_cuda_p2p_handle: 64-byte CUDA IPC handle), the harness all-gathers the handles, and
+ * slas_cuda_p2p_init maps the peers' mailboxes over NVLink.  From then on the *_sharded ops do their
+ * exchange INSIDE the reduction kernel (peer stores + rank-ordered sum, bit-identical on every rank)
+ * instead of calling NCCL.  nranks <= 8 (one NVSwitch domain). */
+int slas_cuda_p2p_handle(void *handle64);
+int slas_cuda_p2p_init(int nranks, int rank, const void *handles /* nranks x 64 bytes, rank order */);
+int slas_cuda_p2p_destroy(void);
 /* Slice [begin, end) of a len-element vector owned by `rank` of `nranks`; boundaries are
  * multiples of 16 bytes' worth of elements (elem_size <= 16). */
 int slas_cuda_shard_range(size_t len, size_t elem_size, int nranks, int rank, size_t *begin, size_t *end);

@@ -99,6 +99,9 @@ SIGNATURES = {
     "slas_cuda_comm_init": [_i, _i, _vp],
     "slas_cuda_comm_destroy": [],
     "slas_cuda_comm_info": [_ip, _ip],
+    "slas_cuda_p2p_handle": [_vp],
+    "slas_cuda_p2p_init": [_i, _i, _vp],
+    "slas_cuda_p2p_destroy": [],
     "slas_cuda_shard_range": [_sz, _sz, _i, _i, _szp, _szp],
     "slas_cuda_sdot_sharded": [_sz, _vp, _vp, _vp],
     "slas_cuda_ddot_sharded": [_sz, _vp, _vp, _vp],

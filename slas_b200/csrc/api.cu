@@ -142,16 +142,22 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
         da = (const T *)d[0];
         db = kind == 1 ? da : (const T *)d[1];
     }
-    const bool need_collective = sharded && comm_nranks() > 1;
+    bool need_collective = sharded && comm_nranks() > 1;
+    // fused collective: the reduction kernel itself exchanges the partial over NVLink peer memory
+    PeerExchange px;
+    const bool fused = need_collective && comm_next_peer_exchange(&px);
+    if (fused) need_collective = false;
     // a device-resident result pointer is written by the kernel itself: one launch, no copy, no sync
     bool out_dev = false;
     if (out) SLAS_TRY(pointer_is_device(out, &out_dev));
-    if (out_dev && len > 0) typed = out;
-    if (len == 0) {
+    if (out_dev && (len > 0 || fused)) typed = out;
+    if (len == 0 && !fused) {
         // the reference returns the empty sum: 0 (and sqrt(0) = 0)
         SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
     } else {
-        SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0));
+        // (a rank with an empty slice still takes part in the fused exchange: its partial is 0)
+        SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0,
+                                  fused ? &px : nullptr));
     }
     if (need_collective) {
         SLAS_TRY(comm_allreduce_f64(res, nres, ctx->stream));
@@ -181,9 +187,13 @@ static int api_normalize(size_t len, T *a, bool sharded) {
         SLAS_TRY(stage_all_begin(ctx, ops, sizes, 1, d));
         da = (T *)d[0];
     }
-    const bool need_collective = sharded && comm_nranks() > 1;
-    if (len == 0) SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
-    else SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, 1, len, da, da, res, need_collective ? nullptr : typed, 1, 0));
+    bool need_collective = sharded && comm_nranks() > 1;
+    PeerExchange px;
+    const bool fused = need_collective && comm_next_peer_exchange(&px);
+    if (fused) need_collective = false;
+    if (len == 0 && !fused) SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
+    else SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, 1, len, da, da, res, need_collective ? nullptr : typed, 1, 0,
+                                   fused ? &px : nullptr));
     if (need_collective) {
         SLAS_TRY(comm_allreduce_f64(res, 1, ctx->stream));
         SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, 1));

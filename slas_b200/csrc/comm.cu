@@ -37,6 +37,12 @@ struct Nccl {
 struct Comm {
     ncclComm_t_ comm = nullptr;
     int nranks = 1, rank = 0;
+    // peer-memory path (p2p.cuh): own mailbox + the peers' mailboxes mapped through CUDA IPC
+    PeerSlot *own_mailbox = nullptr;
+    PeerSlot *mailbox[kMaxPeers] = {};
+    bool p2p = false;
+    int p2p_nranks = 1, p2p_rank = 0;
+    unsigned long long epoch = 0;
 } g_comm;
 std::mutex g_comm_mu;
 
@@ -62,7 +68,16 @@ int load_nccl() {
 }
 }  // namespace
 
-int comm_nranks() { return g_comm.comm ? g_comm.nranks : 1; }
+int comm_nranks() { return g_comm.p2p ? g_comm.p2p_nranks : (g_comm.comm ? g_comm.nranks : 1); }
+
+bool comm_next_peer_exchange(PeerExchange *out) {
+    if (!g_comm.p2p) return false;
+    for (int r = 0; r < kMaxPeers; ++r) out->mailbox[r] = g_comm.mailbox[r];
+    out->nranks = g_comm.p2p_nranks;
+    out->rank = g_comm.p2p_rank;
+    out->epoch = ++g_comm.epoch;
+    return true;
+}
 
 int comm_allreduce_f64(double *dev_inout, size_t count, cudaStream_t st) {
     if (!g_comm.comm || g_comm.nranks == 1) return SLAS_OK;  // single rank: the local partial is the sum
@@ -124,8 +139,70 @@ int slas_cuda_comm_destroy(void) {
 }
 
 int slas_cuda_comm_info(int *nranks, int *rank) {
-    if (nranks) *nranks = g_comm.comm ? g_comm.nranks : 1;
-    if (rank) *rank = g_comm.comm ? g_comm.rank : 0;
+    if (nranks) *nranks = comm_nranks();
+    if (rank) *rank = g_comm.p2p ? g_comm.p2p_rank : (g_comm.comm ? g_comm.rank : 0);
+    return SLAS_OK;
+}
+
+int slas_cuda_p2p_handle(void *handle64) {
+    SLAS_REQUIRE(handle64, "null handle buffer");
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (!g_comm.own_mailbox) {
+        SLAS_CUDA_TRY(cudaMalloc(&g_comm.own_mailbox, kMailboxBytes));
+        SLAS_CUDA_TRY(cudaMemset(g_comm.own_mailbox, 0, kMailboxBytes));
+        SLAS_CUDA_TRY(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    SLAS_CUDA_TRY(cudaIpcGetMemHandle(&h, g_comm.own_mailbox));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, sizeof(h));
+    return SLAS_OK;
+}
+
+int slas_cuda_p2p_init(int nranks, int rank, const void *handles) {
+    SLAS_REQUIRE(nranks >= 1 && nranks <= kMaxPeers && rank >= 0 && rank < nranks, "bad rank %d of %d (max %d peers)", rank,
+                 nranks, kMaxPeers);
+    SLAS_REQUIRE(handles, "null handles");
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    SLAS_REQUIRE(g_comm.own_mailbox, "call slas_cuda_p2p_handle first");
+    SLAS_REQUIRE(!g_comm.p2p, "peer exchange already initialised");
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            g_comm.mailbox[r] = g_comm.own_mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        SLAS_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g_comm.mailbox[r] = (PeerSlot *)p;
+    }
+    g_comm.p2p_nranks = nranks;
+    g_comm.p2p_rank = rank;
+    g_comm.epoch = 0;
+    g_comm.p2p = nranks > 1;
+    return SLAS_OK;
+}
+
+int slas_cuda_p2p_destroy(void) {
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (g_comm.p2p) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < g_comm.p2p_nranks; ++r)
+            if (r != g_comm.p2p_rank && g_comm.mailbox[r]) cudaIpcCloseMemHandle(g_comm.mailbox[r]);
+    }
+    for (int r = 0; r < kMaxPeers; ++r) g_comm.mailbox[r] = nullptr;
+    g_comm.p2p = false;
+    g_comm.p2p_nranks = 1;
+    g_comm.p2p_rank = 0;
+    if (g_comm.own_mailbox) {
+        cudaFree(g_comm.own_mailbox);
+        g_comm.own_mailbox = nullptr;
+    }
     return SLAS_OK;
 }
 

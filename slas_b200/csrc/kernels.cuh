@@ -2,6 +2,7 @@
 // works on DEVICE pointers; api.cu adds the host-pointer staging and the C ABI on top.
 #pragma once
 #include "common.cuh"
+#include "p2p.cuh"
 
 namespace slas {
 
@@ -11,7 +12,7 @@ int launch_ewise(Context *ctx, cudaStream_t st, int op, size_t len, const T *a, 
 // kind 0 dot, 1 squared-norm, 2 complex dotu (len counts REAL scalars); mode 0 cast, 1 sqrt
 template <typename T>
 int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
-                  T *typed_out, int mode, int accumulate);
+                  T *typed_out, int mode, int accumulate, const PeerExchange *peers = nullptr);
 template <typename T> int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode);
 template <typename T> int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, T *a, const T *norm_dev);
 // mode 0 dot, 1 norm, 2 normalize in place

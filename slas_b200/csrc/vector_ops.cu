@@ -13,6 +13,7 @@
 // operations (no fast-math, true division) => bit-exact against the reference.
 #include "common.cuh"
 #include "kernels.cuh"
+#include "p2p.cuh"
 
 namespace slas {
 
@@ -171,10 +172,11 @@ template <typename T, int KIND>
 __global__ void __launch_bounds__(kRedThreads)
 reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised,
               double *__restrict__ partials, unsigned int *__restrict__ ticket, double *__restrict__ result,
-              T *__restrict__ typed_out, int mode, int accumulate) {
+              T *__restrict__ typed_out, int mode, int accumulate, const PeerExchange px) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     __shared__ double red[kRedThreads / 32];
+    __shared__ double peer_vals[2 * kMaxPeers];
     __shared__ bool is_last;
     Reducer<T, KIND> r;
     r.clear();
@@ -256,6 +258,8 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
     }
     p = block_sum<kRedThreads>(p, red);
     if (KIND == 2) p_im = block_sum<kRedThreads>(p_im, red);
+    // multi-GPU: exchange the rank-local partial with the peers over NVLink and add in rank order
+    if (px.nranks > 1) peer_allreduce_sum(px, p, p_im, peer_vals);
     if (threadIdx.x == 0) {
         if (accumulate) { p += result[0]; if (KIND == 2) p_im += result[1]; }
         result[0] = p;
@@ -272,7 +276,7 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
 
 template <typename T, int KIND>
 static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b,
-                              double *result, T *typed_out, int mode, int accumulate) {
+                              double *result, T *typed_out, int mode, int accumulate, const PeerExchange &px) {
     constexpr int N = Vec16<T>::N;
     const bool vec = aligned16(a) && (KIND == 1 || aligned16(b));
     const size_t nvec = vec ? len / N : 0;
@@ -284,25 +288,26 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
     if (blocks == 0) blocks = 1;
     reduce_kernel<T, KIND><<<(unsigned)blocks, kRedThreads, 0, st>>>(
         a, KIND == 1 ? a : b, len, nvec, vec ? 1 : 0, ctx->partials, ctx->ticket, result, typed_out, mode,
-        accumulate);
+        accumulate, px);
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;
 }
 
 template <typename T>
 int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
-                  T *typed_out, int mode, int accumulate) {
+                  T *typed_out, int mode, int accumulate, const PeerExchange *peers) {
+    const PeerExchange px = peers ? *peers : PeerExchange{};
     switch (kind) {
-    case 0: return launch_reduce_kind<T, 0>(ctx, st, len, a, b, result, typed_out, mode, accumulate);
-    case 1: return launch_reduce_kind<T, 1>(ctx, st, len, a, a, result, typed_out, mode, accumulate);
-    case 2: return launch_reduce_kind<T, 2>(ctx, st, len, a, b, result, typed_out, mode, accumulate);
+    case 0: return launch_reduce_kind<T, 0>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
+    case 1: return launch_reduce_kind<T, 1>(ctx, st, len, a, a, result, typed_out, mode, accumulate, px);
+    case 2: return launch_reduce_kind<T, 2>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
     }
     return fail(SLAS_ERR_INVALID, "unknown reduction kind %d", kind);
 }
 template int launch_reduce<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, double *,
-                                  float *, int, int);
+                                  float *, int, int, const PeerExchange *);
 template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const double *, const double *,
-                                   double *, double *, int, int);
+                                   double *, double *, int, int, const PeerExchange *);
 
 // f64 sum -> typed scalar (used after the NCCL allreduce of the sharded ops)
 template <typename T>

@@ -25,12 +25,25 @@ def batch_range(batch: int, nranks: int, rank: int) -> tuple[int, int]:
     return batch * rank // nranks, batch * (rank + 1) // nranks
 
 
-def init_comm(dist) -> None:
-    """Create the library's NCCL communicator over the ranks of an initialised torch.distributed
-    process group (any backend: it only carries the 128-byte unique id)."""
+def init_comm(dist, fused: bool = True) -> str:
+    """Set up the collective of the sharded ops over the ranks of an initialised torch.distributed
+    process group (any backend: it only carries a few bytes of handles).
+
+    fused=True (default, <= 8 ranks of one NVSwitch domain): every rank exports a mailbox through CUDA
+    IPC and maps its peers' -- the reduction kernel then does the exchange itself over NVLink peer
+    memory (slas_b200/csrc/p2p.cuh).  fused=False: the library's NCCL communicator, one
+    ncclAllReduce of the f64 partial behind the kernel.  Returns "p2p", "nccl" or "single"."""
     world, rank = dist.get_world_size(), dist.get_rank()
     if world == 1:
-        return
+        return "single"
+    if fused and world <= 8:
+        buf = (C.c_char * 64)()
+        _lib.call("slas_cuda_p2p_handle", buf)
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(buf.raw))
+        _lib.call("slas_cuda_p2p_init", world, rank, b"".join(handles))
+        dist.barrier()
+        return "p2p"
     ident = [None]
     if rank == 0:
         buf = (C.c_char * 128)()
@@ -38,9 +51,13 @@ def init_comm(dist) -> None:
         ident = [bytes(buf.raw)]
     dist.broadcast_object_list(ident, src=0)
     _lib.call("slas_cuda_comm_init", world, rank, ident[0])
+    return "nccl"
 
 
-def destroy_comm() -> None:
+def destroy_comm(dist=None) -> None:
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()  # nobody unmaps a mailbox a peer may still write to
+    _lib.call("slas_cuda_p2p_destroy")
     _lib.call("slas_cuda_comm_destroy")
 
 
