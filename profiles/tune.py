@@ -69,8 +69,8 @@ def g_transpose():
     set_tunable("transpose_variant", 0)
 
 
-def g_gemm(knob, size, dt, variants):
-    b = 1 << 20
+def g_gemm(knob, size, dt, variants, log2=20):
+    b = 1 << log2
     e = size * size
     (_, a), (_, bb), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2), uniform(b * e, dt, 3)
     for v in variants:
@@ -124,6 +124,9 @@ GROUPS = {
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
     "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),
     "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2)),
+    "gemm64": lambda: (g_gemm("gemm32s_variant", 64, np.float32, (0,), 18), g_gemm("gemm32d_variant", 64, np.float64, (0,), 17),
+                       g_gemm("gemm4s_variant", 8, np.float32, (0,), 22), g_gemm("gemm4s_variant", 8, np.float64, (0,), 22),
+                       g_gemm("gemm4s_variant", 4, np.float64, (0,), 24)),
     "large": lambda: g_large("ffma", "gemm_large_variant", (0, 1, 2, 3)),
     "tc": lambda: g_large("tcgen05", "tc_variant", (0, 1, 2, 3)),
 }

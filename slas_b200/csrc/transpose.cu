@@ -130,6 +130,37 @@ transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_
     }
 }
 
+// n == VW (4x4 of 4-byte, 2x2 of 8-byte elements): one LANE per matrix ROW, so a warp reads and writes
+// 512 consecutive bytes per instruction; the VW x VW transpose runs across the VW lanes of a matrix with
+// VW shuffles.  Round r: lane q sends its element (q - r) mod VW to lane (q - r) mod VW ... i.e. it
+// receives element q of lane (q + r) mod VW, which is exactly output element (q + r) mod VW of row q.
+template <typename E, int VW>
+__global__ void __launch_bounds__(256)
+transpose_tiny_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nrows_total) {
+    struct alignas(16) V { E v[VW]; };
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < ((nrows_total + 31) & ~(size_t)31); t += (size_t)gridDim.x * 256) {
+        const bool live = t < nrows_total;
+        const unsigned q = (unsigned)(t % VW);
+        V x;
+        if (live) x = ld16(reinterpret_cast<const V *>(in) + t);
+        V y;
+#pragma unroll
+        for (int r = 0; r < VW; ++r) {
+            // element this lane contributes in round r: index (q - r) mod VW
+            E send = x.v[0];
+#pragma unroll
+            for (int j = 1; j < VW; ++j)
+                if (((q + VW - r) % VW) == (unsigned)j) send = x.v[j];
+            const unsigned src_lane = (threadIdx.x & ~(VW - 1)) + ((q + r) % VW);
+            const E got = __shfl_sync(0xffffffffu, send, src_lane & 31);
+#pragma unroll
+            for (int j = 0; j < VW; ++j)
+                if (((q + r) % VW) == (unsigned)j) y.v[j] = got;
+        }
+        if (live) __stcs(reinterpret_cast<uint4 *>(out) + t, *reinterpret_cast<uint4 *>(&y));
+    }
+}
+
 template <typename E, int VW, int MULT, bool OUT_MAJOR>
 static int launch_square_vec(Context *ctx, cudaStream_t st, size_t batch, unsigned n, const E *a, E *buffer) {
     const size_t total = batch * (size_t)(n / (MULT * VW)) * (n / VW);
@@ -153,6 +184,17 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
           aligned16(buffer)) {
         const unsigned n = (unsigned)rows;
         const long variant = tunable("transpose_variant");
+        // measured (B200): the lane-per-row shuffle kernel wins for 2x2 of 8-byte elements (0.97 of HBM peak) but
+        // its select chains lose to the thread-per-matrix register transpose for 4x4 of 4-byte ones (0.63 vs 0.82)
+        if (n == (unsigned)VW && (VW == 2 ? variant != 1 : variant == 6)) {
+            const size_t nrows_total = batch * VW;
+            size_t blocks = (nrows_total + 255) / 256;
+            const size_t cap = (size_t)ctx->sm_count * 32;
+            if (blocks > cap) blocks = cap;
+            transpose_tiny_kernel<E, VW><<<(unsigned)blocks, 256, 0, st>>>(a, buffer, nrows_total);
+            SLAS_LAUNCH_CHECK();
+            return SLAS_OK;
+        }
         // default = out-major lanes (full-line stores): measured best or equal for every n, f32 and f64
         // (profiles/r1b_tune.log); variant 1 = the in-major ordering
         if (variant == 1) return launch_square_vec<E, VW, 1, false>(ctx, st, batch, n, a, buffer);
