@@ -9,7 +9,12 @@
 // All three products accumulate into the same fp32 accumulator in TMEM.  Per-product relative
 // error ~3 * 2^-22, far inside the 1e-5 * sqrt(K) budget of north_star.
 //
-// Structure (one CTA per SM, persistent over 128 x 256 output tiles):
+// Two kernels share the split pass, the descriptors and the warp roles.  Default: the CTA-PAIR kernel
+// (sgemm_3xtf32_pair_kernel, tcgen05 cta_group::2, 256 x 256 tiles, three 64 KB stages per CTA; measured 0.535 ms
+// for 4096^3 including the split).  Fallback when m is not a multiple of 256 (or tc_variant = 3): the
+// single-CTA kernel below (0.634 ms).
+//
+// Structure of the single-CTA kernel (one CTA per SM, persistent over 128 x 256 output tiles):
 //   split pass   one streaming kernel writes hi/lo copies of op(A) as [M][K] and of op(B) as
 //                [N][K] (both K-major, so the a_trans/b_trans flags are absorbed here).
 //   warp 0       TMA producer: cp.async.bulk.tensor 2-D tiles (128B swizzle) of A_hi, A_lo,
@@ -279,6 +284,210 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     }
 }
 
+// ---- the CTA-pair variant: tcgen05 cta_group::2 -------------------------------------------------------------
+// Two CTAs on the two SMs of a TPC form a cluster and compute one 256 x 256 tile: CTA r holds rows
+// [128r, 128r + 128) of A and of B^T for the k-block (64 KB per stage instead of 96 KB, so THREE stages fit) and
+// the accumulator rows [128r, +128) in its own TMEM.  The leader CTA's MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 256 or 128) for the pair; both CTAs' TMA loads complete on the
+// LEADER's full barrier; tcgen05.commit multicasts the stage-free and accumulator-ready arrivals to both
+// CTAs; the peer's epilogue warps arrive remotely on the leader's accumulator-empty barrier.
+namespace tc2 {
+constexpr int BM = 256, BN = 256, BK = 32, HALF = 128, STAGES = 3;
+constexpr int A_TILE_BYTES = HALF * BK * 4;   // 16 KB: this CTA's 128 rows of A (hi or lo)
+constexpr int B_TILE_BYTES = HALF * BK * 4;   // 16 KB: this CTA's 128 rows of B^T (hi or lo)
+constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 64 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr int THREADS = 256;
+constexpr int TMEM_COLS = 512;
+}  // namespace tc2
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void *dst_smem, const CUtensorMap *map, int crd_inner, int crd_outer,
+                                                 uint32_t leader_bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst_smem)), "l"(map), "r"(leader_bar_cluster_addr), "r"(crd_inner), "r"(crd_outer)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+
+struct PairItem { uint32_t mb, nb, n_off, n_cols; };
+__device__ __forceinline__ PairItem decode_pair_item(uint32_t item, uint32_t m_blocks, uint32_t full_tiles) {
+    if (item < full_tiles) return {item % m_blocks, item / m_blocks, 0u, (uint32_t)tc2::BN};
+    const uint32_t t = item - full_tiles, tile = full_tiles + (t >> 1);
+    return {tile % m_blocks, tile / m_blocks, (t & 1u) * (tc2::BN / 2), (uint32_t)tc2::BN / 2};
+}
+
+__global__ void __launch_bounds__(tc2::THREADS, 1)
+sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                         const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                         float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t k_blocks, uint32_t num_items,
+                         uint32_t full_tiles) {
+    using namespace tc2;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *acc_full = bars + 2 * STAGES, *acc_empty = bars + 2 * STAGES + 2;
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();           // 0 = leader
+    const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_b_hi); tma_prefetch_desc(&map_b_lo);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_empty + b, 8); }  // 4 epilogue warps x 2 CTAs
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers exist before anything crosses the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): this CTA's halves, completing on the LEADER's full barrier =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t item = pair; item < num_items; item += npairs) {
+                const PairItem w = decode_pair_item(item, m_blocks, full_tiles);
+                const uint32_t half_cols = w.n_cols / 2;                       // B^T rows this CTA contributes
+                const uint32_t a_row = w.mb * BM + rank * HALF;
+                const uint32_t b_row = w.nb * BN + w.n_off + rank * half_cols;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                    unsigned char *st = smem + s * STAGE_BYTES;
+                    const uint32_t leader_full = map_to_cta(smem_u32(full + s), 0);
+                    // the leader posts the byte count of BOTH CTAs' loads
+                    if (rank == 0) mbar_expect_tx(full + s, 2 * (2 * A_TILE_BYTES + 2 * half_cols * BK * 4));
+                    tma_load_2d_pair(st, &map_a_hi, kb * BK, a_row, leader_full);
+                    tma_load_2d_pair(st + A_TILE_BYTES, &map_a_lo, kb * BK, a_row, leader_full);
+                    // B^T arrives as 64-row boxes: two per operand for a full tile, one for a half tile
+                    tma_load_2d_pair(st + 2 * A_TILE_BYTES, &map_b_hi, kb * BK, b_row, leader_full);
+                    tma_load_2d_pair(st + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, kb * BK, b_row, leader_full);
+                    if (w.n_cols == BN) {
+                        tma_load_2d_pair(st + 2 * A_TILE_BYTES + B_TILE_BYTES / 2, &map_b_hi, kb * BK, b_row + HALF / 2, leader_full);
+                        tma_load_2d_pair(st + 2 * A_TILE_BYTES + B_TILE_BYTES + B_TILE_BYTES / 2, &map_b_lo, kb * BK, b_row + HALF / 2, leader_full);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA's elected lane issues for the pair =====
+        if (rank == 0 && lane == 0) {
+            uint32_t it = 0, tile_it = 0;
+            for (uint32_t item = pair; item < num_items; item += npairs, ++tile_it) {
+                const PairItem w = decode_pair_item(item, m_blocks, full_tiles);
+                const uint32_t idesc = umma_idesc_tf32(BM, (int)w.n_cols);
+                const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
+                if (buf_use > 0) mbar_wait(acc_empty + buf, (buf_use - 1) & 1);  // both CTAs' epilogues drained it
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * BN;
+                for (uint32_t kb = 0; kb < k_blocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES, use = it / STAGES;
+                    mbar_wait(full + s, use & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_k_sw128(sa), a_lo = umma_desc_k_sw128(sa + A_TILE_BYTES);
+                    const uint64_t b_hi = umma_desc_k_sw128(sa + 2 * A_TILE_BYTES);
+                    const uint64_t b_lo = umma_desc_k_sw128(sa + 2 * A_TILE_BYTES + B_TILE_BYTES);
+#pragma unroll
+                    for (uint32_t k = 0; k < BK / tc::UMMA_K; ++k) {
+                        const uint64_t adv = (uint64_t)((k * tc::UMMA_K * 4) >> 4);
+                        umma_tf32_pair(tmem_d, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                        umma_tf32_pair(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                        umma_tf32_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, 1);
+                    }
+                    umma_commit_pair(empty + s);
+                    if (kb + 1 == k_blocks) umma_commit_pair(acc_full + buf);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): this CTA's 128 accumulator rows =====
+        const uint32_t q = warp & 3;
+        uint32_t tile_it = 0;
+        for (uint32_t item = pair; item < num_items; item += npairs, ++tile_it) {
+            const PairItem w = decode_pair_item(item, m_blocks, full_tiles);
+            const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
+            mbar_wait(acc_full + buf, buf_use & 1);
+            tc_fence_after();
+            float *crow = c + (size_t)(w.mb * BM + rank * HALF + q * 32 + lane) * ldc + (size_t)w.nb * BN + w.n_off;
+#pragma unroll 1
+            for (uint32_t cc = 0; cc < w.n_cols / 32; ++cc) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((q * 32) << 16) + buf * BN + cc * 32, v);
+                tmem_ld_wait();
+                float4 *dst = reinterpret_cast<float4 *>(crow + cc * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(map_to_cta(smem_u32(acc_empty + buf), 0));  // the leader's barrier
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still touch it
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -334,6 +543,37 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
     else split_tf32_transpose_kernel<<<dim3((unsigned)(n / 32), (unsigned)(k / 32)), 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k);
     SLAS_LAUNCH_CHECK();
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    const long variant = tunable("tc_variant");
+    if (variant != 1 && variant != 3 && m % tc2::BM == 0 && ctx->sm_count >= 2) {
+        // CTA-pair kernel (cta_group::2): 256 x 256 tiles, three 64 KB stages per CTA
+        SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, tc2::HALF));
+        SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, tc2::HALF));
+        SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, tc2::HALF / 2));
+        SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, tc2::HALF / 2));
+        SLAS_CUDA_TRY(cudaFuncSetAttribute(sgemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+        const uint32_t m_blocks = (uint32_t)(m / tc2::BM), n_blocks = (uint32_t)(n / tc2::BN), k_blocks = (uint32_t)(k / BK);
+        const uint32_t pairs_max = (uint32_t)ctx->sm_count / 2, num_tiles = m_blocks * n_blocks;
+        uint32_t full_tiles = num_tiles / pairs_max * pairs_max;
+        if (2 * (num_tiles - full_tiles) > pairs_max) full_tiles = num_tiles;
+        const uint32_t num_items = full_tiles + 2 * (num_tiles - full_tiles);
+        const uint32_t pairs = num_items < pairs_max ? num_items : pairs_max;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(tc2::THREADS);
+        cfg.dynamicSmemBytes = tc2::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SLAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgemm_3xtf32_pair_kernel, ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks,
+                                         k_blocks, num_items, full_tiles));
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+    }
     SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, BM));
     SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, BM));
     SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, BN / 2));
