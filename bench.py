@@ -62,6 +62,31 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
+def ncu_traffic(kernel_prefix: str):
+    """DRAM bytes (read + write) per launch of a kernel, from the newest committed `ncu --set full` summary
+    (profiles/*_ncu_summary.csv, written by profiles/summarize.py).  None when no capture exists."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")), reverse=True):
+        with open(path) as f:
+            rows = list(csv.reader(f))
+        if not rows:
+            continue
+        hdr = rows[0]
+        try:
+            ir = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_read.sum"))
+            iw = next(i for i, h in enumerate(hdr) if h.startswith("dram__bytes_write.sum"))
+        except StopIteration:
+            continue
+        scale = {"[Gbyte]": 1e9, "[Mbyte]": 1e6, "[Kbyte]": 1e3, "[byte]": 1.0}
+        sr = next((v for k, v in scale.items() if k in hdr[ir]), 1.0)
+        sw = next((v for k, v in scale.items() if k in hdr[iw]), 1.0)
+        vals = [float(r[ir]) * sr + float(r[iw]) * sw for r in rows[1:] if r and r[0].startswith(kernel_prefix)]
+        if vals:
+            return {"bytes": sum(vals) / len(vals), "source": os.path.relpath(path, ROOT)}
+    return None
+
+
 # ---- clocks during the timed region --------------------------------------------------------------
 class ClockSampler:
     def __init__(self, index: int):
@@ -425,6 +450,7 @@ def run_cuda(args):
                "all_cores_value": r["gflops_all_cores"], "cores_available": r["cores_available"]}
 
     if rank == 0:
+        traffic = ncu_traffic("void gemm_small_kernel<float, SmallCfg<float, 4, 4, 4")
         line = {
             "metric": "batched matrix_mul GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -433,7 +459,9 @@ def run_cuda(args):
                        "layout": "[[f32; 16]; batch] contiguous row-major, no transposes", "parallelism": f"batch-index shards x{world}, no collective",
                        "l2": "working set 3 GiB per GPU >> 126 MB L2 (no flush needed)"},
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
-                         "traffic": None, "peak_source": peak_src, "kernel": "gemm_small_kernel<float, 4x4x4>",
+                         "traffic": (traffic or {}).get("bytes") if batch == 1 << 24 else None,
+                         "traffic_source": (traffic or {}).get("source"),
+                         "peak_source": peak_src, "kernel": "gemm_small_kernel<float, 4x4x4>",
                          "algorithmic_bytes_per_launch": BYTES_PER_4X4 * batch},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "others": others,
         }

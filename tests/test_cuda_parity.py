@@ -168,6 +168,37 @@ def test_empty_vectors():
     cuda.normalize(np.zeros(0, np.float64))
 
 
+def test_concurrent_callers_like_libtest():
+    """libtest runs the reference's tests on several threads at once and a backend is a stateless ZST, so the
+    library serialises enqueue + scratch internally (SURVEY 8b 'Threading'): 8 threads, mixed ops, exact answers."""
+    import threading
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(40):
+                n = int(rng.integers(1, 5000))
+                a = rng.integers(-8, 9, n).astype(np.float32)   # small integers: every result is exact
+                b = rng.integers(-8, 9, n).astype(np.float32)
+                assert float(cuda.dot(a, b)) == float(np.dot(a.astype(np.float64), b.astype(np.float64)))
+                c = np.empty_like(a)
+                cuda.add(a, b, c)
+                assert np.array_equal(c, a + b)
+                m = rng.integers(-3, 4, 16).astype(np.float32)
+                got = T.matrix(m, 4, 4, cuda).matrix_mul(T.matrix(m, 4, 4, cuda))
+                assert np.array_equal(got.reshape(4, 4), m.reshape(4, 4) @ m.reshape(4, 4))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+
+
 # ---- dot / norm / normalize ------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [1, 2, 7, 8, 100, 750, 4097, 65536 + 5, 1 << 20])
