@@ -117,7 +117,37 @@ def g_bdot():
                nbytes=2.0 * b * length * es)
 
 
+def g_misc():
+    # one large gemv / transpose (single objects), and launch-bound small calls replayed from a CUDA graph
+    n = 8192
+    (_, a), (_, x), (_, y) = uniform(n * n, np.float32, 1), uniform(n, np.float32, 2), uniform(n, np.float32, 3)
+    for ta in (False, True):
+        report(f"gemv {n}x{n} float32 single trans={ta}", timed(lambda: cuda.matrix_vector_mul(a, x, y, n, n, n, ta)), nbytes=4.0 * n * n)
+    (_, c) = uniform(n * n, np.float32, 4)
+    report(f"transpose {n}x{n} float32 single", timed(lambda: cuda.transpose(a, c, n)), nbytes=8.0 * n * n)
+    (_, a8), (_, c8) = uniform(n * n // 2, np.float64, 1), uniform(n * n // 2, np.float64, 4)
+    report(f"transpose {n}x{n // 2} float64 single", timed(lambda: cuda.transpose(a8, c8, n)), nbytes=8.0 * n * n)
+    l20 = 1 << 20
+    ta_, va = uniform(256 * l20, np.float32, 5)
+    tb_, vb = uniform(256 * l20, np.float32, 6)
+    out = torch.zeros(256, device=dev, dtype=torch.float32)
+    L = _lib.lib()
+
+    def loop():
+        for i in range(256):
+            L.slas_cuda_sdot(l20, ta_.data_ptr() + 4 * i * l20, tb_.data_ptr() + 4 * i * l20, out.data_ptr() + 4 * i)
+
+    report("dot 2^20 x 256 calls, eager", timed(loop, 5, 2), nbytes=8.0 * 256 * l20)
+    g = torch.cuda.CUDAGraph()
+    loop()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=stream):
+        loop()
+    report("dot 2^20 x 256 calls, CUDA graph replay", timed(g.replay, 5, 2), nbytes=8.0 * 256 * l20)
+
+
 GROUPS = {
+    "misc": g_misc,
     "gemv": g_gemv,
     "bdot": g_bdot,
     "transpose": g_transpose,

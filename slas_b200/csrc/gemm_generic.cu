@@ -183,11 +183,135 @@ gemv_small_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restric
     }
 }
 
+// One large matrix, y = A x: a warp per row, 128-bit loads, four independent accumulators, x through L1/L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemv_n_vec_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, unsigned m, unsigned n, size_t lda) {
+    constexpr int VW = 16 / (int)sizeof(T);
+    struct alignas(16) V { T v[VW]; };
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned nvec = m / VW;
+    for (size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n; row += (size_t)gridDim.x * 8) {
+        const V *pa = reinterpret_cast<const V *>(a + row * lda);
+        const V *px = reinterpret_cast<const V *>(x);
+        T acc[4] = {T(0), T(0), T(0), T(0)};
+        unsigned j = lane;
+        for (; j + 96 < nvec; j += 128) {
+            V av[4], xv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint4 raw = __ldcs(reinterpret_cast<const uint4 *>(pa + j + 32 * u));
+                av[u] = *reinterpret_cast<const V *>(&raw);
+                xv[u] = px[j + 32 * u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int e = 0; e < VW; ++e) acc[u] = fma(av[u].v[e], xv[u].v[e], acc[u]);
+        }
+        for (; j < nvec; j += 32) {
+            const V av = pa[j], xv = px[j];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[0] = fma(av.v[e], xv.v[e], acc[0]);
+        }
+        T s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        for (unsigned e = nvec * VW + lane; e < m; e += 32) s = fma(a[row * lda + e], x[e], s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[row] = s;
+    }
+}
+
+// One large matrix, y = A^T x: CTA = 32 column-vectors (128-bit each) x 8 row lanes; grid.y splits the rows,
+// each split writes partial[split][m]; gemv_t_finish adds the splits in order (deterministic, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemv_t_split_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ partial, unsigned m, unsigned n,
+                    size_t lda, unsigned rows_per_split) {
+    constexpr int VW = 16 / (int)sizeof(T);
+    struct alignas(16) V { T v[VW]; };
+    __shared__ V red[8][32];
+    const unsigned cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const unsigned col = (blockIdx.x * 32 + cl) * VW;
+    const unsigned r0 = blockIdx.y * rows_per_split;
+    const unsigned r1 = r0 + rows_per_split < n ? r0 + rows_per_split : n;
+    V acc[2];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) { acc[0].v[e] = T(0); acc[1].v[e] = T(0); }
+    if (col < m) {
+        unsigned i = r0 + rl;
+        for (; i + 8 < r1; i += 16) {
+            const uint4 w0 = __ldcs(reinterpret_cast<const uint4 *>(a + (size_t)i * lda + col));
+            const uint4 w1 = __ldcs(reinterpret_cast<const uint4 *>(a + (size_t)(i + 8) * lda + col));
+            const V a0 = *reinterpret_cast<const V *>(&w0), a1 = *reinterpret_cast<const V *>(&w1);
+            const T x0 = x[i], x1 = x[i + 8];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) { acc[0].v[e] = fma(a0.v[e], x0, acc[0].v[e]); acc[1].v[e] = fma(a1.v[e], x1, acc[1].v[e]); }
+        }
+        if (i < r1) {
+            const V a0 = *reinterpret_cast<const V *>(a + (size_t)i * lda + col);
+            const T x0 = x[i];
+#pragma unroll
+            for (int e = 0; e < VW; ++e) acc[0].v[e] = fma(a0.v[e], x0, acc[0].v[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VW; ++e) acc[0].v[e] += acc[1].v[e];
+    red[rl][cl] = acc[0];
+    __syncthreads();
+    if (rl == 0 && col < m) {
+        V s = red[0][cl];
+#pragma unroll
+        for (int r = 1; r < 8; ++r)
+#pragma unroll
+            for (int e = 0; e < VW; ++e) s.v[e] += red[r][cl].v[e];
+        *reinterpret_cast<V *>(partial + (size_t)blockIdx.y * m + col) = s;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) gemv_t_finish_kernel(const T *__restrict__ partial, T *__restrict__ y, unsigned m, unsigned splits) {
+    const unsigned j = blockIdx.x * 256 + threadIdx.x;
+    if (j >= m) return;
+    T s = T(0);
+    for (unsigned sp = 0; sp < splits; ++sp) s += partial[(size_t)sp * m + j];
+    y[j] = s;
+}
+
 template <typename T>
 int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *x, T *y, size_t m, size_t n,
                 size_t lda, int ta, size_t stride_a, size_t stride_x, size_t stride_y) {
     if (batch == 0) return SLAS_OK;
     SLAS_REQUIRE(m <= 0xffffffffu && n <= 0xffffffffu, "gemv: dimension too large");
+    {
+        // one large matrix with 16-byte aligned rows: the vectorised kernels
+        constexpr size_t VW = 16 / sizeof(T);
+        if (batch == 1 && m >= 32 * VW && n >= 64 && aligned16(a) && aligned16(x) && aligned16(y) && lda % VW == 0) {
+            if (!ta) {
+                size_t blocks = (n + 7) / 8;
+                const size_t cap = (size_t)ctx->sm_count * 16;
+                if (blocks > cap) blocks = cap;
+                gemv_n_vec_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, (unsigned)m, (unsigned)n, lda);
+                SLAS_LAUNCH_CHECK();
+                return SLAS_OK;
+            }
+            if (m % VW == 0) {
+                const size_t col_tiles = (m / VW + 31) / 32;
+                size_t splits = ((size_t)ctx->sm_count * 4 + col_tiles - 1) / col_tiles;
+                if (splits > (n + 63) / 64) splits = (n + 63) / 64;
+                if (splits < 1) splits = 1;
+                const size_t rows_per_split = (n + splits - 1) / splits;
+                splits = (n + rows_per_split - 1) / rows_per_split;
+                void *ws = nullptr;
+                SLAS_TRY(ensure_workspace(ctx, splits * m * sizeof(T), &ws));
+                gemv_t_split_kernel<T><<<dim3((unsigned)col_tiles, (unsigned)splits), 256, 0, st>>>(a, x, (T *)ws, (unsigned)m, (unsigned)n,
+                                                                                                  lda, (unsigned)rows_per_split);
+                SLAS_LAUNCH_CHECK();
+                gemv_t_finish_kernel<T><<<(unsigned)((m + 255) / 256), 256, 0, st>>>((const T *)ws, y, (unsigned)m, (unsigned)splits);
+                SLAS_LAUNCH_CHECK();
+                return SLAS_OK;
+            }
+        }
+    }
     {
         // batched dense power-of-two shapes: the coalesced streaming kernel
         constexpr size_t VW = 16 / sizeof(T);

@@ -48,6 +48,42 @@ transpose_tiled_kernel(const E *__restrict__ in, E *__restrict__ out, size_t len
     }
 }
 
+// ---- (1b) tiled, 4-byte elements, 128-bit global accesses: 64 x 64 tiles ----------------------------
+// rows % 64 == 0, columns % 64 == 0, 16-byte aligned.  Each thread moves four 16-byte vectors in and four
+// out; the element transpose happens through a padded (pitch 65) shared tile with scalar accesses.
+__global__ void __launch_bounds__(256)
+transpose_tiled64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t len, unsigned rows,
+                         unsigned columns, unsigned tiles_r, unsigned tiles_c) {
+    __shared__ uint32_t tile[64][65];  // tile[out_row_in_tile][out_col_in_tile]
+    size_t bid = blockIdx.x;
+    const unsigned tr = (unsigned)(bid % tiles_r); bid /= tiles_r;
+    const unsigned tc = (unsigned)(bid % tiles_c); bid /= tiles_c;
+    const uint32_t *src = in + bid * len;
+    uint32_t *dst = out + bid * len;
+    // input: `columns` rows of `rows` elements; this tile = input rows [tc*64, +64), input cols [tr*64, +64)
+    const unsigned vq = threadIdx.x & 15, rr = threadIdx.x >> 4;  // 16 vectors per row, 16 rows per pass
+#pragma unroll
+    for (unsigned p = 0; p < 4; ++p) {
+        const unsigned ir = rr + 16 * p;  // input row within the tile = output column within the tile
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src + (size_t)(tc * 64 + ir) * rows + tr * 64 + vq * 4));
+        tile[vq * 4 + 0][ir] = v.x;
+        tile[vq * 4 + 1][ir] = v.y;
+        tile[vq * 4 + 2][ir] = v.z;
+        tile[vq * 4 + 3][ir] = v.w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (unsigned p = 0; p < 4; ++p) {
+        const unsigned orow = rr + 16 * p;
+        uint4 v;
+        v.x = tile[orow][vq * 4 + 0];
+        v.y = tile[orow][vq * 4 + 1];
+        v.z = tile[orow][vq * 4 + 2];
+        v.w = tile[orow][vq * 4 + 3];
+        __stcs(reinterpret_cast<uint4 *>(dst + (size_t)(tr * 64 + orow) * columns + tc * 64 + vq * 4), v);
+    }
+}
+
 // ---- (2) warp per small object ---------------------------------------------------------------
 template <typename E>
 __global__ void __launch_bounds__(256)
@@ -224,6 +260,18 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
     }
     // (1) tiled
     SLAS_REQUIRE(rows <= 0xffffffffu && columns <= 0xffffffffu, "transpose: dimension too large");
+    if constexpr (sizeof(E) == 4) {
+        if (rows % 64 == 0 && columns % 64 == 0 && len == rows * columns && aligned16(a) && aligned16(buffer) &&
+            tunable("transpose_variant") != 1) {
+            const size_t t_r = rows / 64, t_c = columns / 64, nb = batch * t_r * t_c;
+            SLAS_REQUIRE(nb <= 0x7fffffffu, "transpose: too many tiles (%zu)", nb);
+            transpose_tiled64_kernel<<<(unsigned)nb, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(a),
+                                                                    reinterpret_cast<uint32_t *>(buffer), len, (unsigned)rows,
+                                                                    (unsigned)columns, (unsigned)t_r, (unsigned)t_c);
+            SLAS_LAUNCH_CHECK();
+            return SLAS_OK;
+        }
+    }
     const size_t tiles_r = (rows + 31) / 32, tiles_c = (columns + 31) / 32;
     const size_t blocks = batch * tiles_r * tiles_c;
     SLAS_REQUIRE(blocks <= 0x7fffffffu, "transpose: too many tiles (%zu)", blocks);

@@ -270,7 +270,7 @@ def test_norm_and_normalize(dt, n):
 
 # ---- transpose: bit-exact for any Copy element --------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32])
-@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48)])
+@pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48), (128, 64), (192, 320), (1024, 512)])
 def test_transpose_bit_exact(dt, rows, cols):
     a = np.arange(rows * cols).astype(dt)
     if dt == np.int32:
@@ -403,7 +403,7 @@ def test_large_gemm_ffma_path():
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64), (4, 4), (32, 32), (64, 16),
-                                       (2, 128), (128, 8), (1, 4), (256, 64)])
+                                       (2, 128), (128, 8), (1, 4), (256, 64), (64, 128), (300, 1024), (1000, 516), (2048, 2048)])
 @pytest.mark.parametrize("ta", [False, True])
 def test_gemv_vs_oracle(dt, rows, cols, ta):
     rng = np.random.default_rng(rows + cols)
