@@ -117,6 +117,16 @@ def g_bdot():
                nbytes=2.0 * b * length * es)
 
 
+def g_rect():
+    for (m, n, k, dt, log2) in ((2, 2, 3, np.float32, 24), (3, 3, 3, np.float32, 24), (8, 4, 16, np.float32, 22), (16, 32, 8, np.float32, 20),
+                                (12, 12, 12, np.float64, 20), (4, 4, 4, np.float32, 24)):
+        b = 1 << log2
+        es = np.dtype(dt).itemsize
+        (_, a), (_, bb), (_, c) = uniform(b * m * k, dt, 1), uniform(b * k * n, dt, 2), uniform(b * m * n, dt, 3)
+        report(f"gemm {m}x{k} . {k}x{n} {np.dtype(dt).name} batch 2^{log2}", timed(lambda: cuda.matrix_mul_batched(a, bb, c, m, n, k)),
+               nbytes=float(b) * (m * k + k * n + m * n) * es, flop=2.0 * m * n * k * b)
+
+
 def g_misc():
     # one large gemv / transpose (single objects), and launch-bound small calls replayed from a CUDA graph
     n = 8192
@@ -148,6 +158,7 @@ def g_misc():
 
 GROUPS = {
     "misc": g_misc,
+    "rect": g_rect,
     "gemv": g_gemv,
     "bdot": g_bdot,
     "transpose": g_transpose,

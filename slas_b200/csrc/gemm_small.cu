@@ -224,6 +224,101 @@ static int launch_cfg(Context *ctx, cudaStream_t st, size_t batch, const T *a, c
     return SLAS_OK;
 }
 
+// ---- any small static shape: runtime (m, n, k), same staging ------------------------------------------------
+// Shapes without a register-tiled specialisation (2x3 . 3x2, 8x16 . 16x4, ...) keep the memory side of the design
+// -- persistent CTAs, bulk-TMA chunks of G consecutive matrices into a 3-stage ring, mbarriers -- and compute one
+// C element per thread per step straight out of shared memory (A reads broadcast across a row of C, B reads
+// consecutive), writing C with consecutive threads on consecutive elements.  G is a multiple of 4 so that every
+// chunk is a whole number of 16-byte words whatever the shape.
+template <typename T>
+__global__ void __launch_bounds__(288)
+gemm_small_generic_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t batch, size_t nchunks,
+                          unsigned m, unsigned n, unsigned k, int ta, int tb, unsigned G, unsigned stage_elems) {
+    constexpr int STAGES = 3, CONSUMERS = 256;
+    extern __shared__ __align__(128) unsigned char smem[];
+    T *stage_base = reinterpret_cast<T *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * stage_elems * sizeof(T));
+    uint64_t *empty = full + STAGES;
+    const unsigned mk = m * k, kn = k * n, mn = m * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMERS / 32) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+                const uint32_t s = it % STAGES, use = it / STAGES;
+                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                const size_t first = ch * G;
+                const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+                T *sa = stage_base + (size_t)s * stage_elems;
+                T *sb = sa + (size_t)G * mk;
+                // a ragged final chunk may end on a partial 16-byte word: round the copy up (the staging
+                // buffer has room, the extra elements are never read; the arrays end on a 16-byte boundary
+                // because the caller only takes this path when batch * m * k * sizeof(T) % 16 == 0)
+                const uint32_t bytes_a = (cnt * mk * (uint32_t)sizeof(T) + 15u) & ~15u;
+                const uint32_t bytes_b = (cnt * kn * (uint32_t)sizeof(T) + 15u) & ~15u;
+                mbar_expect_tx(full + s, bytes_a + bytes_b);
+                bulk_g2s(sa, a + first * mk, bytes_a, full + s);
+                bulk_g2s(sb, b + first * kn, bytes_b, full + s);
+            }
+        }
+        return;
+    }
+    uint32_t it = 0;
+    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+        const uint32_t s = it % STAGES, use = it / STAGES;
+        const size_t first = ch * G;
+        const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+        const T *sa = stage_base + (size_t)s * stage_elems;
+        const T *sb = sa + (size_t)G * mk;
+        mbar_wait(full + s, use & 1);
+        T *cc = c + first * mn;
+        for (unsigned e = threadIdx.x; e < cnt * mn; e += CONSUMERS) {
+            const unsigned mat = e / mn, r = e - mat * mn, i = r / n, j = r - i * n;
+            const T *ma = sa + mat * mk, *mb = sb + mat * kn;
+            T acc = T(0);
+            if (!ta && !tb) for (unsigned p = 0; p < k; ++p) acc = fma(ma[i * k + p], mb[p * n + j], acc);
+            else if (ta && !tb) for (unsigned p = 0; p < k; ++p) acc = fma(ma[p * m + i], mb[p * n + j], acc);
+            else if (!ta && tb) for (unsigned p = 0; p < k; ++p) acc = fma(ma[i * k + p], mb[j * k + p], acc);
+            else for (unsigned p = 0; p < k; ++p) acc = fma(ma[p * m + i], mb[j * k + p], acc);
+            cc[e] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+template <typename T>
+static int launch_generic_small(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m,
+                                size_t n, size_t k, int ta, int tb) {
+    const size_t mk = m * k, kn = k * n, per = (mk + kn) * sizeof(T);
+    if (k == 0 || per == 0 || per > 16 * 1024) return SLAS_ERR_UNSUPPORTED;
+    // the final (ragged) chunk is copied in whole 16-byte words: the arrays themselves must end on one
+    if ((batch * mk * sizeof(T)) % 16 || (batch * kn * sizeof(T)) % 16) return SLAS_ERR_UNSUPPORTED;
+    size_t G = (32 * 1024) / per / 4 * 4;
+    if (G < 4) G = 4;
+    if (G > 256) G = 256;
+    const size_t stage_elems = ((G * (mk + kn) * sizeof(T) + 127) & ~(size_t)127) / sizeof(T);
+    const size_t smem = 3 * stage_elems * sizeof(T) + 6 * sizeof(uint64_t);
+    if (smem > 200 * 1024) return SLAS_ERR_UNSUPPORTED;
+    const size_t nchunks = (batch + G - 1) / G;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)ctx->sm_count * per_sm;
+    if (grid > nchunks) grid = nchunks;
+    auto kern = gemm_small_generic_kernel<T>;
+    SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 288, smem, st>>>(a, b, c, batch, nchunks, (unsigned)m, (unsigned)n, (unsigned)k, ta, tb, (unsigned)G,
+                                            (unsigned)stage_elems);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
 //                         T       M   N   K  TM TN CONS   G  STAGES
 using CfgS4 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 128, 4>;
 using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3>;
@@ -248,7 +343,9 @@ template <>
 int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch, const float *a, const float *b,
                                      float *c, size_t m, size_t n, size_t k, int ta, int tb) {
     if (batch == 0) return SLAS_OK;
-    if (!(aligned16(a) && aligned16(b) && aligned16(c)) || m != n || n != k) return SLAS_ERR_UNSUPPORTED;
+    if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
+    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64))
+        return batch >= 64 ? launch_generic_small<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
     switch (m) {
     case 4: return launch_cfg<float, CfgS4>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<float, CfgS8>(ctx, st, batch, a, b, c, ta, tb);
@@ -274,7 +371,9 @@ template <>
 int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batch, const double *a, const double *b,
                                       double *c, size_t m, size_t n, size_t k, int ta, int tb) {
     if (batch == 0) return SLAS_OK;
-    if (!(aligned16(a) && aligned16(b) && aligned16(c)) || m != n || n != k) return SLAS_ERR_UNSUPPORTED;
+    if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
+    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64))
+        return batch >= 64 ? launch_generic_small<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
     switch (m) {
     case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<double, CfgD8>(ctx, st, batch, a, b, c, ta, tb);
