@@ -277,6 +277,30 @@ gemm_small_generic_kernel(const T *__restrict__ a, const T *__restrict__ b, T *_
         const T *sb = sa + (size_t)G * mk;
         mbar_wait(full + s, use & 1);
         T *cc = c + first * mn;
+        constexpr unsigned VW = 16 / sizeof(T);
+        if (!tb && n % VW == 0) {
+            // one 16-byte vector of a C row per thread: A scalar (broadcast), B and C 128-bit
+            struct alignas(16) V { T v[VW]; };
+            const unsigned nq = n / VW, per_mat = m * nq;
+            for (unsigned e = threadIdx.x; e < cnt * per_mat; e += CONSUMERS) {
+                const unsigned mat = e / per_mat, r = e - mat * per_mat, i = r / nq, jq = r - i * nq;
+                const T *ma = sa + mat * mk;
+                const V *mb = reinterpret_cast<const V *>(sb + mat * kn) + jq;
+                V acc;
+#pragma unroll
+                for (unsigned q = 0; q < VW; ++q) acc.v[q] = T(0);
+                for (unsigned p = 0; p < k; ++p) {
+                    const T av = ta ? ma[p * m + i] : ma[i * k + p];
+                    const V bv = mb[p * nq];
+#pragma unroll
+                    for (unsigned q = 0; q < VW; ++q) acc.v[q] = fma(av, bv.v[q], acc.v[q]);
+                }
+                *reinterpret_cast<V *>(cc + (size_t)mat * mn + i * n + jq * VW) = acc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+            continue;
+        }
         for (unsigned e = threadIdx.x; e < cnt * mn; e += CONSUMERS) {
             const unsigned mat = e / mn, r = e - mat * mn, i = r / n, j = r - i * n;
             const T *ma = sa + mat * mk, *mb = sb + mat * kn;
