@@ -45,9 +45,13 @@ __device__ __forceinline__ void stg_vec(T *p, const T (&src)[CNT]) {
     for (int i = 0; i < NV; ++i) __stcs(d + i, s[i]);
 }
 
-template <typename T, int M_, int N_, int K_, int TM_, int TN_, int CONS_, int G_, int STAGES_>
+template <typename T, int M_, int N_, int K_, int TM_, int TN_, int CONS_, int G_, int STAGES_, bool STORE_TMA_ = false>
 struct SmallCfg {
     static constexpr int M = M_, N = N_, K = K_, TM = TM_, TN = TN_;
+    // STORE_TMA: C goes registers -> a double-buffered shared staging tile -> ONE bulk copy per chunk
+    // (cp.async.bulk shared -> global), so HBM sees long write bursts instead of per-warp 512-byte stores
+    static constexpr bool STORE_TMA = STORE_TMA_;
+    static constexpr size_t CSTAGE_BYTES = STORE_TMA_ ? (size_t)G_ * M_ * N_ * sizeof(T) : 0;
     static constexpr int CONSUMERS = CONS_;           // consumer threads
     static constexpr int G = G_;                      // matrices per stage
     static constexpr int STAGES = STAGES_;
@@ -56,7 +60,7 @@ struct SmallCfg {
     static constexpr int PASSES = G / MPP;
     static constexpr int A_ELEMS = M * K, B_ELEMS = K * N, C_ELEMS = M * N;
     static constexpr size_t STAGE_BYTES = (size_t)G * (A_ELEMS + B_ELEMS) * sizeof(T);
-    static constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * sizeof(uint64_t);
+    static constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 2 * CSTAGE_BYTES + 2 * STAGES * sizeof(uint64_t);
     static_assert(M % TM == 0 && N % TN == 0, "tile must divide the matrix");
     static_assert(CONSUMERS % TPM == 0 && G % MPP == 0, "chunk must be whole passes");
     static_assert((A_ELEMS * sizeof(T)) % 16 == 0 && (B_ELEMS * sizeof(T)) % 16 == 0, "bulk copies move 16-byte words");
@@ -74,7 +78,8 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
 
     extern __shared__ __align__(128) unsigned char smem[];
     T *stage_base = reinterpret_cast<T *>(smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES);
+    T *cstage_base = reinterpret_cast<T *>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES + 2 * Cfg::CSTAGE_BYTES);
     uint64_t *empty = full + STAGES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,6 +138,10 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
         const T *sa = stage_base + (size_t)s * (Cfg::STAGE_BYTES / sizeof(T));
         const T *sb = sa + (size_t)G * Cfg::A_ELEMS;
         mbar_wait(full + s, use & 1);
+        T *cst = cstage_base + (size_t)(it & 1) * (Cfg::CSTAGE_BYTES / sizeof(T));
+        // (bulk store) the copy out of this staging buffer issued two chunks ago has been read: thread 0 waited
+        // for it (wait_group.read 1) before arriving here
+        if (Cfg::STORE_TMA) asm volatile("bar.sync 1, %0;" ::"n"(Cfg::CONSUMERS) : "memory");
 #pragma unroll 1
         for (int p = 0; p < PASSES; ++p) {
             const uint32_t mat = p * MPP + slot;
@@ -187,16 +196,39 @@ gemm_small_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
 #pragma unroll
                         for (int j = 0; j < TN; ++j) acc[i][j] = fma(ablk[i][kk], bblk[kk][j], acc[i][j]);
             }
-            T *mc = c + (first + mat) * Cfg::C_ELEMS;
+            if (Cfg::STORE_TMA) {
+                T *mc = cst + (size_t)mat * Cfg::C_ELEMS;
 #pragma unroll
-            for (int i = 0; i < TM; ++i)
+                for (int i = 0; i < TM; ++i)
 #pragma unroll
-                for (int g = 0; g < NG; ++g)
-                    stg_vec<T, KVN>(mc + row_of(i) * N + col_of(g * KVN), *reinterpret_cast<const T(*)[KVN]>(&acc[i][g * KVN]));
+                    for (int g = 0; g < NG; ++g)
+                        *reinterpret_cast<uint4 *>(mc + row_of(i) * N + col_of(g * KVN)) = *reinterpret_cast<const uint4 *>(&acc[i][g * KVN]);
+            } else {
+                T *mc = c + (first + mat) * Cfg::C_ELEMS;
+#pragma unroll
+                for (int i = 0; i < TM; ++i)
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+                        stg_vec<T, KVN>(mc + row_of(i) * N + col_of(g * KVN), *reinterpret_cast<const T(*)[KVN]>(&acc[i][g * KVN]));
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
+        if (Cfg::STORE_TMA) {
+            // make the generic-proxy writes of every consumer visible to the async proxy, then one bulk store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(Cfg::CONSUMERS) : "memory");
+            if (threadIdx.x == 0) {
+                const uint32_t bytes_c = cnt * Cfg::C_ELEMS * (uint32_t)sizeof(T);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(c + first * Cfg::C_ELEMS),
+                             "r"(smem_u32(cst)), "r"(bytes_c)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the OTHER buffer is free again
+            }
+        }
     }
+    if (Cfg::STORE_TMA && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 template <typename T, typename Cfg>
@@ -345,6 +377,12 @@ static int launch_generic_small(Context *ctx, cudaStream_t st, size_t batch, con
 
 //                         T       M   N   K  TM TN CONS   G  STAGES
 using CfgS4 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 128, 4>;
+using CfgS4t = SmallCfg<float, 4, 4, 4, 1, 4, 256, 128, 3, true>;   // bulk-store variants (benchmark knob gemm4s_variant)
+using CfgS4u = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 3, true>;
+using CfgS4v3 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 4, true>;
+using CfgS4v4 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 512, 2, true>;
+using CfgS4v5 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 4, false>;
+using CfgS4v6 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 3, false>;
 using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3>;
 using CfgS16 = SmallCfg<float, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgS32 = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 3>;
@@ -362,6 +400,9 @@ using CfgD32b = SmallCfg<double, 32, 32, 32, 4, 4, 256, 4, 3>;
 using CfgS32b = SmallCfg<float, 32, 32, 32, 8, 8, 128, 8, 3>;
 using CfgS16b = SmallCfg<float, 16, 16, 16, 4, 4, 256, 32, 3>;
 using CfgS16c = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 3>;
+using CfgS16t = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 2, true>;
+using CfgS32t = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 2, true>;
+using CfgD16t = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 2, true>;
 
 template <>
 int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch, const float *a, const float *b,
@@ -371,11 +412,21 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
     if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64))
         return batch >= 64 ? launch_generic_small<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
     switch (m) {
-    case 4: return launch_cfg<float, CfgS4>(ctx, st, batch, a, b, c, ta, tb);
+    case 4:
+        // measured on B200 (2^24 pairs): 256 pairs per stage + bulk C store 0.490 ms (1.00 of the HBM copy
+        // peak); 128 per stage with per-warp stores 0.502-0.506; the other knob values are the rest of the sweep
+        if (tunable("gemm4s_variant") == 1) return launch_cfg<float, CfgS4t>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4s_variant") == 7) return launch_cfg<float, CfgS4>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4s_variant") == 3) return launch_cfg<float, CfgS4v3>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4s_variant") == 4) return launch_cfg<float, CfgS4v4>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4s_variant") == 5) return launch_cfg<float, CfgS4v5>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4s_variant") == 6) return launch_cfg<float, CfgS4v6>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<float, CfgS4u>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<float, CfgS8>(ctx, st, batch, a, b, c, ta, tb);
     case 16:
         // measured on B200 (profiles/r1b_tune.log): 8x4 tiles, 32 matrices per stage = 0.96 of HBM peak
         if (tunable("gemm16s_variant") == 1) return launch_cfg<float, CfgS16b>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm16s_variant") == 3) return launch_cfg<float, CfgS16t>(ctx, st, batch, a, b, c, ta, tb);
         if (tunable("gemm16s_variant") == 2) return launch_cfg<float, CfgS16>(ctx, st, batch, a, b, c, ta, tb);
         return launch_cfg<float, CfgS16c>(ctx, st, batch, a, b, c, ta, tb);
     case 64:
@@ -386,6 +437,7 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
         return launch_cfg<float, CfgS64b>(ctx, st, batch, a, b, c, ta, tb);
     case 32:
         if (tunable("gemm32s_variant") == 1) return launch_cfg<float, CfgS32b>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm32s_variant") == 3) return launch_cfg<float, CfgS32t>(ctx, st, batch, a, b, c, ta, tb);
         return launch_cfg<float, CfgS32>(ctx, st, batch, a, b, c, ta, tb);
     }
     return SLAS_ERR_UNSUPPORTED;
