@@ -383,11 +383,11 @@ using CfgS4v3 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 4, true>;
 using CfgS4v4 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 512, 2, true>;
 using CfgS4v5 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 4, false>;
 using CfgS4v6 = SmallCfg<float, 4, 4, 4, 1, 4, 256, 256, 3, false>;
-using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3>;
+using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3, true>;
 using CfgS16 = SmallCfg<float, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgS32 = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 3>;
 using CfgD4 = SmallCfg<double, 4, 4, 4, 1, 4, 256, 128, 4>;
-using CfgD8 = SmallCfg<double, 8, 8, 8, 2, 4, 256, 32, 3>;
+using CfgD8 = SmallCfg<double, 8, 8, 8, 2, 4, 256, 32, 3, true>;
 using CfgD16 = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgD32 = SmallCfg<double, 32, 32, 32, 8, 4, 128, 4, 3>;
 // 64 x 64: 32 / 64 KB per pair -- compute-bound (10.7 flop/byte), two / one matrices per stage
