@@ -107,6 +107,45 @@ def test_dot_add_len_2_28():
     assert abs(float(cuda.norm(a)) - 1.0) <= 1e-5
 
 
+def test_host_pointer_pipeline_crosses_chunk_boundaries():
+    """The reference's calling convention is HOST pointers; large host operands go through the 3-slot
+    H2D / kernel / D2H pipeline in chunks of ~96 MB.  Every byte must land where the one-shot device path puts it,
+    including ragged final chunks (bit-exact: same kernels, same per-object arithmetic)."""
+    rng = np.random.default_rng(77)
+    # element-wise: 3 operands x 4 B -> 8M-element chunks; 20M + 5 elements = 3 chunks, ragged tail
+    n = 20_000_005
+    a, b = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32) + 0.5
+    c = np.empty_like(a)
+    cuda.div(a, b, c)
+    assert np.array_equal(c, a / b)
+    # batched 4x4 product: 192 B per pair -> 524288-pair chunks; 1.3M + 3 pairs = 3 chunks
+    batch = 1_300_003
+    A = rng.integers(-4, 5, batch * 16).astype(np.float32)
+    B = rng.integers(-4, 5, batch * 16).astype(np.float32)
+    C = np.empty(batch * 16, np.float32)
+    cuda.matrix_mul_batched(A, B, C, 4, 4, 4)
+    assert np.array_equal(C.reshape(batch, 4, 4), A.reshape(batch, 4, 4) @ B.reshape(batch, 4, 4))
+    # batched transpose and batched dot through the same pipeline
+    T16 = rng.random(300_000 * 256, dtype=np.float32)
+    out = np.empty_like(T16)
+    cuda.transpose_batched(T16, out, 256, 16)
+    assert np.array_equal(out.reshape(-1, 16, 16), T16.reshape(-1, 16, 16).transpose(0, 2, 1))
+    va = rng.integers(-3, 4, 1_000_003 * 32).astype(np.float32)
+    vb = rng.integers(-3, 4, 1_000_003 * 32).astype(np.float32)
+    d = np.empty(1_000_003, np.float32)
+    cuda.dot_batched(va, vb, d, 32)
+    assert np.array_equal(d, np.einsum("ij,ij->i", va.reshape(-1, 32), vb.reshape(-1, 32)))
+    # a whole-vector reduction and an in-place normalize staged from the host
+    x = rng.integers(-3, 4, 30_000_001).astype(np.float32)
+    # every product and partial sum is an exact integer, the f64 grid reduction too: the result is the correctly
+    # rounded f32 of the exact sum
+    assert float(cuda.dot(x, x)) == float(np.float32(np.dot(x.astype(np.float64), x.astype(np.float64))))
+    y = x[:5_000_003].copy()
+    nrm = cuda.norm(y)
+    cuda.normalize(y)
+    assert np.array_equal(y, x[:5_000_003] / nrm)
+
+
 @pytest.mark.parametrize("path", ["ffma", "tcgen05"])
 def test_matmul_4096_freivalds(path):
     n = 4096
