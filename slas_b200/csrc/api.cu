@@ -271,6 +271,23 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
             const int r = launch_sgemm_ffma(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb, ldc, ta, tb);
             if (r != SLAS_ERR_UNSUPPORTED) return r;
         }
+        // The FFMA kernel is fastest when A arrives k-major (a_trans) and B n-major (!b_trans): both tiles then go
+        // to shared memory with 128-bit stores (measured 50.6 vs 43.4 TFLOP/s at 4096^3).  For a big enough dense
+        // f32 product it pays to put the operands into that form first with the HBM-speed transpose kernels
+        // (2 x 64 MB at ~6 TB/s = 0.02 ms against 0.4 ms gained); the FMA order per C element is unchanged.
+        if (sizeof(T) == 4 && tunable("gemm_large_variant") != 2 && m * n * k >= ((size_t)1 << 30)) {
+            const bool fix_a = !ta && lda == k, fix_b = tb && ldb == k;
+            if (fix_a || fix_b) {
+                void *ws = nullptr;
+                const size_t ea = fix_a ? m * k : 0, eb = fix_b ? n * k : 0;
+                SLAS_TRY(ensure_workspace(ctx, (ea + eb) * sizeof(T), &ws));
+                T *at = (T *)ws, *bt = at + ea;
+                if (fix_a) SLAS_TRY(launch_transpose(ctx, st, 1, m * k, sizeof(T), a, at, m));  // [m][k] -> [k][m]
+                if (fix_b) SLAS_TRY(launch_transpose(ctx, st, 1, n * k, sizeof(T), b, bt, n));  // [n][k] -> [k][n]
+                return launch_gemm_large<T>(ctx, st, fix_a ? at : a, fix_b ? bt : b, c, m, n, k, fix_a ? m : lda,
+                                            fix_b ? n : ldb, ldc, fix_a ? 1 : ta, fix_b ? 0 : tb);
+            }
+        }
         return launch_gemm_large<T>(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
     }
     return launch_gemm_generic<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);

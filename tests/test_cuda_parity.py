@@ -407,13 +407,16 @@ def test_single_gemm_any_shape(dt, m, n, k, ta, tb):
         assert np.max(np.abs(got[:, :n] - want.reshape(m, ldc)[:, :n])) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
 
 
-def test_large_gemm_ffma_path():
-    rng = np.random.default_rng(12)
-    m = n = k = 512
+@pytest.mark.parametrize("size", [512, 1024])   # 1024^3 and up: operands are first put into the k-major / n-major form
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_large_gemm_ffma_path(size, ta, tb):
+    rng = np.random.default_rng(12 + size)
+    m, n, k = size, size + 64, size
     A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
     c = CudaVec(m * n, np.float32)
-    cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, k, n, n, False, False)
-    ref, mag = _gemm_truth(A, B, m, n, k, False, False)
+    cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
+    ref, mag = _gemm_truth(A, B, m, n, k, ta, tb)
     assert np.all(np.abs(c.to_host() - ref) <= 1e-5 * np.sqrt(k) * mag)
 
 
