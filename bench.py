@@ -295,15 +295,27 @@ def run_cuda(args):
 
     # ---- others: the remaining BASELINE configs (rank-local numbers unless stated) ----
     others = []
+    fma_peak = None
     if not args.no_others:
         del A, B, Cc, vA, vB, vC
         torch.cuda.empty_cache()
         ksteps = max(3, min(args.steps, 20))
 
-        def record(name, ms_, flop=None, bytes_=None, bound="hbm", extra=None):
+        # FP32 / FP64 FMA ceilings measured on this box (register-only 8x8 outer-product loop): the secondary figure
+        # BASELINE asks for next to the HBM fraction of the batched products
+        fma_peak = {}
+        for is_d, key in ((0, "f32"), (1, "f64")):
+            t = C.c_double()
+            _lib.call("slas_cuda_bench_fma_peak", is_d, C.byref(t))
+            fma_peak[key] = t.value
+
+        def record(name, ms_, flop=None, bytes_=None, bound="hbm", extra=None, fma=None):
             row = {"name": name, "ms": ms_}
             if flop is not None:
                 row["gflops"] = flop / (ms_ * 1e-3) / 1e9
+                if fma:
+                    row["fma_pipe_frac_of_measured_peak"] = row["gflops"] / 1e3 / fma_peak[fma]
+                    row["fma_pipe_frac_of_nominal"] = row["gflops"] / 1e3 / (74.5 if fma == "f32" else 37.2)
             if bytes_ is not None:
                 row["gbs"] = bytes_ / (ms_ * 1e-3) / 1e9
                 if bound == "hbm":
@@ -322,7 +334,8 @@ def run_cuda(args):
             c = torch.empty_like(a)
             va, vb, vc = vec(a), vec(b), vec(c)
             ms_, _ = timed(lambda: cuda.matrix_mul_batched(va, vb, vc, n_, n_, n_), ksteps, 3)
-            record(f"batched {n_}x{n_} {name} matrix_mul, batch 2^20", ms_, flop=2.0 * n_ ** 3 * bsz, bytes_=3.0 * n_ * n_ * es * bsz)
+            record(f"batched {n_}x{n_} {name} matrix_mul, batch 2^20", ms_, flop=2.0 * n_ ** 3 * bsz, bytes_=3.0 * n_ * n_ * es * bsz,
+                   fma=name)
             ms_, _ = timed(lambda: cuda.transpose_batched(va, vc, n_ * n_, n_), ksteps, 3)
             record(f"batched {n_}x{n_} {name} transpose, batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
             del a, b, c, va, vb, vc
@@ -342,8 +355,12 @@ def run_cuda(args):
         ms_, _ = timed(lambda: cuda.normalize(va), ksteps, 3)
         record("normalize f32 LEN=2^28 (one call; 12 B/elem: read, read, write)", ms_, bytes_=12.0 * n28)
         l20 = 1 << 20
-        ms_, _ = timed(lambda: cuda.dot_batched(va.view(0, 256 * l20), vb.view(0, 256 * l20), vout.view(0, 256), l20), ksteps, 3)
-        record("dot f32 LEN=2^20 x 256 distinct pairs (one batched launch, 2 GiB)", ms_, flop=2.0 * 256 * l20, bytes_=8.0 * 256 * l20)
+        # (ii) of SURVEY 8d config 1: 1024 DISTINCT 2^20-element pairs (8 GiB >> L2) in one batched launch
+        a4 = dev_uniform(1024 * l20, torch.float32, 8, 0.0, 1.0)
+        b4 = dev_uniform(1024 * l20, torch.float32, 9, 0.0, 1.0)
+        ms_, _ = timed(lambda: cuda.dot_batched(vec(a4), vec(b4), vout, l20), ksteps, 3)
+        record("dot f32 LEN=2^20 x 1024 distinct pairs (one batched launch, 8 GiB)", ms_, flop=2.0 * 1024 * l20, bytes_=8.0 * 1024 * l20)
+        del a4, b4
 
         def dot_loop():
             for i in range(256):
@@ -419,8 +436,7 @@ def run_cuda(args):
                 e0.record(stream); gemm(); e1.record(stream)
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            record("single 4096^2 f32 matrix_mul, FFMA path", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="fp32",
-                   extra={"fp32_peak_frac_nominal_74.5TF": 2.0 * n_ ** 3 / (float(np.median(ts)) * 1e-3) / 74.5e12})
+            record("single 4096^2 f32 matrix_mul, FFMA path", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="fp32", fma="f32")
             try:
                 sl.set_sgemm_path("tcgen05")
                 for _ in range(2):
@@ -463,7 +479,8 @@ def run_cuda(args):
                          "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src, "kernel": "gemm_small_kernel<float, 4x4x4>",
                          "algorithmic_bytes_per_launch": BYTES_PER_4X4 * batch},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "others": others,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "fma_peak_tflops_measured": fma_peak if not args.no_others else None, "others": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -168,6 +168,40 @@ def test_empty_vectors():
     cuda.normalize(np.zeros(0, np.float64))
 
 
+def test_bad_arguments_fail_loudly_not_fatally():
+    """Where the reference asserts or cblas rejects its arguments, the C ABI returns a status (the shim panics)."""
+    import ctypes as C
+    from slas_b200 import _lib
+    L = _lib.lib()
+    a = np.arange(6, dtype=np.float32)
+    d = CudaVec.from_host(a)
+    out = np.zeros(1, np.float32)
+    p = lambda x: x.ctypes.data  # noqa: E731
+    assert L.slas_cuda_sdot(6, None, p(a), p(out)) == _lib.SLAS_ERR_INVALID              # null operand
+    assert L.slas_cuda_sdot(6, p(a), d.as_ptr(), p(out)) == _lib.SLAS_ERR_INVALID         # host and device operands mixed
+    assert b"mix" in L.slas_cuda_last_error()
+    assert L.slas_cuda_sdot(6, p(a), p(a), None) == _lib.SLAS_ERR_INVALID                  # no result pointer
+    assert L.slas_cuda_transpose(6, 4, p(a), p(a), 0) == _lib.SLAS_ERR_INVALID             # columns == 0 (rust.rs:169 divides)
+    assert L.slas_cuda_transpose(6, 3, p(a), p(out), 2) == _lib.SLAS_ERR_INVALID           # element size
+    c = np.zeros(4, np.float32)
+    assert L.slas_cuda_sgemm(p(a), p(a), p(c), 2, 2, 3, 2, 2, 2, 0, 0) == _lib.SLAS_ERR_INVALID   # lda < k
+    assert L.slas_cuda_sgemm(p(a), p(a), p(c), 2, 2, 3, 3, 2, 1, 0, 0) == _lib.SLAS_ERR_INVALID   # ldc < n
+    assert L.slas_cuda_sgemv(p(a), p(a), p(c), 3, 2, 2, 0) == _lib.SLAS_ERR_INVALID               # lda < width
+    assert L.slas_cuda_set_tunable(b"no_such_knob", 1) == _lib.SLAS_ERR_INVALID
+    assert L.slas_cuda_set_sgemm_path(7) == _lib.SLAS_ERR_INVALID
+    # ... and the library keeps working afterwards
+    assert cuda.dot(a, a) == 55.0
+    flag = C.c_int(-1)
+    _lib.call("slas_cuda_is_device_ptr", d.as_ptr(), C.byref(flag))
+    assert flag.value == 1
+    _lib.call("slas_cuda_is_device_ptr", p(a), C.byref(flag))
+    assert flag.value == 0
+    # k == 0: beta = 0 semantics, C becomes zeros (cblas with k = 0)
+    z = np.full(4, 7.0, np.float32)
+    cuda.matrix_mul(np.zeros(0, np.float32), np.zeros(0, np.float32), z, 2, 2, 0, 1, 2, 2, False, False)
+    assert np.array_equal(z, np.zeros(4, np.float32))
+
+
 def test_concurrent_callers_like_libtest():
     """libtest runs the reference's tests on several threads at once and a backend is a stateless ZST, so the
     library serialises enqueue + scratch internally (SURVEY 8b 'Threading'): 8 threads, mixed ops, exact answers."""
