@@ -162,6 +162,39 @@ def cpu_reference_4x4(sample_log2: int, steps: int, warmup: int):
                       f"the reference is single-threaded; pthread split over {cores} cores reported as gflops_all_cores)"}
 
 
+def cpu_reference_config0():
+    """BASELINE configs[0]: f32 dot + add on LEN = 2^20, the reference's Rust backend (C restatement, the lane
+    count an AVX2 build gives it) and its Blas backend (cblas_sdot) on this box's cores."""
+    from oracle import blas_standin as blas
+    from oracle import oracle
+    n = 1 << 20
+    rng = np.random.default_rng(0)
+    a, b = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+
+    def best(fn, reps=30):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return float(np.median(ts))
+
+    out = {"len": n, "cores_available": os.cpu_count() or 1}
+    t = best(lambda: oracle.dot(a, b, lanes=8, fast=True))
+    out["rust_backend_dot_gbs_1_thread"] = 8.0 * n / t / 1e9
+    t = best(lambda: oracle.ewise("add", a, b, fast=True))
+    out["rust_backend_add_gbs_1_thread"] = 12.0 * n / t / 1e9
+    blas.set_threads(1)
+    t = best(lambda: blas.dot(a, b))
+    out["blas_backend_dot_gbs_1_thread"] = 8.0 * n / t / 1e9
+    blas.set_threads(os.cpu_count() or 1)
+    t = best(lambda: blas.dot(a, b))
+    out["blas_backend_dot_gbs_all_cores"] = 8.0 * n / t / 1e9
+    blas.set_threads(1)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -464,6 +497,8 @@ def run_cuda(args):
         r = cpu_reference_4x4(min(args.batch_log2, 22), 3, 1)
         cpu = {"value": r["gflops_1t"], "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": r["sample"],
                "all_cores_value": r["gflops_all_cores"], "cores_available": r["cores_available"]}
+        if not args.no_others:
+            cpu["config0"] = cpu_reference_config0()
 
     if rank == 0:
         traffic = ncu_traffic("void gemm_small_kernel<float, SmallCfg<float, 4, 4, 4")
