@@ -404,23 +404,35 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
                 const V *av = reinterpret_cast<const V *>(pa);
                 const V *bv = reinterpret_cast<const V *>(pb);
                 const size_t nvec = len / N;
-                T acc0 = T(0), acc1 = T(0);
+                T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
                 size_t i = t;
-                for (; i + GROUP < nvec; i += 2 * GROUP) {
-                    V x0 = av[i], x1 = av[i + GROUP];
-                    V y0 = MODE == 0 ? bv[i] : x0, y1 = MODE == 0 ? bv[i + GROUP] : x1;
-                    const T *px0 = reinterpret_cast<const T *>(&x0), *py0 = reinterpret_cast<const T *>(&y0);
-                    const T *px1 = reinterpret_cast<const T *>(&x1), *py1 = reinterpret_cast<const T *>(&y1);
+                // four independent 16-byte loads per operand in flight per thread
+                for (; i + 3 * GROUP < nvec; i += 4 * GROUP) {
+                    V x[4], y[4];
 #pragma unroll
-                    for (int j = 0; j < N; ++j) { acc0 += px0[j] * py0[j]; acc1 += px1[j] * py1[j]; }
+                    for (int u = 0; u < 4; ++u)  // normalize re-reads its vector: keep it cached (no evict-first hint)
+                        x[u] = MODE == 2 ? av[i + u * GROUP] : ld_stream(av + i + u * GROUP);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) y[u] = MODE == 0 ? ld_stream(bv + i + u * GROUP) : x[u];
+                    const T *px0 = reinterpret_cast<const T *>(&x[0]), *py0 = reinterpret_cast<const T *>(&y[0]);
+                    const T *px1 = reinterpret_cast<const T *>(&x[1]), *py1 = reinterpret_cast<const T *>(&y[1]);
+                    const T *px2 = reinterpret_cast<const T *>(&x[2]), *py2 = reinterpret_cast<const T *>(&y[2]);
+                    const T *px3 = reinterpret_cast<const T *>(&x[3]), *py3 = reinterpret_cast<const T *>(&y[3]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        acc0 = fma(px0[j], py0[j], acc0); acc1 = fma(px1[j], py1[j], acc1);
+                        acc2 = fma(px2[j], py2[j], acc2); acc3 = fma(px3[j], py3[j], acc3);
+                    }
                 }
-                if (i < nvec) {
+                for (; i < nvec; i += GROUP) {
                     V x0 = av[i];
                     V y0 = MODE == 0 ? bv[i] : x0;
                     const T *px0 = reinterpret_cast<const T *>(&x0), *py0 = reinterpret_cast<const T *>(&y0);
 #pragma unroll
-                    for (int j = 0; j < N; ++j) acc0 += px0[j] * py0[j];
+                    for (int j = 0; j < N; ++j) acc0 = fma(px0[j], py0[j], acc0);
                 }
+                acc0 += acc2;
+                acc1 += acc3;
                 s = (double)acc0 + (double)acc1;
                 for (size_t j = nvec * N + t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
             } else {
@@ -447,7 +459,20 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
             if (vectorised) {
                 V *mv = reinterpret_cast<V *>(pm);
                 const size_t nvec = len / N;
-                for (size_t i = t; i < nvec; i += GROUP) {
+                size_t i = t;
+                for (; i + 3 * GROUP < nvec; i += 4 * GROUP) {  // second touch: L1/L2 hits, four in flight
+                    V x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = mv[i + u * GROUP];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        T *px = reinterpret_cast<T *>(&x[u]);
+#pragma unroll
+                        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                        st_stream(mv + i + u * GROUP, x[u]);
+                    }
+                }
+                for (; i < nvec; i += GROUP) {
                     V x = mv[i];
                     T *px = reinterpret_cast<T *>(&x);
 #pragma unroll
@@ -677,7 +702,7 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
         return SLAS_OK;
     }
     if (vec && len * sizeof(T) >= 2 * kSegBytes) return launch_batched_segmented<T, MODE>(ctx, st, batch, len, a, b, out, a_mut);
-    if (len <= 2048) {
+    if (len <= 8192) {
         size_t blocks = (batch + 7) / 8;
         if (blocks > cap) blocks = cap;
         batched_reduce_kernel<T, 32, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vec);
