@@ -122,8 +122,6 @@ constexpr int kRedThreads = 256;
 constexpr int kRedUnroll = 4;
 constexpr int kFlushEvery = 16;  // outer iterations between flushes of the fp accumulators into f64
 
-template <typename T> struct Acc2 { T re, im; };
-
 template <typename T, int KIND>
 struct Reducer {
     T acc[kRedUnroll];
@@ -338,11 +336,15 @@ scale_div_vec_kernel(T *__restrict__ a, size_t nvec, size_t len, const T *__rest
         const size_t i = base + (size_t)u * kEwThreads;
         if (i < nvec) r[u] = av[i];  // second touch of the vector: let it hit L2
     }
-    const V dv = [&] { V d; T *p = reinterpret_cast<T *>(&d); for (int j = 0; j < N; ++j) p[j] = nrm; return d; }();
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const size_t i = base + (size_t)u * kEwThreads;
-        if (i < nvec) st_stream(av + i, apply_vec<3>(r[u], dv));
+        if (i < nvec) {
+            T *e = reinterpret_cast<T *>(&r[u]);
+#pragma unroll
+            for (int j = 0; j < N; ++j) e[j] = e[j] / nrm;  // IEEE div.rn: a true division, not a reciprocal multiply
+            st_stream(av + i, r[u]);
+        }
     }
     if (blockIdx.x == 0) {
         const size_t i = nvec * N + threadIdx.x;

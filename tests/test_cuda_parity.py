@@ -325,8 +325,6 @@ def test_transpose_ragged_len_leaves_tail_untouched():
     a = np.arange(11, dtype=np.float32)  # columns = 3 -> rows = 3, elements 9, 10 never written (rust.rs:168-175)
     buf = np.full(11, -7.0, np.float32)
     cuda.transpose(a, buf, 3)
-    want = np.full(11, -7.0, np.float32)
-    want[:] = oracle.transpose(a, 3) if False else want
     ref = np.full(11, -7.0, np.float32)
     for column in range(3):
         for row in range(3):
