@@ -113,7 +113,7 @@ int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c);
 /* ---- Transpose::{transpose, transpose_inplace}  (src/backends.rs:152-154;
  *      Rust: src/backends/rust.rs:151-177).  buffer[columns*row + column] =
  *      a[(len/columns)*column + row]; `columns` is the column count of the OUTPUT.
- *      Generic over any Copy element: elem_size in {4, 8, 16} bytes.  Bit-exact. -------- */
+ *      Generic over any Copy element: elem_size in {1, 2, 4, 8, 16} bytes.  Bit-exact. --- */
 int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns);
 int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns);
 
@@ -150,6 +150,8 @@ int slas_cuda_dgemv_batched(size_t batch, const double *a, const double *x, doub
                             int a_trans);
 int slas_cuda_transpose_batched(size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
                                 size_t columns);
+/* Matrix::deref_mut over a batch (src/tensor.rs:546-564 per object): every object transposed in place */
+int slas_cuda_transpose_inplace_batched(size_t batch, size_t len, size_t elem_size, void *a, size_t columns);
 int slas_cuda_sdot_batched(size_t batch, size_t len, const float *a, const float *b, float *out);
 int slas_cuda_ddot_batched(size_t batch, size_t len, const double *a, const double *b, double *out);
 int slas_cuda_snrm2_batched(size_t batch, size_t len, const float *a, float *out);

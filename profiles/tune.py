@@ -55,7 +55,7 @@ def g_transpose():
         b = 1 << 20
         e = size * size
         (_, a), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
-        for v in range(6):
+        for v in (0, 1, 9, 10):
             set_tunable("transpose_variant", v)
             report(f"transpose {size}x{size} {np.dtype(dt).name} variant {v}", timed(lambda: cuda.transpose_batched(a, c, e, size)),
                    nbytes=2.0 * b * e * np.dtype(dt).itemsize)
@@ -63,10 +63,41 @@ def g_transpose():
     # 4x4 f32 (thread per matrix)
     b, e = 1 << 24, 16
     (_, a), (_, c) = uniform(b * e, np.float32, 1), uniform(b * e, np.float32, 2)
-    for v in (0, 1):
+    for v in (0, 1, 7):
         set_tunable("transpose_variant", v)
         report(f"transpose 4x4 float32 2^24 variant {v}", timed(lambda: cuda.transpose_batched(a, c, e, 4)), nbytes=2.0 * b * e * 4)
     set_tunable("transpose_variant", 0)
+
+
+def g_inplace():
+    """transpose_inplace: thread / warp per object, diagonal tile-pair exchange, temporary fallback; narrow elements"""
+    for size, dt, log2 in ((4, np.float32, 24), (16, np.float32, 20), (32, np.float32, 20), (32, np.float64, 20), (64, np.float32, 18),
+                           (128, np.float32, 16)):
+        b, e = 1 << log2, size * size
+        (_, a) = uniform(b * e, dt, 1)
+        for v in (0, 10):
+            set_tunable("transpose_variant", v)
+            report(f"transpose_inplace {size}x{size} {np.dtype(dt).name} batch 2^{log2} variant {v}",
+                   timed(lambda: cuda.transpose_inplace_batched(a, e, size)), nbytes=2.0 * b * e * np.dtype(dt).itemsize)
+        set_tunable("transpose_variant", 0)
+    n = 8192
+    (t, a) = uniform(n * n, np.float32, 1)
+    report(f"transpose_inplace {n}x{n} float32 single", timed(lambda: cuda.transpose_inplace(a, n)), nbytes=8.0 * n * n)
+    a8 = CudaVec(n * n // 2, np.float64, _ptr=t.data_ptr(), _owner=t)
+    report(f"transpose_inplace {n // 2}x{n} float64 single (temporary)", timed(lambda: cuda.transpose_inplace(a8, n)), nbytes=8.0 * n * n)
+    n8 = 5792  # 5792^2 f64 = 268 MB
+    (t8, a64) = uniform(n8 * n8, np.float64, 2)
+    report(f"transpose_inplace {n8}x{n8} float64 single", timed(lambda: cuda.transpose_inplace(a64, n8)), nbytes=16.0 * n8 * n8)
+    (t2, c) = uniform(n * n, np.float32, 3)
+    for es, dt in ((1, np.uint8), (2, np.int16)):
+        cnt = n * n * 4 // es
+        side = int(cnt ** 0.5) // 64 * 64
+        va = CudaVec(side * side, dt, _ptr=t.data_ptr(), _owner=t)
+        vc = CudaVec(side * side, dt, _ptr=t2.data_ptr(), _owner=t2)
+        report(f"transpose {side}x{side} {np.dtype(dt).name} single", timed(lambda: cuda.transpose(va, vc, side)), nbytes=2.0 * side * side * es)
+        b = 1 << 20
+        vb, vd = CudaVec(b * 256, dt, _ptr=t.data_ptr(), _owner=t), CudaVec(b * 256, dt, _ptr=t2.data_ptr(), _owner=t2)
+        report(f"transpose 16x16 {np.dtype(dt).name} batch 2^20", timed(lambda: cuda.transpose_batched(vb, vd, 256, 16)), nbytes=2.0 * b * 256 * es)
 
 
 def g_gemm(knob, size, dt, variants, log2=20):
@@ -162,6 +193,7 @@ GROUPS = {
     "gemv": g_gemv,
     "bdot": g_bdot,
     "transpose": g_transpose,
+    "inplace": g_inplace,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
     "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),
     "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2)),

@@ -89,6 +89,7 @@ SIGNATURES = {
     "slas_cuda_sgemv_batched": [_sz, _vp, _vp, _vp, _sz, _sz, _i],
     "slas_cuda_dgemv_batched": [_sz, _vp, _vp, _vp, _sz, _sz, _i],
     "slas_cuda_transpose_batched": [_sz, _sz, _sz, _vp, _vp, _sz],
+    "slas_cuda_transpose_inplace_batched": [_sz, _sz, _sz, _vp, _sz],
     "slas_cuda_sdot_batched": [_sz, _sz, _vp, _vp, _vp],
     "slas_cuda_ddot_batched": [_sz, _sz, _vp, _vp, _vp],
     "slas_cuda_snrm2_batched": [_sz, _sz, _vp, _vp],

@@ -91,13 +91,14 @@ class Cuda:
 
     # -- Transpose (src/backends.rs:152-154) --------------------------------------------------------
     def transpose(self, a, buffer, columns: int) -> None:
-        pa, la, dt, ka = operand(a)
-        pb, lb, _, kb = operand(buffer, dt, writable=True)
+        # `impl<T: Copy> Transpose<T>` (src/backends/rust.rs:151): any element type, moved as opaque bytes
+        pa, la, dt, ka = operand(a, any_copy_type=True)
+        pb, lb, _, kb = operand(buffer, dt, writable=True, any_copy_type=True)
         assert la == lb, f"transpose: buffer of {lb} elements for a vector of {la}"
         _lib.call("slas_cuda_transpose", la, dt.itemsize, pa, pb, columns)
 
     def transpose_inplace(self, a, columns: int) -> None:
-        pa, la, dt, ka = operand(a, writable=True)
+        pa, la, dt, ka = operand(a, writable=True, any_copy_type=True)
         _lib.call("slas_cuda_transpose_inplace", la, dt.itemsize, pa, columns)
 
     # -- MatrixMul (src/backends.rs:132-150) --------------------------------------------------------
@@ -121,8 +122,8 @@ class Cuda:
 
     # -- batched views: the same ops over [[T; LEN]; batch] -----------------------------------------
     @staticmethod
-    def _batch_of(x, length):
-        p, total, dt, keep = operand(x)
+    def _batch_of(x, length, any_copy_type=False):
+        p, total, dt, keep = operand(x, any_copy_type=any_copy_type)
         assert length > 0 and total % length == 0, f"{total} elements are not whole objects of {length}"
         return p, total // length, dt, keep
 
@@ -141,10 +142,15 @@ class Cuda:
         _lib.call(f"slas_cuda_{prefix(dt)}gemv_batched", ba, pa, px, py, m, n, int(bool(a_trans)))
 
     def transpose_batched(self, a, buffer, length, columns) -> None:
-        pa, ba, dt, ka = self._batch_of(a, length)
-        pb, lb, _, kb = operand(buffer, dt, writable=True)
+        pa, ba, dt, ka = self._batch_of(a, length, any_copy_type=True)
+        pb, lb, _, kb = operand(buffer, dt, writable=True, any_copy_type=True)
         assert lb == ba * length
         _lib.call("slas_cuda_transpose_batched", ba, length, dt.itemsize, pa, pb, columns)
+
+    def transpose_inplace_batched(self, a, length, columns) -> None:
+        pa, ba, dt, ka = self._batch_of(a, length, any_copy_type=True)
+        operand(a, writable=True, any_copy_type=True)
+        _lib.call("slas_cuda_transpose_inplace_batched", ba, length, dt.itemsize, pa, columns)
 
     def dot_batched(self, a, b, out, length) -> None:
         pa, ba, dt, ka = self._batch_of(a, length)

@@ -209,7 +209,8 @@ static int api_transpose(size_t batch, size_t len, size_t elem, const void *a, v
     Context *ctx;
     SLAS_TRY(get_context(&ctx));
     SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, src/backends/rust.rs:169)");
-    SLAS_REQUIRE(elem == 4 || elem == 8 || elem == 16, "transpose: element size %zu (supported: 4, 8, 16)", elem);
+    SLAS_REQUIRE(elem == 1 || elem == 2 || elem == 4 || elem == 8 || elem == 16,
+                 "transpose: element size %zu (supported: 1, 2, 4, 8, 16)", elem);
     if (len == 0 || batch == 0) return SLAS_OK;
     const void *ptrs[2] = {a, inplace ? a : buffer};
     bool dev = false;
@@ -227,10 +228,16 @@ static int api_transpose(size_t batch, size_t len, size_t elem, const void *a, v
             SLAS_TRY(stage_all_begin(ctx, ops, sizes, 1, d));
             target = d[0];
         }
-        SLAS_TRY(ensure_workspace(ctx, bytes, &tmp));
-        SLAS_CUDA_TRY(cudaMemsetAsync(tmp, 0, bytes, ctx->stream));
-        SLAS_TRY(launch_transpose(ctx, ctx->stream, batch, len, elem, target, tmp, columns));
-        SLAS_CUDA_TRY(cudaMemcpyAsync(target, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        // objects a thread / warp can hold, and square ones (tile pairs swapped across the diagonal), are
+        // transposed in place: one read and one write per element
+        bool handled = false;
+        SLAS_TRY(launch_transpose_inplace(ctx, ctx->stream, batch, len, elem, target, columns, &handled));
+        if (!handled) {
+            SLAS_TRY(ensure_workspace(ctx, bytes, &tmp));
+            if (len % columns || len < columns) SLAS_CUDA_TRY(cudaMemsetAsync(tmp, 0, bytes, ctx->stream));
+            SLAS_TRY(launch_transpose(ctx, ctx->stream, batch, len, elem, target, tmp, columns));
+            SLAS_CUDA_TRY(cudaMemcpyAsync(target, tmp, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
         return SLAS_OK;
     }
@@ -475,6 +482,9 @@ int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffe
 }
 int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns) {
     return api_transpose(1, len, elem_size, a, nullptr, columns, true);
+}
+int slas_cuda_transpose_inplace_batched(size_t batch, size_t len, size_t elem_size, void *a, size_t columns) {
+    return api_transpose(batch, len, elem_size, a, nullptr, columns, true);
 }
 int slas_cuda_transpose_batched(size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
                                 size_t columns) {

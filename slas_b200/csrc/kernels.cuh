@@ -25,6 +25,9 @@ int launch_fill_uniform(Context *ctx, cudaStream_t st, size_t len, T *x, uint64_
 // transpose.cu -- batch objects of `len` elements each
 int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a,
                      void *buffer, size_t columns);
+// in place; *handled == false: no in-place kernel for this shape, use a temporary
+int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, void *a,
+                             size_t columns, bool *handled);
 
 // gemm_small.cu -- batched dense small GEMM; returns SLAS_ERR_UNSUPPORTED when no
 // shape-specialised kernel exists (caller falls back to the generic kernel).

@@ -6,19 +6,55 @@
 // i.e. the input is read as `columns` x `rows` row-major and written `rows` x `columns`
 // row-major; `columns` is the column count of the OUTPUT.  Elements past rows*columns (when
 // columns does not divide len) are never written, exactly like the reference's loop.
-// Pure data movement on opaque 4/8/16-byte elements => bit-exact for any Copy type.
+// Pure data movement on opaque 1/2/4/8/16-byte elements => bit-exact for any Copy type.
 //
 // Kernels: (1) big matrices: 32x32 element tiles through padded shared memory, both sides
 // coalesced; (2) many small objects: one warp per object, coalesced read into a padded
 // per-warp shared tile, coalesced write of the transposed order; (3) square n x n with n a
 // multiple of the 16-byte vector width: 128-bit loads, register micro-transpose, 128-bit
 // stores, no shared memory.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace slas {
 
 struct alignas(16) Elem16 { uint64_t lo, hi; };
+
+// sm_100 has 256-bit global loads / stores (LDG.E.256 / STG.E.256)
+__device__ __forceinline__ void ld256(const uint32_t *p, uint32_t *x) {
+    asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st256(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                      uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e), "r"(f),
+                 "r"(g), "r"(h)
+                 : "memory");
+}
+// 16- or 32-byte vector of elements, streamed
+template <typename V> __device__ __forceinline__ V ldvec(const V *p) {
+    if constexpr (sizeof(V) == 16) {
+        uint4 r = __ldcs(reinterpret_cast<const uint4 *>(p));
+        return *reinterpret_cast<V *>(&r);
+    } else {
+        static_assert(sizeof(V) == 32, "vector of 16 or 32 bytes");
+        union { uint32_t w[8]; V v; } u;
+        ld256(reinterpret_cast<const uint32_t *>(p), u.w);
+        return u.v;
+    }
+}
+template <typename V> __device__ __forceinline__ void stvec(V *p, const V &y) {
+    if constexpr (sizeof(V) == 16) {
+        __stcs(reinterpret_cast<uint4 *>(p), *reinterpret_cast<const uint4 *>(&y));
+    } else {
+        static_assert(sizeof(V) == 32, "vector of 16 or 32 bytes");
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(&y);
+        st256(reinterpret_cast<uint32_t *>(p), w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+    }
+}
 
 // ---- (1) tiled ---------------------------------------------------------------------------
 template <typename E>
@@ -85,10 +121,12 @@ transpose_tiled64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
 }
 
 // ---- (2) warp per small object ---------------------------------------------------------------
-template <typename E>
+// INPLACE: in == out is allowed (the warp holds the whole object in shared memory before it writes), and
+// the elements past rows*columns are zeroed like the reference's zero-initialised temporary (rust.rs:157-159).
+template <typename E, bool INPLACE>
 __global__ void __launch_bounds__(256)
-transpose_small_kernel(const E *__restrict__ in, E *__restrict__ out, size_t batch, unsigned len, unsigned rows,
-                       unsigned columns, unsigned warp_elems /* smem elements per warp */) {
+transpose_small_kernel(const E *in, E *out, size_t batch, unsigned len, unsigned rows, unsigned columns,
+                       unsigned warp_elems /* smem elements per warp */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     E *smem = reinterpret_cast<E *>(smem_raw) + (size_t)(threadIdx.x >> 5) * warp_elems;
     const unsigned lane = threadIdx.x & 31;
@@ -115,6 +153,8 @@ transpose_small_kernel(const E *__restrict__ in, E *__restrict__ out, size_t bat
             orow += qo; ocol += ro;
             if (ocol >= columns) { ocol -= columns; ++orow; }
         }
+        if (INPLACE)
+            for (unsigned e = live + lane; e < len; e += 32) dst[e] = E{};
         __syncwarp();
     }
 }
@@ -138,8 +178,8 @@ template <typename V> __device__ __forceinline__ V ld16(const V *p) {
 // lines per instruction); otherwise the input COLUMN block is fastest (contiguous loads).
 template <typename E, int VW, int MULT, bool OUT_MAJOR>
 __global__ void __launch_bounds__(256)
-transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nblocks_total, unsigned n) {
-    struct alignas(16) V { E v[VW]; };
+transpose_square_vec_kernel(const E *in, E *out, size_t nblocks_total, unsigned n) {
+    struct alignas(VW * sizeof(E)) V { E v[VW]; };
     constexpr int BR = MULT * VW;
     const unsigned row_blocks = n / BR, col_blocks = n / VW;
     const unsigned blocks_per_obj = row_blocks * col_blocks;
@@ -152,7 +192,7 @@ transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_
         E *dst = out + obj * (size_t)n * n + (size_t)(bj * VW) * n + bi * BR;
         V x[BR];
 #pragma unroll
-        for (int s = 0; s < BR; ++s) x[s] = ld16(reinterpret_cast<const V *>(src + (size_t)s * n));
+        for (int s = 0; s < BR; ++s) x[s] = ldvec(reinterpret_cast<const V *>(src + (size_t)s * n));
 #pragma unroll
         for (int s = 0; s < VW; ++s) {
 #pragma unroll
@@ -160,9 +200,24 @@ transpose_square_vec_kernel(const E *__restrict__ in, E *__restrict__ out, size_
                 V y;
 #pragma unroll
                 for (int q = 0; q < VW; ++q) y.v[q] = x[m * VW + q].v[s];
-                __stcs(reinterpret_cast<uint4 *>(dst + (size_t)s * n + m * VW), *reinterpret_cast<uint4 *>(&y));
+                stvec(reinterpret_cast<V *>(dst + (size_t)s * n + m * VW), y);
             }
         }
+    }
+}
+
+// ---- (3b) 64-byte objects (4x4 of 4-byte, 2x2 of 16-byte ... here: 4x4 b32), 256-bit accesses ---------
+// sm_100 has 256-bit global loads / stores (LDG.E.256 / STG.E.256): one thread moves a whole 4x4 matrix
+// with two of each, and every store instruction covers full 32-byte sectors (with 128-bit stores each
+// instruction writes half of every sector it touches).
+__global__ void __launch_bounds__(256)
+transpose_4x4_b32_kernel(const uint32_t *in, uint32_t *out, size_t batch) {
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < batch; t += (size_t)gridDim.x * 256) {
+        uint32_t x[16];
+        ld256(in + t * 16, x);
+        ld256(in + t * 16 + 8, x + 8);
+        st256(out + t * 16, x[0], x[4], x[8], x[12], x[1], x[5], x[9], x[13]);
+        st256(out + t * 16 + 8, x[2], x[6], x[10], x[14], x[3], x[7], x[11], x[15]);
     }
 }
 
@@ -197,6 +252,120 @@ transpose_tiny_kernel(const E *__restrict__ in, E *__restrict__ out, size_t nrow
     }
 }
 
+
+// ---- (4) in place, square n x n: tile pairs across the diagonal exchanged through shared memory --------
+// Block (ti <= tj) loads tile (ti, tj) and its mirror (tj, ti), and writes each one transposed into the
+// other's place: every element is read once and written once (2 * sizeof(E) bytes of traffic per element,
+// against 5 * sizeof(E) for zeroed temporary + transpose + copy back).
+template <typename E>
+__global__ void __launch_bounds__(256)
+transpose_inplace_square_kernel(E *data, size_t batch, unsigned n) {
+    __shared__ E t0[32][33], t1[32][33];
+    const unsigned ti = blockIdx.y, tj = blockIdx.x;
+    if (ti > tj) return;
+    const unsigned tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (size_t o = blockIdx.z; o < batch; o += gridDim.z) {
+        E *obj = data + o * (size_t)n * n;
+#pragma unroll
+        for (unsigned j = 0; j < 32; j += 8) {
+            const unsigned r0 = ti * 32 + ty + j, c0 = tj * 32 + tx;
+            if (r0 < n && c0 < n) t0[ty + j][tx] = obj[(size_t)r0 * n + c0];
+            const unsigned r1 = tj * 32 + ty + j, c1 = ti * 32 + tx;
+            if (ti != tj && r1 < n && c1 < n) t1[ty + j][tx] = obj[(size_t)r1 * n + c1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (unsigned j = 0; j < 32; j += 8) {
+            const unsigned r1 = tj * 32 + ty + j, c1 = ti * 32 + tx;  // mirror position receives t0 transposed
+            if (r1 < n && c1 < n) obj[(size_t)r1 * n + c1] = t0[tx][ty + j];
+            const unsigned r0 = ti * 32 + ty + j, c0 = tj * 32 + tx;
+            if (ti != tj && r0 < n && c0 < n) obj[(size_t)r0 * n + c0] = t1[tx][ty + j];
+        }
+        __syncthreads();
+    }
+}
+
+// 4-byte elements, n % 64 == 0, 16-byte aligned: the same exchange on 64 x 64 tiles with 128-bit accesses
+__global__ void __launch_bounds__(256)
+transpose_inplace_square64_kernel(uint32_t *data, size_t batch, unsigned n) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t (*t0)[65] = reinterpret_cast<uint32_t (*)[65]>(smem_raw);
+    uint32_t (*t1)[65] = t0 + 64;
+    const unsigned ti = blockIdx.y, tj = blockIdx.x;
+    if (ti > tj) return;
+    const unsigned vq = threadIdx.x & 15, rr = threadIdx.x >> 4;
+    for (size_t o = blockIdx.z; o < batch; o += gridDim.z) {
+        uint32_t *obj = data + o * (size_t)n * n;
+#pragma unroll
+        for (unsigned p = 0; p < 4; ++p) {
+            const unsigned ir = rr + 16 * p;
+            const uint4 v = *reinterpret_cast<const uint4 *>(obj + (size_t)(ti * 64 + ir) * n + tj * 64 + vq * 4);
+            t0[vq * 4 + 0][ir] = v.x; t0[vq * 4 + 1][ir] = v.y; t0[vq * 4 + 2][ir] = v.z; t0[vq * 4 + 3][ir] = v.w;
+            if (ti != tj) {
+                const uint4 w = *reinterpret_cast<const uint4 *>(obj + (size_t)(tj * 64 + ir) * n + ti * 64 + vq * 4);
+                t1[vq * 4 + 0][ir] = w.x; t1[vq * 4 + 1][ir] = w.y; t1[vq * 4 + 2][ir] = w.z; t1[vq * 4 + 3][ir] = w.w;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (unsigned p = 0; p < 4; ++p) {
+            const unsigned orow = rr + 16 * p;
+            uint4 v;
+            v.x = t0[orow][vq * 4 + 0]; v.y = t0[orow][vq * 4 + 1]; v.z = t0[orow][vq * 4 + 2]; v.w = t0[orow][vq * 4 + 3];
+            *reinterpret_cast<uint4 *>(obj + (size_t)(tj * 64 + orow) * n + ti * 64 + vq * 4) = v;
+            if (ti != tj) {
+                uint4 w;
+                w.x = t1[orow][vq * 4 + 0]; w.y = t1[orow][vq * 4 + 1]; w.z = t1[orow][vq * 4 + 2]; w.w = t1[orow][vq * 4 + 3];
+                *reinterpret_cast<uint4 *>(obj + (size_t)(ti * 64 + orow) * n + tj * 64 + vq * 4) = w;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- (4b) in place, square n x n (n a multiple of the vector width, n <= 64): register block pairs -----
+// One thread owns the VW x VW blocks (bi, bj) and (bj, bi), bi <= bj: 2*VW 128-bit loads, two register
+// transposes, 2*VW 128-bit stores into the exchanged places.  The upper triangle of the nb x nb block grid
+// is enumerated by folding row q onto row nb-1-q (together nb+1 blocks), so every thread has work.
+__device__ __forceinline__ void tri_decode(unsigned nb, unsigned w, unsigned &bi, unsigned &bj) {
+    if (nb & 1) {  // rows q (>= 1) and nb-q hold nb blocks together; row 0 holds nb alone
+        const unsigned q = w / nb, r = w - q * nb;
+        if (q == 0 || r < nb - q) { bi = q; bj = q + r; }
+        else { bi = nb - q; bj = nb - q + (r - (nb - q)); }
+    } else {       // rows q and nb-1-q hold nb+1 blocks together
+        const unsigned q = w / (nb + 1), r = w - q * (nb + 1);
+        if (r < nb - q) { bi = q; bj = q + r; }
+        else { bi = nb - 1 - q; bj = nb - 1 - q + (r - (nb - q)); }
+    }
+}
+template <typename E, int VW>
+__global__ void __launch_bounds__(256)
+transpose_square_vec_inplace_kernel(E *data, size_t npairs_total, unsigned n) {
+    struct alignas(VW * sizeof(E)) V { E v[VW]; };
+    const unsigned nb = n / VW;
+    const unsigned pairs_per_obj = nb * (nb + 1) / 2;
+    for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < npairs_total; t += (size_t)gridDim.x * 256) {
+        const size_t obj = t / pairs_per_obj;
+        unsigned bi, bj;
+        tri_decode(nb, (unsigned)(t - obj * pairs_per_obj), bi, bj);
+        E *p0 = data + obj * (size_t)n * n + (size_t)(bi * VW) * n + bj * VW;
+        E *p1 = data + obj * (size_t)n * n + (size_t)(bj * VW) * n + bi * VW;
+        V x[VW], z[VW];
+#pragma unroll
+        for (int s = 0; s < VW; ++s) x[s] = ldvec(reinterpret_cast<const V *>(p0 + (size_t)s * n));
+#pragma unroll
+        for (int s = 0; s < VW; ++s) z[s] = ldvec(reinterpret_cast<const V *>(p1 + (size_t)s * n));
+#pragma unroll
+        for (int s = 0; s < VW; ++s) {
+            V y, u;
+#pragma unroll
+            for (int q = 0; q < VW; ++q) { y.v[q] = x[q].v[s]; u.v[q] = z[q].v[s]; }
+            stvec(reinterpret_cast<V *>(p1 + (size_t)s * n), y);
+            if (bi != bj) stvec(reinterpret_cast<V *>(p0 + (size_t)s * n), u);
+        }
+    }
+}
+
 template <typename E, int VW, int MULT, bool OUT_MAJOR>
 static int launch_square_vec(Context *ctx, cudaStream_t st, size_t batch, unsigned n, const E *a, E *buffer) {
     const size_t total = batch * (size_t)(n / (MULT * VW)) * (n / VW);
@@ -214,8 +383,8 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
     const size_t rows = len / columns;
     if (rows == 0 || batch == 0) return SLAS_OK;
     constexpr int VW = 16 / (int)sizeof(E);
-    // (3) square, vector-aligned
-    if constexpr (VW > 1) {
+    // (3) square, vector-aligned (4- and 8-byte elements; narrower ones take the tiled / per-object kernels)
+    if constexpr (VW > 1 && sizeof(E) >= 4) {
       if (rows == columns && len == rows * columns && rows % VW == 0 && rows <= 64 && aligned16(a) &&
           aligned16(buffer)) {
         const unsigned n = (unsigned)rows;
@@ -231,8 +400,28 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
             SLAS_LAUNCH_CHECK();
             return SLAS_OK;
         }
-        // default = out-major lanes (full-line stores): measured best or equal for every n, f32 and f64
-        // (profiles/r1b_tune.log); variant 1 = the in-major ordering
+        if constexpr (sizeof(E) == 4) {
+            if (n == 4 && variant != 7 && variant != 1 && ((uintptr_t)a % 32 == 0) && ((uintptr_t)buffer % 32 == 0)) {
+                size_t blocks = (batch + 255) / 256;
+                const size_t cap = (size_t)ctx->sm_count * 32;
+                if (blocks > cap) blocks = cap;
+                transpose_4x4_b32_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(a),
+                                                                          reinterpret_cast<uint32_t *>(buffer), batch);
+                SLAS_LAUNCH_CHECK();
+                return SLAS_OK;
+            }
+        }
+        if constexpr (sizeof(E) <= 8) {
+            constexpr int VW2 = 2 * VW;  // elements per 32-byte vector
+            // 256-bit vectors: measured (profiles/r1e_tune.log) 0.97-1.04 of HBM peak against 0.90-1.00 with
+            // 128-bit ones for 16..64 f32 / f64; a single VW2 x VW2 block per object (8x8 f32) is the exception
+            if ((variant == 0 || variant == 8 || variant == 9) && n % VW2 == 0 && n > (unsigned)VW2 &&
+                ((uintptr_t)a % 32 == 0) && ((uintptr_t)buffer % 32 == 0)) {
+                if (variant == 9) return launch_square_vec<E, VW2, 1, false>(ctx, st, batch, n, a, buffer);
+                return launch_square_vec<E, VW2, 1, true>(ctx, st, batch, n, a, buffer);
+            }
+        }
+        // 128-bit vectors, out-major lanes (full-line stores; profiles/r1b_tune.log); variant 1 = in-major ordering
         if (variant == 1) return launch_square_vec<E, VW, 1, false>(ctx, st, batch, n, a, buffer);
         if (variant == 2 && n % (2 * VW) == 0) return launch_square_vec<E, VW, 2, true>(ctx, st, batch, n, a, buffer);
         if (variant == 3 && n % (4 * VW) == 0) return launch_square_vec<E, VW, 4, true>(ctx, st, batch, n, a, buffer);
@@ -247,14 +436,14 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
     if (padded * sizeof(E) <= kWarpBytes && len <= 0xffffffffu) {
         const size_t smem = 8 * padded * sizeof(E);
         if (smem > 48 * 1024)
-            SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(8 * kWarpBytes)));
+            SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E, false>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kWarpBytes)));
         size_t blocks = (batch + 7) / 8;
         const size_t cap = (size_t)ctx->sm_count * 8;
         if (blocks > cap) blocks = cap;
-        transpose_small_kernel<E><<<(unsigned)blocks, 256, smem, st>>>(a, buffer, batch, (unsigned)len,
-                                                                       (unsigned)rows, (unsigned)columns,
-                                                                       (unsigned)padded);
+        transpose_small_kernel<E, false><<<(unsigned)blocks, 256, smem, st>>>(a, buffer, batch, (unsigned)len,
+                                                                              (unsigned)rows, (unsigned)columns,
+                                                                              (unsigned)padded);
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
@@ -281,16 +470,112 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
     return SLAS_OK;
 }
 
+
+// In place.  *handled = false when no in-place kernel applies (the caller falls back to the reference's
+// own scheme: zeroed temporary, transpose, copy back).
+template <typename E>
+static int launch_transpose_inplace_typed(Context *ctx, cudaStream_t st, size_t batch, size_t len, E *a, size_t columns,
+                                          bool *handled) {
+    *handled = false;
+    const size_t rows = len / columns;
+    if (rows == 0 || batch == 0) return SLAS_OK;
+    constexpr int VW = 16 / (int)sizeof(E);
+    const bool square = rows == columns && len == rows * columns;
+    // one thread owns the whole VW x VW object: all loads precede its stores
+    if constexpr (VW > 1 && sizeof(E) >= 4) {
+        if (square && rows == (size_t)VW && aligned16(a)) {
+            *handled = true;
+            return launch_square_vec<E, VW, 1, true>(ctx, st, batch, (unsigned)rows, a, a);
+        }
+    }
+    if constexpr (VW > 1 && sizeof(E) >= 4) {
+        if (square && rows % VW == 0 && rows < 64 && aligned16(a) && tunable("transpose_variant") != 1) {
+            const unsigned n = (unsigned)rows;
+            const bool wide = sizeof(E) <= 8 && n % (2 * VW) == 0 && n > 2u * VW && (uintptr_t)a % 32 == 0 &&
+                              tunable("transpose_variant") != 10;
+            const unsigned nb = n / (wide ? 2 * VW : VW);
+            const size_t total = batch * (size_t)(nb * (nb + 1) / 2);
+            size_t blocks = (total + 255) / 256;
+            const size_t cap = (size_t)ctx->sm_count * 32;
+            if (blocks > cap) blocks = cap;
+            if constexpr (sizeof(E) <= 8) {
+                if (wide) transpose_square_vec_inplace_kernel<E, 2 * VW><<<(unsigned)blocks, 256, 0, st>>>(a, total, n);
+            }
+            if (!wide) transpose_square_vec_inplace_kernel<E, VW><<<(unsigned)blocks, 256, 0, st>>>(a, total, n);
+            SLAS_LAUNCH_CHECK();
+            *handled = true;
+            return SLAS_OK;
+        }
+    }
+    // one warp owns the whole object in shared memory
+    const size_t padded = columns * (rows + 1);
+    constexpr size_t kWarpBytes = 12 * 1024;
+    if (padded * sizeof(E) <= kWarpBytes && len <= 0xffffffffu) {
+        const size_t smem = 8 * padded * sizeof(E);
+        if (smem > 48 * 1024)
+            SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * kWarpBytes)));
+        size_t blocks = (batch + 7) / 8;
+        const size_t cap = (size_t)ctx->sm_count * 8;
+        if (blocks > cap) blocks = cap;
+        transpose_small_kernel<E, true><<<(unsigned)blocks, 256, smem, st>>>(a, a, batch, (unsigned)len, (unsigned)rows,
+                                                                             (unsigned)columns, (unsigned)padded);
+        SLAS_LAUNCH_CHECK();
+        *handled = true;
+        return SLAS_OK;
+    }
+    if (!square || rows > 0xffffffffu) return SLAS_OK;
+    const unsigned n = (unsigned)rows;
+    const unsigned gz = (unsigned)std::min<size_t>(batch, 65535);
+    if constexpr (sizeof(E) == 4) {
+        if (n % 64 == 0 && n / 64 <= 65535 && aligned16(a)) {
+            constexpr int kSmem = 2 * 64 * 65 * 4;
+            static bool attr_done = false;
+            if (!attr_done) {
+                SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_inplace_square64_kernel,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+                attr_done = true;
+            }
+            transpose_inplace_square64_kernel<<<dim3(n / 64, n / 64, gz), 256, kSmem, st>>>(
+                reinterpret_cast<uint32_t *>(a), batch, n);
+            SLAS_LAUNCH_CHECK();
+            *handled = true;
+            return SLAS_OK;
+        }
+    }
+    const unsigned tiles = (n + 31) / 32;
+    if (tiles > 65535) return SLAS_OK;
+    transpose_inplace_square_kernel<E><<<dim3(tiles, tiles, gz), 256, 0, st>>>(a, batch, n);
+    SLAS_LAUNCH_CHECK();
+    *handled = true;
+    return SLAS_OK;
+}
+
+int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, void *a,
+                             size_t columns, bool *handled) {
+    SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, rust.rs:169)");
+    switch (elem_size) {
+    case 1: return launch_transpose_inplace_typed<uint8_t>(ctx, st, batch, len, (uint8_t *)a, columns, handled);
+    case 2: return launch_transpose_inplace_typed<uint16_t>(ctx, st, batch, len, (uint16_t *)a, columns, handled);
+    case 4: return launch_transpose_inplace_typed<uint32_t>(ctx, st, batch, len, (uint32_t *)a, columns, handled);
+    case 8: return launch_transpose_inplace_typed<uint64_t>(ctx, st, batch, len, (uint64_t *)a, columns, handled);
+    case 16: return launch_transpose_inplace_typed<Elem16>(ctx, st, batch, len, (Elem16 *)a, columns, handled);
+    }
+    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 1, 2, 4, 8, 16)", elem_size);
+}
+
 int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a,
                      void *buffer, size_t columns) {
     SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, rust.rs:169)");
     SLAS_REQUIRE(a != buffer, "transpose: input and buffer alias (use transpose_inplace)");
     switch (elem_size) {
+    case 1: return launch_transpose_typed<uint8_t>(ctx, st, batch, len, (const uint8_t *)a, (uint8_t *)buffer, columns);
+    case 2: return launch_transpose_typed<uint16_t>(ctx, st, batch, len, (const uint16_t *)a, (uint16_t *)buffer, columns);
     case 4: return launch_transpose_typed<uint32_t>(ctx, st, batch, len, (const uint32_t *)a, (uint32_t *)buffer, columns);
     case 8: return launch_transpose_typed<uint64_t>(ctx, st, batch, len, (const uint64_t *)a, (uint64_t *)buffer, columns);
     case 16: return launch_transpose_typed<Elem16>(ctx, st, batch, len, (const Elem16 *)a, (Elem16 *)buffer, columns);
     }
-    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 4, 8, 16)", elem_size);
+    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 1, 2, 4, 8, 16)", elem_size);
 }
 
 }  // namespace slas

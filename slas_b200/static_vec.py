@@ -38,8 +38,7 @@ class CudaVec:
     """Device-resident `StaticVec<T, LEN>`.  Owns its allocation unless built as a view."""
 
     def __init__(self, length: int, dtype=np.float32, *, _ptr: int | None = None, _owner=None):
-        self.dtype = np.dtype(dtype)
-        prefix(self.dtype)
+        self.dtype = np.dtype(dtype)  # any Copy element may be stored; arithmetic ops check the type
         self.LEN = int(length)
         self._owner = _owner
         if _ptr is None:
@@ -155,14 +154,16 @@ class CudaBatch(CudaVec):
                          _ptr=self._ptr + lo * self.OBJ_LEN * self.dtype.itemsize, _owner=self)
 
 
-def operand(x, dtype=None, *, writable: bool = False):
-    """(pointer, length, dtype, keepalive) of anything that satisfies the StaticVec contract."""
+def operand(x, dtype=None, *, writable: bool = False, any_copy_type: bool = False):
+    """(pointer, length, dtype, keepalive) of anything that satisfies the StaticVec contract.
+    any_copy_type: accept any fixed-size element (Transpose is generic over T: Copy), not only the four
+    number types the arithmetic backends are registered for."""
     if isinstance(x, CudaVec):
         if dtype is not None and x.dtype != np.dtype(dtype):
             raise TypeError(f"operand is {x.dtype}, expected {np.dtype(dtype)}")
         return x.as_ptr(), x.LEN, x.dtype, x
     if hasattr(x, "data") and hasattr(x, "backend") and not isinstance(x, np.ndarray):  # WithStaticBackend
-        return operand(x.data, dtype, writable=writable)
+        return operand(x.data, dtype, writable=writable, any_copy_type=any_copy_type)
     if isinstance(x, np.ndarray):
         if not x.flags.c_contiguous:
             raise ValueError("a StaticVec is LEN contiguous elements (src/static_vec.rs:121-126)")
@@ -171,7 +172,8 @@ def operand(x, dtype=None, *, writable: bool = False):
             raise ValueError("cannot take a mutable pointer to a read-only vector")
         if dtype is not None and x.dtype != np.dtype(dtype):
             raise TypeError(f"operand is {x.dtype}, expected {np.dtype(dtype)}")
-        prefix(x.dtype)
+        if not any_copy_type:
+            prefix(x.dtype)
         return x.ctypes.data, x.size, x.dtype, x
     if writable:
         raise TypeError("output operands must be numpy arrays or CudaVec (need a stable pointer)")

@@ -303,12 +303,14 @@ def test_norm_and_normalize(dt, n):
 
 
 # ---- transpose: bit-exact for any Copy element --------------------------------------------------------
-@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48), (128, 64), (192, 320), (1024, 512)])
 def test_transpose_bit_exact(dt, rows, cols):
-    a = np.arange(rows * cols).astype(dt)
+    a = np.arange(rows * cols).astype(dt)  # int16 / uint8 wrap: still a distinguishing pattern per tile
     if dt == np.int32:
         a = a.view(np.float32)  # opaque 4-byte payloads, NaN patterns included
+    if dt in (np.int16, np.uint8):
+        a = (np.arange(rows * cols) * 2654435761 >> 7).astype(dt)
     want = oracle.transpose(a, cols)
     buf = CudaVec(a.size, a.dtype).zero_()
     cuda.transpose(CudaVec.from_host(a), buf, cols)
@@ -319,6 +321,100 @@ def test_transpose_bit_exact(dt, rows, cols):
     d = CudaVec.from_host(a)
     cuda.transpose_inplace(d, cols)
     assert d.to_host().tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int16, np.uint8])
+@pytest.mark.parametrize("rows,cols", [(4, 4), (2, 2), (8, 8), (12, 12), (16, 16), (20, 20), (33, 33), (48, 48), (60, 60), (64, 64),
+                                       (100, 100), (128, 128), (1000, 1000), (1024, 1024), (2048, 64), (64, 2048), (300, 7)])
+def test_transpose_inplace_kernels_bit_exact(dt, rows, cols):
+    """thread-per-object, warp-per-object, diagonal tile-pair exchange (32- and 64-wide) and the temporary
+    fallback for large non-square objects all give the reference's transpose_inplace (rust.rs:152-160)"""
+    a = (np.arange(rows * cols) * 2654435761 >> 5).astype(dt)
+    want = oracle.transpose(a, cols)
+    d = CudaVec.from_host(a)
+    cuda.transpose_inplace(d, cols)
+    assert d.to_host().tobytes() == want.tobytes()
+    h = a.copy()
+    cuda.transpose_inplace(h, cols)  # host pointer
+    assert h.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("length,cols", [(11, 3), (1000, 7), (5000, 64), (70000, 257), (5, 9)])
+def test_transpose_inplace_ragged_tail_is_zeroed(length, cols):
+    """the reference transposes into a ZEROED temporary and copies all of it back (rust.rs:157-159): in place,
+    the elements past rows*columns become 0 (out of place they keep the buffer's bytes)"""
+    a = np.arange(1, length + 1, dtype=np.float32)
+    rows = length // cols
+    want = np.zeros(length, np.float32)
+    for column in range(cols):
+        for row in range(rows):
+            want[cols * row + column] = a[rows * column + row]
+    d = CudaVec.from_host(a)
+    cuda.transpose_inplace(d, cols)
+    assert np.array_equal(d.to_host(), want)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,cols,batch", [(4, 4, 1001), (12, 12, 100), (16, 16, 257), (20, 20, 33), (32, 32, 65), (3, 5, 77),
+                                             (64, 64, 9), (128, 128, 3), (100, 100, 5), (96, 32, 4)])
+def test_transpose_inplace_batched_bit_exact(dt, rows, cols, batch):
+    rng = np.random.default_rng(rows * cols + batch)
+    e = rows * cols
+    a = _rand(rng, batch * e, dt)
+    want = np.concatenate([oracle.transpose(a[i * e:(i + 1) * e], cols) for i in range(batch)])
+    d = CudaBatch.from_host(a, e)
+    cuda.transpose_inplace_batched(d, e, cols)
+    assert d.to_host().ravel().tobytes() == want.tobytes()
+    h = a.copy()
+    cuda.transpose_inplace_batched(h, e, cols)
+    assert h.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+def test_transpose_benchmark_variants_bit_exact(variant):
+    """every kernel behind the transpose_variant sweep knob (profiles/tune.py) gives the same bytes"""
+    from slas_b200.backends import set_tunable
+    try:
+        set_tunable("transpose_variant", variant)
+        for dt in (np.float32, np.float64):
+            for n, batch in ((2, 999), (4, 1001), (8, 300), (16, 257), (32, 65), (48, 11), (64, 9), (128, 3)):
+                e = n * n
+                a = _rand(np.random.default_rng(n), batch * e, dt)
+                want = np.concatenate([oracle.transpose(a[i * e:(i + 1) * e], n) for i in range(batch)])
+                buf = CudaBatch(batch, e, dt)
+                cuda.transpose_batched(CudaVec.from_host(a), buf, e, n)
+                assert buf.to_host().ravel().tobytes() == want.tobytes(), (dt, n)
+                d = CudaBatch.from_host(a, e)
+                cuda.transpose_inplace_batched(d, e, n)
+                assert d.to_host().ravel().tobytes() == want.tobytes(), (dt, n, "in place")
+    finally:
+        set_tunable("transpose_variant", 0)
+
+
+@pytest.mark.parametrize("knob,size,dt,variants", [
+    ("gemm4s_variant", 4, np.float32, (1, 3, 4, 5, 6, 7)), ("gemm16s_variant", 16, np.float32, (1, 2, 3)),
+    ("gemm32s_variant", 32, np.float32, (1, 3)), ("gemm32s_variant", 64, np.float32, (1, 2)),
+    ("gemm32d_variant", 32, np.float64, (1,))])
+def test_small_gemm_benchmark_variants_keep_parity(knob, size, dt, variants):
+    """the alternative tile configurations behind the sweep knobs meet the same bar as the defaults"""
+    from slas_b200.backends import set_tunable
+    batch = 257
+    rng = np.random.default_rng(size)
+    e = size * size
+    A, B = _rand(rng, batch * e, dt), _rand(rng, batch * e, dt)
+    tol = (1e-5 if dt == np.float32 else 1e-13) * np.sqrt(size)
+    try:
+        for v in variants:
+            set_tunable(knob, v)
+            for ta, tb in ((False, False), (True, False), (False, True), (True, True)):
+                C = CudaBatch(batch, e, dt)
+                cuda.matrix_mul_batched(CudaVec.from_host(A), CudaVec.from_host(B), C, size, size, size, ta, tb)
+                got = C.to_host().reshape(batch, e)
+                for i in (0, 1, batch // 2, batch - 1):
+                    ref, mag = _gemm_truth(A[i * e:(i + 1) * e], B[i * e:(i + 1) * e], size, size, size, ta, tb)
+                    assert np.max(np.abs(got[i] - ref) / np.maximum(mag, 1e-30)) <= tol, (v, ta, tb, i)
+    finally:
+        set_tunable(knob, 0)
 
 
 def test_transpose_ragged_len_leaves_tail_untouched():
@@ -332,11 +428,11 @@ def test_transpose_ragged_len_leaves_tail_untouched():
     assert np.array_equal(buf, ref)
 
 
-@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols,batch", [(4, 4, 1000), (16, 16, 257), (32, 32, 65), (3, 5, 77), (8, 2, 1), (64, 64, 9)])
 def test_transpose_batched_bit_exact(dt, rows, cols, batch):
     rng = np.random.default_rng(rows * cols + batch)
-    a = _rand(rng, batch * rows * cols, dt)
+    a = _rand(rng, batch * rows * cols, dt, -100.0, 100.0)  # integer element types: distinct small values
     want = np.concatenate([oracle.transpose(a[i * rows * cols:(i + 1) * rows * cols], cols) for i in range(batch)])
     buf = CudaBatch(batch, rows * cols, dt)
     cuda.transpose_batched(CudaVec.from_host(a), buf, rows * cols, cols)
