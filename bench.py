@@ -459,6 +459,7 @@ def run_cuda(args):
             def gemm():
                 cuda.matrix_mul(va, vb, vc, n_, n_, n_, n_, n_, n_, False, False)
 
+            sl.set_sgemm_path("ffma")
             for _ in range(2):
                 gemm()
             torch.cuda.synchronize()
@@ -469,7 +470,7 @@ def run_cuda(args):
                 e0.record(stream); gemm(); e1.record(stream)
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
-            record("single 4096^2 f32 matrix_mul, FFMA path", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="fp32", fma="f32")
+            record("single 4096^2 f32 matrix_mul, FFMA path (set_sgemm_path('ffma'))", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="fp32", fma="f32")
             try:
                 sl.set_sgemm_path("tcgen05")
                 for _ in range(2):
@@ -483,10 +484,10 @@ def run_cuda(args):
                     e0.record(stream); gemm(); e1.record(stream)
                     torch.cuda.synchronize()
                     ts.append(e0.elapsed_time(e1))
-                record("single 4096^2 f32 matrix_mul, tcgen05 3xTF32 path", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="tensor",
+                record("single 4096^2 f32 matrix_mul, tcgen05 3xTF32 path (the default at this size)", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="tensor",
                        extra={"launches_per_call": (sl.launch_count() - n_before) / 5})
             finally:
-                sl.set_sgemm_path("ffma")
+                sl.set_sgemm_path("auto")
             del a, b, c, va, vb, vc, flush
         if world > 1:
             dist.barrier()

@@ -110,6 +110,28 @@ int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c);
 int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c);
 int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c);
 
+/* ---- Fused chains: op sequences a slas user issues back to back today, in one pass over
+ *      HBM.  slas leaves lazy execution to its users (CONTRIBUTING.md:7-22), so these are extra entry points,
+ *      not a change of the trait methods; each gives the same bits as the unfused chain on this backend.
+ *      x_dot: c = a (+,-,*,/) b as rust.rs:45-73 (c may be NULL: the intermediate is never materialised), then
+ *             *out = dot(c, d) as rust.rs:20-41 -- 12 (+4 with c) bytes per f32 element instead of 20.
+ *      dot_norms: out3 = { dot(a,b), norm(a), norm(b) } (rust.rs:20-41, 116-121) in one read of a and b
+ *             (cosine similarity = out3[0] / (out3[1] * out3[2])): 8 bytes per f32 element instead of 16.
+ *      normalize_into: out = a / norm(a), a untouched -- the copy-on-write (static_vec.rs:304-318) +
+ *             normalize (rust.rs:122-127) chain without the memcpy pass. ------------------------------------ */
+int slas_cuda_sadd_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out);
+int slas_cuda_ssub_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out);
+int slas_cuda_smul_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out);
+int slas_cuda_sdiv_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out);
+int slas_cuda_dadd_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out);
+int slas_cuda_dsub_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out);
+int slas_cuda_dmul_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out);
+int slas_cuda_ddiv_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out);
+int slas_cuda_sdot_norms(size_t len, const float *a, const float *b, float *out3);
+int slas_cuda_ddot_norms(size_t len, const double *a, const double *b, double *out3);
+int slas_cuda_snormalize_into(size_t len, const float *a, float *out);
+int slas_cuda_dnormalize_into(size_t len, const double *a, double *out);
+
 /* ---- Transpose::{transpose, transpose_inplace}  (src/backends.rs:152-154;
  *      Rust: src/backends/rust.rs:151-177).  buffer[columns*row + column] =
  *      a[(len/columns)*column + row]; `columns` is the column count of the OUTPUT.
@@ -124,8 +146,10 @@ int slas_cuda_sgemm(const float *a, const float *b, float *c, size_t m, size_t n
                     size_t lda, size_t ldb, size_t ldc, int a_trans, int b_trans);
 int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
                     size_t lda, size_t ldb, size_t ldc, int a_trans, int b_trans);
-/* Which kernel a large f32 product runs on: 0 = FFMA (reference-faithful f32, the default),
- * 1 = tcgen05/TMEM 3xTF32 for dense contractions whose m, n, k are multiples of the tile. */
+/* Which kernel a large f32 product runs on: 0 = FFMA only (every C element an ascending-k fp32 FMA chain),
+ * 1 = tcgen05/TMEM 3xTF32 for every contraction its tiling covers (m % 128, n % 256, k % 32 == 0, dense),
+ * 2 = auto, the default: 3xTF32 when the product also has >= 2^27 multiply-adds, FFMA otherwise.  3xTF32 is an
+ * fp32-class result (measured <= 2e-6 * sum|a||b|, inside the 1e-5 * sqrt(K) parity bar). */
 int slas_cuda_set_sgemm_path(int path);
 int slas_cuda_get_sgemm_path(int *path);
 

@@ -136,6 +136,39 @@ struct Cuda {
     }
     SLAS_EWISE(add) SLAS_EWISE(sub) SLAS_EWISE(mul) SLAS_EWISE(div)
 #undef SLAS_EWISE
+    // Fused chains (slas_cuda.h "Fused chains"): X_dot(a, b, d) = dot(a X b, d) without materialising a X b;
+    // X_dot(a, b, d, c) also writes the intermediate.  Same bits as the unfused chain on this backend.
+#define SLAS_EWISE_DOT(NAME)                                                                                    \
+    template <class A, class B, class D> elem_t<A> NAME##_dot(const A &a, const B &b, const D &d) const {       \
+        static_assert(len_v<A> == len_v<B> && len_v<A> == len_v<D>, #NAME "_dot: vectors of different static lengths"); \
+        elem_t<A> out{};                                                                                        \
+        if constexpr (std::is_same_v<elem_t<A>, float>) check(slas_cuda_s##NAME##_dot(len_v<A>, ptr_of(a), ptr_of(b), nullptr, ptr_of(d), &out)); \
+        else check(slas_cuda_d##NAME##_dot(len_v<A>, ptr_of(a), ptr_of(b), nullptr, ptr_of(d), &out));          \
+        return out;                                                                                             \
+    }                                                                                                           \
+    template <class A, class B, class D, class C> elem_t<A> NAME##_dot(const A &a, const B &b, const D &d, C &c) const { \
+        static_assert(len_v<A> == len_v<B> && len_v<A> == len_v<D> && len_v<A> == len_v<C>, #NAME "_dot: vectors of different static lengths"); \
+        elem_t<A> out{};                                                                                        \
+        if constexpr (std::is_same_v<elem_t<A>, float>) check(slas_cuda_s##NAME##_dot(len_v<A>, ptr_of(a), ptr_of(b), mut_ptr_of(c), ptr_of(d), &out)); \
+        else check(slas_cuda_d##NAME##_dot(len_v<A>, ptr_of(a), ptr_of(b), mut_ptr_of(c), ptr_of(d), &out));    \
+        return out;                                                                                             \
+    }
+    SLAS_EWISE_DOT(add) SLAS_EWISE_DOT(sub) SLAS_EWISE_DOT(mul) SLAS_EWISE_DOT(div)
+#undef SLAS_EWISE_DOT
+    // { dot(a, b), norm(a), norm(b) } from one read of both vectors
+    template <class A, class B> std::array<elem_t<A>, 3> dot_norms(const A &a, const B &b) const {
+        static_assert(len_v<A> == len_v<B>, "dot_norms: vectors of different static lengths");
+        std::array<elem_t<A>, 3> out{};
+        if constexpr (std::is_same_v<elem_t<A>, float>) check(slas_cuda_sdot_norms(len_v<A>, ptr_of(a), ptr_of(b), out.data()));
+        else check(slas_cuda_ddot_norms(len_v<A>, ptr_of(a), ptr_of(b), out.data()));
+        return out;
+    }
+    // out = a / norm(a), a untouched (normalising the borrowed side of a StaticCowVec without the copy)
+    template <class A, class O> void normalize_into(const A &a, O &out) const {
+        static_assert(len_v<A> == len_v<O>, "normalize_into: vectors of different static lengths");
+        if constexpr (std::is_same_v<elem_t<A>, float>) check(slas_cuda_snormalize_into(len_v<A>, ptr_of(a), mut_ptr_of(out)));
+        else check(slas_cuda_dnormalize_into(len_v<A>, ptr_of(a), mut_ptr_of(out)));
+    }
     // Transpose (src/backends.rs:152-154): any Copy element
     template <class A> void transpose_inplace(A &a, std::size_t columns) const {
         check(slas_cuda_transpose_inplace(len_v<A>, sizeof(elem_t<A>), mut_ptr_of(a), columns));

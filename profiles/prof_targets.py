@@ -54,7 +54,7 @@ def gemm_large(path):
     for _ in range(2):
         cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False)
     synchronize()
-    set_sgemm_path("ffma")
+    set_sgemm_path("auto")
 
 
 TARGETS = {

@@ -100,6 +100,19 @@ def g_inplace():
         report(f"transpose 16x16 {np.dtype(dt).name} batch 2^20", timed(lambda: cuda.transpose_batched(vb, vd, 256, 16)), nbytes=2.0 * b * 256 * es)
 
 
+def g_fused():
+    """fused chains against the op sequences they replace (bytes = what the FUSED form has to move)"""
+    n = 1 << 28
+    (_, a), (_, b), (_, c), (_, d) = uniform(n, np.float32, 1), uniform(n, np.float32, 2), uniform(n, np.float32, 3), uniform(n, np.float32, 4)
+    report("add then dot (unfused)", timed(lambda: (cuda.add(a, b, c), cuda.dot(c, d))), nbytes=16.0 * n)
+    report("add_dot fused, c written", timed(lambda: cuda.ewise_dot("add", a, b, d, c)), nbytes=16.0 * n)
+    report("add_dot fused, c not materialised", timed(lambda: cuda.ewise_dot("add", a, b, d)), nbytes=12.0 * n)
+    report("dot + norm + norm (unfused)", timed(lambda: (cuda.dot(a, b), cuda.norm(a), cuda.norm(b))), nbytes=8.0 * n)
+    report("dot_norms fused", timed(lambda: cuda.dot_norms(a, b)), nbytes=8.0 * n)
+    report("copy then normalize (unfused)", timed(lambda: (_lib.call("slas_cuda_memcpy_d2d", c.as_ptr(), a.as_ptr(), 4 * n), cuda.normalize(c))), nbytes=12.0 * n)
+    report("normalize_into fused", timed(lambda: cuda.normalize_into(a, c)), nbytes=12.0 * n)
+
+
 def g_gemm(knob, size, dt, variants, log2=20):
     b = 1 << log2
     e = size * size
@@ -120,7 +133,17 @@ def g_large(path, knob, variants):
         report(f"sgemm 4096^3 {path} {knob}={v}", timed(lambda: cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False), 10, 3),
                flop=2.0 * n ** 3)
     set_tunable(knob, 0)
-    sl.set_sgemm_path("ffma")
+    sl.set_sgemm_path("auto")
+
+
+def g_crossover():
+    """FFMA vs tcgen05 3xTF32 across sizes: where the automatic choice should switch"""
+    for n in (512, 768, 1024, 1280, 1536, 2048, 3072, 4096):
+        (_, a), (_, b), (_, c) = uniform(n * n, np.float32, 5), uniform(n * n, np.float32, 6), uniform(n * n, np.float32, 7)
+        for path in ("ffma", "tcgen05"):
+            sl.set_sgemm_path(path)
+            report(f"sgemm {n}^3 {path}", timed(lambda: cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False), 10, 3), flop=2.0 * n ** 3)
+    sl.set_sgemm_path("auto")
 
 
 def g_gemv():
@@ -194,6 +217,8 @@ GROUPS = {
     "bdot": g_bdot,
     "transpose": g_transpose,
     "inplace": g_inplace,
+    "crossover": g_crossover,
+    "fused": g_fused,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
     "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),
     "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2)),

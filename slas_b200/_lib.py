@@ -89,6 +89,11 @@ SIGNATURES = {
     "slas_cuda_sgemv_batched": [_sz, _vp, _vp, _vp, _sz, _sz, _i],
     "slas_cuda_dgemv_batched": [_sz, _vp, _vp, _vp, _sz, _sz, _i],
     "slas_cuda_transpose_batched": [_sz, _sz, _sz, _vp, _vp, _sz],
+    **{f"slas_cuda_{t}{op}_dot": [_sz, _vp, _vp, _vp, _vp, _vp] for t in "sd" for op in ("add", "sub", "mul", "div")},
+    "slas_cuda_sdot_norms": [_sz, _vp, _vp, _vp],
+    "slas_cuda_ddot_norms": [_sz, _vp, _vp, _vp],
+    "slas_cuda_snormalize_into": [_sz, _vp, _vp],
+    "slas_cuda_dnormalize_into": [_sz, _vp, _vp],
     "slas_cuda_transpose_inplace_batched": [_sz, _sz, _sz, _vp, _sz],
     "slas_cuda_sdot_batched": [_sz, _sz, _vp, _vp, _vp],
     "slas_cuda_ddot_batched": [_sz, _sz, _vp, _vp, _vp],

@@ -89,6 +89,46 @@ class Cuda:
     def div(self, a, b, c) -> None:
         self._ewise("div", a, b, c)
 
+    # -- fused chains (include/slas_cuda.h "Fused chains"): one pass over HBM, same bits as the unfused ops -------
+    def ewise_dot(self, op: str, a, b, d, c=None):
+        """dot(a op b, d); the intermediate goes to `c` if given, else it is never materialised."""
+        pa, la, dt, ka = operand(a)
+        pb, lb, _, kb = operand(b, dt)
+        pd, ld, _, kd = operand(d, dt)
+        pc = 0
+        if c is not None:
+            pc, lc, _, kc = operand(c, dt, writable=True)
+            assert lc == la, f"{op}_dot: vectors of different lengths"
+        assert la == lb == ld, f"{op}_dot: vectors of different lengths ({la}, {lb}, {ld})"
+        t = prefix(dt)
+        if t not in "sd" or op not in ("add", "sub", "mul", "div"):
+            raise TypeError(f"{op}_dot is implemented for add/sub/mul/div on f32 and f64")
+        out = np.zeros(1, dtype=dt)
+        _lib.call(f"slas_cuda_{t}{op}_dot", la, pa, pb, pc, pd, out.ctypes.data)
+        return out[0]
+
+    def dot_norms(self, a, b):
+        """(dot(a, b), norm(a), norm(b)) from one read of both vectors."""
+        pa, la, dt, ka = operand(a)
+        pb, lb, _, kb = operand(b, dt)
+        assert la == lb, f"dot_norms: vectors of different lengths ({la} vs {lb})"
+        t = prefix(dt)
+        if t not in "sd":
+            raise TypeError("dot_norms is implemented for f32 and f64")
+        out = np.zeros(3, dtype=dt)
+        _lib.call(f"slas_cuda_{t}dot_norms", la, pa, pb, out.ctypes.data)
+        return out[0], out[1], out[2]
+
+    def normalize_into(self, a, out) -> None:
+        """out = a / norm(a); `a` is left untouched (what normalising a borrowed StaticCowVec does, minus the copy)."""
+        pa, la, dt, ka = operand(a)
+        po, lo, _, ko = operand(out, dt, writable=True)
+        assert la == lo, f"normalize_into: vectors of different lengths ({la} vs {lo})"
+        t = prefix(dt)
+        if t not in "sd":
+            raise TypeError("normalize_into is implemented for f32 and f64")
+        _lib.call(f"slas_cuda_{t}normalize_into", la, pa, po)
+
     # -- Transpose (src/backends.rs:152-154) --------------------------------------------------------
     def transpose(self, a, buffer, columns: int) -> None:
         # `impl<T: Copy> Transpose<T>` (src/backends/rust.rs:151): any element type, moved as opaque bytes
@@ -262,8 +302,9 @@ def set_tunable(name: str, value: int) -> None:
 
 
 def set_sgemm_path(path: str) -> None:
-    """'ffma' (reference-faithful fp32, default) or 'tcgen05' (3xTF32 on the tensor cores)."""
-    _lib.call("slas_cuda_set_sgemm_path", {"ffma": 0, "tcgen05": 1}[path])
+    """'auto' (default: 3xTF32 on the tensor cores for large products whose shape fits its tiles, fp32 FMA
+    otherwise), 'ffma' (always the ascending-k fp32 FMA chain) or 'tcgen05' (tensor cores wherever possible)."""
+    _lib.call("slas_cuda_set_sgemm_path", {"ffma": 0, "tcgen05": 1, "auto": 2}[path])
 
 
 __all__ = ["Cuda", "WithStaticBackend", "CudaVec", "CudaBatch", "device_count", "device_info", "set_stream",

@@ -17,7 +17,7 @@
 
 namespace slas {
 
-static int g_sgemm_path = 0;  // 0 FFMA, 1 tcgen05 3xTF32
+static int g_sgemm_path = 2;  // 0 FFMA only, 1 tcgen05 3xTF32 wherever its tiling applies, 2 auto (default)
 
 // ---- host staging ----------------------------------------------------------------------------
 enum Dir { IN = 1, OUT = 2, INOUT = 3 };
@@ -198,8 +198,64 @@ static int api_normalize(size_t len, T *a, bool sharded) {
         SLAS_TRY(comm_allreduce_f64(res, 1, ctx->stream));
         SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, 1));
     }
-    SLAS_TRY(launch_scale_div<T>(ctx, ctx->stream, len, da, typed));
+    SLAS_TRY(launch_scale_div<T>(ctx, ctx->stream, len, da, da, typed));
     if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
+    return SLAS_OK;
+}
+
+// ---- fused chains ------------------------------------------------------------------------------
+// chain 0..3: c = a op b (c may be null: not materialised), out[0] = dot(c, d);  chain 4: out[0..2] = dot(a,b), |a|, |b|
+template <typename T>
+static int api_fused_chain(int chain, size_t len, const T *a, const T *b, T *c, const T *dd, T *out) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    SLAS_REQUIRE(out, "null result pointer");
+    const int nres = chain == 4 ? 3 : 1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    T *typed = reinterpret_cast<T *>(ctx->scalars + 4);
+    bool out_dev = false;
+    SLAS_TRY(pointer_is_device(out, &out_dev));
+    if (len == 0) {
+        SLAS_CUDA_TRY(cudaMemsetAsync(typed, 0, sizeof(T) * nres, ctx->stream));
+        return deliver_scalar(ctx, typed, out, sizeof(T) * nres);
+    }
+    const void *ptrs[4] = {a, b, chain == 4 ? a : dd, c ? c : a};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 4, &dev));
+    if (dev) {
+        SLAS_TRY(launch_fused_chain<T>(ctx, ctx->stream, chain, len, a, b, c, dd, out_dev ? out : typed));
+        return out_dev ? SLAS_OK : deliver_scalar(ctx, typed, out, sizeof(T) * nres);
+    }
+    const Operand ops[4] = {{a, sizeof(T), IN}, {b, sizeof(T), IN}, {dd, sizeof(T), IN}, {c, sizeof(T), OUT}};
+    const size_t sizes[4] = {len * sizeof(T), len * sizeof(T), chain == 4 ? 0 : len * sizeof(T), c ? len * sizeof(T) : 0};
+    void *d[4];
+    SLAS_TRY(stage_all_begin(ctx, ops, sizes, 4, d));
+    SLAS_TRY(launch_fused_chain<T>(ctx, ctx->stream, chain, len, (const T *)d[0], (const T *)d[1], c ? (T *)d[3] : nullptr,
+                                   (const T *)d[2], out_dev ? out : typed));
+    SLAS_TRY(stage_all_finish(ctx, ops, sizes, 4, d));
+    return out_dev ? SLAS_OK : deliver_scalar(ctx, typed, out, sizeof(T) * nres);
+}
+
+// out = a / |a| without touching a: the copy-on-write + normalize chain (static_vec.rs:304-318 then rust.rs:122-127)
+template <typename T>
+static int api_normalize_into(size_t len, const T *a, T *out) {
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    if (len == 0) return SLAS_OK;
+    SLAS_REQUIRE((const void *)a != (const void *)out, "normalize_into: operands alias (use normalize)");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    double *res = ctx->scalars;
+    T *typed = reinterpret_cast<T *>(ctx->scalars + 4);
+    const void *ptrs[2] = {a, out};
+    bool dev = false;
+    SLAS_TRY(operands_side(ptrs, 2, &dev));
+    const Operand ops[2] = {{a, sizeof(T), IN}, {out, sizeof(T), OUT}};
+    const size_t sizes[2] = {len * sizeof(T), len * sizeof(T)};
+    void *d[2] = {const_cast<T *>(a), out};
+    if (!dev) SLAS_TRY(stage_all_begin(ctx, ops, sizes, 2, d));
+    SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, 1, len, (const T *)d[0], (const T *)d[0], res, typed, 1, 0, nullptr));
+    SLAS_TRY(launch_scale_div<T>(ctx, ctx->stream, len, (const T *)d[0], (T *)d[1], typed));
+    if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 2, d));
     return SLAS_OK;
 }
 
@@ -267,7 +323,11 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
         if (r != SLAS_ERR_UNSUPPORTED) return r;
     }
     if (batch == 1 && m * n >= 64 * 64 && k >= 8) {
-        if (sizeof(T) == 4 && g_sgemm_path == 1) {
+        // auto: the tensor-core path from 512^3 multiply-adds up -- measured 2.3x (512^3) to 5x (4096^3) faster than
+        // the FFMA kernel, profiles/r1e_tune_large.log; its 3xTF32 result is fp32-class (<= 2e-6 * sum|a||b|, inside
+        // the 1e-5 * sqrt(K) bar), the FFMA kernel below is the ascending-k fp32 chain
+        const bool tc_auto = g_sgemm_path == 2 && m * n * k >= ((size_t)1 << 27) && tunable("gemm_large_variant") == 0;
+        if (sizeof(T) == 4 && (g_sgemm_path == 1 || tc_auto)) {
             const int r = launch_sgemm_3xtf32(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb,
                                               ldc, ta, tb);
             if (r != SLAS_ERR_UNSUPPORTED) return r;
@@ -476,6 +536,27 @@ int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c) { re
 int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(2, len, a, b, c); }
 int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(3, len, a, b, c); }
 
+#define SLAS_FUSED_DOT(NAME, CHAIN)                                                                                         \
+    int slas_cuda_s##NAME##_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out) {         \
+        return api_fused_chain<float>(CHAIN, len, a, b, c, d, out);                                                         \
+    }                                                                                                                       \
+    int slas_cuda_d##NAME##_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out) {    \
+        return api_fused_chain<double>(CHAIN, len, a, b, c, d, out);                                                        \
+    }
+SLAS_FUSED_DOT(add, 0)
+SLAS_FUSED_DOT(sub, 1)
+SLAS_FUSED_DOT(mul, 2)
+SLAS_FUSED_DOT(div, 3)
+#undef SLAS_FUSED_DOT
+int slas_cuda_sdot_norms(size_t len, const float *a, const float *b, float *out3) {
+    return api_fused_chain<float>(4, len, a, b, nullptr, nullptr, out3);
+}
+int slas_cuda_ddot_norms(size_t len, const double *a, const double *b, double *out3) {
+    return api_fused_chain<double>(4, len, a, b, nullptr, nullptr, out3);
+}
+int slas_cuda_snormalize_into(size_t len, const float *a, float *out) { return api_normalize_into<float>(len, a, out); }
+int slas_cuda_dnormalize_into(size_t len, const double *a, double *out) { return api_normalize_into<double>(len, a, out); }
+
 // Transpose
 int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns) {
     return api_transpose(1, len, elem_size, a, buffer, columns, false);
@@ -501,7 +582,7 @@ int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_
     return api_gemm<double>(a, b, c, m, n, k, lda, ldb, ldc, a_trans, b_trans);
 }
 int slas_cuda_set_sgemm_path(int path) {
-    SLAS_REQUIRE(path == 0 || path == 1, "sgemm path must be 0 (FFMA) or 1 (tcgen05 3xTF32)");
+    SLAS_REQUIRE(path >= 0 && path <= 2, "sgemm path must be 0 (FFMA), 1 (tcgen05 3xTF32) or 2 (auto)");
     g_sgemm_path = path;
     return SLAS_OK;
 }

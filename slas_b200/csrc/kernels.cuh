@@ -14,7 +14,11 @@ template <typename T>
 int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
                   T *typed_out, int mode, int accumulate, const PeerExchange *peers = nullptr);
 template <typename T> int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode);
-template <typename T> int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, T *a, const T *norm_dev);
+template <typename T> int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, const T *in, T *a, const T *norm_dev);
+// fused chains: 0..3 = (add, sub, mul, div) -> dot with d (c optional), 4 = dot(a,b), |a|, |b|; results to typed_out (device)
+template <typename T>
+int launch_fused_chain(Context *ctx, cudaStream_t st, int chain, size_t len, const T *a, const T *b, T *c, const T *d,
+                       T *typed_out);
 // mode 0 dot, 1 norm, 2 normalize in place
 template <typename T>
 int launch_batched_reduce(Context *ctx, cudaStream_t st, int mode, size_t batch, size_t len, const T *a,

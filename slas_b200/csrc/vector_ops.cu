@@ -324,17 +324,18 @@ template int launch_finish_scalar<double>(cudaStream_t, const double *, double *
 // ---- normalize scale pass: a[i] = a[i] / *norm (true division, rust.rs:125) --------------------
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kEwThreads)
-scale_div_vec_kernel(T *__restrict__ a, size_t nvec, size_t len, const T *__restrict__ norm_ptr) {
+scale_div_vec_kernel(const T *in, T *a, size_t nvec, size_t len, const T *__restrict__ norm_ptr) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     const T nrm = *norm_ptr;
     V *av = reinterpret_cast<V *>(a);
+    const V *iv = reinterpret_cast<const V *>(in);  // == av for the in-place normalize
     const size_t base = (size_t)blockIdx.x * (kEwThreads * UNROLL) + threadIdx.x;
     V r[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
         const size_t i = base + (size_t)u * kEwThreads;
-        if (i < nvec) r[u] = av[i];  // second touch of the vector: let it hit L2
+        if (i < nvec) r[u] = iv[i];  // second touch of the vector: let it hit L2
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
@@ -348,38 +349,174 @@ scale_div_vec_kernel(T *__restrict__ a, size_t nvec, size_t len, const T *__rest
     }
     if (blockIdx.x == 0) {
         const size_t i = nvec * N + threadIdx.x;
-        if (i < len) a[i] = a[i] / nrm;
+        if (i < len) a[i] = in[i] / nrm;
     }
 }
 template <typename T>
-__global__ void __launch_bounds__(kEwThreads) scale_div_scalar_kernel(T *a, size_t len, const T *norm_ptr) {
+__global__ void __launch_bounds__(kEwThreads) scale_div_scalar_kernel(const T *in, T *a, size_t len, const T *norm_ptr) {
     const T nrm = *norm_ptr;
     for (size_t i = (size_t)blockIdx.x * kEwThreads + threadIdx.x; i < len; i += (size_t)gridDim.x * kEwThreads)
-        a[i] = a[i] / nrm;
+        a[i] = in[i] / nrm;
 }
 
 template <typename T>
-int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, T *a, const T *norm_dev) {
+int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, const T *in, T *a, const T *norm_dev) {
     constexpr int N = Vec16<T>::N;
     constexpr int UNROLL = 4;
     if (len == 0) return SLAS_OK;
-    if (aligned16(a)) {
+    if (aligned16(a) && aligned16(in)) {
         const size_t nvec = len / N;
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
         if (blocks == 0) blocks = 1;
         SLAS_REQUIRE(blocks <= 0x7fffffffu, "normalize: vector too long (%zu elements)", len);
-        scale_div_vec_kernel<T, UNROLL><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, nvec, len, norm_dev);
+        scale_div_vec_kernel<T, UNROLL><<<(unsigned)blocks, kEwThreads, 0, st>>>(in, a, nvec, len, norm_dev);
     } else {
         size_t blocks = (len + kEwThreads - 1) / kEwThreads;
         const size_t cap = (size_t)ctx->sm_count * 32;
         if (blocks > cap) blocks = cap;
-        scale_div_scalar_kernel<T><<<(unsigned)blocks, kEwThreads, 0, st>>>(a, len, norm_dev);
+        scale_div_scalar_kernel<T><<<(unsigned)blocks, kEwThreads, 0, st>>>(in, a, len, norm_dev);
     }
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;
 }
-template int launch_scale_div<float>(Context *, cudaStream_t, size_t, float *, const float *);
-template int launch_scale_div<double>(Context *, cudaStream_t, size_t, double *, const double *);
+template int launch_scale_div<float>(Context *, cudaStream_t, size_t, const float *, float *, const float *);
+template int launch_scale_div<double>(Context *, cudaStream_t, size_t, const double *, double *, const double *);
+
+// ---- fused chains: sequences a slas user writes as separate ops, in one pass over HBM ----------
+// Same launch geometry, vector tiling, accumulator layout and partial order as reduce_kernel, and the element-wise
+// step is the same single IEEE operation => the results carry the same bits as the unfused chain on this backend.
+//
+// CHAIN 0..3: x = a (+,-,*,/) b  [written to c when WRITE_C]; result = sum x*d      (add -> dot)
+// CHAIN 4:    results = sum a*b, sum a*a, sum b*b                                  (dot + both norms: cosine)
+template <typename T, int CHAIN, bool WRITE_C>
+__global__ void __launch_bounds__(kRedThreads)
+fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, const T *__restrict__ d, size_t len,
+                   size_t nvec, int vectorised, double *__restrict__ partials, unsigned int *__restrict__ ticket,
+                   T *__restrict__ typed_out) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    constexpr int NRES = CHAIN == 4 ? 3 : 1;
+    constexpr int OP = CHAIN < 4 ? CHAIN : 0;
+    __shared__ double red[kRedThreads / 32];
+    __shared__ bool is_last;
+    Reducer<T, 0> r0, r1, r2;
+    r0.clear(); r1.clear(); r2.clear();
+    const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * kRedThreads;
+    if (vectorised) {
+        const V *av = reinterpret_cast<const V *>(a);
+        const V *bv = reinterpret_cast<const V *>(b);
+        const V *dv = reinterpret_cast<const V *>(d);
+        V *cv = reinterpret_cast<V *>(c);
+        const size_t stride = nthreads * kRedUnroll;
+        size_t i = (size_t)blockIdx.x * (kRedThreads * kRedUnroll) + threadIdx.x;
+        int since_flush = 0;
+        auto step = [&](int u, size_t j) {
+            const V x = ld_stream(av + j), y = ld_stream(bv + j);
+            if (CHAIN == 4) {
+                r0.add(u, x, y); r1.add(u, x, x); r2.add(u, y, y);
+            } else {
+                const V e = apply_vec<OP>(x, y);
+                if (WRITE_C) st_stream(cv + j, e);
+                r0.add(u, e, ld_stream(dv + j));
+            }
+        };
+        for (; i + (size_t)(kRedUnroll - 1) * kRedThreads < nvec; i += stride) {
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) step(u, i + (size_t)u * kRedThreads);
+            if (++since_flush == kFlushEvery) {
+                r0.flush();
+                if (CHAIN == 4) { r1.flush(); r2.flush(); }
+                since_flush = 0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRedUnroll; ++u) {
+            const size_t j = i + (size_t)u * kRedThreads;
+            if (j < nvec) step(u, j);
+        }
+        r0.flush();
+        if (CHAIN == 4) { r1.flush(); r2.flush(); }
+        const size_t j = nvec * N + tid;
+        if (j < len) {
+            if (CHAIN == 4) {
+                r0.add_scalar(a[j], b[j]); r1.add_scalar(a[j], a[j]); r2.add_scalar(b[j], b[j]);
+            } else {
+                const T e = apply_op<OP>(a[j], b[j]);
+                if (WRITE_C) c[j] = e;
+                r0.add_scalar(e, d[j]);
+            }
+        }
+    } else {
+        for (size_t j = tid; j < len; j += nthreads) {
+            if (CHAIN == 4) {
+                r0.add_scalar(a[j], b[j]); r1.add_scalar(a[j], a[j]); r2.add_scalar(b[j], b[j]);
+            } else {
+                const T e = apply_op<OP>(a[j], b[j]);
+                if (WRITE_C) c[j] = e;
+                r0.add_scalar(e, d[j]);
+            }
+        }
+    }
+    double s[3];
+    s[0] = block_sum<kRedThreads>(r0.sum, red);
+    if (CHAIN == 4) { s[1] = block_sum<kRedThreads>(r1.sum, red); s[2] = block_sum<kRedThreads>(r2.sum, red); }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < NRES; ++q) partials[(size_t)q * gridDim.x + blockIdx.x] = s[q];
+        __threadfence();
+        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int q = 0; q < NRES; ++q) {
+        double p = 0.0;
+        for (unsigned int j = threadIdx.x; j < gridDim.x; j += kRedThreads) p += __ldcg(partials + (size_t)q * gridDim.x + j);
+        p = block_sum<kRedThreads>(p, red);
+        if (threadIdx.x == 0) typed_out[q] = (CHAIN == 4 && q > 0) ? (T)sqrt(p) : (T)p;
+    }
+}
+
+template <typename T, int CHAIN>
+static int launch_fused_chain_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b, T *c, const T *d,
+                                   T *typed_out) {
+    constexpr int N = Vec16<T>::N;
+    const bool vec = aligned16(a) && aligned16(b) && (CHAIN == 4 || aligned16(d)) && (c == nullptr || aligned16(c));
+    const size_t nvec = vec ? len / N : 0;
+    const size_t work = vec ? nvec : len;
+    size_t blocks = (work + (size_t)kRedThreads * kRedUnroll - 1) / ((size_t)kRedThreads * kRedUnroll);
+    const size_t cap = (size_t)ctx->sm_count * 8;  // 3 * cap <= 2 * kMaxPartials
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    if (c)
+        fused_chain_kernel<T, CHAIN, true><<<(unsigned)blocks, kRedThreads, 0, st>>>(a, b, c, d, len, nvec, vec ? 1 : 0,
+                                                                                      ctx->partials, ctx->ticket, typed_out);
+    else
+        fused_chain_kernel<T, CHAIN, false><<<(unsigned)blocks, kRedThreads, 0, st>>>(a, b, c, d, len, nvec, vec ? 1 : 0,
+                                                                                       ctx->partials, ctx->ticket, typed_out);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+template <typename T>
+int launch_fused_chain(Context *ctx, cudaStream_t st, int chain, size_t len, const T *a, const T *b, T *c, const T *d,
+                       T *typed_out) {
+    switch (chain) {
+    case 0: return launch_fused_chain_kind<T, 0>(ctx, st, len, a, b, c, d, typed_out);
+    case 1: return launch_fused_chain_kind<T, 1>(ctx, st, len, a, b, c, d, typed_out);
+    case 2: return launch_fused_chain_kind<T, 2>(ctx, st, len, a, b, c, d, typed_out);
+    case 3: return launch_fused_chain_kind<T, 3>(ctx, st, len, a, b, c, d, typed_out);
+    case 4: return launch_fused_chain_kind<T, 4>(ctx, st, len, a, b, nullptr, nullptr, typed_out);
+    }
+    return fail(SLAS_ERR_INVALID, "unknown fused chain %d", chain);
+}
+template int launch_fused_chain<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, float *, const float *,
+                                       float *);
+template int launch_fused_chain<double>(Context *, cudaStream_t, int, size_t, const double *, const double *, double *,
+                                        const double *, double *);
 
 // ---- batched dot / norm / normalize over [[T; len]; batch] -----------------------------------
 // One group of GROUP threads per vector (GROUP = 32: a warp per vector, several vectors per

@@ -219,6 +219,31 @@ int main() {
         for (int i = 0; i < 4; ++i) CHECK(b[i] == a[i] / n);
     });
 
+    // ---- fused chains and the 1-/2-byte transposes: same answers as the op sequences of the cases above ----
+    run("fused: add -> dot equals the chain (main.rs:41-46 operands)", [] {
+        std::array<float, 4> a{0, 1, 2, 3}, b{0, -1, -2, 3}, d{1, 2, 3, 4}, c{}, t{};
+        Cuda{}.add(a, b, t);
+        CHECK(Cuda{}.add_dot(a, b, d) == Cuda{}.dot(t, d));
+        CHECK(Cuda{}.add_dot(a, b, d, c) == 24.f && c == t);
+        CHECK(Cuda{}.mul_dot(a, b, d) == 0.f * 1 - 1.f * 2 - 4.f * 3 + 9.f * 4);
+    });
+    run("fused: dot_norms / normalize_into", [] {
+        std::array<double, 4> a{3, 4, 0, 12}, b{1, 0, 0, 1}, o{};
+        const auto r = Cuda{}.dot_norms(a, b);
+        CHECK(r[0] == 15.0 && r[1] == 13.0 && r[2] == std::sqrt(2.0));
+        Cuda{}.normalize_into(a, o);
+        for (int i = 0; i < 4; ++i) CHECK(o[i] == a[i] / 13.0);
+        CHECK(a[3] == 12.0);
+    });
+    run("transpose of 1- and 2-byte Copy elements (rust.rs:151: any T: Copy)", [] {
+        std::array<unsigned char, 6> a{1, 2, 3, 4, 5, 6}, o{};
+        Cuda{}.transpose(a, o, 2);  // input 2 x 3 row-major -> 3 x 2
+        CHECK(eq(o, {(unsigned char)1, (unsigned char)4, (unsigned char)2, (unsigned char)5, (unsigned char)3, (unsigned char)6}));
+        std::array<short, 6> s{1, 2, 3, 4, 5, 6};
+        Cuda{}.transpose_inplace(s, 2);
+        CHECK(eq(s, {(short)1, (short)4, (short)2, (short)5, (short)3, (short)6}));
+    });
+
     std::printf("\ntest result: %s. %d passed; %d failed\n", g_failed ? "FAILED" : "ok", g_run - g_failed, g_failed);
     return g_failed ? 1 : 0;
 }

@@ -154,7 +154,7 @@ def test_matmul_4096_freivalds(path):
     try:
         cuda.matrix_mul(a, b, c, n, n, n, n, n, n, False, False)
     finally:
-        set_sgemm_path("ffma")
+        set_sgemm_path("auto")
     A, B, Cm = (v.to_host().reshape(n, n).astype(np.float64) for v in (a, b, c))
     rng = np.random.default_rng(4)
     for _ in range(3):  # Freivalds: C x == A (B x) for random probes, in f64 on the host

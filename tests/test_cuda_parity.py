@@ -302,6 +302,75 @@ def test_norm_and_normalize(dt, n):
     assert np.array_equal(h, got)
 
 
+# ---- fused chains: same results as the op sequence they replace ---------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 5, 1000, 4097, (1 << 20) + 3])
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "div"])
+def test_fused_ewise_dot_matches_the_chain(dt, n, op):
+    """`c = a op b` then `dot(c, d)`: the intermediate is the reference's bit-exact element-wise result
+    (rust.rs:45-73), the dot is within the reduction bar AND carries the same bits as the unfused GPU chain"""
+    rng = np.random.default_rng(n + len(op))
+    a, b, d = _rand(rng, n, dt, -4, 4), _rand(rng, n, dt, 0.25, 4), _rand(rng, n, dt)
+    want_c = oracle.ewise(op, a, b)
+    truth = float(np.sum(want_c.astype(np.longdouble) * d.astype(np.longdouble)))
+    mag = float(np.sum(np.abs(want_c.astype(np.longdouble) * d.astype(np.longdouble))))
+    da, db, dd = CudaVec.from_host(a), CudaVec.from_host(b), CudaVec.from_host(d)
+    tmp = CudaVec(n, dt)
+    getattr(cuda, op)(da, db, tmp)
+    unfused = cuda.dot(tmp, dd)
+    dc = CudaVec(n, dt).zero_()
+    got = cuda.ewise_dot(op, da, db, dd, dc)
+    assert np.array_equal(dc.to_host(), want_c)
+    assert got.tobytes() == unfused.tobytes()
+    assert abs(float(got) - truth) <= TOL[np.dtype(dt)] * np.sqrt(n) * mag
+    assert cuda.ewise_dot(op, da, db, dd).tobytes() == unfused.tobytes()  # intermediate never materialised
+    hc = np.zeros_like(a)
+    assert cuda.ewise_dot(op, a, b, d, hc).tobytes() == unfused.tobytes()  # host pointers
+    assert np.array_equal(hc, want_c)
+    if n > 8:  # unaligned device views: scalar path, within the bar
+        g = cuda.ewise_dot(op, da.view(1, n - 1), db.view(1, n - 1), dd.view(1, n - 1))
+        t1 = float(np.sum(want_c[1:].astype(np.longdouble) * d[1:].astype(np.longdouble)))
+        assert abs(float(g) - t1) <= TOL[np.dtype(dt)] * np.sqrt(n) * mag
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 1000, 4097, (1 << 20) + 1])
+def test_fused_dot_norms_matches_the_three_ops(dt, n):
+    rng = np.random.default_rng(n + 11)
+    a, b = _rand(rng, n, dt), _rand(rng, n, dt)
+    da, db = CudaVec.from_host(a), CudaVec.from_host(b)
+    dot, na, nb = cuda.dot_norms(da, db)
+    assert dot.tobytes() == cuda.dot(da, db).tobytes()
+    assert na.tobytes() == cuda.norm(da).tobytes() and nb.tobytes() == cuda.norm(db).tobytes()
+    rel = TOL[np.dtype(dt)] * np.sqrt(n)
+    assert abs(float(na) - float(oracle.norm(a))) <= 2 * rel * float(oracle.norm(a))
+    assert abs(float(dot) - float(oracle.dot(a, b))) <= 2 * rel * float(np.sum(np.abs(a.astype(np.float64) * b)))
+    assert cuda.dot_norms(a, b)[0].tobytes() == dot.tobytes()  # host pointers
+
+
+def test_fused_chains_of_empty_vectors():
+    e = np.zeros(0, np.float32)
+    assert cuda.ewise_dot("add", e, e, e) == 0.0
+    assert cuda.dot_norms(e, e) == (0.0, 0.0, 0.0)
+    cuda.normalize_into(e, np.zeros(0, np.float32))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [1, 3, 1000, (1 << 20) + 1])
+def test_normalize_into_is_normalize_of_a_copy(dt, n):
+    a = _rand(np.random.default_rng(n + 5), n, dt)
+    da = CudaVec.from_host(a)
+    out = CudaVec(n, dt).zero_()
+    cuda.normalize_into(da, out)
+    ref = CudaVec.from_host(a)
+    cuda.normalize(ref)
+    assert np.array_equal(out.to_host(), ref.to_host())
+    assert np.array_equal(da.to_host(), a)  # the source is untouched (the borrowed side of a StaticCowVec)
+    h = np.zeros_like(a)
+    cuda.normalize_into(a, h)
+    assert np.array_equal(h, ref.to_host())
+
+
 # ---- transpose: bit-exact for any Copy element --------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48), (128, 64), (192, 320), (1024, 512)])
@@ -548,6 +617,29 @@ def test_large_gemm_ffma_path(size, ta, tb):
     assert np.all(np.abs(c.to_host() - ref) <= 1e-5 * np.sqrt(k) * mag)
 
 
+def test_large_sgemm_automatic_path_choice():
+    """default ('auto'): tensor cores from 2^27 multiply-adds up when the shape fits the tiles, FFMA otherwise"""
+    from slas_b200.backends import set_sgemm_path
+    rng = np.random.default_rng(5)
+    for (m, n, k), launches in (((512, 512, 512), 3), ((512, 576, 512), 1), ((256, 256, 256), 1)):
+        A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
+        c = CudaVec(m * n, np.float32)
+        n0 = launch_count()
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, k, n, n, False, False)
+        assert launch_count() - n0 == launches, (m, n, k)
+        ref, mag = _gemm_truth(A, B, m, n, k, False, False)
+        assert np.all(np.abs(c.to_host() - ref) <= 1e-5 * np.sqrt(k) * mag)
+    set_sgemm_path("ffma")
+    try:
+        A, B = _rand(rng, 512 * 512, np.float32), _rand(rng, 512 * 512, np.float32)
+        c = CudaVec(512 * 512, np.float32)
+        n0 = launch_count()
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, 512, 512, 512, 512, 512, 512, False, False)
+        assert launch_count() - n0 == 1
+    finally:
+        set_sgemm_path("auto")
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64), (4, 4), (32, 32), (64, 16),
                                        (2, 128), (128, 8), (1, 4), (256, 64), (64, 128), (300, 1024), (1000, 516), (2048, 2048)])
@@ -608,7 +700,7 @@ def test_sgemm_3xtf32_tcgen05(m, n, k, ta, tb):
         cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
         assert launch_count() - n0 == 3, "expected split(A), split(B) and the tcgen05 kernel"
     finally:
-        set_sgemm_path("ffma")
+        set_sgemm_path("auto")
     ref, mag = _gemm_truth(A, B, m, n, k, ta, tb)
     err = np.abs(c.to_host() - ref)
     assert np.all(err <= 1e-5 * np.sqrt(k) * mag), f"max err/mag {np.max(err / mag):.3e}"
