@@ -323,10 +323,17 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
         if (r != SLAS_ERR_UNSUPPORTED) return r;
     }
     if (batch == 1 && m * n >= 64 * 64 && k >= 8) {
-        // auto: the tensor-core path from 512^3 multiply-adds up -- measured 2.3x (512^3) to 5x (4096^3) faster than
-        // the FFMA kernel, profiles/r1e_tune_large.log; its 3xTF32 result is fp32-class (<= 2e-6 * sum|a||b|, inside
-        // the 1e-5 * sqrt(K) bar), the FFMA kernel below is the ascending-k fp32 chain
-        const bool tc_auto = g_sgemm_path == 2 && m * n * k >= ((size_t)1 << 27) && tunable("gemm_large_variant") == 0;
+        // auto: the tensor-core path from 2^27 multiply-adds up -- measured 2.3x (512^3) to 5x (4096^3) faster than
+        // the FFMA kernel, profiles/r1e_tune_large.log -- unless padding (m, n, k) up to whole tiles would add more
+        // than 60 % of work.  Its 3xTF32 result is fp32-class (<= 2e-6 * sum|a||b|, inside the 1e-5 * sqrt(K) bar);
+        // the FFMA kernel below is the ascending-k fp32 chain.
+        bool tc_auto = false;
+        if (sizeof(T) == 4 && g_sgemm_path == 2 && m * n * k >= ((size_t)1 << 27) && tunable("gemm_large_variant") == 0) {
+            size_t mp, np, kp;
+            bool pair;
+            sgemm_3xtf32_padded(m, n, k, &mp, &np, &kp, &pair);
+            tc_auto = (double)mp * (double)np * (double)kp <= 1.6 * (double)m * (double)n * (double)k;
+        }
         if (sizeof(T) == 4 && (g_sgemm_path == 1 || tc_auto)) {
             const int r = launch_sgemm_3xtf32(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb,
                                               ldc, ta, tb);

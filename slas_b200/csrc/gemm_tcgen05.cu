@@ -118,36 +118,65 @@ __device__ __forceinline__ void split1(float x, float &hi, float &lo) {
     lo = rna_tf32(x - hi);
 }
 
-// src is [rows][cols] (ld) and already K-major: hi/lo are dense [rows][cols]
+// The hi/lo copies are dense [rows_p][cols_p] arrays padded with zeros up to whole tiles (rows_p >= rows a
+// multiple of the tile height, cols_p >= cols a multiple of BK), so the GEMM kernels only ever see whole tiles
+// and any (m, n, k) is covered; zero rows / columns add nothing to the products.
+// src is [rows][cols] (ld) and already K-major.  vec: 128-bit loads allowed (aligned base, ld % 4 == 0)
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float *__restrict__ src, size_t ld, float *__restrict__ hi, float *__restrict__ lo, size_t rows,
-                  size_t cols) {
-    const size_t total = rows * (cols / 4);
+                  size_t cols, size_t rows_p, size_t cols_p, int vec) {
+    const size_t q = cols_p / 4, total = rows_p * q;
     for (size_t t = (size_t)blockIdx.x * 256 + threadIdx.x; t < total; t += (size_t)gridDim.x * 256) {
-        const size_t r = t / (cols / 4), c = (t % (cols / 4)) * 4;
-        const float4 x = *reinterpret_cast<const float4 *>(src + r * ld + c);
+        const size_t r = t / q, c = (t % q) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows) {
+            const float *p = src + r * ld + c;
+            if (vec && c + 4 <= cols) x = *reinterpret_cast<const float4 *>(p);
+            else {
+                if (c < cols) x.x = p[0];
+                if (c + 1 < cols) x.y = p[1];
+                if (c + 2 < cols) x.z = p[2];
+                if (c + 3 < cols) x.w = p[3];
+            }
+        }
         float4 h, l;
         split1(x.x, h.x, l.x); split1(x.y, h.y, l.y); split1(x.z, h.z, l.z); split1(x.w, h.w, l.w);
-        *reinterpret_cast<float4 *>(hi + r * cols + c) = h;
-        *reinterpret_cast<float4 *>(lo + r * cols + c) = l;
+        *reinterpret_cast<float4 *>(hi + r * cols_p + c) = h;
+        *reinterpret_cast<float4 *>(lo + r * cols_p + c) = l;
     }
 }
-// src is [k][rows_out] (ld): transpose while splitting, hi/lo are dense [rows_out][k]
+// src is [k][rows_out] (ld): transpose while splitting, hi/lo are [rows_p][k_p]; grid = (rows_p / 32, k_p / 32)
 __global__ void __launch_bounds__(256)
 split_tf32_transpose_kernel(const float *__restrict__ src, size_t ld, float *__restrict__ hi, float *__restrict__ lo,
-                            size_t rows_out, size_t k) {
+                            size_t rows_out, size_t k, size_t k_p) {
     __shared__ float tile[32][33];
     const size_t r0 = (size_t)blockIdx.x * 32, k0 = (size_t)blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) tile[ty + j][tx] = src[(k0 + ty + j) * ld + r0 + tx];
+    for (int j = 0; j < 32; j += 8)
+        tile[ty + j][tx] = (k0 + ty + j < k && r0 + tx < rows_out) ? src[(k0 + ty + j) * ld + r0 + tx] : 0.f;
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 32; j += 8) {
         float h, l;
         split1(tile[tx][ty + j], h, l);
-        hi[(r0 + ty + j) * k + k0 + tx] = h;
-        lo[(r0 + ty + j) * k + k0 + tx] = l;
+        hi[(r0 + ty + j) * k_p + k0 + tx] = h;
+        lo[(r0 + ty + j) * k_p + k0 + tx] = l;
+    }
+}
+
+// one accumulator row segment (32 columns) -> C; cols_left = columns of C from dst to the end of the row
+__device__ __forceinline__ void store_acc_row(float *dst, const uint32_t (&v)[32], uint32_t cols_left, bool vec_ok) {
+    if (vec_ok && cols_left >= 32) {
+        float4 *d4 = reinterpret_cast<float4 *>(dst);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            d4[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if ((uint32_t)j < cols_left) dst[j] = __uint_as_float(v[j]);
     }
 }
 
@@ -167,7 +196,7 @@ __global__ void __launch_bounds__(tc::THREADS, 1)
 sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                     float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t k_blocks, uint32_t num_items,
-                    uint32_t full_tiles) {
+                    uint32_t full_tiles, uint32_t m, uint32_t n, uint32_t vec_ok) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     // 128-byte swizzle atoms need 1024-byte aligned tiles
@@ -259,17 +288,14 @@ sgemm_3xtf32_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
             mbar_wait(acc_full + buf, buf_use & 1);
             tc_fence_after();
-            float *crow = c + (size_t)(w.mb * BM + q * 32 + lane) * ldc + (size_t)w.nb * BN + w.n_off;
+            const uint32_t row = w.mb * BM + q * 32 + lane, col0 = w.nb * BN + w.n_off;
+            float *crow = c + (size_t)row * ldc + col0;
 #pragma unroll 1
             for (uint32_t cc = 0; cc < w.n_cols / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((q * 32) << 16) + buf * BN + cc * 32, v);
                 tmem_ld_wait();
-                float4 *dst = reinterpret_cast<float4 *>(crow + cc * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                if (row < m && col0 + cc * 32 < n) store_acc_row(crow + cc * 32, v, n - (col0 + cc * 32), vec_ok != 0);
             }
             tc_fence_before();
             __syncwarp();
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(tc2::THREADS, 1)
 sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                          const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                          float *__restrict__ c, uint32_t ldc, uint32_t m_blocks, uint32_t k_blocks, uint32_t num_items,
-                         uint32_t full_tiles) {
+                         uint32_t full_tiles, uint32_t m, uint32_t n, uint32_t vec_ok) {
     using namespace tc2;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -462,17 +488,14 @@ sgemm_3xtf32_pair_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __g
             const uint32_t buf = tile_it & 1, buf_use = tile_it >> 1;
             mbar_wait(acc_full + buf, buf_use & 1);
             tc_fence_after();
-            float *crow = c + (size_t)(w.mb * BM + rank * HALF + q * 32 + lane) * ldc + (size_t)w.nb * BN + w.n_off;
+            const uint32_t row = w.mb * BM + rank * HALF + q * 32 + lane, col0 = w.nb * BN + w.n_off;
+            float *crow = c + (size_t)row * ldc + col0;
 #pragma unroll 1
             for (uint32_t cc = 0; cc < w.n_cols / 32; ++cc) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((q * 32) << 16) + buf * BN + cc * 32, v);
                 tmem_ld_wait();
-                float4 *dst = reinterpret_cast<float4 *>(crow + cc * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                if (row < m && col0 + cc * 32 < n) store_acc_row(crow + cc * 32, v, n - (col0 + cc * 32), vec_ok != 0);
             }
             tc_fence_before();
             __syncwarp();
@@ -520,38 +543,55 @@ static int make_map(EncodeTiledFn enc, CUtensorMap *map, const float *base, size
     return SLAS_OK;
 }
 
+static inline size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Padded problem the kernels run on: k to whole k-blocks, n to whole 256-column tiles, m to the CTA-pair
+// tile (256) unless that wastes more than ~15 % over the single-CTA tile (128).
+void sgemm_3xtf32_padded(size_t m, size_t n, size_t k, size_t *mp, size_t *np, size_t *kp, bool *pair) {
+    using namespace tc;
+    const size_t m128 = round_up(m, BM), m256 = round_up(m, tc2::BM);
+    const long variant = tunable("tc_variant");
+    *pair = variant != 1 && variant != 3 && (double)m256 <= 1.15 * (double)m128;
+    *mp = *pair ? m256 : m128;
+    *np = round_up(n, BN);
+    *kp = round_up(k, BK);
+}
+
 int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m, size_t n,
                         size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb) {
     using namespace tc;
-    // whole tiles only; everything else runs on the FFMA kernel
-    if (m % BM || n % BN || k % BK || m == 0 || n == 0 || k == 0) return SLAS_ERR_UNSUPPORTED;
-    if (!aligned16(a) || !aligned16(b) || !aligned16(c) || lda % 4 || ldb % 4 || ldc % 4) return SLAS_ERR_UNSUPPORTED;
-    if (m > 0x7fffffffu || n > 0x7fffffffu || k > 0x7fffffffu) return SLAS_ERR_UNSUPPORTED;
+    if (m == 0 || n == 0 || k == 0) return SLAS_ERR_UNSUPPORTED;
+    if (m > 0x7fffff00u || n > 0x7fffff00u || k > 0x7fffff00u || ldc > 0xffffffffu) return SLAS_ERR_UNSUPPORTED;
+    size_t mp, np, kp;
+    bool use_pair;
+    sgemm_3xtf32_padded(m, n, k, &mp, &np, &kp, &use_pair);
+    if (ctx->sm_count < 2) { use_pair = false; mp = round_up(m, BM); }
     EncodeTiledFn enc;
     SLAS_TRY(get_encode_fn(&enc));
     void *ws = nullptr;
-    const size_t a_elems = m * k, b_elems = n * k;
+    const size_t a_elems = mp * kp, b_elems = np * kp;
     SLAS_TRY(ensure_workspace(ctx, 2 * (a_elems + b_elems) * sizeof(float), &ws));
     float *a_hi = (float *)ws, *a_lo = a_hi + a_elems, *b_hi = a_lo + a_elems, *b_lo = b_hi + b_elems;
     const unsigned cap = (unsigned)ctx->sm_count * 8;
-    // op(A) as [m][k]
-    if (!ta) split_tf32_kernel<<<cap, 256, 0, st>>>(a, lda, a_hi, a_lo, m, k);
-    else split_tf32_transpose_kernel<<<dim3((unsigned)(m / 32), (unsigned)(k / 32)), 256, 0, st>>>(a, lda, a_hi, a_lo, m, k);
+    const int vec_a = aligned16(a) && lda % 4 == 0, vec_b = aligned16(b) && ldb % 4 == 0;
+    const uint32_t vec_c = aligned16(c) && ldc % 4 == 0;
+    // op(A) as [mp][kp]
+    if (!ta) split_tf32_kernel<<<cap, 256, 0, st>>>(a, lda, a_hi, a_lo, m, k, mp, kp, vec_a);
+    else split_tf32_transpose_kernel<<<dim3((unsigned)(mp / 32), (unsigned)(kp / 32)), 256, 0, st>>>(a, lda, a_hi, a_lo, m, k, kp);
     SLAS_LAUNCH_CHECK();
-    // op(B)^T as [n][k]
-    if (tb) split_tf32_kernel<<<cap, 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k);
-    else split_tf32_transpose_kernel<<<dim3((unsigned)(n / 32), (unsigned)(k / 32)), 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k);
+    // op(B)^T as [np][kp]
+    if (tb) split_tf32_kernel<<<cap, 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k, np, kp, vec_b);
+    else split_tf32_transpose_kernel<<<dim3((unsigned)(np / 32), (unsigned)(kp / 32)), 256, 0, st>>>(b, ldb, b_hi, b_lo, n, k, kp);
     SLAS_LAUNCH_CHECK();
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    const long variant = tunable("tc_variant");
-    if (variant != 1 && variant != 3 && m % tc2::BM == 0 && ctx->sm_count >= 2) {
+    if (use_pair) {
         // CTA-pair kernel (cta_group::2): 256 x 256 tiles, three 64 KB stages per CTA
-        SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, tc2::HALF));
-        SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, tc2::HALF));
-        SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, tc2::HALF / 2));
-        SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, tc2::HALF / 2));
+        SLAS_TRY(make_map(enc, &ma_hi, a_hi, mp, kp, tc2::HALF));
+        SLAS_TRY(make_map(enc, &ma_lo, a_lo, mp, kp, tc2::HALF));
+        SLAS_TRY(make_map(enc, &mb_hi, b_hi, np, kp, tc2::HALF / 2));
+        SLAS_TRY(make_map(enc, &mb_lo, b_lo, np, kp, tc2::HALF / 2));
         SLAS_CUDA_TRY(cudaFuncSetAttribute(sgemm_3xtf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-        const uint32_t m_blocks = (uint32_t)(m / tc2::BM), n_blocks = (uint32_t)(n / tc2::BN), k_blocks = (uint32_t)(k / BK);
+        const uint32_t m_blocks = (uint32_t)(mp / tc2::BM), n_blocks = (uint32_t)(np / tc2::BN), k_blocks = (uint32_t)(kp / BK);
         const uint32_t pairs_max = (uint32_t)ctx->sm_count / 2, num_tiles = m_blocks * n_blocks;
         uint32_t full_tiles = num_tiles / pairs_max * pairs_max;
         if (2 * (num_tiles - full_tiles) > pairs_max) full_tiles = num_tiles;
@@ -570,16 +610,16 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         SLAS_CUDA_TRY(cudaLaunchKernelEx(&cfg, sgemm_3xtf32_pair_kernel, ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks,
-                                         k_blocks, num_items, full_tiles));
+                                         k_blocks, num_items, full_tiles, (uint32_t)m, (uint32_t)n, vec_c));
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    SLAS_TRY(make_map(enc, &ma_hi, a_hi, m, k, BM));
-    SLAS_TRY(make_map(enc, &ma_lo, a_lo, m, k, BM));
-    SLAS_TRY(make_map(enc, &mb_hi, b_hi, n, k, BN / 2));
-    SLAS_TRY(make_map(enc, &mb_lo, b_lo, n, k, BN / 2));
+    SLAS_TRY(make_map(enc, &ma_hi, a_hi, mp, kp, BM));
+    SLAS_TRY(make_map(enc, &ma_lo, a_lo, mp, kp, BM));
+    SLAS_TRY(make_map(enc, &mb_hi, b_hi, np, kp, BN / 2));
+    SLAS_TRY(make_map(enc, &mb_lo, b_lo, np, kp, BN / 2));
     SLAS_CUDA_TRY(cudaFuncSetAttribute(sgemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    const uint32_t m_blocks = (uint32_t)(m / BM), n_blocks = (uint32_t)(n / BN), k_blocks = (uint32_t)(k / BK);
+    const uint32_t m_blocks = (uint32_t)(mp / BM), n_blocks = (uint32_t)(np / BN), k_blocks = (uint32_t)(kp / BK);
     const uint32_t sms = (uint32_t)ctx->sm_count, num_tiles = m_blocks * n_blocks;
     uint32_t full_tiles = num_tiles / sms * sms;
     const uint32_t tail = num_tiles - full_tiles;
@@ -588,7 +628,7 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
     const unsigned grid = num_items < sms ? num_items : sms;
     (void)n_blocks;
     sgemm_3xtf32_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, c, (uint32_t)ldc, m_blocks, k_blocks,
-                                                           num_items, full_tiles);
+                                                           num_items, full_tiles, (uint32_t)m, (uint32_t)n, vec_c);
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;
 }

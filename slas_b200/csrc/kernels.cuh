@@ -59,6 +59,8 @@ int launch_sgemm_ffma(Context *ctx, cudaStream_t st, const float *a, const float
 
 // gemm_tcgen05.cu -- 3xTF32 on the 5th-gen tensor cores (TMA + TMEM); SLAS_ERR_UNSUPPORTED
 // when the shape does not fit its tiles.
+// the zero-padded problem size the tcgen05 kernels would run (m, n, k) on, and whether the CTA-pair kernel is used
+void sgemm_3xtf32_padded(size_t m, size_t n, size_t k, size_t *mp, size_t *np, size_t *kp, bool *pair);
 int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m,
                         size_t n, size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb);
 

@@ -612,16 +612,48 @@ def test_large_gemm_ffma_path(size, ta, tb):
     m, n, k = size, size + 64, size
     A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
     c = CudaVec(m * n, np.float32)
-    cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
+    from slas_b200.backends import set_sgemm_path
+    set_sgemm_path("ffma")
+    try:
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
+    finally:
+        set_sgemm_path("auto")
     ref, mag = _gemm_truth(A, B, m, n, k, ta, tb)
     assert np.all(np.abs(c.to_host() - ref) <= 1e-5 * np.sqrt(k) * mag)
+
+
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_sgemm_3xtf32_strided_unaligned_operands(ta, tb):
+    """leading dimensions wider than the matrices, not multiples of 4, and a C base that is not 16-byte aligned:
+    the split pass and the epilogue fall back to scalar accesses; untouched C padding keeps its bytes"""
+    from slas_b200.backends import set_sgemm_path
+    m, n, k = 200, 300, 150
+    lda, ldb, ldc = (m if ta else k) + 3, (k if tb else n) + 1, n + 5
+    rng = np.random.default_rng(77)
+    A = _rand(rng, (k if ta else m) * lda, np.float32)
+    B = _rand(rng, (n if tb else k) * ldb, np.float32)
+    cfull = CudaVec.from_host(np.full(1 + m * ldc, -7.0, np.float32))
+    set_sgemm_path("tcgen05")
+    try:
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), cfull.view(1, m * ldc), m, n, k, lda, ldb, ldc, ta, tb)
+    finally:
+        set_sgemm_path("auto")
+    got = cfull.to_host()[1:].reshape(m, ldc)
+    Am = A.reshape(k, lda)[:, :m].T if ta else A.reshape(m, lda)[:, :k]
+    Bm = B.reshape(n, ldb)[:, :k].T if tb else B.reshape(k, ldb)[:, :n]
+    ref = Am.astype(np.float64) @ Bm.astype(np.float64)
+    mag = np.abs(Am).astype(np.float64) @ np.abs(Bm).astype(np.float64)
+    assert np.all(np.abs(got[:, :n] - ref) <= 1e-5 * np.sqrt(k) * mag)
+    assert np.all(got[:, n:] == -7.0) and cfull.to_host()[0] == -7.0
 
 
 def test_large_sgemm_automatic_path_choice():
     """default ('auto'): tensor cores from 2^27 multiply-adds up when the shape fits the tiles, FFMA otherwise"""
     from slas_b200.backends import set_sgemm_path
     rng = np.random.default_rng(5)
-    for (m, n, k), launches in (((512, 512, 512), 3), ((512, 576, 512), 1), ((256, 256, 256), 1)):
+    # 520 x 260 would be padded to 640 x 512 (2.4x the work): FFMA; 256^3 is below the 2^27 threshold
+    for (m, n, k), launches in (((512, 512, 512), 3), ((500, 520, 530), 3), ((520, 260, 1024), 1), ((256, 256, 256), 1)):
         A, B = _rand(rng, m * k, np.float32), _rand(rng, k * n, np.float32)
         c = CudaVec(m * n, np.float32)
         n0 = launch_count()
@@ -686,7 +718,8 @@ def test_batched_reductions(dt, length, batch):
 
 
 # ---- the tensor-core path for one large f32 product: 3xTF32 on tcgen05 / TMEM -----------------------------
-@pytest.mark.parametrize("m,n,k", [(128, 256, 32), (128, 256, 64), (256, 512, 96), (384, 256, 1024), (1024, 1024, 512)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 32), (128, 256, 64), (256, 512, 96), (384, 256, 1024), (1024, 1024, 512),
+                                   (100, 70, 50), (129, 257, 33), (300, 500, 700), (1000, 1000, 1000), (257, 64, 8)])
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
 def test_sgemm_3xtf32_tcgen05(m, n, k, ta, tb):
