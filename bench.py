@@ -315,12 +315,22 @@ def run_cuda(args):
             e2e_step()
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+        # the PCIe roofline of that step, measured here: one pinned 1 GiB host->device copy on its own (the step
+        # moves 2x the batch down and 1x up; both directions run concurrently, so H2D bounds it)
+        h2d_gbs = None
+        if rank == 0:
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(3):
+                _lib.call("slas_cuda_memcpy_h2d", A.data_ptr(), hp[0].value, nbytes)
+            h2d_gbs = 3 * nbytes / (time.perf_counter() - t1) / 1e9
         # spot-check the host result against the device-resident one
         _lib.call("slas_cuda_memcpy_d2h", hp[0].value, Cc.data_ptr(), 4096)
         assert np.array_equal(hA[:1024], hC[:1024]), "host-path result differs from the device-resident result"
         e2e = {"value": FLOP_PER_4X4 * batch * world / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "pcie_gbs": 3 * nbytes / (e2e_ms * 1e-3) / 1e9,
+               "h2d_gbs_in_step": 2 * nbytes / (e2e_ms * 1e-3) / 1e9, "h2d_gbs_copy_alone": h2d_gbs,
                "api": "slas_cuda_sgemm_batched with pinned host pointers (3-slot H2D/kernel/D2H pipeline)"}
         for p in hp:
             _lib.call("slas_cuda_free_host", p.value)

@@ -172,7 +172,9 @@ def g_bdot():
 
 
 def g_rect():
-    for (m, n, k, dt, log2) in ((2, 2, 3, np.float32, 24), (3, 3, 3, np.float32, 24), (8, 4, 16, np.float32, 22), (16, 32, 8, np.float32, 20),
+    for (m, n, k, dt, log2) in ((2, 2, 3, np.float32, 24), (3, 3, 3, np.float32, 24), (3, 3, 3, np.float64, 24), (2, 2, 2, np.float32, 24),
+                                (4, 4, 2, np.float32, 24), (4, 1, 4, np.float32, 24), (2, 4, 4, np.float64, 24),
+                                (8, 4, 16, np.float32, 22), (16, 32, 8, np.float32, 20),
                                 (12, 12, 12, np.float64, 20), (4, 4, 4, np.float32, 24)):
         b = 1 << log2
         es = np.dtype(dt).itemsize

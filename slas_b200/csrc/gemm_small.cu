@@ -409,8 +409,11 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
                                      float *c, size_t m, size_t n, size_t k, int ta, int tb) {
     if (batch == 0) return SLAS_OK;
     if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
-    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64))
+    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64)) {
+        const int r = launch_gemm_tiny_batched<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+        if (r != SLAS_ERR_UNSUPPORTED) return r;
         return batch >= 64 ? launch_generic_small<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
+    }
     switch (m) {
     case 4:
         // measured on B200 (2^24 pairs): 256 pairs per stage + bulk C store 0.490 ms (1.00 of the HBM copy
@@ -448,8 +451,11 @@ int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batc
                                       double *c, size_t m, size_t n, size_t k, int ta, int tb) {
     if (batch == 0) return SLAS_OK;
     if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
-    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64))
+    if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64)) {
+        const int r = launch_gemm_tiny_batched<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+        if (r != SLAS_ERR_UNSUPPORTED) return r;
         return batch >= 64 ? launch_generic_small<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
+    }
     switch (m) {
     case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<double, CfgD8>(ctx, st, batch, a, b, c, ta, tb);

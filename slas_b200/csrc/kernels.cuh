@@ -33,6 +33,11 @@ int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, si
 int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, void *a,
                              size_t columns, bool *handled);
 
+// gemm_tiny.cu -- every dimension in 1..4: one thread per matrix; SLAS_ERR_UNSUPPORTED otherwise
+template <typename T>
+int launch_gemm_tiny_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                             size_t k, int ta, int tb);
+
 // gemm_small.cu -- batched dense small GEMM; returns SLAS_ERR_UNSUPPORTED when no
 // shape-specialised kernel exists (caller falls back to the generic kernel).
 template <typename T>

@@ -560,6 +560,40 @@ def test_batched_rectangular_shapes_vs_oracle(dt, m, n, k, ta, tb):
         assert np.max(np.abs(dc.to_host().ravel() - want)) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_batched_tiny_shapes_thread_per_matrix(dt, ta, tb):
+    """every (m, n, k) in 1..4 (2x3 . 3x2 of the reference's tests, 3x3, ...): the thread-per-matrix family, with
+    whole and ragged final chunks; batches whose byte size is not a whole number of 16-byte words fall back"""
+    from slas_b200.backends import set_tunable
+    rng = np.random.default_rng(int(ta) * 2 + int(tb))
+    for m in range(1, 5):
+        for n in range(1, 5):
+            for k in range(1, 5):
+                for batch in (1024, 4100, 4098):
+                    A, B = _rand(rng, batch * m * k, dt), _rand(rng, batch * k * n, dt)
+                    want = oracle.gemm_batched(A, B, batch, m, n, k, ta, tb)
+                    dc = CudaBatch(batch + 1, m * n, dt)
+                    _lib_fill = np.full((batch + 1) * m * n, -3.0, dt)
+                    dc.copy_from_host(_lib_fill)
+                    cuda.matrix_mul_batched(CudaVec.from_host(A), CudaVec.from_host(B), dc.view(0, batch * m * n), m, n, k, ta, tb)
+                    got = dc.to_host().ravel()
+                    assert np.max(np.abs(got[:batch * m * n] - want)) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k, (m, n, k, batch)
+                    assert np.all(got[batch * m * n:] == -3.0), (m, n, k, batch)  # nothing written past the last matrix
+    # the same answers as the runtime-shape kernel it replaces (ascending-k FMA chain in both): bit-identical
+    m, n, k, batch = 3, 3, 3, 4096
+    A, B = _rand(rng, batch * m * k, dt), _rand(rng, batch * k * n, dt)
+    c0, c1 = CudaBatch(batch, m * n, dt), CudaBatch(batch, m * n, dt)
+    cuda.matrix_mul_batched(CudaVec.from_host(A), CudaVec.from_host(B), c0, m, n, k, ta, tb)
+    set_tunable("gemm_tiny_variant", 1)
+    try:
+        cuda.matrix_mul_batched(CudaVec.from_host(A), CudaVec.from_host(B), c1, m, n, k, ta, tb)
+    finally:
+        set_tunable("gemm_tiny_variant", 0)
+    assert np.array_equal(c0.to_host(), c1.to_host())
+
+
 def test_batched_view_api_and_integer_exactness():
     # small-integer entries: every product and sum is exact in f32, so == numpy exactly
     rng = np.random.default_rng(3)
