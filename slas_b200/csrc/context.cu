@@ -1,7 +1,10 @@
 // context.cu -- process-global context, error reporting and the device-resident storage
 // entry points of the C ABI (include/slas_cuda.h).  A reference backend is a stateless ZST
 // (src/backends/rust.rs:2-3), so all device state lives here.
+#include <sched.h>
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -267,11 +270,58 @@ int slas_cuda_free(void *dptr) {
     return SLAS_OK;
 }
 
+// CPUs of the NUMA node the device's PCIe root port hangs off (sysfs), or false when the platform does not say.
+static bool device_local_cpus(int device, cpu_set_t *set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) return false;
+    for (char *p = bus; *p; ++p)
+        if (*p >= 'A' && *p <= 'F') *p = (char)(*p - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int n = sscanf(tok, "%d-%d", &lo, &hi);
+        if (n < 1) continue;
+        if (n == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) { CPU_SET(c, set); ++count; }
+    }
+    return count > 0;
+}
+
+// Pinned host memory on the NUMA node next to the current device: the pages are placed by the allocating thread
+// (first touch inside the driver), so the thread is moved onto the device-local CPUs for the duration of the call.
+// With one process per GPU on a two-socket host this is what keeps eight ranks' H2D/D2H traffic off the
+// inter-socket link.  SLAS_CUDA_HOST_NUMA=0 turns it off.
 int slas_cuda_malloc_host(void **hptr, size_t bytes) {
     SLAS_REQUIRE(hptr, "null hptr");
     Context *c;
     SLAS_TRY(get_context(&c));
-    SLAS_CUDA_TRY(cudaMallocHost(hptr, bytes ? bytes : 16));
+    cpu_set_t before, local;
+    bool moved = false;
+    const char *env = getenv("SLAS_CUDA_HOST_NUMA");
+    if (!(env && env[0] == '0') && sched_getaffinity(0, sizeof(before), &before) == 0 && device_local_cpus(c->device, &local)) {
+        cpu_set_t want;
+        CPU_AND(&want, &before, &local);  // never leave the cpuset the process was given
+        if (CPU_COUNT(&want) > 0) moved = sched_setaffinity(0, sizeof(want), &want) == 0;
+    }
+    const cudaError_t e = cudaMallocHost(hptr, bytes ? bytes : 16);
+    if (moved) sched_setaffinity(0, sizeof(before), &before);
+    SLAS_CUDA_TRY(e);
     return SLAS_OK;
 }
 

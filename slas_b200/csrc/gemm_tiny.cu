@@ -196,9 +196,13 @@ int launch_gemm_tiny_batched(Context *ctx, cudaStream_t st, size_t batch, const 
     }
     return SLAS_ERR_UNSUPPORTED;
 }
+// built twice (Makefile): -DSLAS_TINY_F64 selects the double instantiations, so the two halves compile in parallel
+#ifndef SLAS_TINY_F64
 template int launch_gemm_tiny_batched<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *, size_t,
                                              size_t, size_t, int, int);
+#else
 template int launch_gemm_tiny_batched<double>(Context *, cudaStream_t, size_t, const double *, const double *, double *, size_t,
                                               size_t, size_t, int, int);
+#endif
 
 }  // namespace slas
