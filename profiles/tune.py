@@ -146,6 +146,16 @@ def g_crossover():
     sl.set_sgemm_path("auto")
 
 
+def g_dgemm():
+    """large f64 product, all four transposition flags (FP64 pipe bound: 26.6 TFLOP/s measured DFMA peak)"""
+    for n in (1024, 2048, 4096):
+        (_, a), (_, b), (_, c) = uniform(n * n, np.float64, 5), uniform(n * n, np.float64, 6), uniform(n * n, np.float64, 7)
+        for ta in (False, True):
+            for tb in (False, True):
+                report(f"dgemm {n}^3 ta={int(ta)} tb={int(tb)}", timed(lambda: cuda.matrix_mul(a, b, c, n, n, n, n, n, n, ta, tb), 5, 2),
+                       flop=2.0 * n ** 3)
+
+
 def g_gemv():
     for size, dt, log2 in ((4, np.float32, 24), (16, np.float32, 20), (32, np.float32, 20), (16, np.float64, 20), (32, np.float64, 20),
                            (64, np.float32, 18)):
@@ -220,6 +230,7 @@ GROUPS = {
     "transpose": g_transpose,
     "inplace": g_inplace,
     "crossover": g_crossover,
+    "dgemm": g_dgemm,
     "fused": g_fused,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
     "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),

@@ -362,6 +362,22 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
                                             fix_b ? n : ldb, ldc, fix_a ? 1 : ta, fix_b ? 0 : tb);
             }
         }
+        // The DFMA kernels are the other way round (measured at 4096^3, profiles/r1e_tune_dgemm*.log: row-major A and
+        // k-contiguous B 23.8 TFLOP/s, row-major B 22.3, transposed A 14.3 on the 64 x 64 kernel): put both operands
+        // into k-contiguous form first (two HBM-speed transposes, ~1 % of the product's time)
+        if (sizeof(T) == 8 && m * n * k >= ((size_t)1 << 30) && tunable("gemm_large_variant") != 2) {
+            const bool fix_a = ta && lda == m, fix_b = !tb && ldb == n;
+            if (fix_a || fix_b) {
+                void *ws = nullptr;
+                const size_t ea = fix_a ? m * k : 0, eb = fix_b ? n * k : 0;
+                SLAS_TRY(ensure_workspace(ctx, (ea + eb) * sizeof(T), &ws));
+                T *ar = (T *)ws, *br = ar + ea;
+                if (fix_a) SLAS_TRY(launch_transpose(ctx, st, 1, m * k, sizeof(T), a, ar, k));  // [k][m] -> [m][k]
+                if (fix_b) SLAS_TRY(launch_transpose(ctx, st, 1, n * k, sizeof(T), b, br, k));  // [k][n] -> [n][k]
+                return launch_gemm_large<T>(ctx, st, fix_a ? ar : a, fix_b ? br : b, c, m, n, k, fix_a ? k : lda,
+                                            fix_b ? k : ldb, ldc, fix_a ? 0 : ta, fix_b ? 1 : tb);
+            }
+        }
         return launch_gemm_large<T>(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
     }
     return launch_gemm_generic<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);

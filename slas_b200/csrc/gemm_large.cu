@@ -151,8 +151,12 @@ template <typename T>
 int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *c, size_t m, size_t n, size_t k,
                       size_t lda, size_t ldb, size_t ldc, int ta, int tb) {
     using C = LargeCfg<T>;
-    (void)ctx;
     if (m == 0 || n == 0) return SLAS_OK;
+    if constexpr (sizeof(T) == 8) {
+        // at least one full wave of 128 x 128 tiles: the big-tile DFMA kernel (gemm_large_f64.cu)
+        if (((m + 127) / 128) * ((n + 127) / 128) >= (size_t)ctx->sm_count && tunable("gemm_large_variant") != 3)
+            return launch_dgemm_big(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
+    }
     const size_t gx = (n + C::BN - 1) / C::BN, gy = (m + C::BM - 1) / C::BM;
     SLAS_REQUIRE(gx <= 0x7fffffffu && gy <= 65535, "gemm: grid too large (%zu x %zu tiles)", gx, gy);
     const int vec_a = aligned16(a) && (lda * sizeof(T)) % 16 == 0;

@@ -64,6 +64,9 @@ int launch_sgemm_ffma(Context *ctx, cudaStream_t st, const float *a, const float
 
 // gemm_tcgen05.cu -- 3xTF32 on the 5th-gen tensor cores (TMA + TMEM); SLAS_ERR_UNSUPPORTED
 // when the shape does not fit its tiles.
+// gemm_large_f64.cu -- 128 x 128 tiles, 8 x 8 per thread
+int launch_dgemm_big(Context *ctx, cudaStream_t st, const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
+                     size_t lda, size_t ldb, size_t ldc, int ta, int tb);
 // the zero-padded problem size the tcgen05 kernels would run (m, n, k) on, and whether the CTA-pair kernel is used
 void sgemm_3xtf32_padded(size_t m, size_t n, size_t k, size_t *mp, size_t *np, size_t *kp, bool *pair);
 int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m,

@@ -638,6 +638,19 @@ def test_single_gemm_any_shape(dt, m, n, k, ta, tb):
         assert np.max(np.abs(got[:, :n] - want.reshape(m, ldc)[:, :n])) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
 
 
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_large_dgemm(ta, tb):
+    """f64 products from 2^30 multiply-adds up materialise a lazily transposed A first (the DFMA kernel's fast layout)"""
+    rng = np.random.default_rng(31)
+    m, n, k = 1024, 1088, 1024
+    A, B = _rand(rng, m * k, np.float64), _rand(rng, k * n, np.float64)
+    c = CudaVec(m * n, np.float64)
+    cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, m if ta else k, k if tb else n, n, ta, tb)
+    ref, mag = _gemm_truth(A, B, m, n, k, ta, tb)  # numpy f64 (pairwise / blocked sums): well inside the bar itself
+    assert np.all(np.abs(c.to_host() - ref) <= 1e-13 * np.sqrt(k) * mag)
+
+
 @pytest.mark.parametrize("size", [512, 1024])   # 1024^3 and up: operands are first put into the k-major / n-major form
 @pytest.mark.parametrize("ta", [False, True])
 @pytest.mark.parametrize("tb", [False, True])
