@@ -293,7 +293,8 @@ static bool device_local_cpus(int device, cpu_set_t *set) {
     if (!ok) return false;
     CPU_ZERO(set);
     int count = 0;
-    for (char *tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    char *save = nullptr;
+    for (char *tok = strtok_r(list, ",\n", &save); tok; tok = strtok_r(nullptr, ",\n", &save)) {
         int lo = 0, hi = 0;
         const int n = sscanf(tok, "%d-%d", &lo, &hi);
         if (n < 1) continue;

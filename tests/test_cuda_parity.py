@@ -744,7 +744,11 @@ def test_gemv_vs_oracle(dt, rows, cols, ta):
 
 # ---- batched dot / norm / normalize --------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5)])
+@pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
+                                          # register-resident normalize: warp / CTA per vector, ragged piece counts,
+                                          # more vectors than groups in the grid; and the lengths either side of it
+                                          (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
+                                          (32768, 5), (32772, 3), (65536, 3)])
 def test_batched_reductions(dt, length, batch):
     rng = np.random.default_rng(length + batch)
     a, b = _rand(rng, batch * length, dt), _rand(rng, batch * length, dt)
