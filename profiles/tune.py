@@ -156,6 +156,31 @@ def g_dgemm():
                        flop=2.0 * n ** 3)
 
 
+def g_e2e():
+    """host-pointer pipeline (pinned operands through the C ABI): slot size sweep on the headline workload"""
+    import ctypes as C
+    import time
+    b = 1 << 24
+    nbytes = b * 64
+    hp = [C.c_void_p() for _ in range(3)]
+    for p in hp:
+        _lib.call("slas_cuda_malloc_host", C.byref(p), nbytes)
+    hA, hB, hC = [np.ctypeslib.as_array((C.c_float * (b * 16)).from_address(p.value)) for p in hp]
+    hA[:] = 0.5
+    hB[:] = 0.25
+    for mb in (0, 16, 32, 48, 64, 128, 192):
+        set_tunable("host_slot_mb", mb)
+        cuda.matrix_mul_batched(hA, hB, hC, 4, 4, 4)
+        t0 = time.perf_counter()
+        for _ in range(4):
+            cuda.matrix_mul_batched(hA, hB, hC, 4, 4, 4)
+        ms = (time.perf_counter() - t0) * 1e3 / 4
+        report(f"e2e 4x4 f32 2^24 pinned host operands, slot {mb or 96} MB", ms, nbytes=3.0 * nbytes, flop=128.0 * b)
+    set_tunable("host_slot_mb", 0)
+    for p in hp:
+        _lib.call("slas_cuda_free_host", p.value)
+
+
 def g_gemv():
     for size, dt, log2 in ((4, np.float32, 24), (16, np.float32, 20), (32, np.float32, 20), (16, np.float64, 20), (32, np.float64, 20),
                            (64, np.float32, 18)):
@@ -231,6 +256,7 @@ GROUPS = {
     "transpose": g_transpose,
     "inplace": g_inplace,
     "crossover": g_crossover,
+    "e2e": g_e2e,
     "dgemm": g_dgemm,
     "fused": g_fused,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),

@@ -61,7 +61,9 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
     if (units == 0) return SLAS_OK;
     size_t unit_total = 0;
     for (int i = 0; i < n; ++i) unit_total += ops[i].unit_bytes;
-    constexpr size_t kSlotBytes = (size_t)96 << 20;
+    // 96 MB slots by default; "host_slot_mb" is the sweep knob (profiles/tune.py e2e)
+    const long slot_mb = tunable("host_slot_mb");
+    const size_t kSlotBytes = (size_t)(slot_mb > 0 ? slot_mb : 96) << 20;
     size_t chunk = kSlotBytes / (unit_total ? unit_total : 1);
     chunk = chunk / granule * granule;
     if (chunk == 0) chunk = granule;
