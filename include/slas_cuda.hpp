@@ -79,6 +79,42 @@ template <class T, std::size_t N> struct static_vec_traits<CudaVec<T, N>> {
     static T *mut_ptr(CudaVec<T, N> &v) { return v.as_mut_ptr(); }
 };
 
+// `StaticCowVec<'a, T, LEN>` (src/lib.rs:395-456; StaticVec impl src/static_vec.rs:294-319): borrows a host array
+// until the first mutable access, which copies it ("moo": copy on write).  as_ptr() never copies.
+template <class T, std::size_t N> class StaticCowVec {
+  public:
+    static constexpr std::size_t LEN = N;
+    using value_type = T;
+    explicit StaticCowVec(const std::array<T, N> &borrowed) : borrowed_(&borrowed) {}
+    static StaticCowVec from_owned(const std::array<T, N> &a) {
+        StaticCowVec v(a);
+        v.owned_ = a;
+        v.borrowed_ = nullptr;
+        return v;
+    }
+    bool is_owned() const { return borrowed_ == nullptr; }
+    bool is_borrowed() const { return !is_owned(); }
+    const T *as_ptr() const { return is_owned() ? owned_.data() : borrowed_->data(); }
+    T *as_mut_ptr() {  // deref_mut: `self.data.owned = *self.data.borrowed` (src/lib.rs:446-455)
+        if (!is_owned()) {
+            owned_ = *borrowed_;
+            borrowed_ = nullptr;
+        }
+        return owned_.data();
+    }
+    const T &operator[](std::size_t i) const { return as_ptr()[i]; }
+
+  private:
+    const std::array<T, N> *borrowed_;
+    std::array<T, N> owned_{};
+};
+template <class T, std::size_t N> struct static_vec_traits<StaticCowVec<T, N>> {
+    using value_type = T;
+    static constexpr std::size_t LEN = N;
+    static const T *ptr(const StaticCowVec<T, N> &v) { return v.as_ptr(); }
+    static T *mut_ptr(StaticCowVec<T, N> &v) { return v.as_mut_ptr(); }
+};
+
 template <class V> using elem_t = typename static_vec_traits<std::remove_cv_t<std::remove_reference_t<V>>>::value_type;
 template <class V> constexpr std::size_t len_v = static_vec_traits<std::remove_cv_t<std::remove_reference_t<V>>>::LEN;
 template <class V> const elem_t<V> *ptr_of(const V &v) { return static_vec_traits<V>::ptr(v); }

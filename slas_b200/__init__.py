@@ -5,11 +5,11 @@ interface for that path (backends.Cuda, static_vec.CudaVec/CudaBatch, tensor.Mat
 from . import _lib
 from .backends import (Cuda, WithStaticBackend, device_count, device_info, launch_count, set_sgemm_path, set_stream,
                        synchronize)
-from .static_vec import CudaBatch, CudaVec, moo
+from .static_vec import CudaBatch, CudaVec, StaticCowVec, moo
 from .tensor import BatchedMatrix, Matrix, MatrixShape, Tensor, matrix, reshape, tensor_index
 
 slas_backend = type("slas_backend", (), {"Cuda": Cuda})
 
-__all__ = ["Cuda", "WithStaticBackend", "CudaVec", "CudaBatch", "moo", "Matrix", "BatchedMatrix", "MatrixShape",
+__all__ = ["Cuda", "WithStaticBackend", "CudaVec", "CudaBatch", "StaticCowVec", "moo", "Matrix", "BatchedMatrix", "MatrixShape",
            "Tensor", "matrix", "reshape", "tensor_index", "device_count", "device_info", "launch_count",
            "set_sgemm_path", "set_stream", "synchronize", "slas_backend"]

@@ -18,7 +18,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .static_vec import CudaBatch, CudaVec, operand, prefix
+from .static_vec import CudaBatch, CudaVec, StaticCowVec, operand, prefix
 
 _REAL = {np.dtype(np.float32): np.float32, np.dtype(np.float64): np.float64,
          np.dtype(np.complex64): np.float32, np.dtype(np.complex128): np.float64}
@@ -63,6 +63,14 @@ class Cuda:
         return out[0]
 
     def normalize(self, a) -> None:
+        if isinstance(a, StaticCowVec) and a.is_borrowed() and prefix(a.dtype) in "sd":
+            # the copy-on-write copy (static_vec.rs:304-318) and the normalize in one pass: the owned side is written
+            # directly with source / norm(source) instead of being copied first and scaled in place afterwards
+            src = a.moo_ref()
+            dst = CudaVec(a.LEN, a.dtype) if isinstance(src, CudaVec) else np.empty_like(src)
+            self.normalize_into(src, dst)
+            a.adopt(dst)
+            return
         pa, la, dt, ka = operand(a, writable=True)
         _lib.call(f"slas_cuda_{prefix(dt)}normalize", la, pa)
 

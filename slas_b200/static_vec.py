@@ -154,10 +154,73 @@ class CudaBatch(CudaVec):
                          _ptr=self._ptr + lo * self.OBJ_LEN * self.dtype.itemsize, _owner=self)
 
 
+class StaticCowVec:
+    """`StaticCowVec<'a, T, LEN>` (src/lib.rs:395-456; its StaticVec impl src/static_vec.rs:294-319): borrows its
+    source -- a host array or a device-resident CudaVec -- until the first MUTABLE access (`as_mut_ptr` /
+    `mut_moo_ref`), which copies it; `as_ptr` / `moo_ref` never copy."""
+
+    def __init__(self, source, *, owned: bool = False):
+        assert isinstance(source, (np.ndarray, CudaVec)), "a StaticCowVec wraps a host array or a CudaVec"
+        self._data = source
+        self._owned = bool(owned)
+
+    @classmethod
+    def from_owned(cls, data) -> "StaticCowVec":
+        return cls(data, owned=True)
+
+    def is_owned(self) -> bool:
+        return self._owned
+
+    def is_borrowed(self) -> bool:
+        return not self._owned
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+    @property
+    def LEN(self) -> int:
+        return self._data.LEN if isinstance(self._data, CudaVec) else self._data.size
+
+    def __len__(self) -> int:
+        return self.LEN
+
+    def moo_ref(self):
+        return self._data
+
+    def mut_moo_ref(self):
+        """deref_mut (src/lib.rs:446-455): `self.data.owned = *self.data.borrowed` on first use."""
+        if not self._owned:
+            if isinstance(self._data, CudaVec):
+                copy = CudaVec(self._data.LEN, self._data.dtype)
+                _lib.call("slas_cuda_memcpy_d2d", copy.as_ptr(), self._data.as_ptr(), self._data.nbytes)
+                self._data = copy
+            else:
+                self._data = np.array(self._data, copy=True)
+            self._owned = True
+        return self._data
+
+    def adopt(self, owned_data) -> None:
+        """Become owned with `owned_data` as the storage (a fused op already produced the mutated copy)."""
+        self._data = owned_data
+        self._owned = True
+
+    def as_ptr(self) -> int:
+        return operand(self._data)[0]
+
+    def as_mut_ptr(self) -> int:
+        return operand(self.mut_moo_ref(), writable=True)[0]
+
+    def to_host(self) -> np.ndarray:
+        return self._data.to_host() if isinstance(self._data, CudaVec) else np.array(self._data, copy=True)
+
+
 def operand(x, dtype=None, *, writable: bool = False, any_copy_type: bool = False):
     """(pointer, length, dtype, keepalive) of anything that satisfies the StaticVec contract.
     any_copy_type: accept any fixed-size element (Transpose is generic over T: Copy), not only the four
     number types the arithmetic backends are registered for."""
+    if isinstance(x, StaticCowVec):  # a mutable access copies a borrowed vector first (static_vec.rs:304-318)
+        return operand(x.mut_moo_ref() if writable else x.moo_ref(), dtype, writable=writable, any_copy_type=any_copy_type)
     if isinstance(x, CudaVec):
         if dtype is not None and x.dtype != np.dtype(dtype):
             raise TypeError(f"operand is {x.dtype}, expected {np.dtype(dtype)}")

@@ -219,6 +219,17 @@ int main() {
         for (int i = 0; i < 4; ++i) CHECK(b[i] == a[i] / n);
     });
 
+    // ---- StaticCowVec: copy on first mutable access (src/lib.rs:433-456, static_vec.rs:294-319) ----
+    run("moo::copy on write (lib.rs:255-268 doc example, on Cuda)", [] {
+        std::array<float, 3> source{1, 2, 3};
+        StaticCowVec<float, 3> v(source);
+        CHECK(v.is_borrowed() && v.as_ptr() == source.data());
+        CHECK(Cuda{}.dot(v, source) == 14.f && v.is_borrowed());  // reads never copy
+        Cuda{}.normalize(v);                                       // mutable access: copies, the source is untouched
+        CHECK(v.is_owned() && source[2] == 3.f);
+        const float n = Cuda{}.norm(source);
+        for (int i = 0; i < 3; ++i) CHECK(v[i] == source[i] / n);
+    });
     // ---- fused chains and the 1-/2-byte transposes: same answers as the op sequences of the cases above ----
     run("fused: add -> dot equals the chain (main.rs:41-46 operands)", [] {
         std::array<float, 4> a{0, 1, 2, 3}, b{0, -1, -2, 3}, d{1, 2, 3, 4}, c{}, t{};

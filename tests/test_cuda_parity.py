@@ -371,6 +371,26 @@ def test_normalize_into_is_normalize_of_a_copy(dt, n):
     assert np.array_equal(h, ref.to_host())
 
 
+def test_static_cow_vec_on_the_device():
+    """a borrowed StaticCowVec over device memory: reads never copy, normalize writes the owned side in one fused
+    pass (normalize_into) and leaves the source untouched; other mutable uses copy device-to-device first"""
+    from slas_b200.static_vec import StaticCowVec
+    a = _rand(np.random.default_rng(9), 5000, np.float32)
+    src = CudaVec.from_host(a)
+    v = StaticCowVec(src)
+    assert cuda.dot(v, src).tobytes() == cuda.dot(src, src).tobytes() and v.is_borrowed()
+    cuda.normalize(v)
+    ref = CudaVec.from_host(a)
+    cuda.normalize(ref)
+    assert v.is_owned() and np.array_equal(v.to_host(), ref.to_host()) and np.array_equal(src.to_host(), a)
+    w = StaticCowVec(src)
+    cuda.add(src, src, w)  # output operand: as_mut_ptr -> copy, then overwritten
+    assert w.is_owned() and np.array_equal(w.to_host(), a + a) and np.array_equal(src.to_host(), a)
+    h = StaticCowVec(a)  # host source
+    cuda.normalize(h)
+    assert h.is_owned() and np.array_equal(h.to_host(), ref.to_host()) and a[0] == src.to_host()[0]
+
+
 # ---- transpose: bit-exact for any Copy element --------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48), (128, 64), (192, 320), (1024, 512)])

@@ -214,3 +214,25 @@ def test_moo_and_static_backend():
     ro.flags.writeable = False
     with pytest.raises(ValueError):
         Cuda().normalize(ro)  # `&T` implementors panic on as_mut_ptr (src/static_vec.rs:252-258)
+
+
+def test_static_cow_vec_copies_on_first_mutable_access():
+    """src/lib.rs:433-456 + src/static_vec.rs:294-319: as_ptr / moo_ref never copy; as_mut_ptr / mut_moo_ref copy a
+    borrowed vector once, after which it is owned (the README's `moo` example, lib.rs:255-268)."""
+    from slas_b200.static_vec import StaticCowVec, operand
+    source = np.array([1.0, 2.0, 3.0], np.float32)
+    v = StaticCowVec(source)
+    assert v.is_borrowed() and not v.is_owned() and v.LEN == 3 and len(v) == 3
+    assert v.as_ptr() == source.ctypes.data and v.moo_ref() is source
+    assert operand(v)[0] == source.ctypes.data and v.is_borrowed()          # read access through the backend
+    p = operand(v, writable=True)[0]                                         # mutable access: the copy happens here
+    assert v.is_owned() and p != source.ctypes.data and p == v.as_mut_ptr() == v.as_ptr()
+    v.mut_moo_ref()[0] = 9.0
+    assert source[0] == 1.0 and v.moo_ref()[0] == 9.0                        # the source is untouched
+    owned = StaticCowVec.from_owned(np.zeros(4, np.float64))
+    q = owned.as_ptr()
+    assert owned.is_owned() and owned.as_mut_ptr() == q                      # an owned vector is never copied
+    ro = np.arange(3, dtype=np.float32)
+    ro.flags.writeable = False
+    w = StaticCowVec(ro)                                                     # borrowing an immutable source is the point
+    assert operand(w, writable=True)[3].flags.writeable and ro[1] == 1.0
