@@ -36,6 +36,13 @@ def transpose_batched(size, dt, log2):
     synchronize()
 
 
+def transpose_single(side, dt):
+    a, c = CudaVec(side * side, dt).zero_(), CudaVec(side * side, dt)
+    for _ in range(2):
+        cuda.transpose(a, c, side)
+    synchronize()
+
+
 def vector_ops():
     n = 1 << 28
     a, b, c = uniform(n, np.float32, 3, 0, 1), uniform(n, np.float32, 4, 0, 1), CudaVec(n, np.float32)
@@ -66,6 +73,8 @@ TARGETS = {
     "tr16_f32": lambda: transpose_batched(16, np.float32, 20),
     "tr32_f32": lambda: transpose_batched(32, np.float32, 20),
     "tr32_f64": lambda: transpose_batched(32, np.float64, 20),
+    "tr_u8": lambda: transpose_single(8192, np.uint8),
+    "tr_i16": lambda: transpose_single(8192, np.int16),
     "vector": vector_ops,
     "gemm4096_ffma": lambda: gemm_large("ffma"),
     "gemm4096_tc": lambda: gemm_large("tcgen05"),

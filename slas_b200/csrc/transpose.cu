@@ -120,6 +120,65 @@ transpose_tiled64_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__
     }
 }
 
+// ---- (1c) tiled, 1- and 2-byte elements: 128-byte rows in, 32-byte sectors out ---------------------------------
+// The element-granular kernels move one narrow element per thread and instruction (0.22 / 0.44 of HBM peak for
+// 1- / 2-byte elements).  Here a tile is 128 x 128 elements: row segments of 128 * sizeof(E) bytes in and out.  Warps read whole input rows as 32-bit words into shared memory; then a lane owns one WORD COLUMN (EPW =
+// 4 / sizeof(E) input columns = EPW output rows) of one sector's worth of input rows (32 / sizeof(E)): it reads that
+// column word by word (consecutive lanes, consecutive words: conflict-free), transposes each EPW x EPW element
+// block in registers with byte permutes (PRMT), and ends up holding one complete 32-byte sector for each of its EPW
+// output rows, which leave with 256-bit stores.  Whole tiles only: rows % T == 0, columns % 128 == 0, 32-byte bases.
+// With 2-byte elements a lane does this for two word columns (lane, lane + 32).  Measured: 0.66-0.73 (1-byte) and
+// 0.55 (2-byte) of HBM peak at 8192^2 .. 16384^2, against 0.23 / 0.46 before; loads stall on DRAM latency (ncu: long
+// scoreboard) -- narrow row segments at large strides, not instruction issue, are what is left.
+template <typename E>
+__global__ void __launch_bounds__(256)
+transpose_tiled_narrow_kernel(const E *__restrict__ in, E *__restrict__ out, size_t len, unsigned rows, unsigned columns,
+                              unsigned tiles_r, unsigned tiles_c) {
+    constexpr unsigned WPL = sizeof(E);                // word columns per lane (measured best: 1-byte 1, 2-byte 2)
+    constexpr unsigned T = WPL * 128 / sizeof(E);      // tile width in elements (input columns)
+    constexpr unsigned TRI = 128;                      // tile height (input rows): output row segments of 128 * sizeof(E) bytes
+    constexpr unsigned RPS = 32 / sizeof(E);           // input rows per 32-byte output sector
+    constexpr unsigned NW = TRI / RPS;                 // warps = sectors per output row segment (4 / 8)
+    constexpr unsigned EPW = 4 / sizeof(E);            // elements per 32-bit word
+    __shared__ uint32_t sm[TRI][32 * WPL];
+    size_t bid = blockIdx.x;
+    const unsigned tr = (unsigned)(bid % tiles_r); bid /= tiles_r;
+    const unsigned tc = (unsigned)(bid % tiles_c); bid /= tiles_c;
+    const E *src = in + bid * len;
+    E *dst = out + bid * len;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;  // NW warps = the sectors of an output row segment
+    // input: `columns` rows of `rows` elements; this tile = input rows [tc*TRI, +TRI), input columns [tr*T, +T)
+    for (unsigned r = warp; r < TRI; r += NW) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(src + (size_t)(tc * TRI + r) * rows + tr * T);
+#pragma unroll
+        for (unsigned h = 0; h < WPL; ++h) sm[r][lane + 32 * h] = __ldcs(row + lane + 32 * h);
+    }
+    __syncthreads();
+#pragma unroll
+    for (unsigned h = 0; h < WPL; ++h) {
+        const unsigned wc = lane + 32 * h;  // word column = output rows wc * EPW + k
+        uint32_t o[EPW][8];                 // o[k] = the sector of output row wc * EPW + k
+#pragma unroll
+        for (unsigned q = 0; q < 8; ++q) {
+            const unsigned r0 = warp * RPS + q * EPW;  // first of the EPW input rows that make output word q
+            if constexpr (sizeof(E) == 1) {
+                const uint32_t w0 = sm[r0][wc], w1 = sm[r0 + 1][wc], w2 = sm[r0 + 2][wc], w3 = sm[r0 + 3][wc];
+                const uint32_t a = __byte_perm(w0, w1, 0x5140), b = __byte_perm(w0, w1, 0x7362);
+                const uint32_t c = __byte_perm(w2, w3, 0x5140), d = __byte_perm(w2, w3, 0x7362);
+                o[0][q] = __byte_perm(a, c, 0x5410); o[1][q] = __byte_perm(a, c, 0x7632);
+                o[2][q] = __byte_perm(b, d, 0x5410); o[3][q] = __byte_perm(b, d, 0x7632);
+            } else {
+                const uint32_t w0 = sm[r0][wc], w1 = sm[r0 + 1][wc];
+                o[0][q] = __byte_perm(w0, w1, 0x5410); o[1][q] = __byte_perm(w0, w1, 0x7632);
+            }
+        }
+#pragma unroll
+        for (unsigned k = 0; k < EPW; ++k)
+            st256(reinterpret_cast<uint32_t *>(dst + (size_t)(tr * T + wc * EPW + k) * columns + tc * TRI + warp * RPS), o[k][0],
+                  o[k][1], o[k][2], o[k][3], o[k][4], o[k][5], o[k][6], o[k][7]);
+    }
+}
+
 // ---- (2) warp per small object ---------------------------------------------------------------
 // INPLACE: in == out is allowed (the warp holds the whole object in shared memory before it writes), and
 // the elements past rows*columns are zeroed like the reference's zero-initialised temporary (rust.rs:157-159).
@@ -429,6 +488,20 @@ static int launch_transpose_typed(Context *ctx, cudaStream_t st, size_t batch, s
         if (variant == 5 && n % (4 * VW) == 0) return launch_square_vec<E, VW, 4, false>(ctx, st, batch, n, a, buffer);
         return launch_square_vec<E, VW, 1, true>(ctx, st, batch, n, a, buffer);
       }
+    }
+    // (1c) narrow elements in whole 128-byte tiles
+    if constexpr (sizeof(E) <= 2) {
+        SLAS_REQUIRE(rows <= 0xffffffffu && columns <= 0xffffffffu, "transpose: dimension too large");
+        constexpr size_t T = 128, TRI = 128;  // tile: 128 input rows of 128 elements
+        if (rows % T == 0 && columns % TRI == 0 && len == rows * columns && (uintptr_t)a % 32 == 0 && (uintptr_t)buffer % 32 == 0 &&
+            tunable("transpose_variant") != 1) {
+            const size_t t_r = rows / T, t_c = columns / TRI, nb = batch * t_r * t_c;
+            SLAS_REQUIRE(nb <= 0x7fffffffu, "transpose: too many tiles (%zu)", nb);
+            transpose_tiled_narrow_kernel<E><<<(unsigned)nb, 32 * (TRI * sizeof(E) / 32), 0, st>>>(a, buffer, len, (unsigned)rows, (unsigned)columns,
+                                                                          (unsigned)t_r, (unsigned)t_c);
+            SLAS_LAUNCH_CHECK();
+            return SLAS_OK;
+        }
     }
     // (2) small objects: padded tile must fit the per-warp shared slice
     const size_t padded = columns * (rows + 1);

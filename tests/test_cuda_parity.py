@@ -506,6 +506,24 @@ def test_small_gemm_benchmark_variants_keep_parity(knob, size, dt, variants):
         set_tunable(knob, 0)
 
 
+@pytest.mark.parametrize("dt", [np.uint8, np.int16])
+@pytest.mark.parametrize("rows,cols,batch", [(128, 128, 1), (128, 256, 3), (384, 128, 2), (64, 64, 5), (64, 128, 2), (64, 384, 2),
+                                             (256, 128, 2), (512, 256, 3), (768, 128, 1), (1024, 2048, 1), (128, 192, 1), (192, 128, 3)])
+def test_transpose_narrow_elements_tiled(dt, rows, cols, batch):
+    """1- and 2-byte elements in whole 128-byte tiles: word loads, byte gathers, 256-bit sector stores"""
+    e = rows * cols
+    a = (np.arange(batch * e, dtype=np.int64) * 2654435761 >> 9).astype(dt)
+    want = np.concatenate([oracle.transpose(a[i * e:(i + 1) * e], cols) for i in range(batch)])
+    buf = CudaBatch(batch, e, dt)
+    cuda.transpose_batched(CudaVec.from_host(a), buf, e, cols)
+    assert buf.to_host().ravel().tobytes() == want.tobytes()
+    # a base that is only element-aligned takes the element-granular kernels: same bytes
+    big = CudaVec.from_host(np.concatenate([np.zeros(1, dt), a]))
+    out = CudaVec((batch * e) + 1, dt).zero_()
+    cuda.transpose_batched(big.view(1, batch * e), out.view(1, batch * e), e, cols)
+    assert out.to_host()[1:].tobytes() == want.tobytes()
+
+
 def test_transpose_ragged_len_leaves_tail_untouched():
     a = np.arange(11, dtype=np.float32)  # columns = 3 -> rows = 3, elements 9, 10 never written (rust.rs:168-175)
     buf = np.full(11, -7.0, np.float32)
