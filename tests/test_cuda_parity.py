@@ -759,7 +759,8 @@ def test_large_sgemm_automatic_path_choice():
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (3, 2), (2, 3), (16, 16), (33, 100), (257, 64), (4, 4), (32, 32), (64, 16),
-                                       (2, 128), (128, 8), (1, 4), (256, 64), (64, 128), (300, 1024), (1000, 516), (2048, 2048)])
+                                       (2, 128), (128, 8), (1, 4), (256, 64), (64, 128), (300, 1024), (1000, 516), (2048, 2048),
+                                       (5, 24), (7, 40), (3, 256)])  # lane-per-row kernel: any row count, rows of whole 32-byte chunks
 @pytest.mark.parametrize("ta", [False, True])
 def test_gemv_vs_oracle(dt, rows, cols, ta):
     rng = np.random.default_rng(rows + cols)
@@ -783,8 +784,8 @@ def test_gemv_vs_oracle(dt, rows, cols, ta):
 # ---- batched dot / norm / normalize --------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
-                                          # register-resident normalize: warp / CTA per vector, ragged piece counts,
-                                          # more vectors than groups in the grid; and the lengths either side of it
+                                          # warp / CTA per vector with ragged piece counts, more vectors than groups in
+                                          # the grid, and the lengths either side of every kernel switch
                                           (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
                                           (32768, 5), (32772, 3), (65536, 3)])
 def test_batched_reductions(dt, length, batch):
