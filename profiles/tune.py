@@ -195,7 +195,8 @@ def g_gemv():
 def g_bdot():
     for length, log2, dt in ((1 << 20, 8, np.float32), (1 << 16, 12, np.float32), (1 << 15, 13, np.float32), (1 << 14, 14, np.float32),
                              (4096, 16, np.float32), (2048, 17, np.float32), (2048, 16, np.float64), (1 << 14, 13, np.float64),
-                             (256, 20, np.float32), (16, 24, np.float32), (1 << 20, 7, np.float64)):
+                             (256, 20, np.float32), (64, 22, np.float32), (16, 24, np.float32), (8, 24, np.float32), (16, 23, np.float64),
+                             (1 << 20, 7, np.float64)):
         b = 1 << log2
         es = np.dtype(dt).itemsize
         (_, a), (_, bb), (_, o) = uniform(b * length, dt, 1), uniform(b * length, dt, 2), uniform(b, dt, 3)

@@ -784,6 +784,7 @@ def test_gemv_vs_oracle(dt, rows, cols, ta):
 # ---- batched dot / norm / normalize --------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
+                                          (4, 3001), (8, 777), (24, 1025), (32, 33), (40, 999), (64, 257), (72, 100),  # a lane per vector (<= 256 bytes)
                                           # warp / CTA per vector with ragged piece counts, more vectors than groups in
                                           # the grid, and the lengths either side of every kernel switch
                                           (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
