@@ -322,6 +322,110 @@ template <class B, std::size_t M, std::size_t K, class U> Matrix<U, B, M, K> mat
     return Matrix<U, B, M, K>(data);
 }
 
+// ---- batched views: `[[T; LEN]; batch]` contiguous, the static object shape as template parameters -------------------
+// north_star's "batched view over many same-shape objects": what a slas user holds as a slice of static vectors /
+// matrices and loops over today (a loop of Matrix::matrix_mul calls, src/tensor.rs:441-454).  Storage is either
+// device-resident (CudaBatch) or a host buffer (HostBatch: staged by the library's H2D / kernel / D2H pipeline).
+template <class T, std::size_t OBJ_LEN> class CudaBatch {
+  public:
+    using value_type = T;
+    static constexpr std::size_t LEN = OBJ_LEN;
+    explicit CudaBatch(std::size_t batch) : batch_(batch) { check(slas_cuda_malloc(reinterpret_cast<void **>(&p_), bytes())); }
+    CudaBatch(std::size_t batch, const T *host) : CudaBatch(batch) { check(slas_cuda_memcpy_h2d(p_, host, bytes())); }
+    CudaBatch(const CudaBatch &) = delete;
+    CudaBatch &operator=(const CudaBatch &) = delete;
+    CudaBatch(CudaBatch &&o) noexcept : p_(o.p_), batch_(o.batch_) { o.p_ = nullptr; }
+    ~CudaBatch() { slas_cuda_free(p_); }
+    std::size_t batch() const { return batch_; }
+    std::size_t bytes() const { return batch_ * OBJ_LEN * sizeof(T); }
+    const T *as_ptr() const { return p_; }
+    T *as_mut_ptr() { return p_; }
+    void to_host(T *out) const { check(slas_cuda_memcpy_d2h(out, p_, bytes())); }
+
+  private:
+    T *p_ = nullptr;
+    std::size_t batch_;
+};
+template <class T, std::size_t OBJ_LEN> class HostBatch {  // non-owning view of caller memory
+  public:
+    using value_type = T;
+    static constexpr std::size_t LEN = OBJ_LEN;
+    HostBatch(T *data, std::size_t batch) : p_(data), batch_(batch) {}
+    std::size_t batch() const { return batch_; }
+    const T *as_ptr() const { return p_; }
+    T *as_mut_ptr() { return p_; }
+
+  private:
+    T *p_;
+    std::size_t batch_;
+};
+
+// Batch of dense M x K matrices with the lazy-transpose flag of Matrix (tensor.rs:512-522): the flag is passed to the
+// batched kernel as a_trans / b_trans, never materialised.
+template <class S, class B, std::size_t M, std::size_t K, bool IS_TRANS = false> class BatchedMatrix {
+  public:
+    using T = typename S::value_type;
+    static_assert(S::LEN == M * K, "Cannot reshape the objects of this batch as M x K matrices");
+    explicit BatchedMatrix(S &storage) : s_(&storage) {}
+    static constexpr std::size_t rows() { return IS_TRANS ? K : M; }
+    static constexpr std::size_t columns() { return IS_TRANS ? M : K; }
+    std::size_t batch() const { return s_->batch(); }
+    BatchedMatrix<S, B, M, K, !IS_TRANS> transpose() const { return BatchedMatrix<S, B, M, K, !IS_TRANS>(*s_); }
+    const S &storage() const { return *s_; }
+    // C_i = op(A_i) . op(B_i) for every i: one batched kernel launch
+    template <class S2, std::size_t M2, std::size_t K2, bool T2, class S3>
+    void matrix_mul_buffer(const BatchedMatrix<S2, B, M2, K2, T2> &other, S3 &buffer) const {
+        constexpr std::size_t m = rows(), k = BatchedMatrix<S2, B, M2, K2, T2>::rows(), n = BatchedMatrix<S2, B, M2, K2, T2>::columns();
+        static_assert(columns() == k, "BatchedMatrix::matrix_mul: inner dimensions differ");
+        static_assert(S3::LEN == m * n, "BatchedMatrix::matrix_mul_buffer: buffer objects of the wrong length");
+        SLAS_ASSERT(other.batch() == batch() && buffer.batch() == batch(), "BatchedMatrix::matrix_mul: batches differ");
+        if constexpr (std::is_same_v<T, float>)
+            check(slas_cuda_sgemm_batched(batch(), s_->as_ptr(), other.storage().as_ptr(), buffer.as_mut_ptr(), m, n, k, IS_TRANS, T2));
+        else
+            check(slas_cuda_dgemm_batched(batch(), s_->as_ptr(), other.storage().as_ptr(), buffer.as_mut_ptr(), m, n, k, IS_TRANS, T2));
+    }
+    // y_i = op(A_i) . x_i; the C ABI takes the trait's m = width, n = height (tensor.rs:428-437)
+    template <class S2, class S3> void vector_mul_buffer(const S2 &x, S3 &y) const {
+        static_assert(S2::LEN == columns() && S3::LEN == rows(), "BatchedMatrix::vector_mul: vector lengths differ from the matrix");
+        SLAS_ASSERT(x.batch() == batch() && y.batch() == batch(), "BatchedMatrix::vector_mul: batches differ");
+        if constexpr (std::is_same_v<T, float>) check(slas_cuda_sgemv_batched(batch(), s_->as_ptr(), x.as_ptr(), y.as_mut_ptr(), K, M, IS_TRANS));
+        else check(slas_cuda_dgemv_batched(batch(), s_->as_ptr(), x.as_ptr(), y.as_mut_ptr(), K, M, IS_TRANS));
+    }
+    // every object transposed out of place / in place (Matrix::deref_mut per object, tensor.rs:546-564)
+    template <class S3> void materialize_transpose(S3 &buffer) const {
+        static_assert(S3::LEN == M * K, "BatchedMatrix::materialize_transpose: buffer objects of the wrong length");
+        check(slas_cuda_transpose_batched(batch(), M * K, sizeof(T), s_->as_ptr(), buffer.as_mut_ptr(), M));
+    }
+    void materialize_transpose_inplace() { check(slas_cuda_transpose_inplace_batched(batch(), M * K, sizeof(T), s_->as_mut_ptr(), M)); }
+
+  private:
+    S *s_;
+};
+template <class B, std::size_t M, std::size_t K, class S> BatchedMatrix<S, B, M, K> batched_matrix(S &storage) {
+    return BatchedMatrix<S, B, M, K>(storage);
+}
+
+// batched DotProduct / Normalize over the objects of a batch
+template <class S, class O> void dot_batched(const S &a, const S &b, O &out) {
+    using T = typename S::value_type;
+    static_assert(O::LEN == 1, "dot_batched: one result per object");
+    SLAS_ASSERT(a.batch() == b.batch() && out.batch() == a.batch(), "dot_batched: batches differ");
+    if constexpr (std::is_same_v<T, float>) check(slas_cuda_sdot_batched(a.batch(), S::LEN, a.as_ptr(), b.as_ptr(), out.as_mut_ptr()));
+    else check(slas_cuda_ddot_batched(a.batch(), S::LEN, a.as_ptr(), b.as_ptr(), out.as_mut_ptr()));
+}
+template <class S, class O> void norm_batched(const S &a, O &out) {
+    using T = typename S::value_type;
+    static_assert(O::LEN == 1, "norm_batched: one result per object");
+    SLAS_ASSERT(out.batch() == a.batch(), "norm_batched: batches differ");
+    if constexpr (std::is_same_v<T, float>) check(slas_cuda_snrm2_batched(a.batch(), S::LEN, a.as_ptr(), out.as_mut_ptr()));
+    else check(slas_cuda_dnrm2_batched(a.batch(), S::LEN, a.as_ptr(), out.as_mut_ptr()));
+}
+template <class S> void normalize_batched(S &a) {
+    using T = typename S::value_type;
+    if constexpr (std::is_same_v<T, float>) check(slas_cuda_snormalize_batched(a.batch(), S::LEN, a.as_mut_ptr()));
+    else check(slas_cuda_dnormalize_batched(a.batch(), S::LEN, a.as_mut_ptr()));
+}
+
 namespace slas_backend = backends;
 
 }  // namespace slas

@@ -219,6 +219,76 @@ int main() {
         for (int i = 0; i < 4; ++i) CHECK(b[i] == a[i] / n);
     });
 
+    // ---- batched views: the matrix cases above over [[T; LEN]; batch], device-resident and host storage ----
+    run("batched: matrix_multiplication (main.rs:289-301) x 1000 objects, lazy transposes, gemv, transposes", [] {
+        constexpr std::size_t batch = 1000;
+        std::vector<float> a(batch * 6), b(batch * 6), c(batch * 4), c2(batch * 4);
+        for (std::size_t i = 0; i < batch; ++i)
+            for (int j = 0; j < 6; ++j) { a[i * 6 + j] = float(j + 1) + float(i % 7); b[i * 6 + j] = float(j) - float(i % 5); }
+        CudaBatch<float, 6> da(batch, a.data()), db(batch, b.data());
+        CudaBatch<float, 4> dc(batch);
+        auto A = batched_matrix<Cuda, 2, 3>(da);
+        auto Bm = batched_matrix<Cuda, 3, 2>(db);
+        A.matrix_mul_buffer(Bm, dc);
+        dc.to_host(c.data());
+        HostBatch<float, 6> ha(a.data(), batch), hb(b.data(), batch);  // the same product through host pointers
+        HostBatch<float, 4> hc(c2.data(), batch);
+        batched_matrix<Cuda, 2, 3>(ha).matrix_mul_buffer(batched_matrix<Cuda, 3, 2>(hb), hc);
+        for (std::size_t i = 0; i < batch; ++i) {
+            std::array<float, 6> ai{}, bi{};
+            for (int j = 0; j < 6; ++j) { ai[j] = a[i * 6 + j]; bi[j] = b[i * 6 + j]; }
+            const auto want = matrix<Cuda, 2, 3>(ai).matrix_mul(matrix<Cuda, 3, 2>(bi));  // small integers: exact
+            for (int j = 0; j < 4; ++j) CHECK(c[i * 4 + j] == want[j] && c2[i * 4 + j] == want[j]);
+        }
+        // A^T (3 x 2) . A (2 x 3) -> 3 x 3 with the lazy flag on the left operand
+        CudaBatch<float, 9> dg(batch);
+        A.transpose().matrix_mul_buffer(A, dg);
+        std::vector<float> g(batch * 9);
+        dg.to_host(g.data());
+        for (std::size_t i = 0; i < batch; i += 97)
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 3; ++q)
+                    CHECK(g[i * 9 + r * 3 + q] == a[i * 6 + r] * a[i * 6 + q] + a[i * 6 + 3 + r] * a[i * 6 + 3 + q]);
+        // y = A x per object
+        std::vector<float> x(batch * 3, 1.f), y(batch * 2);
+        CudaBatch<float, 3> dx(batch, x.data());
+        CudaBatch<float, 2> dy(batch);
+        A.vector_mul_buffer(dx, dy);
+        dy.to_host(y.data());
+        for (std::size_t i = 0; i < batch; i += 91) CHECK(y[i * 2] == a[i * 6] + a[i * 6 + 1] + a[i * 6 + 2]);
+        // materialised transposes, out of place and in place
+        CudaBatch<float, 6> dt(batch);
+        A.materialize_transpose(dt);
+        A.materialize_transpose_inplace();
+        std::vector<float> t1(batch * 6), t2(batch * 6);
+        dt.to_host(t1.data());
+        da.to_host(t2.data());
+        for (std::size_t i = 0; i < batch; i += 89)
+            for (int r = 0; r < 3; ++r)
+                for (int q = 0; q < 2; ++q) CHECK(t1[i * 6 + r * 2 + q] == a[i * 6 + q * 3 + r] && t2[i * 6 + r * 2 + q] == t1[i * 6 + r * 2 + q]);
+    });
+    run("batched: dot / norm / normalize per object", [] {
+        constexpr std::size_t batch = 513;
+        std::vector<double> a(batch * 4), b(batch * 4);
+        for (std::size_t i = 0; i < batch; ++i) {
+            const double s = double(i % 9 + 1);
+            a[i * 4] = 3 * s; a[i * 4 + 1] = 4 * s; a[i * 4 + 2] = 0; a[i * 4 + 3] = 12 * s;
+            b[i * 4] = 1; b[i * 4 + 1] = 0; b[i * 4 + 2] = 5; b[i * 4 + 3] = 1;
+        }
+        CudaBatch<double, 4> da(batch, a.data()), db(batch, b.data());
+        CudaBatch<double, 1> dd(batch), dn(batch);
+        dot_batched(da, db, dd);
+        norm_batched(da, dn);
+        normalize_batched(da);
+        std::vector<double> d(batch), n(batch), u(batch * 4);
+        dd.to_host(d.data()); dn.to_host(n.data()); da.to_host(u.data());
+        for (std::size_t i = 0; i < batch; ++i) {
+            const double s = double(i % 9 + 1);
+            CHECK(d[i] == 15 * s && n[i] == 13 * s);
+            for (int j = 0; j < 4; ++j) CHECK(u[i * 4 + j] == a[i * 4 + j] / n[i]);
+        }
+    });
+
     // ---- StaticCowVec: copy on first mutable access (src/lib.rs:433-456, static_vec.rs:294-319) ----
     run("moo::copy on write (lib.rs:255-268 doc example, on Cuda)", [] {
         std::array<float, 3> source{1, 2, 3};
