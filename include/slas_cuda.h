@@ -57,6 +57,17 @@ int slas_cuda_synchronize(void);
 /* Number of kernels this library launched on the calling process so far (bench.py's gpu_launches). */
 uint64_t slas_cuda_launch_count(void);
 
+/* CUDA graphs for launch-bound sequences (BASELINE config 1: dot / add at LEN 2^20 are a few microseconds of HBM
+ * time each).  Between graph_begin and graph_end every op called with DEVICE pointers (results included: a host
+ * result pointer needs a synchronising copy and fails the capture) is recorded on the backend's stream instead
+ * of executed; graph_launch replays the whole sequence with one launch.  Scratch buffers that grow during the
+ * capture are allocated then and kept (relaxed capture mode).  Calls from other threads between begin and end are
+ * recorded too; replays are stream-ordered with every other op. */
+int slas_cuda_graph_begin(void);
+int slas_cuda_graph_end(void **graph_exec);
+int slas_cuda_graph_launch(void *graph_exec);
+int slas_cuda_graph_destroy(void *graph_exec);
+
 /* Kernel-selection knobs for benchmarking and profiling (not part of the reference interface): a
  * named integer, e.g. "transpose_variant", "gemm32d_variant".  Unknown names are rejected. */
 int slas_cuda_set_tunable(const char *name, long value);

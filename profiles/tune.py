@@ -247,6 +247,9 @@ def g_misc():
     with torch.cuda.graph(g, stream=stream):
         loop()
     report("dot 2^20 x 256 calls, CUDA graph replay", timed(g.replay, 5, 2), nbytes=8.0 * 256 * l20)
+    with sl.Graph() as own:  # the library's own capture API (slas_cuda_graph_begin / _end / _launch)
+        loop()
+    report("dot 2^20 x 256 calls, slas_cuda_graph replay", timed(own.launch, 5, 2), nbytes=8.0 * 256 * l20)
 
 
 GROUPS = {

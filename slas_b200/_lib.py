@@ -49,6 +49,10 @@ SIGNATURES = {
     "slas_cuda_set_stream": [_vp],
     "slas_cuda_synchronize": [],
     "slas_cuda_launch_count": [],
+    "slas_cuda_graph_begin": [],
+    "slas_cuda_graph_end": [C.POINTER(C.c_void_p)],
+    "slas_cuda_graph_launch": [_vp],
+    "slas_cuda_graph_destroy": [_vp],
     "slas_cuda_set_tunable": [C.c_char_p, C.c_long],
     "slas_cuda_get_tunable": [C.c_char_p, C.POINTER(C.c_long)],
     "slas_cuda_bench_fma_peak": [_i, C.POINTER(C.c_double)],

@@ -309,6 +309,39 @@ def set_tunable(name: str, value: int) -> None:
     _lib.call("slas_cuda_set_tunable", name.encode(), int(value))
 
 
+class Graph:
+    """A recorded sequence of device-pointer ops (CUDA graph): `with Graph() as g: ...ops...`, then `g.launch()`.
+    Ops inside the block are recorded, not executed; scalar results must go to device memory (`*_into` forms /
+    C-ABI calls with a device result pointer)."""
+
+    def __init__(self):
+        self._exec = C.c_void_p()
+
+    def __enter__(self):
+        _lib.call("slas_cuda_graph_begin")
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            _lib.call("slas_cuda_graph_end", C.byref(self._exec))
+        else:  # close the capture, keep the original exception
+            tmp = C.c_void_p()
+            _lib.lib().slas_cuda_graph_end(C.byref(tmp))
+            if tmp.value:
+                _lib.lib().slas_cuda_graph_destroy(tmp)
+        return False
+
+    def launch(self) -> None:
+        _lib.call("slas_cuda_graph_launch", self._exec)
+
+    def __del__(self):
+        try:
+            if self._exec.value:
+                _lib.lib().slas_cuda_graph_destroy(self._exec)
+        except Exception:
+            pass
+
+
 def set_sgemm_path(path: str) -> None:
     """'auto' (default: 3xTF32 on the tensor cores for large products whose shape fits its tiles, fp32 FMA
     otherwise), 'ffma' (always the ascending-k fp32 FMA chain) or 'tcgen05' (tensor cores wherever possible)."""
@@ -316,4 +349,4 @@ def set_sgemm_path(path: str) -> None:
 
 
 __all__ = ["Cuda", "WithStaticBackend", "CudaVec", "CudaBatch", "device_count", "device_info", "set_stream",
-           "synchronize", "launch_count", "set_sgemm_path"]
+           "synchronize", "launch_count", "set_sgemm_path", "Graph"]

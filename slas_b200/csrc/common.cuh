@@ -19,9 +19,11 @@ int fail(int code, const char *fmt, ...);
 #define SLAS_CUDA_TRY(expr)                                                                 \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \
-        if (_e != cudaSuccess)                                                              \
+        if (_e != cudaSuccess) {                                                            \
+            cudaGetLastError(); /* do not leave it behind for the next launch check */      \
             return ::slas::fail(SLAS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,              \
                                 cudaGetErrorString(_e), __FILE__, __LINE__);                \
+        }                                                                                   \
     } while (0)
 
 #define SLAS_TRY(expr)                  \

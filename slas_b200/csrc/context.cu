@@ -256,6 +256,45 @@ int slas_cuda_synchronize(void) {
 
 uint64_t slas_cuda_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// ---- CUDA graphs: a launch-bound sequence of device-pointer ops recorded once, replayed with one launch ----------
+int slas_cuda_graph_begin(void) {
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    SLAS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    return SLAS_OK;
+}
+
+int slas_cuda_graph_end(void **graph_exec) {
+    SLAS_REQUIRE(graph_exec, "null graph_exec");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    cudaGraph_t graph = nullptr;
+    SLAS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    SLAS_CUDA_TRY(e);
+    *graph_exec = exec;
+    return SLAS_OK;
+}
+
+int slas_cuda_graph_launch(void *graph_exec) {
+    SLAS_REQUIRE(graph_exec, "null graph_exec");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    SLAS_CUDA_TRY(cudaGraphLaunch((cudaGraphExec_t)graph_exec, c->stream));
+    return SLAS_OK;
+}
+
+int slas_cuda_graph_destroy(void *graph_exec) {
+    if (!graph_exec) return SLAS_OK;
+    SLAS_CUDA_TRY(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return SLAS_OK;
+}
+
 int slas_cuda_malloc(void **dptr, size_t bytes) {
     SLAS_REQUIRE(dptr, "null dptr");
     Context *c;

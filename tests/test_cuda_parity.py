@@ -391,6 +391,47 @@ def test_static_cow_vec_on_the_device():
     assert h.is_owned() and np.array_equal(h.to_host(), ref.to_host()) and a[0] == src.to_host()[0]
 
 
+def test_cuda_graph_records_and_replays_a_sequence():
+    """a launch-bound chain of device-pointer ops recorded once and replayed: same bytes as the eager chain, also
+    after the inputs change (the graph holds pointers, not values)"""
+    from slas_b200 import Graph, _lib as L
+    rng = np.random.default_rng(21)
+    n, batch = 1 << 16, 2048
+    a, b = _rand(rng, n, np.float32), _rand(rng, n, np.float32)
+    A, B = _rand(rng, batch * 16, np.float32), _rand(rng, batch * 16, np.float32)
+    da, db, dc, dres = CudaVec.from_host(a), CudaVec.from_host(b), CudaVec(n, np.float32), CudaVec(4, np.float32)
+    dA, dB, dC, dT = CudaVec.from_host(A), CudaVec.from_host(B), CudaBatch(batch, 16, np.float32), CudaBatch(batch, 16, np.float32)
+
+    def chain():
+        cuda.add(da, db, dc)
+        L.call("slas_cuda_sdot", n, dc.as_ptr(), db.as_ptr(), dres.as_ptr())          # device result pointer
+        L.call("slas_cuda_snrm2", n, dc.as_ptr(), dres.as_ptr() + 4)
+        cuda.matrix_mul_batched(dA, dB, dC, 4, 4, 4)
+        cuda.transpose_batched(dC, dT, 16, 4)
+
+    chain()  # eager: the expected bytes, and every scratch buffer at its final size
+    want = (dc.to_host(), dres.to_host()[:2].copy(), dT.to_host().copy())
+    for v in (dc, dres, dC, dT):
+        v.zero_()
+    n0 = launch_count()
+    with Graph() as g:
+        chain()
+    assert np.all(dT.to_host() == 0), "ops inside the capture must be recorded, not executed"
+    g.launch()
+    got = (dc.to_host(), dres.to_host()[:2], dT.to_host())
+    for w, x in zip(want, got):
+        assert np.array_equal(w, x)
+    da.copy_from_host(b)  # new inputs, same graph
+    g.launch()
+    assert np.array_equal(dc.to_host(), b + b)
+    assert launch_count() > n0
+    # a host result pointer cannot be captured: the call fails, the capture is closed, the library stays usable
+    with pytest.raises(Exception):
+        with Graph():
+            cuda.dot(da, db)
+    assert cuda.dot(da, db).tobytes() == cuda.dot(da, db).tobytes()
+
+
 # ---- transpose: bit-exact for any Copy element --------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int32, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols", [(1, 1), (1, 7), (7, 1), (2, 3), (4, 4), (16, 16), (32, 32), (5, 64), (33, 65), (100, 257), (1024, 48), (128, 64), (192, 320), (1024, 512)])
