@@ -302,6 +302,29 @@ def test_norm_and_normalize(dt, n):
     assert np.array_equal(h, got)
 
 
+def test_reductions_special_values_and_overflow_policy():
+    """IEEE propagation through the reductions, the normalize of a zero vector, and overflow of the sum of squares:
+    like the Rust backend's naive f32 sum (rust.rs:116-121) a norm overflows to infinity when squares or a thread's
+    partial sum overflow f32; partial sums are COMBINED in f64, so where only the grand total would overflow the
+    result can stay finite (the Blas backend's scaled nrm2 answer, blas.rs:156-162) -- never the other way round."""
+    f = np.float32
+    with np.errstate(all="ignore"):
+        assert np.isinf(cuda.dot(np.array([np.inf, 1], f), np.array([1, 1], f)))
+        assert np.isnan(cuda.dot(np.array([np.inf, -np.inf], f), np.array([1, 1], f)))
+        assert np.isnan(cuda.dot(np.array([np.nan, 1], f), np.array([1, 1], f)))
+        assert np.isnan(cuda.norm(np.array([1, np.nan, 2], f))) and np.isinf(cuda.norm(np.array([1, -np.inf], f)))
+        z = np.zeros(5, f)
+        cuda.normalize(z)  # 0 / 0, as the reference's `a[i] /= norm`
+        assert np.all(np.isnan(z))
+        one = np.array([3e38, 3e38, 0, 0], f)  # each square overflows f32 on its own: inf, as in the reference
+        assert np.isinf(cuda.norm(one)) and np.isinf(oracle.norm(one))
+        big = np.full(1 << 12, 1.5e19, f)  # squares are finite in f32 (2.25e38), four of them in one accumulator are not
+        assert np.isinf(cuda.norm(big)) and np.isinf(oracle.norm(big))
+        two = np.array([1.5e19, 1.5e19], f)  # 4.5e38 only in total: inf for the naive f32 sum, finite here (f64 combine)
+        got = cuda.norm(two)
+        assert np.isinf(oracle.norm(two)) and np.isfinite(got) and abs(float(got) - 1.5e19 * np.sqrt(2)) <= 1e-5 * 3e19
+
+
 # ---- fused chains (SURVEY 8 f3): same results as the op sequence they replace ---------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [1, 3, 5, 1000, 4097, (1 << 20) + 3])
