@@ -1,0 +1,222 @@
+// gemm_jit.cu -- run-time specialisation of the batched static-shape GEMM kernel for shapes that have no
+// ahead-of-time instantiation.
+//
+// In slas a matrix shape is a compile-time constant (MatrixShape<M, K>, src/tensor.rs:108-115): rustc monomorphises
+// Matrix::matrix_mul for every shape a program uses.  The C ABI receives the shape as run-time integers, and the
+// library can only carry so many instantiations ({4, 8, 16, 32, 64}^3 and everything up to 4 x 4 x 4).  For the rest
+// (8x16 . 16x4, 12x12 . 12x12, 6x6 . 6x6, ...) this file does what rustc does: it compiles
+// gemm_small_kernel<T, SmallCfg<T, M, N, K, ...>, TA, TB> -- the very kernel text of gemm_small_kernel.cuh, embedded
+// at build time -- for sm_100a with NVRTC the first time a shape is seen (~1 s), keeps the CUfunction in a cache and
+// launches it like the built-in ones from then on.  NVRTC and the driver API are bound at run time (dlopen /
+// cudaGetDriverEntryPoint); if either is missing, or a shape does not fit the kernel's tiling rules, the caller falls
+// back to the runtime-shape kernel (SLAS_ERR_UNSUPPORTED) -- never to the CPU.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace slas {
+
+static const char *kKernelSource =
+#include "gemm_small_jit_src.inc"
+    ;
+
+// ---- NVRTC + driver entry points, bound once -------------------------------------------------------------------
+struct JitApi {
+    bool ok = false;
+    nvrtcResult (*CreateProgram)(nvrtcProgram *, const char *, const char *, int, const char *const *, const char *const *);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram *);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char *const *);
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char *);
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char *, const char **);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char *);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t *);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char *);
+    CUresult (*ModuleLoadData)(CUmodule *, const void *);
+    CUresult (*ModuleGetFunction)(CUfunction *, CUmodule, const char *);
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int);
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void **,
+                             void **);
+};
+static JitApi g_api;
+static std::once_flag g_api_once;
+
+template <typename F> static bool driver_fn(const char *name, F *out) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    *out = reinterpret_cast<F>(fn);
+    return true;
+}
+
+static void bind_api() {
+    void *h = nullptr;
+    for (const char *name : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (h) break;
+    }
+    if (!h) return;
+    bool ok = true;
+#define SLAS_NVRTC_SYM(field, sym) ok = ok && ((g_api.field = reinterpret_cast<decltype(g_api.field)>(dlsym(h, sym))) != nullptr)
+    SLAS_NVRTC_SYM(CreateProgram, "nvrtcCreateProgram");
+    SLAS_NVRTC_SYM(DestroyProgram, "nvrtcDestroyProgram");
+    SLAS_NVRTC_SYM(CompileProgram, "nvrtcCompileProgram");
+    SLAS_NVRTC_SYM(AddNameExpression, "nvrtcAddNameExpression");
+    SLAS_NVRTC_SYM(GetLoweredName, "nvrtcGetLoweredName");
+    SLAS_NVRTC_SYM(GetCUBINSize, "nvrtcGetCUBINSize");
+    SLAS_NVRTC_SYM(GetCUBIN, "nvrtcGetCUBIN");
+    SLAS_NVRTC_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize");
+    SLAS_NVRTC_SYM(GetProgramLog, "nvrtcGetProgramLog");
+#undef SLAS_NVRTC_SYM
+    ok = ok && driver_fn("cuModuleLoadData", &g_api.ModuleLoadData) && driver_fn("cuModuleGetFunction", &g_api.ModuleGetFunction) &&
+         driver_fn("cuFuncSetAttribute", &g_api.FuncSetAttribute) && driver_fn("cuLaunchKernel", &g_api.LaunchKernel);
+    g_api.ok = ok;
+}
+
+// ---- tile configuration for an arbitrary (M, N, K) ---------------------------------------------------------------
+struct JitCfg {
+    int tm = 0, tn = 0, g = 0, cons = 256, stages = 3;
+    size_t smem = 0;
+};
+
+// The rules of SmallCfg / gemm_small_kernel: K and TN whole 16-byte vectors, TM | M, TN | N, threads per matrix
+// (M/TM)*(N/TN) a power of two dividing the consumer count, a chunk = whole passes, the stage ring within the
+// shared-memory budget.  Among the configurations that fit: big, squarish register tiles (fewer shared-memory loads
+// per FMA), at least two CTAs per SM, three stages and 256 consumers when possible.
+static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
+    const size_t kvn = 16 / elem;
+    if (m == 0 || n == 0 || k == 0 || n % kvn || k % kvn) return false;
+    const size_t per_pair = (m * k + k * n) * elem;
+    if (per_pair > 16 * 1024) return false;
+    const size_t max_tile = 32;  // accumulators per thread
+    double best = -1.0;
+    for (size_t tm = 1; tm <= m; ++tm) {
+        if (m % tm) continue;
+        for (size_t tn = kvn; tn <= n; tn += kvn) {
+            if (n % tn || tm * tn > max_tile) continue;
+            const size_t tpm = (m / tm) * (n / tn);
+            if (tpm > 256 || (tpm & (tpm - 1))) continue;
+            for (size_t cons = 256; cons >= 128; cons /= 2) {
+                if (tpm > cons) continue;
+                const size_t mpp = cons / tpm;
+                size_t g = (32 * 1024 / per_pair) / mpp * mpp;
+                if (g < mpp) g = mpp;
+                if (g > 256) g = 256 / mpp * mpp;
+                if (g == 0) continue;
+                for (int stages = 3; stages >= 2; --stages) {
+                    const size_t smem = (size_t)stages * g * per_pair + 2 * stages * sizeof(uint64_t);
+                    if (smem > 200 * 1024) continue;
+                    const size_t per_sm = (size_t)227 * 1024 / (smem + 1024);
+                    double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm) + 1e-3 * (double)tn;
+                    if (per_sm < 2) score *= 0.6;
+                    if (stages == 2) score *= 0.9;
+                    if (cons == 128) score *= 0.95;
+                    if (score > best) {
+                        best = score;
+                        out->tm = (int)tm; out->tn = (int)tn; out->g = (int)g; out->cons = (int)cons; out->stages = stages;
+                        out->smem = smem;
+                    }
+                }
+            }
+        }
+    }
+    return best > 0;
+}
+
+// ---- compile + cache ---------------------------------------------------------------------------------------------
+struct JitKernel {
+    CUfunction fn = nullptr;
+    JitCfg cfg;
+    bool failed = false;
+};
+using JitKey = std::tuple<int, int, size_t, size_t, size_t, int, int>;  // device (a module belongs to its context), elem size, m, n, k, ta, tb
+static std::map<JitKey, JitKernel> g_cache;
+static std::mutex g_cache_mu;
+
+static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, int tb, JitKernel *kern) {
+    const char *tname = elem == 4 ? "float" : "double";
+    char expr[256];
+    snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>", tname,
+             tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages, ta ? "true" : "false",
+             tb ? "true" : "false");
+    nvrtcProgram prog = nullptr;
+    if (g_api.CreateProgram(&prog, kKernelSource, "gemm_small_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return false;
+    bool ok = g_api.AddNameExpression(prog, expr) == NVRTC_SUCCESS;
+    const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
+    if (ok && g_api.CompileProgram(prog, 3, opts) != NVRTC_SUCCESS) {
+        ok = false;
+        size_t len = 0;
+        if (g_api.GetProgramLogSize(prog, &len) == NVRTC_SUCCESS && len > 1) {
+            std::string log(len, '\0');
+            g_api.GetProgramLog(prog, &log[0]);
+            fail(SLAS_ERR_CUDA, "NVRTC could not specialise %s: %.400s", expr, log.c_str());
+        }
+    }
+    const char *lowered = nullptr;
+    ok = ok && g_api.GetLoweredName(prog, expr, &lowered) == NVRTC_SUCCESS && lowered;
+    size_t size = 0;
+    ok = ok && g_api.GetCUBINSize(prog, &size) == NVRTC_SUCCESS && size > 0;
+    std::string cubin;
+    if (ok) {
+        cubin.resize(size);
+        ok = g_api.GetCUBIN(prog, &cubin[0]) == NVRTC_SUCCESS;
+    }
+    CUmodule mod = nullptr;
+    ok = ok && g_api.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS;  // the module lives as long as the process
+    ok = ok && g_api.ModuleGetFunction(&kern->fn, mod, lowered) == CUDA_SUCCESS;
+    ok = ok && g_api.FuncSetAttribute(kern->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kern->cfg.smem) == CUDA_SUCCESS;
+    g_api.DestroyProgram(&prog);
+    return ok;
+}
+
+template <typename T>
+int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                            size_t k, int ta, int tb) {
+    if (tunable("gemm_jit") == 1 || batch < 64) return SLAS_ERR_UNSUPPORTED;
+    std::call_once(g_api_once, bind_api);
+    if (!g_api.ok) return SLAS_ERR_UNSUPPORTED;
+    JitKernel kern;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        const JitKey key{ctx->device, (int)sizeof(T), m, n, k, ta ? 1 : 0, tb ? 1 : 0};
+        auto it = g_cache.find(key);
+        if (it == g_cache.end()) {
+            JitKernel fresh;
+            fresh.failed = !choose_cfg(sizeof(T), m, n, k, &fresh.cfg) || !compile_kernel(sizeof(T), m, n, k, ta, tb, &fresh);
+            it = g_cache.emplace(key, fresh).first;
+        }
+        kern = it->second;
+    }
+    if (kern.failed) return SLAS_ERR_UNSUPPORTED;
+    const size_t G = (size_t)kern.cfg.g, nchunks = (batch + G - 1) / G;
+    int per_sm = (int)((size_t)227 * 1024 / (kern.cfg.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    size_t grid = (size_t)ctx->sm_count * per_sm;
+    if (grid > nchunks) grid = nchunks;
+    size_t batch_arg = batch, nchunks_arg = nchunks;
+    void *params[] = {(void *)&a, (void *)&b, (void *)&c, (void *)&batch_arg, (void *)&nchunks_arg};
+    const CUresult r = g_api.LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)kern.cfg.cons + 32, 1, 1, (unsigned)kern.cfg.smem,
+                                          (CUstream)st, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(SLAS_ERR_CUDA, "launch of the run-time specialised GEMM kernel failed (CUresult %d)", (int)r);
+    count_launch();
+    return SLAS_OK;
+}
+template int launch_gemm_jit_batched<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *, size_t, size_t,
+                                            size_t, int, int);
+template int launch_gemm_jit_batched<double>(Context *, cudaStream_t, size_t, const double *, const double *, double *, size_t,
+                                             size_t, size_t, int, int);
+
+}  // namespace slas

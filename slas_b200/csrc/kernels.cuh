@@ -33,6 +33,12 @@ int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, si
 int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, void *a,
                              size_t columns, bool *handled);
 
+// gemm_jit.cu -- the gemm_small kernel specialised at run time (NVRTC) for shapes without a built-in instantiation;
+// SLAS_ERR_UNSUPPORTED when the shape does not fit its tiling rules or NVRTC is not available
+template <typename T>
+int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                            size_t k, int ta, int tb);
+
 // gemm_tiny.cu -- every dimension in 1..4: one thread per matrix; SLAS_ERR_UNSUPPORTED otherwise
 template <typename T>
 int launch_gemm_tiny_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,

@@ -696,6 +696,39 @@ def test_batched_tiny_shapes_thread_per_matrix(dt, ta, tb):
     assert np.array_equal(c0.to_host(), c1.to_host())
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("m,n,k", [(8, 4, 16), (16, 32, 8), (12, 12, 12), (32, 8, 64), (6, 6, 6), (24, 8, 12), (5, 8, 4), (8, 8, 16),
+                                   (48, 16, 4)])
+def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
+    """shapes without a built-in instantiation: the gemm_small kernel compiled for the shape with NVRTC on first use
+    (gemm_jit.cu).  Without b_trans every C element is the same ascending-k FMA chain as in the runtime-shape kernel it
+    replaces => identical bits (with b_trans the k-chunks are visited in a rotated order: same bar, different rounding);
+    shapes that do not fit the tiling rules (f32 6x6x6: K is not a whole 16-byte vector) still take that kernel."""
+    from slas_b200.backends import set_tunable
+    rng = np.random.default_rng(m * 100 + n * 10 + k)
+    for batch in (64, 1000, 1003):
+        A, B = _rand(rng, batch * m * k, dt), _rand(rng, batch * k * n, dt)
+        dA, dB = CudaVec.from_host(A), CudaVec.from_host(B)
+        for ta in (False, True):
+            for tb in (False, True):
+                want = oracle.gemm_batched(A, B, batch, m, n, k, ta, tb)
+                c0, c1 = CudaBatch(batch + 1, m * n, dt), CudaBatch(batch, m * n, dt)
+                c0.copy_from_host(np.full((batch + 1) * m * n, -5.0, dt))
+                cuda.matrix_mul_batched(dA, dB, c0.view(0, batch * m * n), m, n, k, ta, tb)
+                got = c0.to_host().ravel()
+                assert np.max(np.abs(got[:batch * m * n] - want)) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k, (batch, ta, tb)
+                assert np.all(got[batch * m * n:] == -5.0)
+                set_tunable("gemm_jit", 1)  # the runtime-shape kernel
+                try:
+                    cuda.matrix_mul_batched(dA, dB, c1, m, n, k, ta, tb)
+                finally:
+                    set_tunable("gemm_jit", 0)
+                if not tb:
+                    assert np.array_equal(c1.to_host().ravel(), got[:batch * m * n]), (batch, ta, tb)
+                else:
+                    assert np.max(np.abs(c1.to_host().ravel() - want)) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
+
+
 def test_batched_view_api_and_integer_exactness():
     # small-integer entries: every product and sum is exact in f32, so == numpy exactly
     rng = np.random.default_rng(3)
