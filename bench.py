@@ -382,6 +382,33 @@ def run_cuda(args):
             ms_, _ = timed(lambda: cuda.transpose_batched(va, vc, n_ * n_, n_), ksteps, 3)
             record(f"batched {n_}x{n_} {name} transpose, batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
             del a, b, c, va, vb, vc
+        # the callers either side of the path: other static shapes, matrix_vector_mul, in-place transposes
+        for (m_, n_, k_, tdt, name, log2, how) in ((3, 3, 3, torch.float32, "f32", 24, "thread per matrix"),
+                                                   (2, 2, 3, torch.float32, "f32", 24, "thread per matrix"),
+                                                   (8, 4, 16, torch.float32, "f32", 22, "specialised at run time (NVRTC)"),
+                                                   (12, 12, 12, torch.float64, "f64", 20, "specialised at run time (NVRTC)")):
+            bsz = 1 << log2
+            es = 4 if tdt == torch.float32 else 8
+            a, b = dev_uniform(bsz * m_ * k_, tdt, 2), dev_uniform(bsz * k_ * n_, tdt, 3)
+            c = torch.empty(bsz * m_ * n_, device=dev, dtype=tdt)
+            va, vb, vc = vec(a), vec(b), vec(c)
+            ms_, _ = timed(lambda: cuda.matrix_mul_batched(va, vb, vc, m_, n_, k_), ksteps, 3)
+            record(f"batched {m_}x{k_} . {k_}x{n_} {name} matrix_mul, batch 2^{log2} ({how})", ms_, flop=2.0 * m_ * n_ * k_ * bsz,
+                   bytes_=float(m_ * k_ + k_ * n_ + m_ * n_) * es * bsz)
+            del a, b, c, va, vb, vc
+        for n_, tdt, name in ((32, torch.float32, "f32"), (32, torch.float64, "f64")):
+            bsz = 1 << 20
+            es = 4 if tdt == torch.float32 else 8
+            a, x = dev_uniform(bsz * n_ * n_, tdt, 2), dev_uniform(bsz * n_, tdt, 3)
+            y = torch.empty_like(x)
+            va, vx, vy = vec(a), vec(x), vec(y)
+            for ta_ in (False, True):
+                ms_, _ = timed(lambda: cuda.matrix_vector_mul_batched(va, vx, vy, n_, n_, ta_), ksteps, 3)
+                record(f"batched {n_}x{n_} {name} matrix_vector_mul, a_trans={ta_}, batch 2^20", ms_, flop=2.0 * n_ * n_ * bsz,
+                       bytes_=float(n_ * n_ + 2 * n_) * es * bsz)
+            ms_, _ = timed(lambda: cuda.transpose_inplace_batched(va, n_ * n_, n_), ksteps, 3)
+            record(f"batched {n_}x{n_} {name} transpose_inplace (Matrix::deref_mut per object), batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
+            del a, x, y, va, vx, vy
         # config 1: dot + add, f32.  LEN = 2^20 is L2-resident and launch-bound as one call, so report
         # (i) one 2^28-element call, (ii) 1024 distinct 2^20 pairs in one batched launch, (iii) call latency.
         n28 = 1 << 28
@@ -397,6 +424,10 @@ def run_cuda(args):
         record("norm f32 LEN=2^28 (one call)", ms_, bytes_=4.0 * n28)
         ms_, _ = timed(lambda: cuda.normalize(va), ksteps, 3)
         record("normalize f32 LEN=2^28 (one call; 12 B/elem: read, read, write)", ms_, bytes_=12.0 * n28)
+        ms_, _ = timed(lambda: _lib.call("slas_cuda_sadd_dot", n28, a.data_ptr(), b.data_ptr(), None, c.data_ptr(), out.data_ptr()), ksteps, 3)
+        record("fused add -> dot f32 LEN=2^28 (intermediate never materialised, 12 B/elem instead of 20)", ms_, bytes_=12.0 * n28)
+        ms_, _ = timed(lambda: _lib.call("slas_cuda_sdot_norms", n28, a.data_ptr(), b.data_ptr(), out.data_ptr()), ksteps, 3)
+        record("fused dot + norm + norm f32 LEN=2^28 (8 B/elem instead of 16)", ms_, bytes_=8.0 * n28)
         l20 = 1 << 20
         # (ii) of SURVEY 8d config 1: 1024 DISTINCT 2^20-element pairs (8 GiB >> L2) in one batched launch
         a4 = dev_uniform(1024 * l20, torch.float32, 8, 0.0, 1.0)
