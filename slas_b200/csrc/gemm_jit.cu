@@ -87,9 +87,31 @@ static void bind_api() {
 
 // ---- tile configuration for an arbitrary (M, N, K) ---------------------------------------------------------------
 struct JitCfg {
+    int tiny = 0;  // 1: gemm_tiny_kernel (a thread per matrix), 0: gemm_small_kernel (register tiles)
     int tm = 0, tn = 0, g = 0, cons = 256, stages = 3;
-    size_t smem = 0;
+    size_t smem = 0, stage_elems = 0, cstage_elems = 0;
 };
+
+// Thread per matrix (gemm_tiny_kernel<T, M, N, K, G>): any m, n, k -- no vector-width rules -- as long as the operands
+// and the result of one product fit a thread's registers (~160 32-bit registers) and three input stages plus two C
+// stages of G matrices fit shared memory.  G = consumer threads: as many as leave room for two CTAs per SM.
+static bool choose_tiny_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
+    const size_t words = (m * k + k * n + m * n) * (elem / 4);
+    if (m == 0 || n == 0 || k == 0 || words > 160) return false;
+    for (size_t g = 256; g >= 64; g /= 2) {
+        const size_t stage = (g * (m * k + k * n) * elem + 127) / 128 * 128, cstage = (g * m * n * elem + 127) / 128 * 128;
+        const size_t smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);
+        if (smem > (g > 64 ? 110 : 200) * 1024) continue;
+        out->tiny = 1;
+        out->g = (int)g;
+        out->cons = (int)g;
+        out->smem = smem;
+        out->stage_elems = stage / elem;
+        out->cstage_elems = cstage / elem;
+        return true;
+    }
+    return false;
+}
 
 // The rules of SmallCfg / gemm_small_kernel: K and TN whole 16-byte vectors, TM | M, TN | N, threads per matrix
 // (M/TM)*(N/TN) a power of two dividing the consumer count, a chunk = whole passes, the stage ring within the
@@ -148,9 +170,12 @@ static std::mutex g_cache_mu;
 static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, int tb, JitKernel *kern) {
     const char *tname = elem == 4 ? "float" : "double";
     char expr[256];
-    snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>", tname,
-             tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages, ta ? "true" : "false",
-             tb ? "true" : "false");
+    if (kern->cfg.tiny)
+        snprintf(expr, sizeof(expr), "slas::gemm_tiny_kernel<%s, %zu, %zu, %zu, %d>", tname, m, n, k, kern->cfg.g);
+    else
+        snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>",
+                 tname, tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages,
+                 ta ? "true" : "false", tb ? "true" : "false");
     nvrtcProgram prog = nullptr;
     if (g_api.CreateProgram(&prog, kKernelSource, "gemm_small_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return false;
     bool ok = g_api.AddNameExpression(prog, expr) == NVRTC_SUCCESS;
@@ -190,11 +215,17 @@ int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T
     JitKernel kern;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
-        const JitKey key{ctx->device, (int)sizeof(T), m, n, k, ta ? 1 : 0, tb ? 1 : 0};
+        // register tiles where the kernel's vector-width rules allow; else a thread per matrix if one fits a thread
+        // (its a_trans / b_trans are run-time arguments: one specialisation serves all four flag pairs)
+        JitCfg cfg;
+        const bool tiled = choose_cfg(sizeof(T), m, n, k, &cfg);
+        const bool tiny = !tiled && choose_tiny_cfg(sizeof(T), m, n, k, &cfg);
+        const JitKey key{ctx->device, (int)sizeof(T), m, n, k, tiny ? 0 : (ta ? 1 : 0), tiny ? 0 : (tb ? 1 : 0)};
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {
             JitKernel fresh;
-            fresh.failed = !choose_cfg(sizeof(T), m, n, k, &fresh.cfg) || !compile_kernel(sizeof(T), m, n, k, ta, tb, &fresh);
+            fresh.cfg = cfg;
+            fresh.failed = !(tiled || tiny) || !compile_kernel(sizeof(T), m, n, k, ta, tb, &fresh);
             it = g_cache.emplace(key, fresh).first;
         }
         kern = it->second;
@@ -207,7 +238,13 @@ int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T
     size_t grid = (size_t)ctx->sm_count * per_sm;
     if (grid > nchunks) grid = nchunks;
     size_t batch_arg = batch, nchunks_arg = nchunks;
-    void *params[] = {(void *)&a, (void *)&b, (void *)&c, (void *)&batch_arg, (void *)&nchunks_arg};
+    int ta_arg = ta ? 1 : 0, tb_arg = tb ? 1 : 0;
+    unsigned stage_arg = (unsigned)kern.cfg.stage_elems, cstage_arg = (unsigned)kern.cfg.cstage_elems;
+    // gemm_small_kernel(a, b, c, batch, nchunks) / gemm_tiny_kernel(a, b, c, batch, nchunks, ta, tb, stage_elems, cstage_elems)
+    void *params[] = {(void *)&a,      (void *)&b,      (void *)&c,         (void *)&batch_arg, (void *)&nchunks_arg,
+                      (void *)&ta_arg, (void *)&tb_arg, (void *)&stage_arg, (void *)&cstage_arg};
+    if (kern.cfg.tiny && ((batch * m * k * sizeof(T)) % 16 || (batch * k * n * sizeof(T)) % 16))
+        return SLAS_ERR_UNSUPPORTED;  // its ragged last chunk is copied in whole 16-byte words
     const CUresult r = g_api.LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)kern.cfg.cons + 32, 1, 1, (unsigned)kern.cfg.smem,
                                           (CUstream)st, params, nullptr);
     if (r != CUDA_SUCCESS) return fail(SLAS_ERR_CUDA, "launch of the run-time specialised GEMM kernel failed (CUresult %d)", (int)r);
