@@ -212,7 +212,7 @@ def g_rect():
     for (m, n, k, dt, log2) in ((2, 2, 3, np.float32, 24), (3, 3, 3, np.float32, 24), (3, 3, 3, np.float64, 24), (2, 2, 2, np.float32, 24),
                                 (4, 4, 2, np.float32, 24), (4, 1, 4, np.float32, 24), (2, 4, 4, np.float64, 24),
                                 (5, 5, 5, np.float32, 23), (6, 6, 6, np.float32, 22), (6, 6, 6, np.float64, 22), (7, 7, 7, np.float32, 22),
-                                (9, 9, 9, np.float32, 21),
+                                (9, 9, 9, np.float32, 21), (10, 10, 10, np.float32, 21), (15, 15, 15, np.float64, 19), (5, 9, 13, np.float32, 21),
                                 (8, 4, 16, np.float32, 22), (16, 32, 8, np.float32, 20),
                                 (12, 12, 12, np.float64, 20), (4, 4, 4, np.float32, 24)):
         b = 1 << log2

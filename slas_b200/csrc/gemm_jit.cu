@@ -87,7 +87,8 @@ static void bind_api() {
 
 // ---- tile configuration for an arbitrary (M, N, K) ---------------------------------------------------------------
 struct JitCfg {
-    int tiny = 0;  // 1: gemm_tiny_kernel (a thread per matrix), 0: gemm_small_kernel (register tiles)
+    int tiny = 0;  // 0: gemm_small_kernel (vector register tiles), 1: gemm_tiny_kernel (a thread per matrix),
+                   // 2: gemm_rect_kernel (scalar register tiles)
     int tm = 0, tn = 0, g = 0, cons = 256, stages = 3;
     size_t smem = 0, stage_elems = 0, cstage_elems = 0;
 };
@@ -157,6 +158,43 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
     return best > 0;
 }
 
+// Scalar register tiles (gemm_rect_kernel<T, M, N, K, TM, TN, G>): any divisors TM | M, TN | N with at most 256 threads per
+// matrix; G = a whole number of passes of MPP = 256 / TPM matrices, sized so that three input stages and two C stages
+// leave room for two CTAs per SM when possible.
+static bool choose_rect_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
+    if (m == 0 || n == 0 || k == 0) return false;
+    const size_t per_in = (m * k + k * n) * elem, per_out = m * n * elem;
+    if (per_in > 16 * 1024) return false;
+    double best = -1.0;
+    for (size_t tm = 1; tm <= m; ++tm) {
+        if (m % tm) continue;
+        for (size_t tn = 1; tn <= n; ++tn) {
+            if (n % tn || tm * tn > 32) continue;
+            const size_t tpm = (m / tm) * (n / tn);
+            if (tpm > 256) continue;
+            const size_t mpp = 256 / tpm;
+            // G % 4 == 0 keeps every chunk of A, B and C on a 16-byte boundary whatever the shape
+            size_t g = (24 * 1024 / (per_in + per_out)) / 4 * 4;
+            if (g < mpp) g = (mpp + 3) / 4 * 4;
+            if (g < 4) g = 4;
+            if (g > 1024) g = 1024;
+            const size_t stage = (g * per_in + 127) / 128 * 128, cstage = (g * per_out + 127) / 128 * 128;
+            const size_t smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);
+            if (smem > 200 * 1024) continue;
+            double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm);         // FMAs per shared-memory load
+            score *= (double)(mpp * tpm) / 256.0;                                 // busy threads
+            if ((size_t)227 * 1024 / (smem + 1024) < 2) score *= 0.6;
+            if (score > best) {
+                best = score;
+                out->tiny = 2;
+                out->tm = (int)tm; out->tn = (int)tn; out->g = (int)g; out->cons = 256; out->smem = smem;
+                out->stage_elems = stage / elem; out->cstage_elems = cstage / elem;
+            }
+        }
+    }
+    return best > 0;
+}
+
 // ---- compile + cache ---------------------------------------------------------------------------------------------
 struct JitKernel {
     CUfunction fn = nullptr;
@@ -170,8 +208,11 @@ static std::mutex g_cache_mu;
 static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, int tb, JitKernel *kern) {
     const char *tname = elem == 4 ? "float" : "double";
     char expr[256];
-    if (kern->cfg.tiny)
+    if (kern->cfg.tiny == 1)
         snprintf(expr, sizeof(expr), "slas::gemm_tiny_kernel<%s, %zu, %zu, %zu, %d>", tname, m, n, k, kern->cfg.g);
+    else if (kern->cfg.tiny == 2)
+        snprintf(expr, sizeof(expr), "slas::gemm_rect_kernel<%s, %zu, %zu, %zu, %d, %d, %d>", tname, m, n, k, kern->cfg.tm, kern->cfg.tn,
+                 kern->cfg.g);
     else
         snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>",
                  tname, tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages,
@@ -218,8 +259,9 @@ int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T
         // register tiles where the kernel's vector-width rules allow; else a thread per matrix if one fits a thread
         // (its a_trans / b_trans are run-time arguments: one specialisation serves all four flag pairs)
         JitCfg cfg;
+        // ... and scalar register tiles for whatever is left (9x9, 10x10 f32, 5x9 ...)
         const bool tiled = choose_cfg(sizeof(T), m, n, k, &cfg);
-        const bool tiny = !tiled && choose_tiny_cfg(sizeof(T), m, n, k, &cfg);
+        const bool tiny = !tiled && (choose_tiny_cfg(sizeof(T), m, n, k, &cfg) || choose_rect_cfg(sizeof(T), m, n, k, &cfg));
         const JitKey key{ctx->device, (int)sizeof(T), m, n, k, tiny ? 0 : (ta ? 1 : 0), tiny ? 0 : (tb ? 1 : 0)};
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {

@@ -698,13 +698,14 @@ def test_batched_tiny_shapes_thread_per_matrix(dt, ta, tb):
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("m,n,k", [(8, 4, 16), (16, 32, 8), (12, 12, 12), (32, 8, 64), (6, 6, 6), (24, 8, 12), (5, 8, 4), (8, 8, 16),
-                                   (48, 16, 4), (5, 5, 5), (3, 7, 5), (7, 7, 7), (1, 6, 9), (9, 9, 9)])
+                                   (48, 16, 4), (5, 5, 5), (3, 7, 5), (7, 7, 7), (1, 6, 9), (9, 9, 9), (10, 10, 10), (5, 9, 13), (33, 3, 7),
+                                   (15, 15, 15)])
 def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
     """shapes without a built-in instantiation: the gemm_small kernel compiled for the shape with NVRTC on first use
     (gemm_jit.cu).  Without b_trans every C element is the same ascending-k FMA chain as in the runtime-shape kernel it
     replaces => identical bits (with b_trans the k-chunks are visited in a rotated order: same bar, different rounding);
     shapes outside the tiling rules (f32 6x6x6, 5x5x5: K is not a whole 16-byte vector) get the thread-per-matrix kernel
-    specialised instead if a product fits one thread's registers, and the runtime-shape kernel otherwise (9x9x9)."""
+    specialised instead if a product fits one thread's registers, and scalar register tiles otherwise (9x9x9, 5x9x13)."""
     from slas_b200.backends import set_tunable
     rng = np.random.default_rng(m * 100 + n * 10 + k)
     for batch in (64, 1000, 1003):
@@ -724,7 +725,7 @@ def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
                     cuda.matrix_mul_batched(dA, dB, c1, m, n, k, ta, tb)
                 finally:
                     set_tunable("gemm_jit", 0)
-                if not tb or max(m, n, k) <= 7:
+                if not tb or n % (16 // np.dtype(dt).itemsize) or k % (16 // np.dtype(dt).itemsize):
                     assert np.array_equal(c1.to_host().ravel(), got[:batch * m * n]), (batch, ta, tb)
                 else:
                     assert np.max(np.abs(c1.to_host().ravel() - want)) <= 2 * TOL[np.dtype(dt)] * np.sqrt(k) * k
