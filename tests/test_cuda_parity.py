@@ -588,6 +588,26 @@ def test_transpose_narrow_elements_tiled(dt, rows, cols, batch):
     assert out.to_host()[1:].tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int16, np.uint8])
+@pytest.mark.parametrize("rows,cols,batch", [(3, 3, 4096), (2, 3, 1000), (5, 5, 777), (3, 5, 4099), (9, 9, 513), (24, 8, 300), (100, 3, 260),
+                                             (1, 7, 5000), (7, 1, 5000), (12, 12, 1024), (33, 31, 256)])
+def test_transpose_many_small_objects_staged(dt, rows, cols, batch):
+    """batches of small objects of any shape: bulk-TMA staged gather, out of place and in place, whole and ragged
+    final chunks; bytes that do not make whole 16-byte words fall back to the per-warp kernel -- same result"""
+    e = rows * cols
+    a = (np.arange(batch * e, dtype=np.int64) * 2654435761 >> 11).astype(dt)
+    want = np.concatenate([oracle.transpose(a[i * e:(i + 1) * e], cols) for i in range(batch)])
+    buf = CudaBatch(batch + 1, e, dt)
+    buf.copy_from_host(np.full((batch + 1) * e, 7, dt))
+    cuda.transpose_batched(CudaVec.from_host(a), buf.view(0, batch * e), e, cols)
+    got = buf.to_host().ravel()
+    assert got[:batch * e].tobytes() == want.tobytes()
+    assert np.all(got[batch * e:] == np.array(7, dt))  # nothing written past the last object
+    d = CudaBatch.from_host(a, e)
+    cuda.transpose_inplace_batched(d, e, cols)
+    assert d.to_host().ravel().tobytes() == want.tobytes()
+
+
 def test_transpose_ragged_len_leaves_tail_untouched():
     a = np.arange(11, dtype=np.float32)  # columns = 3 -> rows = 3, elements 9, 10 never written (rust.rs:168-175)
     buf = np.full(11, -7.0, np.float32)
