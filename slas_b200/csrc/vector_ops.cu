@@ -11,6 +11,7 @@
 // the partials in index order.  No float atomics anywhere => same input, same launch
 // geometry, same bits.  Element-wise ops and the normalize divide are single IEEE
 // operations (no fast-math, true division) => bit-exact against the reference.
+#include "async.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
 #include "p2p.cuh"
@@ -770,6 +771,142 @@ batched_reduce_lane_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
     }
 }
 
+// Short vectors that are NOT whole 16-byte words (3-vectors, LEN 5, 7, 30 ...): the vector kernels above cannot load
+// them with aligned vectors and a warp per vector idles on three elements (LEN 3 f32: 0.02 of HBM peak).  Same cure as
+// for the small transposes and products: HBM only sees 1-D bulk copies.  A producer warp streams chunks of G
+// consecutive vectors of a (and b) into a three-stage shared-memory ring; each consumer thread owns whole vectors of
+// the chunk -- a plain ascending loop of FMAs in T, exactly the reference's naive loop (rust.rs:116-121) -- and writes
+// its result to consecutive out[] (dot / norm), or the scaled vector to a double-buffered shared tile that leaves with
+// one bulk store per chunk (normalize).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(288)
+batched_reduce_staged_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, T *a_mut, size_t batch,
+                             size_t nchunks, unsigned len, unsigned G, unsigned stage_bytes) {
+    constexpr int CONSUMERS = 256, STAGES = 3;
+    constexpr int NIN = MODE == 0 ? 2 : 1;  // operands per stage
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *out_base = smem_raw + (size_t)STAGES * NIN * stage_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(out_base + (MODE == 2 ? 2 * (size_t)stage_bytes : 0));
+    uint64_t *empty = full + STAGES;
+    T *norms = reinterpret_cast<T *>(empty + STAGES);  // MODE 2: the chunk's G norms
+    // measured: up to 8 elements the owning thread scales its own vector (LEN 3 f32 0.72 against 0.59); longer ones are
+    // scaled by all threads over consecutive elements (LEN 38 f32 0.64 against 0.53, LEN 19 f64 0.80 against 0.67)
+    const bool coop_scale = len > 8;
+    const T *abase = MODE == 2 ? a_mut : a;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == CONSUMERS / 32) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+                const uint32_t s = it % STAGES, use = it / STAGES;
+                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                const size_t first = ch * G;
+                const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+                const uint32_t bytes = (cnt * len * (uint32_t)sizeof(T) + 15u) & ~15u;  // the arrays end on a 16-byte word
+                mbar_expect_tx(full + s, NIN * bytes);
+                bulk_g2s(smem_raw + (size_t)s * NIN * stage_bytes, abase + first * len, bytes, full + s);
+                if (MODE == 0) bulk_g2s(smem_raw + (size_t)s * NIN * stage_bytes + stage_bytes, b + first * len, bytes, full + s);
+            }
+        }
+        return;
+    }
+    uint32_t it = 0;
+    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+        const uint32_t s = it % STAGES, use = it / STAGES;
+        const size_t first = ch * G;
+        const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
+        const T *sa = reinterpret_cast<const T *>(smem_raw + (size_t)s * NIN * stage_bytes);
+        const T *sb = MODE == 0 ? reinterpret_cast<const T *>(smem_raw + (size_t)s * NIN * stage_bytes + stage_bytes) : sa;
+        T *cst = reinterpret_cast<T *>(out_base + (size_t)(it & 1) * stage_bytes);
+        mbar_wait(full + s, use & 1);
+        if (MODE == 2) asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");  // the bulk store that read this tile is done
+        for (uint32_t v = threadIdx.x; v < cnt; v += CONSUMERS) {
+            const T *pa = sa + (size_t)v * len, *pb = sb + (size_t)v * len;
+            T acc = T(0);
+            for (unsigned i = 0; i < len; ++i) acc = fma(pa[i], pb[i], acc);
+            if (MODE == 0) {
+                out[first + v] = acc;
+            } else if (MODE == 1) {
+                out[first + v] = sqrt(acc);  // correctly rounded in T (sqrt.rn): the same bits as rounding a wider sqrt
+            } else if (coop_scale) {
+                norms[v] = sqrt(acc);
+            } else {
+                const T nrm = sqrt(acc);
+                T *pc = cst + (size_t)v * len;
+                for (unsigned i = 0; i < len; ++i) pc[i] = pa[i] / nrm;
+            }
+        }
+        if (MODE == 2 && coop_scale) {
+            // scale pass over the chunk's elements, all threads, consecutive elements (no bank conflicts, no idle lanes);
+            // (vector, element) of the linear index kept up to date with additions
+            asm volatile("bar.sync 3, %0;" ::"n"(CONSUMERS) : "memory");
+            const unsigned total = cnt * len, step_v = CONSUMERS / len, step_i = CONSUMERS % len;
+            unsigned v = threadIdx.x / len, i = threadIdx.x % len;
+            for (unsigned e = threadIdx.x; e < total; e += CONSUMERS) {
+                cst[e] = sa[e] / norms[v];
+                v += step_v; i += step_i;
+                if (i >= len) { i -= len; ++v; }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+        if (MODE == 2) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 2, %0;" ::"n"(CONSUMERS) : "memory");
+            if (threadIdx.x == 0) {
+                const size_t total = (size_t)cnt * len, cbytes = total * sizeof(T);
+                const uint32_t whole = (uint32_t)(cbytes & ~(size_t)15);
+                if (whole)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a_mut + first * len),
+                                 "r"(smem_u32(cst)), "r"(whole)
+                                 : "memory");
+                for (size_t e = whole / sizeof(T); e < total; ++e) a_mut[first * len + e] = cst[e];
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            }
+        }
+    }
+    if (MODE == 2 && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <typename T, int MODE>
+static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t batch, size_t len, const T *a, const T *b, T *out,
+                                        T *a_mut, bool *handled) {
+    *handled = false;
+    const T *base = MODE == 2 ? a_mut : a;
+    const size_t vbytes = len * sizeof(T);
+    // longer vectors leave too few of them per chunk to keep a thread-per-vector CTA busy (measured: normalize of
+    // LEN 127 f32 0.25 of HBM peak): the warp-per-vector kernel keeps those
+    if (len == 0 || vbytes > 160 || batch < 256 || !aligned16(base) || (MODE == 0 && !aligned16(b)) || (batch * vbytes) % 16 ||
+        tunable("bdot_variant") == 2)
+        return SLAS_OK;
+    size_t galign = 16;
+    while (galign > 1 && vbytes % (16 / (galign / 2)) == 0) galign /= 2;  // 16 / gcd(vbytes, 16): chunks start on 16-byte words
+    size_t G = (16 * 1024 / vbytes) / galign * galign;
+    if (G > 1024) G = 1024 / galign * galign;
+    if (G < galign) G = galign;
+    const size_t stage_bytes = (G * vbytes + 127) / 128 * 128;
+    const size_t smem = (3 * (MODE == 0 ? 2 : 1) + (MODE == 2 ? 2 : 0)) * stage_bytes + 6 * sizeof(uint64_t) +
+                        (MODE == 2 ? G * sizeof(T) : 0);
+    const size_t nchunks = (batch + G - 1) / G;
+    int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    size_t grid = (size_t)ctx->sm_count * per_sm;
+    if (grid > nchunks) grid = nchunks;
+    auto kern = batched_reduce_staged_kernel<T, MODE>;
+    SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 288, smem, st>>>(a, b, out, a_mut, batch, nchunks, (unsigned)len, (unsigned)G, (unsigned)stage_bytes);
+    SLAS_LAUNCH_CHECK();
+    *handled = true;
+    return SLAS_OK;
+}
+
 // Long vectors: every vector is cut into segments of kSegElems elements, one CTA per segment, so the
 // grid fills the chip even for a handful of vectors.  partial[v][s] (f64) -> batched_finish_kernel adds
 // the segments of a vector in index order (deterministic) -> out / norms.
@@ -900,6 +1037,12 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
         else batched_reduce_lane_kernel<T, MODE, 8><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, chunks);
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
+    }
+    if (!vec || len < (size_t)N) {
+        // not whole 16-byte words (3-vectors, LEN 5, 30 ...): bulk-TMA staged, a thread per vector
+        bool staged = false;
+        SLAS_TRY((launch_batched_reduce_staged<T, MODE>(ctx, st, batch, len, a, b, out, a_mut, &staged)));
+        if (staged) return SLAS_OK;
     }
     if (vec && len >= (size_t)N && len / N <= 32 * 8) {
         // tiny: sub-warp groups, registers only

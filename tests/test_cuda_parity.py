@@ -904,6 +904,8 @@ def test_gemv_vs_oracle(dt, rows, cols, ta):
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
                                           (4, 3001), (8, 777), (24, 1025), (32, 33), (40, 999), (64, 257), (72, 100),  # a lane per vector (<= 256 bytes)
+                                          (3, 5000), (5, 1000), (7, 4099), (9, 257), (30, 1025), (100, 300), (127, 256), (1, 4096),
+                                          (6, 2000), (3, 4097),  # not whole 16-byte words: bulk-TMA staged, a thread per vector
                                           # warp / CTA per vector with ragged piece counts, more vectors than groups in
                                           # the grid, and the lengths either side of every kernel switch
                                           (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
