@@ -94,11 +94,11 @@ struct JitCfg {
 };
 
 // Thread per matrix (gemm_tiny_kernel<T, M, N, K, G>): any m, n, k -- no vector-width rules -- as long as the operands
-// and the result of one product fit a thread's registers (~160 32-bit registers) and three input stages plus two C
+// and the result of one product fit a thread's registers (<= 200 32-bit registers) and three input stages plus two C
 // stages of G matrices fit shared memory.  G = consumer threads: as many as leave room for two CTAs per SM.
 static bool choose_tiny_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
     const size_t words = (m * k + k * n + m * n) * (elem / 4);
-    if (m == 0 || n == 0 || k == 0 || words > 160) return false;
+    if (m == 0 || n == 0 || k == 0 || words > 200) return false;
     for (size_t g = 256; g >= 64; g /= 2) {
         const size_t stage = (g * (m * k + k * n) * elem + 127) / 128 * 128, cstage = (g * m * n * elem + 127) / 128 * 128;
         const size_t smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);

@@ -900,6 +900,27 @@ def test_gemv_vs_oracle(dt, rows, cols, ta):
         assert np.max(np.abs(got[i] - w)) <= tol
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("rows,cols", [(3, 3), (4, 3), (3, 4), (6, 6), (5, 5), (9, 9), (12, 12), (7, 3), (1, 5), (5, 1), (20, 6)])
+@pytest.mark.parametrize("ta", [False, True])
+def test_gemv_batched_small_odd_shapes(dt, rows, cols, ta):
+    """3x3 . 3-vector and friends, large batches: routed through the shape-specialised batched GEMM kernels (B with one
+    column); whole and ragged chunks, nothing written past the last result"""
+    rng = np.random.default_rng(rows * 31 + cols)
+    for batch in (64, 1000, 4099):
+        xl, yl = (rows, cols) if ta else (cols, rows)
+        A, x = _rand(rng, batch * rows * cols, dt), _rand(rng, batch * xl, dt)
+        y = CudaBatch(batch + 1, yl, dt)
+        y.copy_from_host(np.full((batch + 1) * yl, -9.0, dt))
+        cuda.matrix_vector_mul_batched(CudaVec.from_host(A), CudaVec.from_host(x), y.view(0, batch * yl), cols, rows, ta)
+        got = y.to_host().ravel()
+        A3 = A.reshape(batch, rows, cols).astype(np.float64)
+        ref = np.einsum("bji,bj->bi" if ta else "bij,bj->bi", A3, x.reshape(batch, xl).astype(np.float64)).ravel()
+        mag = np.einsum("bji,bj->bi" if ta else "bij,bj->bi", np.abs(A3), np.abs(x.reshape(batch, xl)).astype(np.float64)).ravel()
+        assert np.all(np.abs(got[:batch * yl] - ref) <= TOL[np.dtype(dt)] * np.sqrt(xl) * mag + 1e-300), (batch,)
+        assert np.all(got[batch * yl:] == -9.0)
+
+
 # ---- batched dot / norm / normalize --------------------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
