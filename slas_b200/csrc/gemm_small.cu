@@ -196,17 +196,39 @@ using CfgS16t = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 2, true>;
 using CfgS32t = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 2, true>;
 using CfgD16t = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 2, true>;
 
+// Shapes without a built-in cube configuration: thread per matrix (every dimension <= 4), the run-time specialised
+// kernels, the runtime-shape kernel.  All of them stream whole 16-byte words, so a batch whose byte count is not a
+// multiple of 16 (1001 3x3 f32 matrices ...) is split: the largest prefix that is goes through them, the last one to
+// three objects through the plain kernel -- instead of the whole batch falling off the fast path.
+template <typename T>
+static int launch_other_shapes(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                               size_t k, int ta, int tb) {
+    const int r = launch_gemm_tiny_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+    if (r != SLAS_ERR_UNSUPPORTED) return r;
+    const int rj = launch_gemm_jit_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+    if (rj != SLAS_ERR_UNSUPPORTED) return rj;
+    return batch >= 64 ? launch_generic_small<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
+}
+template <typename T>
+static int launch_other_shapes_split(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m,
+                                     size_t n, size_t k, int ta, int tb) {
+    const bool ragged = (batch * m * k * sizeof(T)) % 16 || (batch * k * n * sizeof(T)) % 16;
+    if (!ragged) return launch_other_shapes<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+    const size_t unit = 16 / sizeof(T), rem = batch % unit, main = batch - rem;  // `unit` objects are always whole words
+    if (main < 1024 || rem == 0) return SLAS_ERR_UNSUPPORTED;
+    const int r = launch_other_shapes<T>(ctx, st, main, a, b, c, m, n, k, ta, tb);
+    if (r != SLAS_OK) return r;
+    return launch_gemm_generic<T>(ctx, st, rem, a + main * m * k, b + main * k * n, c + main * m * n, m, n, k, ta ? m : k,
+                                  tb ? k : n, n, ta, tb, m * k, k * n, m * n);
+}
+
 template <>
 int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch, const float *a, const float *b,
                                      float *c, size_t m, size_t n, size_t k, int ta, int tb) {
     if (batch == 0) return SLAS_OK;
     if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
     if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64)) {
-        const int r = launch_gemm_tiny_batched<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
-        if (r != SLAS_ERR_UNSUPPORTED) return r;
-        const int rj = launch_gemm_jit_batched<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
-        if (rj != SLAS_ERR_UNSUPPORTED) return rj;
-        return batch >= 64 ? launch_generic_small<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
+        return launch_other_shapes_split<float>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
     }
     switch (m) {
     case 4:
@@ -246,11 +268,7 @@ int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batc
     if (batch == 0) return SLAS_OK;
     if (!(aligned16(a) && aligned16(b) && aligned16(c))) return SLAS_ERR_UNSUPPORTED;
     if (m != n || n != k || (m != 4 && m != 8 && m != 16 && m != 32 && m != 64)) {
-        const int r = launch_gemm_tiny_batched<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
-        if (r != SLAS_ERR_UNSUPPORTED) return r;
-        const int rj = launch_gemm_jit_batched<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
-        if (rj != SLAS_ERR_UNSUPPORTED) return rj;
-        return batch >= 64 ? launch_generic_small<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb) : SLAS_ERR_UNSUPPORTED;
+        return launch_other_shapes_split<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
     }
     switch (m) {
     case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);

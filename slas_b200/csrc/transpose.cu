@@ -305,11 +305,35 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     *handled = false;
     const size_t obj_bytes = len * sizeof(E);
     if (len != rows * columns || obj_bytes > 8 * 1024 || batch < 256 || !aligned16(a) || !aligned16(buffer) ||
-        (batch * obj_bytes) % 16 || tunable("transpose_variant") == 11)
+        tunable("transpose_variant") == 11)
         return SLAS_OK;
     // G objects per chunk: ~16 KB, a multiple of 16 / gcd(object bytes, 16) so that every chunk starts on a 16-byte boundary
     size_t galign = 16;
     while (galign > 1 && obj_bytes % (16 / (galign / 2)) == 0) galign /= 2;  // 16 / gcd(obj_bytes, 16)
+    // the kernel moves whole 16-byte words: a batch that does not end on one (1001 3x3 f32 objects ...) leaves its last
+    // < galign objects to the warp-per-object kernel (which also works in place) instead of falling off the fast path
+    const size_t rem = batch % galign;
+    if (rem) {
+        const size_t main = batch - rem, padded = columns * (rows + 1);
+        if (main < 256 || padded * sizeof(E) > 12 * 1024) return SLAS_OK;
+        SLAS_TRY(launch_transpose_staged<E>(ctx, st, main, len, a, buffer, rows, columns, handled));
+        if (!*handled) return SLAS_OK;
+        const size_t smem = 8 * padded * sizeof(E);
+        const bool inplace = a == buffer;
+        if (smem > 48 * 1024) {
+            if (inplace) SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            else SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_small_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        }
+        const unsigned blocks = (unsigned)((rem + 7) / 8);
+        if (inplace)
+            transpose_small_kernel<E, true><<<blocks, 256, smem, st>>>(a + main * len, buffer + main * len, rem, (unsigned)len, (unsigned)rows,
+                                                                       (unsigned)columns, (unsigned)padded);
+        else
+            transpose_small_kernel<E, false><<<blocks, 256, smem, st>>>(a + main * len, buffer + main * len, rem, (unsigned)len, (unsigned)rows,
+                                                                        (unsigned)columns, (unsigned)padded);
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+    }
     size_t G = (16 * 1024 / obj_bytes) / galign * galign;
     if (G < galign) G = galign;
     const size_t stage_bytes = (G * obj_bytes + 127) / 128 * 128;

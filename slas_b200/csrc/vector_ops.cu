@@ -882,11 +882,24 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
     const size_t vbytes = len * sizeof(T);
     // longer vectors leave too few of them per chunk to keep a thread-per-vector CTA busy (measured: normalize of
     // LEN 127 f32 0.25 of HBM peak): the warp-per-vector kernel keeps those
-    if (len == 0 || vbytes > 160 || batch < 256 || !aligned16(base) || (MODE == 0 && !aligned16(b)) || (batch * vbytes) % 16 ||
-        tunable("bdot_variant") == 2)
+    if (len == 0 || vbytes > 160 || batch < 256 || !aligned16(base) || (MODE == 0 && !aligned16(b)) || tunable("bdot_variant") == 2)
         return SLAS_OK;
     size_t galign = 16;
     while (galign > 1 && vbytes % (16 / (galign / 2)) == 0) galign /= 2;  // 16 / gcd(vbytes, 16): chunks start on 16-byte words
+    // the kernel streams whole 16-byte words: a batch that does not end on one (1001 3-vectors ...) keeps its last
+    // < galign vectors for the warp-per-vector kernel instead of falling off the fast path altogether
+    const size_t rem = batch % galign;
+    if (rem) {
+        const size_t main = batch - rem;
+        if (main < 256) return SLAS_OK;
+        SLAS_TRY((launch_batched_reduce_staged<T, MODE>(ctx, st, main, len, a, b, out, a_mut, handled)));
+        if (!*handled) return SLAS_OK;
+        batched_reduce_kernel<T, 32, MODE><<<(unsigned)((rem + 7) / 8), 256, 0, st>>>(
+            a ? a + main * len : nullptr, b ? b + main * len : nullptr, out ? out + main : nullptr, a_mut ? a_mut + main * len : nullptr,
+            rem, len, 0);
+        SLAS_LAUNCH_CHECK();
+        return SLAS_OK;
+    }
     size_t G = (16 * 1024 / vbytes) / galign * galign;
     if (G > 1024) G = 1024 / galign * galign;
     if (G < galign) G = galign;
