@@ -409,6 +409,23 @@ def run_cuda(args):
             ms_, _ = timed(lambda: cuda.transpose_inplace_batched(va, n_ * n_, n_), ksteps, 3)
             record(f"batched {n_}x{n_} {name} transpose_inplace (Matrix::deref_mut per object), batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
             del a, x, y, va, vx, vy
+        # 3-D geometry sizes: 3x3 matrices and 3-vectors (not whole 16-byte words: bulk-TMA staged thread-per-object kernels)
+        bsz = 1 << 24
+        a, x = dev_uniform(bsz * 9, torch.float32, 2), dev_uniform(bsz * 3, torch.float32, 3)
+        y = torch.empty_like(x)
+        o = torch.empty(bsz, device=dev, dtype=torch.float32)
+        va, vx, vy, vo = vec(a), vec(x), vec(y), vec(o)
+        ms_, _ = timed(lambda: cuda.matrix_vector_mul_batched(va, vx, vy, 3, 3, False), ksteps, 3)
+        record("batched 3x3 f32 matrix_vector_mul (3x3 . 3-vector), batch 2^24", ms_, flop=18.0 * bsz, bytes_=60.0 * bsz)
+        at = torch.empty_like(a)
+        vat = vec(at)
+        ms_, _ = timed(lambda: cuda.transpose_batched(va, vat, 9, 3), ksteps, 3)
+        record("batched 3x3 f32 transpose, batch 2^24", ms_, bytes_=72.0 * bsz)
+        ms_, _ = timed(lambda: cuda.dot_batched(vx, vy, vo, 3), ksteps, 3)
+        record("batched 3-vector f32 dot, batch 2^24", ms_, bytes_=24.0 * bsz)
+        ms_, _ = timed(lambda: cuda.normalize_batched(vx, 3), ksteps, 3)
+        record("batched 3-vector f32 normalize, batch 2^24", ms_, bytes_=24.0 * bsz)
+        del a, x, y, o, at, va, vx, vy, vo, vat
         # config 1: dot + add, f32.  LEN = 2^20 is L2-resident and launch-bound as one call, so report
         # (i) one 2^28-element call, (ii) 1024 distinct 2^20 pairs in one batched launch, (iii) call latency.
         n28 = 1 << 28
