@@ -382,6 +382,10 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
         }
         return launch_gemm_large<T>(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
     }
+    // a batch of medium-sized products (past the shared-memory staged kernels): the register-tiled kernel, one grid layer
+    // per object (100x100 f32, batch 4096: 3.9 TFLOP/s on the plain kernel)
+    if (batch > 1 && m * n >= 32 * 32 && k >= 8)
+        return launch_gemm_large_batched<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);
     return launch_gemm_generic<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, m * k, k * n, m * n);
 }
 

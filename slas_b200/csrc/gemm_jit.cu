@@ -122,8 +122,8 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
     const size_t kvn = 16 / elem;
     if (m == 0 || n == 0 || k == 0 || n % kvn || k % kvn) return false;
     const size_t per_pair = (m * k + k * n) * elem;
-    if (per_pair > 16 * 1024) return false;
-    const size_t max_tile = 32;  // accumulators per thread
+    if (per_pair > 40 * 1024) return false;
+    const size_t max_tile = 64;  // accumulators per thread (24^3 f32 needs 3 x 12, 20^3 f64 5 x 10)
     double best = -1.0;
     for (size_t tm = 1; tm <= m; ++tm) {
         if (m % tm) continue;

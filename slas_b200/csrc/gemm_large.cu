@@ -76,8 +76,13 @@ __device__ __forceinline__ void tile_stash(T (*S)[LargeCfg<T>::BM + LargeCfg<T>:
 template <typename T, bool TA, bool TB>
 __global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1)
 gemm_large_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t m, size_t n, size_t k,
-                  size_t lda, size_t ldb, size_t ldc, int vec_a, int vec_b, int vec_c) {
+                  size_t lda, size_t ldb, size_t ldc, int vec_a, int vec_b, int vec_c, size_t stride_a, size_t stride_b,
+                  size_t stride_c) {
     using C = LargeCfg<T>;
+    // blockIdx.z = object of a batch of medium-sized products (strides in elements; 0 for a single product)
+    a += blockIdx.z * stride_a;
+    b += blockIdx.z * stride_b;
+    c += blockIdx.z * stride_c;
     constexpr int VW = C::VW, BM = C::BM, BN = C::BN, BK = C::BK, PAD = C::PAD;
     __shared__ __align__(16) T As[2][BK][BM + PAD];
     __shared__ __align__(16) T Bs[2][BK][BN + PAD];
@@ -148,28 +153,59 @@ gemm_large_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
 }
 
 template <typename T>
+static int launch_gemm_large_z(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                               size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a, size_t stride_b,
+                               size_t stride_c) {
+    using C = LargeCfg<T>;
+    (void)ctx;
+    const size_t gx = (n + C::BN - 1) / C::BN, gy = (m + C::BM - 1) / C::BM;
+    SLAS_REQUIRE(gx <= 0x7fffffffu && gy <= 65535, "gemm: grid too large (%zu x %zu tiles)", gx, gy);
+    const int vec_a = aligned16(a) && (lda * sizeof(T)) % 16 == 0 && (stride_a * sizeof(T)) % 16 == 0;
+    const int vec_b = aligned16(b) && (ldb * sizeof(T)) % 16 == 0 && (stride_b * sizeof(T)) % 16 == 0;
+    const int vec_c = aligned16(c) && (ldc * sizeof(T)) % 16 == 0 && (stride_c * sizeof(T)) % 16 == 0;
+    for (size_t done = 0; done < batch; done += 65535) {
+        const size_t cnt = batch - done < 65535 ? batch - done : 65535;
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)cnt);
+        const T *pa = a + done * stride_a, *pb = b + done * stride_b;
+        T *pc = c + done * stride_c;
+#define SLAS_LARGE_LAUNCH(TA_, TB_)                                                                                        \
+        gemm_large_kernel<T, TA_, TB_><<<grid, 256, 0, st>>>(pa, pb, pc, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c, stride_a, \
+                                                             stride_b, stride_c)
+        if (!ta && !tb) SLAS_LARGE_LAUNCH(false, false);
+        else if (ta && !tb) SLAS_LARGE_LAUNCH(true, false);
+        else if (!ta && tb) SLAS_LARGE_LAUNCH(false, true);
+        else SLAS_LARGE_LAUNCH(true, true);
+#undef SLAS_LARGE_LAUNCH
+        SLAS_LAUNCH_CHECK();
+    }
+    return SLAS_OK;
+}
+
+template <typename T>
 int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *c, size_t m, size_t n, size_t k,
                       size_t lda, size_t ldb, size_t ldc, int ta, int tb) {
-    using C = LargeCfg<T>;
     if (m == 0 || n == 0) return SLAS_OK;
     if constexpr (sizeof(T) == 8) {
         // at least one full wave of 128 x 128 tiles: the big-tile DFMA kernel (gemm_large_f64.cu)
         if (((m + 127) / 128) * ((n + 127) / 128) >= (size_t)ctx->sm_count && tunable("gemm_large_variant") != 3)
             return launch_dgemm_big(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
     }
-    const size_t gx = (n + C::BN - 1) / C::BN, gy = (m + C::BM - 1) / C::BM;
-    SLAS_REQUIRE(gx <= 0x7fffffffu && gy <= 65535, "gemm: grid too large (%zu x %zu tiles)", gx, gy);
-    const int vec_a = aligned16(a) && (lda * sizeof(T)) % 16 == 0;
-    const int vec_b = aligned16(b) && (ldb * sizeof(T)) % 16 == 0;
-    const int vec_c = aligned16(c) && (ldc * sizeof(T)) % 16 == 0;
-    dim3 grid((unsigned)gx, (unsigned)gy);
-    if (!ta && !tb) gemm_large_kernel<T, false, false><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
-    else if (ta && !tb) gemm_large_kernel<T, true, false><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
-    else if (!ta && tb) gemm_large_kernel<T, false, true><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
-    else gemm_large_kernel<T, true, true><<<grid, 256, 0, st>>>(a, b, c, m, n, k, lda, ldb, ldc, vec_a, vec_b, vec_c);
-    SLAS_LAUNCH_CHECK();
-    return SLAS_OK;
+    return launch_gemm_large_z<T>(ctx, st, 1, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, 0, 0, 0);
 }
+
+// A batch of medium-sized products (too big for the shared-memory staged batched kernels, 48x48 f32 / 40x40 f64 and up):
+// the same register-tiled FFMA / DFMA kernel, one grid layer per object.
+template <typename T>
+int launch_gemm_large_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                              size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a, size_t stride_b,
+                              size_t stride_c) {
+    if (m == 0 || n == 0 || batch == 0) return SLAS_OK;
+    return launch_gemm_large_z<T>(ctx, st, batch, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, stride_a, stride_b, stride_c);
+}
+template int launch_gemm_large_batched<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *, size_t,
+                                              size_t, size_t, size_t, size_t, size_t, int, int, size_t, size_t, size_t);
+template int launch_gemm_large_batched<double>(Context *, cudaStream_t, size_t, const double *, const double *, double *, size_t,
+                                               size_t, size_t, size_t, size_t, size_t, int, int, size_t, size_t, size_t);
 template int launch_gemm_large<float>(Context *, cudaStream_t, const float *, const float *, float *, size_t, size_t,
                                       size_t, size_t, size_t, size_t, int, int);
 template int launch_gemm_large<double>(Context *, cudaStream_t, const double *, const double *, double *, size_t,

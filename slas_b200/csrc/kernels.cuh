@@ -70,6 +70,11 @@ int launch_sgemm_ffma(Context *ctx, cudaStream_t st, const float *a, const float
 
 // gemm_tcgen05.cu -- 3xTF32 on the 5th-gen tensor cores (TMA + TMEM); SLAS_ERR_UNSUPPORTED
 // when the shape does not fit its tiles.
+// gemm_large.cu -- a batch of medium-sized products on the register-tiled FFMA / DFMA kernel, one grid layer per object
+template <typename T>
+int launch_gemm_large_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
+                              size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a, size_t stride_b,
+                              size_t stride_c);
 // gemm_large_f64.cu -- 128 x 128 tiles, 8 x 8 per thread
 int launch_dgemm_big(Context *ctx, cudaStream_t st, const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
                      size_t lda, size_t ldb, size_t ldc, int ta, int tb);

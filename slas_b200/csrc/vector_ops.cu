@@ -880,9 +880,12 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
     *handled = false;
     const T *base = MODE == 2 ? a_mut : a;
     const size_t vbytes = len * sizeof(T);
-    // longer vectors leave too few of them per chunk to keep a thread-per-vector CTA busy (measured: normalize of
-    // LEN 127 f32 0.25 of HBM peak): the warp-per-vector kernel keeps those
-    if (len == 0 || vbytes > 160 || batch < 256 || !aligned16(base) || (MODE == 0 && !aligned16(b)) || tunable("bdot_variant") == 2)
+    // longer vectors leave too few of them per chunk to keep a thread-per-vector CTA busy: measured crossover against
+    // the warp-per-vector kernel (profiles/r1e_tune_short_vectors.log) ~800 bytes for dot / norm (LEN 127 f32: 0.88 / 0.76
+    // against 0.58 / 0.32), ~600 bytes for normalize
+    // (norm and normalize must switch at the same length: normalize divides by the bits norm returns)
+    const size_t limit = tunable("bdot_limit") > 0 ? (size_t)tunable("bdot_limit") : (MODE == 0 ? 832 : 640);
+    if (len == 0 || vbytes > limit || batch < 256 || !aligned16(base) || (MODE == 0 && !aligned16(b)) || tunable("bdot_variant") == 2)
         return SLAS_OK;
     size_t galign = 16;
     while (galign > 1 && vbytes % (16 / (galign / 2)) == 0) galign /= 2;  // 16 / gcd(vbytes, 16): chunks start on 16-byte words

@@ -719,7 +719,7 @@ def test_batched_tiny_shapes_thread_per_matrix(dt, ta, tb):
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("m,n,k", [(8, 4, 16), (16, 32, 8), (12, 12, 12), (32, 8, 64), (6, 6, 6), (24, 8, 12), (5, 8, 4), (8, 8, 16),
                                    (48, 16, 4), (5, 5, 5), (3, 7, 5), (7, 7, 7), (1, 6, 9), (9, 9, 9), (10, 10, 10), (5, 9, 13), (33, 3, 7),
-                                   (15, 15, 15)])
+                                   (15, 15, 15), (20, 20, 20), (24, 24, 24), (48, 48, 48), (40, 40, 40), (100, 100, 100), (70, 33, 50)])
 def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
     """shapes without a built-in instantiation: the gemm_small kernel compiled for the shape with NVRTC on first use
     (gemm_jit.cu).  Without b_trans every C element is the same ascending-k FMA chain as in the runtime-shape kernel it
@@ -728,7 +728,7 @@ def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
     specialised instead if a product fits one thread's registers, and scalar register tiles otherwise (9x9x9, 5x9x13)."""
     from slas_b200.backends import set_tunable
     rng = np.random.default_rng(m * 100 + n * 10 + k)
-    for batch in (64, 1000, 1003):
+    for batch in ((64, 1000, 1003) if m * n * k <= 4096 else (64, 131)):  # medium sizes: also the one-layer-per-object kernel
         A, B = _rand(rng, batch * m * k, dt), _rand(rng, batch * k * n, dt)
         dA, dB = CudaVec.from_host(A), CudaVec.from_host(B)
         for ta in (False, True):
@@ -926,7 +926,8 @@ def test_gemv_batched_small_odd_shapes(dt, rows, cols, ta):
 @pytest.mark.parametrize("length,batch", [(1, 5), (3, 100), (16, 1000), (100, 333), (750, 64), (4096, 9), (20000, 5),
                                           (4, 3001), (8, 777), (24, 1025), (32, 33), (40, 999), (64, 257), (72, 100),  # a lane per vector (<= 256 bytes)
                                           (3, 5000), (5, 1000), (7, 4099), (9, 257), (30, 1025), (100, 300), (127, 256), (1, 4096),
-                                          (6, 2000), (3, 4097),  # not whole 16-byte words: bulk-TMA staged, a thread per vector
+                                          (6, 2000), (3, 4097), (50, 700), (127, 300), (150, 513), (201, 257),
+                                          # ^ not whole 16-byte words: bulk-TMA staged, a thread per vector
                                           # warp / CTA per vector with ragged piece counts, more vectors than groups in
                                           # the grid, and the lengths either side of every kernel switch
                                           (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
