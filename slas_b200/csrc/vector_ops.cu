@@ -11,6 +11,8 @@
 // the partials in index order.  No float atomics anywhere => same input, same launch
 // geometry, same bits.  Element-wise ops and the normalize divide are single IEEE
 // operations (no fast-math, true division) => bit-exact against the reference.
+#include <algorithm>
+
 #include "async.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
@@ -87,6 +89,15 @@ static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a
     constexpr int N = Vec16<T>::N;
     constexpr int UNROLL = 4;
     if (len == 0) return SLAS_OK;
+    // views at an odd offset: when all three operands share one misalignment the few elements up to the first 16-byte
+    // boundary go through the scalar kernel and the rest through the vector kernel (0.74 -> 1.0 of HBM peak)
+    const uintptr_t mis = (uintptr_t)a % 16;
+    if (mis && mis == (uintptr_t)b % 16 && mis == (uintptr_t)c % 16 && mis % sizeof(T) == 0) {
+        const size_t head = std::min<size_t>((16 - mis) / sizeof(T), len);
+        ewise_scalar_kernel<T, OP><<<1, kEwThreads, 0, st>>>(a, b, c, head);
+        SLAS_LAUNCH_CHECK();
+        return launch_ewise_op<T, OP>(ctx, st, len - head, a + head, b + head, c + head);
+    }
     if (aligned16(a) && aligned16(b) && aligned16(c)) {
         const size_t nvec = len / N;
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
@@ -171,7 +182,7 @@ template <typename T, int KIND>
 __global__ void __launch_bounds__(kRedThreads)
 reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised,
               double *__restrict__ partials, unsigned int *__restrict__ ticket, double *__restrict__ result,
-              T *__restrict__ typed_out, int mode, int accumulate, const PeerExchange px) {
+              T *__restrict__ typed_out, int mode, int accumulate, const PeerExchange px, unsigned head) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     __shared__ double red[kRedThreads / 32];
@@ -182,8 +193,10 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
     const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * kRedThreads;
     if (vectorised) {
-        const V *av = reinterpret_cast<const V *>(a);
-        const V *bv = reinterpret_cast<const V *>(b);
+        // operands that share a misalignment (views at an odd offset): `head` elements up to the first 16-byte boundary
+        // are scalar work like the tail, the body starts on the boundary
+        const V *av = reinterpret_cast<const V *>(a + head);
+        const V *bv = reinterpret_cast<const V *>(b + head);
         const size_t stride = nthreads * kRedUnroll;
         size_t i = (size_t)blockIdx.x * (kRedThreads * kRedUnroll) + threadIdx.x;
         int since_flush = 0;
@@ -214,12 +227,18 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
         // scalar tail: the len % N elements past the last whole vector (N is even, so a complex
         // pair is never split: the complex tail is whole (re, im) pairs)
         if (KIND != 2) {
-            const size_t j = nvec * N + tid;
+            const size_t j = head + nvec * N + tid;
             if (j < len) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+            if (tid < head) r.add_scalar(a[tid], KIND == 1 ? a[tid] : b[tid]);
         } else {
-            const size_t j = nvec * N + 2 * tid;
+            const size_t j = head + nvec * N + 2 * tid;
             if (j + 1 < len) {
                 const double ar = a[j], ai = a[j + 1], br = b[j], bi = b[j + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
+            if (2 * tid + 1 < head) {
+                const double ar = a[2 * tid], ai = a[2 * tid + 1], br = b[2 * tid], bi = b[2 * tid + 1];
                 r.sum += ar * br - ai * bi;
                 r.sum_im += ar * bi + ai * br;
             }
@@ -233,7 +252,22 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
                 r.sum_im += ar * bi + ai * br;
             }
         } else {
-            for (size_t j = tid; j < len; j += nthreads) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+            // operands with different misalignments: coalesced 4-byte / 8-byte loads, four in flight per thread, T
+            // accumulators flushed into f64 like the vector body (one DFMA per element was 0.35 of HBM peak)
+            size_t j = tid;
+            int since_flush = 0;
+            for (; j + 3 * nthreads < len; j += 4 * nthreads) {
+                T x[4], y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = a[j + u * nthreads];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = KIND == 1 ? x[u] : b[j + u * nthreads];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) r.acc[u] = fma(x[u], y[u], r.acc[u]);
+                if (++since_flush == kFlushEvery * 4) { r.flush(); since_flush = 0; }
+            }
+            r.flush();
+            for (; j < len; j += nthreads) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
         }
     }
     double s = block_sum<kRedThreads>(r.sum, red);
@@ -277,8 +311,14 @@ template <typename T, int KIND>
 static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b,
                               double *result, T *typed_out, int mode, int accumulate, const PeerExchange &px) {
     constexpr int N = Vec16<T>::N;
-    const bool vec = aligned16(a) && (KIND == 1 || aligned16(b));
-    const size_t nvec = vec ? len / N : 0;
+    // vector body when the operands are aligned, or share one misalignment that is whole elements (for complex: whole
+    // pairs) away from a 16-byte boundary
+    const uintptr_t ma = (uintptr_t)a % 16, mb = (uintptr_t)(KIND == 1 ? a : b) % 16;
+    const size_t unit = sizeof(T) * (KIND == 2 ? 2 : 1);
+    const bool vec = ma == mb && ma % unit == 0;
+    size_t head = vec && ma ? (16 - ma) / sizeof(T) : 0;
+    if (head > len) head = len;
+    const size_t nvec = vec ? (len - head) / N : 0;
     const size_t work = vec ? nvec : len;
     size_t blocks = (work + (size_t)kRedThreads * kRedUnroll - 1) / ((size_t)kRedThreads * kRedUnroll);
     const size_t cap = (size_t)ctx->sm_count * 8;
@@ -287,7 +327,7 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
     if (blocks == 0) blocks = 1;
     reduce_kernel<T, KIND><<<(unsigned)blocks, kRedThreads, 0, st>>>(
         a, KIND == 1 ? a : b, len, nvec, vec ? 1 : 0, ctx->partials, ctx->ticket, result, typed_out, mode,
-        accumulate, px);
+        accumulate, px, (unsigned)head);
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;
 }
@@ -365,6 +405,13 @@ int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, const T *in, T *
     constexpr int N = Vec16<T>::N;
     constexpr int UNROLL = 4;
     if (len == 0) return SLAS_OK;
+    const uintptr_t mis = (uintptr_t)a % 16;
+    if (mis && mis == (uintptr_t)in % 16 && mis % sizeof(T) == 0) {  // a view at an odd offset: scalar head, vector body
+        const size_t head = std::min<size_t>((16 - mis) / sizeof(T), len);
+        scale_div_scalar_kernel<T><<<1, kEwThreads, 0, st>>>(in, a, head, norm_dev);
+        SLAS_LAUNCH_CHECK();
+        return launch_scale_div<T>(ctx, st, len - head, in + head, a + head, norm_dev);
+    }
     if (aligned16(a) && aligned16(in)) {
         const size_t nvec = len / N;
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);

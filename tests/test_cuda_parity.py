@@ -302,6 +302,36 @@ def test_norm_and_normalize(dt, n):
     assert np.array_equal(h, got)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 1000, (1 << 18) + 7])
+def test_views_at_odd_offsets(dt, n):
+    """device views that start 1, 2 or 3 elements past a 16-byte boundary (static_slice at an odd offset): a shared
+    misalignment is peeled (scalar head, vector body), different misalignments take the scalar loop -- same results"""
+    rng = np.random.default_rng(n)
+    pad = 4
+    cplx = np.dtype(dt).kind == "c"
+    mk = (lambda k: (_rand(rng, k, np.float32) + 1j * _rand(rng, k, np.float32)).astype(dt)) if cplx else (lambda k: _rand(rng, k, dt))
+    A, B = mk(n + pad), mk(n + pad)
+    dA, dB, dC = CudaVec.from_host(A), CudaVec.from_host(B), CudaVec(n + pad, dt)
+    rel = (1e-5 if np.dtype(dt).itemsize in (4, 8) and dt != np.float64 else 1e-13) * np.sqrt(n)
+    for oa, ob in ((1, 1), (2, 2), (3, 3), (0, 1), (2, 1)):
+        a, b = A[oa:oa + n], B[ob:ob + n]
+        got = cuda.dot(dA.view(oa, n), dB.view(ob, n))
+        truth = np.sum(a.astype(np.complex128 if cplx else np.longdouble) * b)
+        assert abs(complex(got) - complex(truth)) <= rel * float(np.sum(np.abs(a) * np.abs(b))) + 1e-300, (oa, ob)
+        nrm = cuda.norm(dA.view(oa, n))
+        assert abs(float(nrm) - float(np.sqrt(np.sum(np.abs(a.astype(np.complex128)) ** 2)))) <= 2 * rel * float(nrm) + 1e-300
+        if not cplx:
+            dC.zero_()
+            cuda.add(dA.view(oa, n), dB.view(ob, n), dC.view(oa, n))
+            c = dC.to_host()
+            assert np.array_equal(c[oa:oa + n], a + b) and np.all(c[:oa] == 0) and np.all(c[oa + n:] == 0), (oa, ob)
+            dN = CudaVec.from_host(A)
+            cuda.normalize(dN.view(oa, n))
+            h = dN.to_host()
+            assert np.array_equal(h[oa:oa + n], a / nrm) and np.array_equal(h[:oa], A[:oa]) and np.array_equal(h[oa + n:], A[oa + n:])
+
+
 def test_reductions_special_values_and_overflow_policy():
     """IEEE propagation through the reductions, the normalize of a zero vector, and overflow of the sum of squares:
     like the Rust backend's naive f32 sum (rust.rs:116-121) a norm overflows to infinity when squares or a thread's
