@@ -161,10 +161,14 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
 // Scalar register tiles (gemm_rect_kernel<T, M, N, K, TM, TN, G>): any divisors TM | M, TN | N with at most 256 threads per
 // matrix; G = a whole number of passes of MPP = 256 / TPM matrices, sized so that three input stages and two C stages
 // leave room for two CTAs per SM when possible.
+static size_t gcd_sz(size_t a, size_t b) { return b ? gcd_sz(b, a % b) : a; }
+
 static bool choose_rect_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
     if (m == 0 || n == 0 || k == 0) return false;
     const size_t per_in = (m * k + k * n) * elem, per_out = m * n * elem;
-    if (per_in > 16 * 1024) return false;
+    if (per_in > 48 * 1024) return false;
+    // G objects per chunk must keep every chunk of A, B and C on a 16-byte boundary
+    const size_t galign = 16 / gcd_sz(gcd_sz(gcd_sz(m * k * elem, k * n * elem), m * n * elem), 16);
     double best = -1.0;
     for (size_t tm = 1; tm <= m; ++tm) {
         if (m % tm) continue;
@@ -173,11 +177,10 @@ static bool choose_rect_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *o
             const size_t tpm = (m / tm) * (n / tn);
             if (tpm > 256) continue;
             const size_t mpp = 256 / tpm;
-            // G % 4 == 0 keeps every chunk of A, B and C on a 16-byte boundary whatever the shape
-            size_t g = (24 * 1024 / (per_in + per_out)) / 4 * 4;
-            if (g < mpp) g = (mpp + 3) / 4 * 4;
-            if (g < 4) g = 4;
-            if (g > 1024) g = 1024;
+            size_t g = (24 * 1024 / (per_in + per_out)) / galign * galign;
+            if (g < mpp) g = (mpp + galign - 1) / galign * galign;
+            if (g < galign) g = galign;
+            if (g > 1024) g = 1024 / galign * galign;
             const size_t stage = (g * per_in + 127) / 128 * 128, cstage = (g * per_out + 127) / 128 * 128;
             const size_t smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);
             if (smem > 200 * 1024) continue;
