@@ -32,7 +32,7 @@ int fail(int code, const char *fmt, ...) {
 struct Tunable { const char *name; long value; };
 static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0}, {"gemm32s_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
-                               {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}};
+                               {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;

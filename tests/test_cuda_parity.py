@@ -620,7 +620,8 @@ def test_transpose_narrow_elements_tiled(dt, rows, cols, batch):
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex128, np.int16, np.uint8])
 @pytest.mark.parametrize("rows,cols,batch", [(3, 3, 4096), (2, 3, 1000), (5, 5, 777), (3, 5, 4099), (9, 9, 513), (24, 8, 300), (100, 3, 260),
-                                             (1, 7, 5000), (7, 1, 5000), (12, 12, 1024), (33, 31, 256)])
+                                             (1, 7, 5000), (7, 1, 5000), (12, 12, 1024), (33, 31, 256), (100, 100, 260), (70, 50, 257),
+                                             (32, 8, 300), (96, 96, 256), (16, 3, 1000), (64, 48, 256), (48, 5, 513)])
 def test_transpose_many_small_objects_staged(dt, rows, cols, batch):
     """batches of small objects of any shape: bulk-TMA staged gather, out of place and in place, whole and ragged
     final chunks; bytes that do not make whole 16-byte words fall back to the per-warp kernel -- same result"""
