@@ -374,7 +374,7 @@ int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T
         // any other small dense shape (3x3 . 3-vector, 6x6, 12x12 ...): y = op(A) x is the batched product with a one-column
         // B, which the shape-specialised batched GEMM kernels run at HBM speed (a warp per row of a 3x3 matrix: 0.02)
         if (batch >= 64 && m > 0 && n > 0 && lda == m && stride_a == m * n && stride_x == xlen && stride_y == ylen &&
-            m * n * sizeof(T) <= 16 * 1024 && aligned16(a) && aligned16(x) && aligned16(y) && tunable("gemv_variant") != 2) {
+            m * n * sizeof(T) <= 44 * 1024 && aligned16(a) && aligned16(x) && aligned16(y) && tunable("gemv_variant") != 2) {
             // trait: A is n (height) x m (width); y = A x: M = n, K = m; y = A^T x: M = m, K = n with a_trans
             const int r = launch_gemm_small_batched<T>(ctx, st, batch, a, x, y, ta ? m : n, 1, ta ? n : m, ta, 0);
             if (r != SLAS_ERR_UNSUPPORTED) return r;

@@ -181,11 +181,16 @@ static bool choose_rect_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *o
             if (g < mpp) g = (mpp + galign - 1) / galign * galign;
             if (g < galign) g = galign;
             if (g > 1024) g = 1024 / galign * galign;
-            const size_t stage = (g * per_in + 127) / 128 * 128, cstage = (g * per_out + 127) / 128 * 128;
-            const size_t smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);
+            size_t stage = 0, cstage = 0, smem = 0;
+            for (;; g -= galign) {  // big objects: fewer per chunk than a pass could take (some thread groups idle)
+                stage = (g * per_in + 127) / 128 * 128;
+                cstage = (g * per_out + 127) / 128 * 128;
+                smem = 3 * stage + 2 * cstage + 6 * sizeof(uint64_t);
+                if (smem <= 200 * 1024 || g <= galign) break;
+            }
             if (smem > 200 * 1024) continue;
             double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm);         // FMAs per shared-memory load
-            score *= (double)(mpp * tpm) / 256.0;                                 // busy threads
+            score *= (double)((g < mpp ? g : mpp) * tpm) / 256.0;                // busy threads
             if ((size_t)227 * 1024 / (smem + 1024) < 2) score *= 0.6;
             if (score > best) {
                 best = score;
