@@ -43,6 +43,24 @@ def transpose_single(side, dt):
     synchronize()
 
 
+def small_odd():
+    """3-D geometry sizes and a run-time specialised shape: the bulk-TMA staged thread-per-object kernels"""
+    b = 1 << 24
+    a, x, y = uniform(b * 9, np.float32, 1), uniform(b * 3, np.float32, 2), CudaVec(b * 3, np.float32)
+    c, o = CudaVec(b * 9, np.float32), CudaVec(b, np.float32)
+    for _ in range(2):
+        cuda.matrix_mul_batched(a, a, c, 3, 3, 3)
+        cuda.matrix_vector_mul_batched(a, x, y, 3, 3, False)
+        cuda.transpose_batched(a, c, 9, 3)
+        cuda.dot_batched(x, y, o, 3)
+        cuda.normalize_batched(x, 3)
+    b2 = 1 << 22
+    p, q, r = uniform(b2 * 128, np.float32, 3), uniform(b2 * 64, np.float32, 4), CudaVec(b2 * 32, np.float32)
+    for _ in range(2):
+        cuda.matrix_mul_batched(p, q, r, 8, 4, 16)
+    synchronize()
+
+
 def vector_ops():
     n = 1 << 28
     a, b, c = uniform(n, np.float32, 3, 0, 1), uniform(n, np.float32, 4, 0, 1), CudaVec(n, np.float32)
@@ -75,6 +93,7 @@ TARGETS = {
     "tr32_f64": lambda: transpose_batched(32, np.float64, 20),
     "tr_u8": lambda: transpose_single(8192, np.uint8),
     "tr_i16": lambda: transpose_single(8192, np.int16),
+    "small_odd": small_odd,
     "vector": vector_ops,
     "gemm4096_ffma": lambda: gemm_large("ffma"),
     "gemm4096_tc": lambda: gemm_large("tcgen05"),
