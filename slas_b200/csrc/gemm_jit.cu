@@ -85,6 +85,8 @@ static void bind_api() {
     g_api.ok = ok;
 }
 
+static size_t gcd_sz(size_t a, size_t b) { return b ? gcd_sz(b, a % b) : a; }
+
 // ---- tile configuration for an arbitrary (M, N, K) ---------------------------------------------------------------
 struct JitCfg {
     int tiny = 0;  // 0: gemm_small_kernel (vector register tiles), 1: gemm_tiny_kernel (a thread per matrix),
@@ -115,7 +117,7 @@ static bool choose_tiny_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *o
 }
 
 // The rules of SmallCfg / gemm_small_kernel: K and TN whole 16-byte vectors, TM | M, TN | N, threads per matrix
-// (M/TM)*(N/TN) a power of two dividing the consumer count, a chunk = whole passes, the stage ring within the
+// (M/TM)*(N/TN) dividing the consumer count (whole warps, at most 512 threads), a chunk = whole passes, the stage ring within the
 // shared-memory budget.  Among the configurations that fit: big, squarish register tiles (fewer shared-memory loads
 // per FMA), at least two CTAs per SM, three stages and 256 consumers when possible.
 static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
@@ -130,9 +132,18 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
         for (size_t tn = kvn; tn <= n; tn += kvn) {
             if (n % tn || tm * tn > max_tile) continue;
             const size_t tpm = (m / tm) * (n / tn);
-            if (tpm > 256 || (tpm & (tpm - 1))) continue;
-            for (size_t cons = 256; cons >= 128; cons /= 2) {
-                if (tpm > cons) continue;
+            if (tpm > 512) continue;
+            // consumer threads: whole warps and whole matrices -- multiples of lcm(tpm, 32) up to 512 (20x20: 5 x 4 tiles,
+            // 20 threads per matrix, 160 consumers; powers of two get the usual 256 / 128)
+            const size_t unit = tpm / gcd_sz(tpm, 32) * 32;
+            if (unit > 512) continue;
+            const bool pow2 = (tpm & (tpm - 1)) == 0;
+            // powers of two: 256 or 128 consumers (as measured for the built-in shapes); otherwise the largest whole
+            // number of matrices within 256 threads, or one `unit` when that is already more
+            const size_t cands[2] = {unit <= 256 ? 256 / unit * unit : unit, pow2 && tpm <= 128 ? (size_t)128 : 0};
+            for (size_t ci = 0; ci < 2; ++ci) {
+                const size_t cons = cands[ci];
+                if (cons == 0 || cons < tpm) continue;
                 const size_t mpp = cons / tpm;
                 size_t g = (32 * 1024 / per_pair) / mpp * mpp;
                 if (g < mpp) g = mpp;
@@ -145,7 +156,7 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
                     double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm) + 1e-3 * (double)tn;
                     if (per_sm < 2) score *= 0.6;
                     if (stages == 2) score *= 0.9;
-                    if (cons == 128) score *= 0.95;
+                    if (cons < 192) score *= 0.95;
                     if (score > best) {
                         best = score;
                         out->tm = (int)tm; out->tn = (int)tn; out->g = (int)g; out->cons = (int)cons; out->stages = stages;
@@ -161,8 +172,6 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
 // Scalar register tiles (gemm_rect_kernel<T, M, N, K, TM, TN, G>): any divisors TM | M, TN | N with at most 256 threads per
 // matrix; G = a whole number of passes of MPP = 256 / TPM matrices, sized so that three input stages and two C stages
 // leave room for two CTAs per SM when possible.
-static size_t gcd_sz(size_t a, size_t b) { return b ? gcd_sz(b, a % b) : a; }
-
 static bool choose_rect_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
     if (m == 0 || n == 0 || k == 0) return false;
     const size_t per_in = (m * k + k * n) * elem, per_out = m * n * elem;

@@ -750,7 +750,8 @@ def test_batched_tiny_shapes_thread_per_matrix(dt, ta, tb):
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("m,n,k", [(8, 4, 16), (16, 32, 8), (12, 12, 12), (32, 8, 64), (6, 6, 6), (24, 8, 12), (5, 8, 4), (8, 8, 16),
                                    (48, 16, 4), (5, 5, 5), (3, 7, 5), (7, 7, 7), (1, 6, 9), (9, 9, 9), (10, 10, 10), (5, 9, 13), (33, 3, 7),
-                                   (15, 15, 15), (20, 20, 20), (24, 24, 24), (48, 48, 48), (40, 40, 40), (100, 100, 100), (70, 33, 50)])
+                                   (15, 15, 15), (20, 20, 20), (24, 24, 24), (48, 48, 48), (40, 40, 40), (100, 100, 100), (70, 33, 50),
+                                   (28, 28, 28), (36, 36, 36), (44, 20, 12)])
 def test_batched_shapes_specialised_at_run_time(dt, m, n, k):
     """shapes without a built-in instantiation: the gemm_small kernel compiled for the shape with NVRTC on first use
     (gemm_jit.cu).  Without b_trans every C element is the same ascending-k FMA chain as in the runtime-shape kernel it
