@@ -566,7 +566,7 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
     bool use_pair;
     sgemm_3xtf32_padded(m, n, k, &mp, &np, &kp, &use_pair);
     if (ctx->sm_count < 2) { use_pair = false; mp = round_up(m, BM); }
-    EncodeTiledFn enc;
+    EncodeTiledFn enc = nullptr;
     SLAS_TRY(get_encode_fn(&enc));
     void *ws = nullptr;
     const size_t a_elems = mp * kp, b_elems = np * kp;
