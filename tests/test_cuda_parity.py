@@ -168,6 +168,34 @@ def test_empty_vectors():
     cuda.normalize(np.zeros(0, np.float64))
 
 
+def test_bad_arguments_of_the_newer_entry_points():
+    """fused chains, the batched in-place transpose and the graph API reject what they cannot do and leave the library usable"""
+    import ctypes as C
+    from slas_b200 import _lib
+    L = _lib.lib()
+    a = np.arange(8, dtype=np.float32)
+    d = CudaVec.from_host(a)
+    out = np.zeros(3, np.float32)
+    p = lambda x: x.ctypes.data  # noqa: E731
+    assert L.slas_cuda_sadd_dot(8, p(a), d.as_ptr(), None, p(a), p(out)) == _lib.SLAS_ERR_INVALID      # host / device mixed
+    assert L.slas_cuda_sadd_dot(8, p(a), p(a), None, p(a), None) == _lib.SLAS_ERR_INVALID             # no result pointer
+    assert L.slas_cuda_sdot_norms(8, p(a), None, p(out)) == _lib.SLAS_ERR_INVALID                      # null operand
+    assert L.slas_cuda_snormalize_into(8, p(a), p(a)) == _lib.SLAS_ERR_INVALID                         # aliasing: use normalize
+    assert L.slas_cuda_transpose_inplace_batched(2, 4, 3, p(a), 2) == _lib.SLAS_ERR_INVALID           # element size
+    assert L.slas_cuda_transpose_inplace_batched(2, 4, 4, p(a), 0) == _lib.SLAS_ERR_INVALID           # columns == 0
+    assert L.slas_cuda_transpose_inplace_batched(0, 4, 4, p(a), 2) == _lib.SLAS_OK                     # empty batch: nothing to do
+    g = C.c_void_p()
+    assert L.slas_cuda_graph_end(C.byref(g)) != _lib.SLAS_OK                                           # no capture in progress
+    assert L.slas_cuda_graph_launch(None) == _lib.SLAS_ERR_INVALID
+    assert L.slas_cuda_graph_destroy(None) == _lib.SLAS_OK
+    # ... and everything still works
+    assert cuda.ewise_dot("add", a, a, a) == 2 * float(np.sum(a * a))
+    assert cuda.dot_norms(a, a)[0] == 140.0
+    h = a.copy()
+    cuda.transpose_inplace_batched(h, 4, 2)
+    assert list(h) == [0, 2, 1, 3, 4, 6, 5, 7]
+
+
 def test_bad_arguments_fail_loudly_not_fatally():
     """Where the reference asserts or cblas rejects its arguments, the C ABI returns a status (the shim panics)."""
     import ctypes as C
