@@ -1,5 +1,7 @@
 """Variant sweep for the benchmark knobs (slas_cuda_set_tunable): CUDA-event timings on one B200.
-Usage: python profiles/tune.py [group ...]   groups: transpose gemm32d gemm32s gemm16s large tc"""
+Usage: python profiles/tune.py [group ...]   groups: misc rect gemv bdot transpose inplace crossover e2e dgemm fused
+gemm32d gemm32s gemm16s gemm64 large tc (see GROUPS at the bottom); the r1*_tune_*.log files next to this script are
+its output on a B200."""
 import json
 import os
 import sys
