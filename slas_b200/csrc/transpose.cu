@@ -758,12 +758,9 @@ static int launch_transpose_inplace_typed(Context *ctx, cudaStream_t st, size_t 
     if constexpr (sizeof(E) == 4) {
         if (n % 64 == 0 && n / 64 <= 65535 && aligned16(a)) {
             constexpr int kSmem = 2 * 64 * 65 * 4;
-            static bool attr_done = false;
-            if (!attr_done) {
-                SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_inplace_square64_kernel,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-                attr_done = true;
-            }
+            // (per call: the attribute belongs to the function ON THIS DEVICE, a process may drive several)
+            SLAS_CUDA_TRY(cudaFuncSetAttribute(transpose_inplace_square64_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
             transpose_inplace_square64_kernel<<<dim3(n / 64, n / 64, gz), 256, kSmem, st>>>(
                 reinterpret_cast<uint32_t *>(a), batch, n);
             SLAS_LAUNCH_CHECK();
