@@ -300,6 +300,32 @@ int main() {
         const float n = Cuda{}.norm(source);
         for (int i = 0; i < 3; ++i) CHECK(v[i] == source[i] / n);
     });
+    run("moo::mutations (main.rs:168-177)", [] {
+        const std::array<float, 3> src{3, 2, 3};
+        StaticCowVec<float, 3> t(src);
+        CHECK(t.is_borrowed());
+        t.as_mut_ptr()[0] = 1.f;  // IndexMut -> deref_mut -> copy
+        CHECK(t.is_owned() && t[0] == 1.f && t[1] == 2.f && t[2] == 3.f && src[0] == 3.f);
+        t.as_mut_ptr()[0] = 0.f;
+        CHECK(t[0] == 0.f && t[1] == 2.f && t[2] == 3.f);
+    });
+    run("moo::dot with a StaticCowVec operand (main.rs:189-193)", [] {
+        const auto a = moo_range<float, 4>(0);
+        const std::array<float, 4> bs{0, -1, -2, 3};
+        StaticCowVec<float, 4> b(bs);
+        CHECK(Cuda{}.dot(a, b) == 4.f && b.is_borrowed());
+    });
+    run("moo::from_readme (main.rs:214-226)", [] {
+        std::array<float, 3> source{1, 2, 3};
+        StaticCowVec<float, 3> v(source);
+        source[1] = 3.f;          // v still borrows: it sees this
+        v.as_mut_ptr()[0] = 0.f;  // first mutable access: v copies [1, 3, 3] and becomes owned
+        source[2] = 4.f;          // ... so it does not see this
+        CHECK(v[0] == 0.f && v[1] == 3.f && v[2] == 3.f);
+        CHECK(source[0] == 1.f && source[1] == 3.f && source[2] == 4.f);
+        CHECK(Cuda{}.dot(v, source) == 0.f * 1 + 3.f * 3 + 3.f * 4);
+    });
+
     // ---- fused chains and the 1-/2-byte transposes: same answers as the op sequences of the cases above ----
     run("fused: add -> dot equals the chain (main.rs:41-46 operands)", [] {
         std::array<float, 4> a{0, 1, 2, 3}, b{0, -1, -2, 3}, d{1, 2, 3, 4}, c{}, t{};
