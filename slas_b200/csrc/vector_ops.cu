@@ -586,11 +586,20 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
         const T *pa = (MODE == 2 ? a_mut : a) + (live ? v : 0) * len;
         const T *pb = MODE == 0 ? b + (live ? v : 0) * len : pa;
         double s = 0.0;
+        // vectorised == 2: vectors of an odd length start at a different misalignment each, shared by both operands (the
+        // bases are aligned alike): `head` scalar elements up to the vector's first 16-byte boundary, a 128-bit body, a
+        // scalar tail.  vectorised == 1: every vector is whole aligned words (head = 0).
+        size_t head = 0;
+        if (vectorised == 2) {
+            const uintptr_t mis = (uintptr_t)pa % 16;
+            head = mis ? (16 - mis) / sizeof(T) : 0;
+            if (head > len) head = len;
+        }
         if (live) {
             if (vectorised) {
-                const V *av = reinterpret_cast<const V *>(pa);
-                const V *bv = reinterpret_cast<const V *>(pb);
-                const size_t nvec = len / N;
+                const V *av = reinterpret_cast<const V *>(pa + head);
+                const V *bv = reinterpret_cast<const V *>(pb + head);
+                const size_t nvec = (len - head) / N;
                 T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
                 size_t i = t;
                 // four independent 16-byte loads per operand in flight per thread
@@ -621,7 +630,8 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
                 acc0 += acc2;
                 acc1 += acc3;
                 s = (double)acc0 + (double)acc1;
-                for (size_t j = nvec * N + t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
+                for (size_t j = head + nvec * N + t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
+                if ((size_t)t < head) s += (double)pa[t] * (double)pb[t];
             } else {
                 for (size_t j = t; j < len; j += GROUP) s += (double)pa[j] * (double)pb[j];
             }
@@ -644,8 +654,8 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
             const T nrm = (T)sqrt(s);
             T *pm = a_mut + v * len;
             if (vectorised) {
-                V *mv = reinterpret_cast<V *>(pm);
-                const size_t nvec = len / N;
+                V *mv = reinterpret_cast<V *>(pm + head);
+                const size_t nvec = (len - head) / N;
                 size_t i = t;
                 for (; i + 3 * GROUP < nvec; i += 4 * GROUP) {  // second touch: L1/L2 hits, four in flight
                     V x[4];
@@ -666,7 +676,8 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
                     for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
                     st_stream(mv + i, x);
                 }
-                for (size_t j = nvec * N + t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
+                for (size_t j = head + nvec * N + t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
+                if ((size_t)t < head) pm[t] = pm[t] / nrm;
             } else {
                 for (size_t j = t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
             }
@@ -1129,14 +1140,18 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
     // (normalize: a register-resident variant -- vector held in registers between the reduction and the scale pass --
     // measured SLOWER than re-reading from L2, 0.50-0.81 against 0.79-0.98 of HBM peak for 1.5K..32K elements:
     // 160+ registers per thread leave one CTA per SM and its load / reduce / store phases do not overlap)
+    // odd lengths: every vector peels its own head when both operands' bases are misaligned alike (element-aligned)
+    const bool peel = !vec && len >= 64 && (uintptr_t)base % sizeof(T) == 0 &&
+                      (MODE != 0 || (uintptr_t)base % 16 == (uintptr_t)b % 16) && tunable("bdot_variant") != 3;
+    const int vmode = vec ? 1 : (peel ? 2 : 0);
     if (len <= 8192) {
         size_t blocks = (batch + 7) / 8;
         if (blocks > cap) blocks = cap;
-        batched_reduce_kernel<T, 32, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vec);
+        batched_reduce_kernel<T, 32, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vmode);
     } else {
         size_t blocks = batch;
         if (blocks > cap) blocks = cap;
-        batched_reduce_kernel<T, 256, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vec);
+        batched_reduce_kernel<T, 256, MODE><<<(unsigned)blocks, 256, 0, st>>>(a, b, out, a_mut, batch, len, vmode);
     }
     SLAS_LAUNCH_CHECK();
     return SLAS_OK;

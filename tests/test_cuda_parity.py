@@ -987,6 +987,7 @@ def test_gemv_batched_small_odd_shapes(dt, rows, cols, ta):
                                           (4, 3001), (8, 777), (24, 1025), (32, 33), (40, 999), (64, 257), (72, 100),  # a lane per vector (<= 256 bytes)
                                           (3, 5000), (5, 1000), (7, 4099), (9, 257), (30, 1025), (100, 300), (127, 256), (1, 4096),
                                           (6, 2000), (3, 4097), (50, 700), (127, 300), (150, 513), (201, 257),
+                                          (1001, 37), (333, 100), (5001, 9), (8195, 5), (65, 300), (251, 64),  # odd lengths: per-vector peeling
                                           # ^ not whole 16-byte words: bulk-TMA staged, a thread per vector
                                           # warp / CTA per vector with ragged piece counts, more vectors than groups in
                                           # the grid, and the lengths either side of every kernel switch
