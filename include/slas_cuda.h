@@ -160,8 +160,8 @@ int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_
 /* Which kernel a large f32 product runs on: 0 = FFMA only (every C element an ascending-k fp32 FMA chain),
  * 1 = tcgen05/TMEM 3xTF32 for every contraction its tiling covers (m % 128, n % 256, k % 32 == 0, dense),
  * 2 = auto, the default: 3xTF32 when the product also has >= 2^27 multiply-adds, FFMA otherwise.  3xTF32 is an
- * fp32-class result (measured <= 2e-6 * sum|a||b|, inside the 1e-5 * sqrt(K) parity bar).  Infinite operands come out
- * as NaN on that path (0 * Inf in the split's cross terms); use path 0 where infinities are meaningful. */
+ * fp32-class result (measured <= 2e-6 * sum|a||b|, inside the 1e-5 * sqrt(K) parity bar).  Infinities and NaNs
+ * propagate as in the fp32 chain (the split pass keeps an infinity out of the cross terms). */
 int slas_cuda_set_sgemm_path(int path);
 int slas_cuda_get_sgemm_path(int *path);
 

@@ -113,9 +113,24 @@ __device__ __forceinline__ float rna_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// IEEE specials.  With x = hi + lo an infinity must not sit in `hi`: the cross term hi_a * lo_b would then be Inf * lo_b
+// with the sign of the ROUNDING ERROR lo_b (or 0 * Inf = NaN when lo_b == 0), and Inf - Inf = NaN where the fp32 chain
+// gives a signed infinity.  So an infinite x is split as hi = +-1, lo = +-Inf: the only product that sees the infinity is
+// lo_a * hi_b (or hi_a * lo_b), whose sign is the true one and which is NaN exactly when the other operand is 0, as in
+// IEEE.  A finite x that rounds up to an infinite tf32 keeps a finite hi (the largest tf32).  NaN stays NaN.
 __device__ __forceinline__ void split1(float x, float &hi, float &lo) {
     hi = rna_tf32(x);
-    lo = rna_tf32(x - hi);
+    if (isfinite(hi)) {
+        lo = rna_tf32(x - hi);
+    } else if (isinf(x)) {
+        hi = copysignf(1.f, x);
+        lo = x;
+    } else if (isfinite(x)) {  // |x| within 2^-11 of FLT_MAX
+        hi = copysignf(__uint_as_float(0x7f7fe000u), x);
+        lo = rna_tf32(x - hi);
+    } else {
+        lo = x;  // NaN
+    }
 }
 
 // The hi/lo copies are dense [rows_p][cols_p] arrays padded with zeros up to whole tiles (rows_p >= rows a

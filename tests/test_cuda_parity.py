@@ -912,6 +912,37 @@ def test_sgemm_3xtf32_strided_unaligned_operands(ta, tb):
     assert np.all(got[:, n:] == -7.0) and cfull.to_host()[0] == -7.0
 
 
+def test_sgemm_3xtf32_infinities_and_nans_follow_ieee():
+    """an infinite operand must give the signed infinity of the fp32 chain, not the NaN a naive hi/lo split produces
+    (0 * Inf in the cross terms); NaN and Inf * 0 stay NaN"""
+    from slas_b200.backends import set_sgemm_path
+    m, n, k = 128, 256, 64
+    rng = np.random.default_rng(3)
+    A = (rng.random(m * k) + 0.5).astype(np.float32)   # all positive
+    B = (rng.random(k * n) + 0.5).astype(np.float32)
+    A2, B2 = A.reshape(m, k).copy(), B.reshape(k, n).copy()
+    A2[3, 5] = np.inf          # row 3 of C -> +inf
+    A2[7, 1] = -np.inf         # row 7 -> -inf
+    B2[9, 11] = np.inf         # column 11 -> +inf (rows 3 and 7 too: inf + inf, -inf + inf = nan)
+    A2[20, 2] = np.nan         # row 20 -> nan
+    A2[30, :] = 1.0            # exactly representable in tf32 (lo == 0) against the infinite B entry
+    B2[0, 40] = 0.0
+    A2[50, 0] = np.inf         # inf * 0 in (50, 40) -> nan
+    set_sgemm_path("tcgen05")
+    try:
+        c = CudaVec(m * n, np.float32)
+        cuda.matrix_mul(CudaVec.from_host(A2.ravel()), CudaVec.from_host(B2.ravel()), c, m, n, k, k, n, n, False, False)
+    finally:
+        set_sgemm_path("auto")
+    got = c.to_host().reshape(m, n)
+    with np.errstate(all="ignore"):
+        want = A2.astype(np.float64) @ B2.astype(np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(np.isposinf(got), np.isposinf(want)) and np.array_equal(np.isneginf(got), np.isneginf(want))
+    fin = np.isfinite(want)
+    assert np.all(np.abs(got[fin] - want[fin]) <= 1e-5 * np.sqrt(k) * np.abs(want[fin]))
+
+
 def test_large_sgemm_automatic_path_choice():
     """default ('auto'): tensor cores from 2^27 multiply-adds up when the shape fits the tiles, FFMA otherwise"""
     from slas_b200.backends import set_sgemm_path
