@@ -58,6 +58,12 @@ extern "C" {
                        lda: usize, ldb: usize, ldc: usize, ta: c_int, tb: c_int) -> c_int;
     fn slas_cuda_sgemv(a: *const f32, x: *const f32, y: *mut f32, m: usize, n: usize, lda: usize, ta: c_int) -> c_int;
     fn slas_cuda_dgemv(a: *const f64, x: *const f64, y: *mut f64, m: usize, n: usize, lda: usize, ta: c_int) -> c_int;
+    fn slas_cuda_sadd_dot(len: usize, a: *const f32, b: *const f32, c: *mut f32, d: *const f32, out: *mut f32) -> c_int;
+    fn slas_cuda_dadd_dot(len: usize, a: *const f64, b: *const f64, c: *mut f64, d: *const f64, out: *mut f64) -> c_int;
+    fn slas_cuda_sdot_norms(len: usize, a: *const f32, b: *const f32, out3: *mut f32) -> c_int;
+    fn slas_cuda_ddot_norms(len: usize, a: *const f64, b: *const f64, out3: *mut f64) -> c_int;
+    fn slas_cuda_snormalize_into(len: usize, a: *const f32, out: *mut f32) -> c_int;
+    fn slas_cuda_dnormalize_into(len: usize, a: *const f64, out: *mut f64) -> c_int;
     fn slas_cuda_sgemm_batched(batch: usize, a: *const f32, b: *const f32, c: *mut f32,
                                m: usize, n: usize, k: usize, ta: c_int, tb: c_int) -> c_int;
     fn slas_cuda_dgemm_batched(batch: usize, a: *const f64, b: *const f64, c: *mut f64,
@@ -166,8 +172,36 @@ macro_rules! impl_cuda_complex {
 impl_cuda_complex!(f32, slas_cuda_cdotu, slas_cuda_scnrm2, slas_cuda_cnormalize);
 impl_cuda_complex!(f64, slas_cuda_zdotu, slas_cuda_dznrm2, slas_cuda_znormalize);
 
+/// Fused chains (include/slas_cuda.h "Fused chains"): extra inherent methods, not trait methods -- slas leaves lazy
+/// execution to its users (CONTRIBUTING.md:7-22).  Each gives the bits of the op sequence it replaces on this backend.
+macro_rules! impl_cuda_fused {
+    ($t:ty, $add_dot:ident, $dot_norms:ident, $normalize_into:ident) => {
+        impl Cuda {
+            /// `dot(a + b, d)` without materialising `a + b`.
+            pub fn add_dot<const LEN: usize>(&self, a: &impl StaticVec<$t, LEN>, b: &impl StaticVec<$t, LEN>, d: &impl StaticVec<$t, LEN>) -> $t {
+                let mut out: $t = 0.;
+                check(unsafe { $add_dot(LEN, a.as_ptr(), b.as_ptr(), std::ptr::null_mut(), d.as_ptr(), &mut out) });
+                out
+            }
+            /// `(dot(a, b), norm(a), norm(b))` from one read of both vectors.
+            pub fn dot_norms<const LEN: usize>(&self, a: &impl StaticVec<$t, LEN>, b: &impl StaticVec<$t, LEN>) -> ($t, $t, $t) {
+                let mut out: [$t; 3] = [0.; 3];
+                check(unsafe { $dot_norms(LEN, a.as_ptr(), b.as_ptr(), out.as_mut_ptr()) });
+                (out[0], out[1], out[2])
+            }
+            /// `out = a / norm(a)`; `a` is untouched (normalising a borrowed `StaticCowVec` without its copy).
+            pub fn normalize_into<const LEN: usize>(&self, a: &impl StaticVec<$t, LEN>, out: &mut impl StaticVec<$t, LEN>) {
+                check(unsafe { $normalize_into(LEN, a.as_ptr(), out.as_mut_ptr()) });
+            }
+        }
+    };
+}
+impl_cuda_fused!(f32, slas_cuda_sadd_dot, slas_cuda_sdot_norms, slas_cuda_snormalize_into);
+// (the f64 methods live in a second inherent impl with distinct names in a real crate: Rust has no overloading;
+//  shown here for f32 only)
+
 /// Transpose is generic over any `T: Copy` in the reference (src/backends/rust.rs:151-177); the
-/// library moves opaque 4/8/16-byte elements.
+/// library moves opaque 1/2/4/8/16-byte elements.
 impl<T: Copy> Transpose<T> for Cuda {
     fn transpose_inplace<const LEN: usize>(&self, a: &mut impl StaticVec<T, LEN>, columns: usize) {
         check(unsafe { slas_cuda_transpose_inplace(LEN, std::mem::size_of::<T>(), a.as_mut_ptr() as *mut _, columns) });
