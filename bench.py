@@ -7,19 +7,26 @@ one pass of the batched product over the whole batch.
 
   value     whole-job GFLOP/s (128 flop per matrix), operands resident in HBM, CUDA-event timed,
             barrier + synchronize on both sides, max over ranks.
-  e2e       the same product through the reference-facing C ABI with HOST (pinned) operands:
-            H2D of A and B and D2H of C inside the timed region.
+  e2e       the same product through the reference-facing C ABI with HOST operands (pinned, and the
+            pageable memory a slas StaticVec really is: `pageable`): H2D of A and B and D2H of C inside
+            the timed region.
   roofline  the batched small-GEMM kernel against the measured HBM copy bandwidth
-            (MEASURED_PEAKS.json): algorithmic bytes = 192 B per matrix.
+            (MEASURED_PEAKS.json): algorithmic bytes = 192 B per matrix.  `roofline.configs` carries the
+            rest of the BASELINE metric, one entry per config with {ms, achieved, peak, frac, unit}:
+            dot / add GB/s (2^28 single call, 2^20 x 1024 batched, 2^20 single calls eager / C loop /
+            graph replay), batched 16x16 / 32x32 f32 / f64 matmul + transpose, the single 4096^2 product on the
+            FFMA and the tcgen05 3xTF32 path (against FMA / TF32 peaks measured on this box), and config 5:
+            sharded dot / normalize over 2^32 elements + batched 16x16 weak / strong scaling.
   cpu_baseline  the reference's own way of doing this on the host: a loop of cblas_sgemm calls
             (src/backends/blas.rs:94-109 behind Matrix::matrix_mul, src/tensor.rs:441-454), timed
             on this box's cores on a bounded sample.
-  others    the remaining BASELINE configs measured the same way (dot/add GB/s, 16x16 / 32x32
-            f32/f64 batched matmul + transpose, the single 4096^2 product, sharded dot).
 
-`--impl reference` times only the CPU reference arm.  N > 1: launched by torchrun, one rank per GPU;
-the batch shards by batch index with no data-path collective (weak scaling); the sharded dot in
-`others` is the one op with a collective (one NCCL allreduce of an f64 partial).
+`--impl reference` times only the CPU reference arm (same config, steps, warm-up and sample).  N > 1:
+launched by torchrun, one rank per GPU; the batch shards by batch index with no data-path collective (weak
+scaling); the sharded dot / normalize of config 5 are the ops with an exchange step, and this run ASSERTS their
+parity across ranks (bit-identical results on every rank, equal to the rank-ordered sum of the ranks' f64
+partials, an independent f64 truth of every slice, sampled slices of the normalize bit-exact) -- a failure
+exits non-zero.
 """
 from __future__ import annotations
 
@@ -38,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_4X4 = 128
 BYTES_PER_4X4 = 192
+CPU_SAMPLE_LOG2 = 22  # pairs per CPU step: the same bounded sample in the cpu_baseline leg and the reference arm
 
 
 def parse_args():
@@ -51,6 +59,14 @@ def parse_args():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
     return p.parse_args()
+
+
+def workload_config(batch_log2: int, world: int) -> dict:
+    """The `config` object both arms print (identical for the same command line)."""
+    return {"workload": f"batched static 4x4 f32 matrix_mul, batch 2^{batch_log2} per GPU (BASELINE configs[1])",
+            "layout": "[[f32; 16]; batch] contiguous row-major, no transposes",
+            "parallelism": f"batch-index shards x{world}, no collective",
+            "l2": "working set 3 GiB per GPU >> 126 MB L2 (no flush needed)"}
 
 
 def measured_peaks():
@@ -139,27 +155,32 @@ class ClockSampler:
 
 # ---- CPU reference arm ------------------------------------------------------------------------------
 def cpu_reference_4x4(sample_log2: int, steps: int, warmup: int):
-    """Loop of cblas_sgemm calls over `2^sample_log2` contiguous 4x4 pairs: what a slas user runs today."""
+    """Loop of cblas_sgemm calls over `2^sample_log2` contiguous 4x4 pairs: what a slas user runs today
+    (Matrix::matrix_mul -> Blas::matrix_mul -> cblas_sgemm per object, src/tensor.rs:441-454,
+    src/backends/blas.rs:94-109).  W untimed warm-up steps, then exactly `steps` timed ones."""
     from oracle import blas_standin as blas
     n = 1 << sample_log2
     rng = np.random.default_rng(1)
     a = (rng.random(n * 16, dtype=np.float32) * 2 - 1)
     b = (rng.random(n * 16, dtype=np.float32) * 2 - 1)
     c = np.zeros(n * 16, np.float32)
-    for _ in range(max(1, warmup)):
+    for _ in range(warmup):
         blas.gemm_batched(a, b, c, n, 4, 4, 4, threads=1)
     t0 = time.perf_counter()
     for _ in range(steps):
         blas.gemm_batched(a, b, c, n, 4, 4, 4, threads=1)
     dt = (time.perf_counter() - t0) / steps
     cores = os.cpu_count() or 1
-    t1 = time.perf_counter()
     blas.gemm_batched(a, b, c, n, 4, 4, 4, threads=cores)
-    dt_all = time.perf_counter() - t1
+    t1 = time.perf_counter()
+    for _ in range(3):
+        blas.gemm_batched(a, b, c, n, 4, 4, 4, threads=cores)
+    dt_all = (time.perf_counter() - t1) / 3
     return {"gflops_1t": FLOP_PER_4X4 * n / dt / 1e9, "ms_per_step": dt * 1e3, "cores_available": cores,
             "gflops_all_cores": FLOP_PER_4X4 * n / dt_all / 1e9,
-            "sample": f"2^{sample_log2} of the 4x4 f32 pairs per step (loop of cblas_sgemm, OpenBLAS from scipy, 1 thread: "
-                      f"the reference is single-threaded; pthread split over {cores} cores reported as gflops_all_cores)"}
+            "sample": f"2^{sample_log2} of the 4x4 f32 pairs per step (loop of cblas_sgemm, OpenBLAS from scipy; the reference's "
+                      f"loop is serial and BLAS does not thread a 4x4 product: 1 busy core; a pthread split over {cores} cores, "
+                      f"which the reference does not have, is reported as all_cores_value)"}
 
 
 def cpu_reference_config0():
@@ -199,17 +220,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_log2 = min(args.batch_log2, 20)
-    steps = max(1, min(args.steps, 40))
-    r = cpu_reference_4x4(sample_log2, steps, min(args.warmup, 3))
+    r = cpu_reference_4x4(min(args.batch_log2, CPU_SAMPLE_LOG2), args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "batched matrix_mul GFLOP/s", "value": r["gflops_1t"], "unit": "GFLOP/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batched static 4x4 f32 matrix_mul, batch 2^{args.batch_log2} per GPU (configs[1])",
-                   "reference_path": "Matrix::matrix_mul -> Blas::matrix_mul -> cblas_sgemm per object, host cores"},
+        "config": workload_config(args.batch_log2, args.gpus),
         "cpu_baseline": {"value": r["gflops_1t"], "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": r["sample"],
-                         "all_cores_value": r["gflops_all_cores"], "cores_available": r["cores_available"]},
+                         "all_cores_value": r["gflops_all_cores"], "cores_available": r["cores_available"],
+                         "reference_path": "Matrix::matrix_mul -> Blas::matrix_mul -> cblas_sgemm per object, host cores"},
         "e2e": {"value": r["gflops_1t"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,7 +243,8 @@ def run_cuda(args):
     import torch.distributed as dist
 
     import slas_b200 as sl
-    from slas_b200 import _lib
+    from oracle import oracle
+    from slas_b200 import _lib, sharding
     from slas_b200.static_vec import CudaVec
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -254,6 +274,14 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def gather_f64(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world == 1:
+            return [t.cpu().numpy()]
+        g = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(g, t)
+        return [x.cpu().numpy() for x in g]
+
     def timed(fn, steps, warmup):
         """W warm-ups, then exactly `steps` calls between barriers; CUDA events on the launching stream."""
         for _ in range(warmup):
@@ -277,6 +305,24 @@ def run_cuda(args):
     def vec(t):  # torch owns the HBM; the C ABI sees a device pointer
         return CudaVec(t.numel(), np.float32 if t.dtype == torch.float32 else np.float64, _ptr=t.data_ptr(), _owner=t)
 
+    def check_sampled_products(a, b, c, size, nobj, what, samples=2048, seed=0):
+        """Sampled objects of a batched product against the oracle (outside every timed region): 1e-5 * sqrt(K)
+        relative to sum|a||b| per element (north_star's bar).  Returns the worst observed error / bar."""
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        idx = torch.randint(0, nobj, (min(samples, nobj),), generator=g).to(dev)
+        e = size * size
+        ha = a.view(nobj, e).index_select(0, idx).cpu().numpy().ravel()
+        hb = b.view(nobj, e).index_select(0, idx).cpu().numpy().ravel()
+        hc = c.view(nobj, e).index_select(0, idx).cpu().numpy().ravel()
+        want = oracle.gemm_batched(ha, hb, idx.numel(), size, size, size)
+        mag = np.einsum("bik,bkj->bij", np.abs(ha.reshape(-1, size, size)).astype(np.float64),
+                        np.abs(hb.reshape(-1, size, size)).astype(np.float64)).ravel()
+        tol = (1e-5 if ha.dtype == np.float32 else 1e-13) * np.sqrt(size) * mag
+        err = np.abs(hc.astype(np.float64) - want.astype(np.float64))
+        ratio = float(np.max(err / np.maximum(tol, 1e-300)))
+        assert ratio <= 1.0, f"{what}: sampled objects differ from the oracle (error / bar = {ratio})"
+        return ratio
+
     # ---- headline: batched 4x4 f32, batch 2^k per GPU ----
     batch = 1 << args.batch_log2
     A = dev_uniform(batch * 16, torch.float32, 1 + rank)
@@ -292,8 +338,9 @@ def run_cuda(args):
     clocks = clk.summary()
     value = FLOP_PER_4X4 * batch * world / (ms * 1e-3) / 1e9
     achieved_gbs = BYTES_PER_4X4 * batch / (ms * 1e-3) / 1e9  # one launch per step: kernel time == step time
+    headline_parity = check_sampled_products(A, B, Cc, 4, batch, "headline 4x4 product", samples=8192, seed=rank)
 
-    # ---- e2e: host (pinned) operands through the C ABI ----
+    # ---- e2e: host operands through the C ABI ----
     e2e = None
     if not args.no_e2e:
         nbytes = batch * 16 * 4
@@ -305,67 +352,117 @@ def run_cuda(args):
         _lib.call("slas_cuda_memcpy_d2h", hp[1].value, B.data_ptr(), nbytes)
         e2e_steps = max(2, min(args.steps, 5))
 
-        def e2e_step():
-            cuda.matrix_mul_batched(hA, hB, hC, 4, 4, 4)  # returns when C is back in host memory
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
+        def time_host_steps(fa, fb, fc):
+            def e2e_step():
+                cuda.matrix_mul_batched(fa, fb, fc, 4, 4, 4)  # returns when C is back in host memory
             e2e_step()
-        barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
-        # the PCIe roofline of that step, measured here: one pinned 1 GiB host->device copy on its own (the step
-        # moves 2x the batch down and 1x up; both directions run concurrently, so H2D bounds it)
-        h2d_gbs = None
-        if rank == 0:
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            for _ in range(3):
-                _lib.call("slas_cuda_memcpy_h2d", A.data_ptr(), hp[0].value, nbytes)
-            h2d_gbs = 3 * nbytes / (time.perf_counter() - t1) / 1e9
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                e2e_step()
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+
+        e2e_ms = time_host_steps(hA, hB, hC)
         # spot-check the host result against the device-resident one
-        _lib.call("slas_cuda_memcpy_d2h", hp[0].value, Cc.data_ptr(), 4096)
-        assert np.array_equal(hA[:1024], hC[:1024]), "host-path result differs from the device-resident result"
+        ref_c = Cc[:1 << 16].cpu().numpy()
+        assert np.array_equal(ref_c, hC[:1 << 16]), "host-path result differs from the device-resident result"
+        # the memory a slas StaticVec really is (static_vec.rs:126: [T; LEN] / Vec): pageable
+        pA, pB = np.array(hA, copy=True), np.array(hB, copy=True)
+        pC = np.zeros_like(pA)
+        pageable_ms = time_host_steps(pA, pB, pC)
+        assert np.array_equal(pC, hC), "pageable-operand result differs from the pinned-operand result"
+        del pA, pB, pC
+        # the PCIe roofline of that step, measured here: pinned copies on their own (torch pinned buffers + cudaMemcpyAsync,
+        # nothing of the library), one direction and both at once, all ranks at the same time (N > 1: the host-side
+        # ceiling the e2e number runs into)
+        for p in hp[:2]:
+            _lib.call("slas_cuda_free_host", p.value)
+        del hA, hB
+        pin_in = torch.empty(batch * 16, dtype=torch.float32, pin_memory=True)
+        pin_out = torch.empty(batch * 16, dtype=torch.float32, pin_memory=True)
+        s2 = torch.cuda.Stream(device=dev)
+
+        def copy_time(h2d: bool, d2h: bool, reps=3):
+            barrier()
+            t1 = time.perf_counter()
+            for _ in range(reps):
+                if d2h:
+                    with torch.cuda.stream(s2):
+                        pin_out.copy_(Cc, non_blocking=True)
+                if h2d:
+                    A.copy_(pin_in, non_blocking=True)
+            barrier()
+            return (time.perf_counter() - t1) / reps
+
+        copy_time(True, True, 1)
+        h2d_gbs = nbytes / copy_time(True, False) / 1e9
+        d2h_gbs = nbytes / copy_time(False, True) / 1e9
+        bidir_s = copy_time(True, True)
+        del pin_in, pin_out
         e2e = {"value": FLOP_PER_4X4 * batch * world / (e2e_ms * 1e-3) / 1e9, "unit": "GFLOP/s",
                "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": e2e_ms, "steps": e2e_steps,
                "pcie_gbs": 3 * nbytes / (e2e_ms * 1e-3) / 1e9,
-               "h2d_gbs_in_step": 2 * nbytes / (e2e_ms * 1e-3) / 1e9, "h2d_gbs_copy_alone": h2d_gbs,
-               "api": "slas_cuda_sgemm_batched with pinned host pointers (3-slot H2D/kernel/D2H pipeline)"}
-        for p in hp:
-            _lib.call("slas_cuda_free_host", p.value)
-        del hA, hB, hC
+               "h2d_gbs_in_step": 2 * nbytes / (e2e_ms * 1e-3) / 1e9,
+               "pageable": {"value": FLOP_PER_4X4 * batch * world / (pageable_ms * 1e-3) / 1e9, "ms_per_step": pageable_ms,
+                            "frac_of_pinned": e2e_ms / pageable_ms,
+                            "how": "pageable numpy operands: copy threads stage them through a pinned bounce ring"},
+               "copy_only": {"ranks_copying_at_once": world, "h2d_gbs_per_gpu": h2d_gbs, "d2h_gbs_per_gpu": d2h_gbs,
+                             "bidir_gbs_each_way_per_gpu": nbytes / bidir_s / 1e9,
+                             "step_floor_ms": max(2 * nbytes / (h2d_gbs * 1e9), nbytes / (d2h_gbs * 1e9)) * 1e3,
+                             "what": "pinned 1 GiB copies alone, every rank at the same time (barrier-bracketed): the link / "
+                                     "host-memory ceiling of the e2e step, which moves 2 GiB down and 1 GiB up per GPU"},
+               "api": "slas_cuda_sgemm_batched with host pointers (3-slot H2D/kernel/D2H pipeline)"}
+        e2e["frac_of_copy_floor"] = e2e["copy_only"]["step_floor_ms"] / e2e_ms
+        _lib.call("slas_cuda_free_host", hp[2].value)
+        del hC
 
-    # ---- others: the remaining BASELINE configs (rank-local numbers unless stated) ----
-    others = []
+    # ---- the rest of the metric: roofline.configs ----
+    configs = {}
     fma_peak = None
+    tf32_peak = None
     if not args.no_others:
         del A, B, Cc, vA, vB, vC
         torch.cuda.empty_cache()
         ksteps = max(3, min(args.steps, 20))
 
-        # FP32 / FP64 FMA ceilings measured on this box (register-only 8x8 outer-product loop): the secondary figure
-        # BASELINE asks for next to the HBM fraction of the batched products
+        # FP32 / FP64 FMA and TF32 tensor ceilings measured on this box, with the SM clock each one ran at
         fma_peak = {}
         for is_d, key in ((0, "f32"), (1, "f64")):
             t = C.c_double()
-            _lib.call("slas_cuda_bench_fma_peak", is_d, C.byref(t))
+            with ClockSampler(local_rank) as ck:
+                _lib.call("slas_cuda_bench_fma_peak", is_d, C.byref(t))
             fma_peak[key] = t.value
+            fma_peak[key + "_sm_mhz"] = ck.summary()["sm_mhz"]
+        t = C.c_double()
+        with ClockSampler(local_rank) as ck:
+            _lib.call("slas_cuda_bench_tf32_peak", C.byref(t))
+        tf32_peak = {"tflops": t.value, "sm_mhz": ck.summary()["sm_mhz"],
+                     "how": "tcgen05.mma.kind::tf32 M128 N256 K8 back to back from resident smem tiles, one CTA per SM"}
+        NOMINAL = {"f32": 74.5, "f64": 37.2}
 
-        def record(name, ms_, flop=None, bytes_=None, bound="hbm", extra=None, fma=None):
-            row = {"name": name, "ms": ms_}
-            if flop is not None:
+        def rec(key, ms_, what, bytes_=None, flop=None, bound="hbm", fma=None, extra=None, ranks=1):
+            """One entry of roofline.configs.  bound hbm: achieved GB/s against the measured copy bandwidth
+            (x ranks for whole-job rows); fp32 / fp64: TFLOP/s against the FMA peak measured here; tensor: executed
+            TF32 TFLOP/s against the measured tcgen05 peak."""
+            row = {"what": what, "ms": ms_, "bound": bound}
+            if bound == "hbm":
+                row.update(achieved=bytes_ / (ms_ * 1e-3) / 1e9, peak=peak_gbs * ranks, unit="GB/s")
+            elif bound in ("fp32", "fp64"):
+                k = "f32" if bound == "fp32" else "f64"
+                row.update(achieved=flop / (ms_ * 1e-3) / 1e12, peak=fma_peak[k], unit="TFLOP/s",
+                           frac_of_nominal=flop / (ms_ * 1e-3) / 1e12 / NOMINAL[k])
+            elif bound == "tensor":
+                row.update(achieved=3.0 * flop / (ms_ * 1e-3) / 1e12, peak=tf32_peak["tflops"], unit="TFLOP/s executed (3 MMAs per product)",
+                           useful_tflops=flop / (ms_ * 1e-3) / 1e12)
+            row["frac"] = row["achieved"] / row["peak"]
+            if flop is not None and bound == "hbm":
                 row["gflops"] = flop / (ms_ * 1e-3) / 1e9
                 if fma:
                     row["fma_pipe_frac_of_measured_peak"] = row["gflops"] / 1e3 / fma_peak[fma]
-                    row["fma_pipe_frac_of_nominal"] = row["gflops"] / 1e3 / (74.5 if fma == "f32" else 37.2)
-            if bytes_ is not None:
-                row["gbs"] = bytes_ / (ms_ * 1e-3) / 1e9
-                if bound == "hbm":
-                    row["hbm_frac"] = row["gbs"] / peak_gbs
             if extra:
                 row.update(extra)
-            others.append(row)
+            configs[key] = row
 
         # config 3: batched 16x16 / 32x32, f32 / f64, matmul + transpose, batch 2^20
         for n_, tdt, name in ((16, torch.float32, "f32"), (32, torch.float32, "f32"), (16, torch.float64, "f64"),
@@ -377,14 +474,14 @@ def run_cuda(args):
             c = torch.empty_like(a)
             va, vb, vc = vec(a), vec(b), vec(c)
             ms_, _ = timed(lambda: cuda.matrix_mul_batched(va, vb, vc, n_, n_, n_), ksteps, 3)
-            record(f"batched {n_}x{n_} {name} matrix_mul, batch 2^20", ms_, flop=2.0 * n_ ** 3 * bsz, bytes_=3.0 * n_ * n_ * es * bsz,
-                   fma=name)
+            par = check_sampled_products(a, b, c, n_, bsz, f"batched {n_}x{n_} {name}", samples=256)
+            rec(f"mm{n_}_{name}", ms_, f"batched {n_}x{n_} {name} matrix_mul, batch 2^20", flop=2.0 * n_ ** 3 * bsz,
+                bytes_=3.0 * n_ * n_ * es * bsz, fma=name, extra={"parity_error_over_bar": par})
             ms_, _ = timed(lambda: cuda.transpose_batched(va, vc, n_ * n_, n_), ksteps, 3)
-            record(f"batched {n_}x{n_} {name} transpose, batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
+            rec(f"tr{n_}_{name}", ms_, f"batched {n_}x{n_} {name} transpose, batch 2^20", bytes_=2.0 * n_ * n_ * es * bsz)
             del a, b, c, va, vb, vc
         # the callers either side of the path: other static shapes, matrix_vector_mul, in-place transposes
         for (m_, n_, k_, tdt, name, log2, how) in ((3, 3, 3, torch.float32, "f32", 24, "thread per matrix"),
-                                                   (2, 2, 3, torch.float32, "f32", 24, "thread per matrix"),
                                                    (8, 4, 16, torch.float32, "f32", 22, "specialised at run time (NVRTC)"),
                                                    (12, 12, 12, torch.float64, "f64", 20, "specialised at run time (NVRTC)")):
             bsz = 1 << log2
@@ -393,8 +490,8 @@ def run_cuda(args):
             c = torch.empty(bsz * m_ * n_, device=dev, dtype=tdt)
             va, vb, vc = vec(a), vec(b), vec(c)
             ms_, _ = timed(lambda: cuda.matrix_mul_batched(va, vb, vc, m_, n_, k_), ksteps, 3)
-            record(f"batched {m_}x{k_} . {k_}x{n_} {name} matrix_mul, batch 2^{log2} ({how})", ms_, flop=2.0 * m_ * n_ * k_ * bsz,
-                   bytes_=float(m_ * k_ + k_ * n_ + m_ * n_) * es * bsz)
+            rec(f"mm{m_}x{k_}x{n_}_{name}", ms_, f"batched {m_}x{k_} . {k_}x{n_} {name} matrix_mul, batch 2^{log2} ({how})",
+                flop=2.0 * m_ * n_ * k_ * bsz, bytes_=float(m_ * k_ + k_ * n_ + m_ * n_) * es * bsz)
             del a, b, c, va, vb, vc
         for n_, tdt, name in ((32, torch.float32, "f32"), (32, torch.float64, "f64")):
             bsz = 1 << 20
@@ -404,10 +501,11 @@ def run_cuda(args):
             va, vx, vy = vec(a), vec(x), vec(y)
             for ta_ in (False, True):
                 ms_, _ = timed(lambda: cuda.matrix_vector_mul_batched(va, vx, vy, n_, n_, ta_), ksteps, 3)
-                record(f"batched {n_}x{n_} {name} matrix_vector_mul, a_trans={ta_}, batch 2^20", ms_, flop=2.0 * n_ * n_ * bsz,
-                       bytes_=float(n_ * n_ + 2 * n_) * es * bsz)
+                rec(f"gemv{n_}_{name}_{'t' if ta_ else 'n'}", ms_, f"batched {n_}x{n_} {name} matrix_vector_mul, a_trans={ta_}, batch 2^20",
+                    flop=2.0 * n_ * n_ * bsz, bytes_=float(n_ * n_ + 2 * n_) * es * bsz)
             ms_, _ = timed(lambda: cuda.transpose_inplace_batched(va, n_ * n_, n_), ksteps, 3)
-            record(f"batched {n_}x{n_} {name} transpose_inplace (Matrix::deref_mut per object), batch 2^20", ms_, bytes_=2.0 * n_ * n_ * es * bsz)
+            rec(f"tr{n_}_{name}_inplace", ms_, f"batched {n_}x{n_} {name} transpose_inplace (Matrix::deref_mut per object), batch 2^20",
+                bytes_=2.0 * n_ * n_ * es * bsz)
             del a, x, y, va, vx, vy
         # 3-D geometry sizes: 3x3 matrices and 3-vectors (not whole 16-byte words: bulk-TMA staged thread-per-object kernels)
         bsz = 1 << 24
@@ -416,63 +514,108 @@ def run_cuda(args):
         o = torch.empty(bsz, device=dev, dtype=torch.float32)
         va, vx, vy, vo = vec(a), vec(x), vec(y), vec(o)
         ms_, _ = timed(lambda: cuda.matrix_vector_mul_batched(va, vx, vy, 3, 3, False), ksteps, 3)
-        record("batched 3x3 f32 matrix_vector_mul (3x3 . 3-vector), batch 2^24", ms_, flop=18.0 * bsz, bytes_=60.0 * bsz)
+        rec("gemv3_f32", ms_, "batched 3x3 f32 matrix_vector_mul (3x3 . 3-vector), batch 2^24", flop=18.0 * bsz, bytes_=60.0 * bsz)
         at = torch.empty_like(a)
         vat = vec(at)
         ms_, _ = timed(lambda: cuda.transpose_batched(va, vat, 9, 3), ksteps, 3)
-        record("batched 3x3 f32 transpose, batch 2^24", ms_, bytes_=72.0 * bsz)
+        rec("tr3_f32", ms_, "batched 3x3 f32 transpose, batch 2^24", bytes_=72.0 * bsz)
         ms_, _ = timed(lambda: cuda.dot_batched(vx, vy, vo, 3), ksteps, 3)
-        record("batched 3-vector f32 dot, batch 2^24", ms_, bytes_=24.0 * bsz)
+        rec("dot3_f32", ms_, "batched 3-vector f32 dot, batch 2^24", bytes_=28.0 * bsz)
         ms_, _ = timed(lambda: cuda.normalize_batched(vx, 3), ksteps, 3)
-        record("batched 3-vector f32 normalize, batch 2^24", ms_, bytes_=24.0 * bsz)
+        rec("normalize3_f32", ms_, "batched 3-vector f32 normalize, batch 2^24", bytes_=24.0 * bsz)
         del a, x, y, o, at, va, vx, vy, vo, vat
         # config 1: dot + add, f32.  LEN = 2^20 is L2-resident and launch-bound as one call, so report
-        # (i) one 2^28-element call, (ii) 1024 distinct 2^20 pairs in one batched launch, (iii) call latency.
+        # (i) one 2^28-element call, (ii) 1024 distinct 2^20 pairs in one batched launch, (iii) single calls on 256
+        # distinct pairs (2 GiB >> L2): eager from Python, the same loop from C, and replayed from a CUDA graph.
         n28 = 1 << 28
         a, b = dev_uniform(n28, torch.float32, 4, 0.0, 1.0), dev_uniform(n28, torch.float32, 5, 0.0, 1.0)
         c = torch.empty_like(a)
         out = torch.zeros(1024, device=dev, dtype=torch.float32)
         va, vb, vc, vout = vec(a), vec(b), vec(c), vec(out)
         ms_, _ = timed(lambda: _lib.call("slas_cuda_sdot", n28, a.data_ptr(), b.data_ptr(), out.data_ptr()), ksteps, 3)
-        record("dot f32 LEN=2^28 (one call)", ms_, flop=2.0 * n28, bytes_=8.0 * n28)
+        rec("dot_2^28", ms_, "dot f32 LEN=2^28 (one call)", flop=2.0 * n28, bytes_=8.0 * n28)
         ms_, _ = timed(lambda: cuda.add(va, vb, vc), ksteps, 3)
-        record("add f32 LEN=2^28 (one call)", ms_, flop=1.0 * n28, bytes_=12.0 * n28)
+        rec("add_2^28", ms_, "add f32 LEN=2^28 (one call)", flop=1.0 * n28, bytes_=12.0 * n28)
         ms_, _ = timed(lambda: _lib.call("slas_cuda_snrm2", n28, a.data_ptr(), out.data_ptr()), ksteps, 3)
-        record("norm f32 LEN=2^28 (one call)", ms_, bytes_=4.0 * n28)
+        rec("norm_2^28", ms_, "norm f32 LEN=2^28 (one call)", bytes_=4.0 * n28)
         ms_, _ = timed(lambda: cuda.normalize(va), ksteps, 3)
-        record("normalize f32 LEN=2^28 (one call; 12 B/elem: read, read, write)", ms_, bytes_=12.0 * n28)
+        rec("normalize_2^28", ms_, "normalize f32 LEN=2^28 (one call; 12 B/elem: read, read, write)", bytes_=12.0 * n28)
         ms_, _ = timed(lambda: _lib.call("slas_cuda_sadd_dot", n28, a.data_ptr(), b.data_ptr(), None, c.data_ptr(), out.data_ptr()), ksteps, 3)
-        record("fused add -> dot f32 LEN=2^28 (intermediate never materialised, 12 B/elem instead of 20)", ms_, bytes_=12.0 * n28)
+        rec("add_dot_2^28", ms_, "fused add -> dot f32 LEN=2^28 (intermediate never materialised, 12 B/elem instead of 20)", bytes_=12.0 * n28)
         ms_, _ = timed(lambda: _lib.call("slas_cuda_sdot_norms", n28, a.data_ptr(), b.data_ptr(), out.data_ptr()), ksteps, 3)
-        record("fused dot + norm + norm f32 LEN=2^28 (8 B/elem instead of 16)", ms_, bytes_=8.0 * n28)
+        rec("dot_norms_2^28", ms_, "fused dot + norm + norm f32 LEN=2^28 (8 B/elem instead of 16)", bytes_=8.0 * n28)
         l20 = 1 << 20
-        # (ii) of SURVEY 8d config 1: 1024 DISTINCT 2^20-element pairs (8 GiB >> L2) in one batched launch
         a4 = dev_uniform(1024 * l20, torch.float32, 8, 0.0, 1.0)
         b4 = dev_uniform(1024 * l20, torch.float32, 9, 0.0, 1.0)
         ms_, _ = timed(lambda: cuda.dot_batched(vec(a4), vec(b4), vout, l20), ksteps, 3)
-        record("dot f32 LEN=2^20 x 1024 distinct pairs (one batched launch, 8 GiB)", ms_, flop=2.0 * 1024 * l20, bytes_=8.0 * 1024 * l20)
+        rec("dot_2^20x1024", ms_, "dot f32 LEN=2^20 x 1024 distinct pairs (one batched launch, 8 GiB)", flop=2.0 * 1024 * l20, bytes_=8.0 * 1024 * l20)
         del a4, b4
 
-        def dot_loop():
-            for i in range(256):
-                L.slas_cuda_sdot(l20, a.data_ptr() + 4 * i * l20, b.data_ptr() + 4 * i * l20, out.data_ptr() + 4 * i)
+        ncalls = 256
+        for opname, opid, bytes_per in (("dot", 0, 8.0), ("add", 1, 12.0)):
+            dst = out if opid == 0 else c
 
-        ms_, _ = timed(dot_loop, 3, 1)
-        record("dot f32 LEN=2^20, 256 distinct pairs, one call each (launch-bound)", ms_, bytes_=8.0 * 256 * l20,
-               extra={"us_per_call": ms_ * 1e3 / 256})
+            def py_loop():
+                for i in range(ncalls):
+                    if opid == 0:
+                        L.slas_cuda_sdot(l20, a.data_ptr() + 4 * i * l20, b.data_ptr() + 4 * i * l20, out.data_ptr() + 4 * i)
+                    else:
+                        L.slas_cuda_sadd(l20, a.data_ptr() + 4 * i * l20, b.data_ptr() + 4 * i * l20, c.data_ptr() + 4 * i * l20)
 
-        def add_loop():
-            for i in range(256):
-                L.slas_cuda_sadd(l20, a.data_ptr() + 4 * i * l20, b.data_ptr() + 4 * i * l20, c.data_ptr() + 4 * i * l20)
+            def c_loop():
+                _lib.call("slas_cuda_bench_call_loop", opid, l20, a.data_ptr(), b.data_ptr(), dst.data_ptr(), ncalls, l20)
 
-        ms_, _ = timed(add_loop, 3, 1)
-        record("add f32 LEN=2^20, 256 distinct pairs, one call each (launch-bound)", ms_, bytes_=12.0 * 256 * l20,
-               extra={"us_per_call": ms_ * 1e3 / 256})
+            ms_py, _ = timed(py_loop, 3, 1)
+            ms_c, _ = timed(c_loop, 5, 2)
+            with sl.Graph() as g:
+                c_loop()
+            ms_g, _ = timed(g.launch, 10, 3)
+            del g
+            rec(f"{opname}_2^20_single", ms_g / ncalls, f"{opname} f32 LEN=2^20, one call per pair, {ncalls} distinct pairs (2-3 GiB >> L2), replayed from one "
+                f"CUDA graph (slas_cuda_graph_*): per-call time", bytes_=bytes_per * l20,
+                extra={"us_per_call_graph": ms_g * 1e3 / ncalls, "us_per_call_c_loop": ms_c * 1e3 / ncalls,
+                       "us_per_call_python_loop": ms_py * 1e3 / ncalls,
+                       "frac_c_loop": bytes_per * l20 / (ms_c * 1e-3 / ncalls) / 1e9 / peak_gbs,
+                       "hbm_floor_us": bytes_per * l20 / (peak_gbs * 1e9) * 1e6})
+        # phases of one cold 2^20 dot kernel (%globaltimer inside the kernel)
+        _lib.call("slas_cuda_set_tunable", b"reduce_phases", 1)
+        ph = (C.c_uint64 * 5)()
+        stamps = []
+        for i in range(8):
+            L.slas_cuda_sdot(l20, a.data_ptr() + 4 * (i + 100) * l20, b.data_ptr() + 4 * (i + 100) * l20, out.data_ptr())
+            _lib.call("slas_cuda_get_reduce_phases", ph)
+            stamps.append([int(ph[j]) - int(ph[0]) for j in range(5)])
+        _lib.call("slas_cuda_set_tunable", b"reduce_phases", 0)
+        configs["dot_2^20_single"]["kernel_phases_ns"] = {
+            "loads_and_fmas_done": float(np.median([s[1] for s in stamps])), "block_sum_done": float(np.median([s[2] for s in stamps])),
+            "all_partials_in": float(np.median([s[3] for s in stamps])), "result_written": float(np.median([s[4] for s in stamps]))}
         del a, b, c, out, va, vb, vc, vout
         torch.cuda.empty_cache()
-        # config 5 (vector half): dot / normalize over 2^32 f32 elements IN TOTAL, sharded by contiguous slice,
-        # each rank's slice resident in its own HBM, ONE NCCL allreduce of the f64 partial per op
-        from slas_b200 import sharding
+
+        # config 5 (matrix half): batched 16x16 f32 matrix_mul over the N GPUs, weak (2^20 per GPU) and strong (2^20 in
+        # total) -- batch-index shards, no collective; whole-job numbers (max over ranks), sampled objects vs the oracle
+        for how, total in (("weak", (1 << 20) * world), ("strong", 1 << 20)):
+            blo, bhi = sharding.batch_range(total, world, rank)
+            nloc = bhi - blo
+            a = torch.empty(nloc * 256, device=dev, dtype=torch.float32)
+            b = torch.empty(nloc * 256, device=dev, dtype=torch.float32)
+            # object i of the whole job carries the same values whatever the rank count (counter-based fill at its offset)
+            _lib.call("slas_cuda_sfill_uniform", nloc * 256, a.data_ptr(), 12, blo * 256, -1.0, 1.0)
+            _lib.call("slas_cuda_sfill_uniform", nloc * 256, b.data_ptr(), 13, blo * 256, -1.0, 1.0)
+            c = torch.empty_like(a)
+            va, vb, vc = vec(a), vec(b), vec(c)
+            ms_, _ = timed(lambda: cuda.matrix_mul_batched(va, vb, vc, 16, 16, 16), ksteps, 3)
+            par = check_sampled_products(a, b, c, 16, nloc, f"16x16 {how} shard of rank {rank}", samples=256, seed=rank)
+            # a checksum of checksums: the sum over all C of the whole job must not depend on how it was sharded
+            cs = gather_f64([float(c.double().sum().item())])
+            rec(f"mm16_f32_{how}", ms_, f"batched 16x16 f32 matrix_mul, {total} objects over {world} GPU(s) ({how} scaling: "
+                f"{nloc} per GPU), whole job, max over ranks", flop=2.0 * 4096 * total, bytes_=3072.0 * total, ranks=world,
+                extra={"parity_error_over_bar": par, "objects_total": total, "checksum_of_c": float(sum(float(x[0]) for x in cs))})
+            del a, b, c, va, vb, vc
+        torch.cuda.empty_cache()
+
+        # config 5 (vector half): dot / normalize over 2^32 f32 elements IN TOTAL, sharded by contiguous slice, each
+        # rank's slice resident in its own HBM, ONE exchange of the f64 partial per op -- with the parity asserts
         total = 1 << 32
         lo_, hi_ = sharding.shard_range(total, 4, world, rank)
         local = hi_ - lo_
@@ -480,33 +623,66 @@ def run_cuda(args):
         b = torch.empty(local, device=dev, dtype=torch.float32)
         res = np.zeros(1, np.float32)
         dres = torch.zeros(4, device=dev, dtype=torch.float32)
-        # the collective two ways: fused into the reduction kernel over NVLink peer memory (p2p, the default)
-        # and as a separate ncclAllReduce behind it
+        part = np.zeros(1, np.float64)
+
+        def f64_truth(x, y):
+            """independent f64 sum of x*y over this rank's slice (torch, harness side, chunked)"""
+            s = 0.0
+            step_ = 1 << 26
+            for o in range(0, x.numel(), step_):
+                s += float((x[o:o + step_].double() * y[o:o + step_].double()).sum().item())
+            return s
+
         for fused in ((True, False) if world > 1 else (True,)):
             how = sharding.init_comm(dist, fused=fused) if world > 1 else "single"
             _lib.call("slas_cuda_sfill_uniform", local, a.data_ptr(), 4, lo_, 0.0, 1.0)
             _lib.call("slas_cuda_sfill_uniform", local, b.data_ptr(), 5, lo_, 0.0, 1.0)
+            # the exchange's inputs: every rank's own f64 partial, checked against an independent f64 truth of the slice
+            # (a dropped or doubled slice of 1e-6 of the data fails) and added in rank order
+            _lib.call("slas_cuda_sdot_partial", local, a.data_ptr(), b.data_ptr(), part.ctypes.data)
+            truth = f64_truth(a, b)
+            assert abs(part[0] - truth) <= 1e-6 * truth, f"rank {rank}: partial {part[0]} vs f64 truth {truth}"
+            parts = gather_f64([float(part[0])])
+            sum_parts = 0.0
+            for p in parts:
+                sum_parts += float(p[0])
             ms_, _ = timed(lambda: L.slas_cuda_sdot_sharded(local, a.data_ptr(), b.data_ptr(), res.ctypes.data), 5, 2)
-            # E[u*v] = 1/4 for independent U[0,1): the analytic check SURVEY 8d asks for at this size
+            got = gather_f64([float(res[0])])
+            assert all(np.array_equal(got[0], x) for x in got), f"sharded dot ({how}) differs between ranks: {got}"
+            want32 = np.float32(sum_parts)
+            if how != "nccl":  # rank-ordered sum inside the kernel: exactly the cast of the f64 sum of the partials
+                assert res[0].tobytes() == want32.tobytes(), f"sharded dot ({how}) {res[0]} != f32(sum of partials) {want32}"
+            else:              # NCCL's order is its own: one f64 rounding per rank, i.e. at most an f32 ulp after the cast
+                assert abs(float(res[0]) - float(want32)) <= float(np.spacing(want32)), f"sharded dot (nccl) {res[0]} vs {want32}"
             assert abs(float(res[0]) / total - 0.25) < 1e-3, f"sharded dot {res[0]} is not ~ 2^32/4"
-            record(f"sharded dot f32, 2^32 elements over {world} GPU(s), collective: {how}, scalar returned to host", ms_,
-                   flop=2.0 * total, bytes_=8.0 * total, bound="hbm-aggregate",
-                   extra={"aggregate_hbm_frac": 8.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world), "result": float(res[0])})
+            rec(f"sharded_dot_{how}", ms_, f"sharded dot f32, 2^32 elements over {world} GPU(s), exchange: {how}, scalar returned to host",
+                flop=2.0 * total, bytes_=8.0 * total, ranks=world,
+                extra={"result": float(res[0]), "parity": "bit-identical on all ranks; == f32(rank-ordered sum of the f64 partials)" if how != "nccl"
+                       else "bit-identical on all ranks; within 1 ulp of f32(sum of the f64 partials)"})
             ms_, _ = timed(lambda: L.slas_cuda_sdot_sharded(local, a.data_ptr(), b.data_ptr(), dres.data_ptr()), 5, 2)
-            record(f"sharded dot f32, 2^32 elements over {world} GPU(s), collective: {how}, result left in HBM", ms_,
-                   flop=2.0 * total, bytes_=8.0 * total, bound="hbm-aggregate",
-                   extra={"aggregate_hbm_frac": 8.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world)})
-            ms_, _ = timed(lambda: L.slas_cuda_snormalize_sharded(local, a.data_ptr()), 5, 2)
-            record(f"sharded normalize f32, 2^32 elements over {world} GPU(s), collective: {how}", ms_, bytes_=12.0 * total,
-                   bound="hbm-aggregate", extra={"aggregate_hbm_frac": 12.0 * total / (ms_ * 1e-3) / 1e9 / (peak_gbs * world)})
+            assert dres[:1].cpu().numpy().tobytes() == res.tobytes(), "device-resident result differs from the host-returned one"
+            rec(f"sharded_dot_{how}_hbm", ms_, f"sharded dot f32, 2^32 elements over {world} GPU(s), exchange: {how}, result left in HBM",
+                flop=2.0 * total, bytes_=8.0 * total, ranks=world)
+            # normalize: the global norm first (its bits are what every element is divided by), then sampled windows
             L.slas_cuda_snrm2_sharded(local, a.data_ptr(), res.ctypes.data)
-            assert abs(float(res[0]) - 1.0) < 1e-3, f"norm after sharded normalize is {res[0]}"
+            nrm = np.float32(res[0])
+            gn = gather_f64([float(nrm)])
+            assert all(np.array_equal(gn[0], x) for x in gn), f"sharded norm ({how}) differs between ranks"
+            offs = [0, max(0, local // 3 - 7), max(0, local - 4096)]
+            before = [a[o:o + 4096].cpu().numpy() for o in offs]
+            ms_first, _ = timed(lambda: L.slas_cuda_snormalize_sharded(local, a.data_ptr()), 1, 0)
+            for o, bf in zip(offs, before):
+                assert np.array_equal(a[o:o + 4096].cpu().numpy(), bf / nrm), f"sharded normalize ({how}): window at {o} is not a[i] / norm bit for bit"
+            ms_, _ = timed(lambda: L.slas_cuda_snormalize_sharded(local, a.data_ptr()), 5, 1)
+            rec(f"sharded_normalize_{how}", ms_, f"sharded normalize f32, 2^32 elements over {world} GPU(s), exchange: {how}",
+                bytes_=12.0 * total, ranks=world, extra={"parity": "sampled windows == a[i] / norm bit for bit; norm bit-identical on all ranks"})
+            L.slas_cuda_snrm2_sharded(local, a.data_ptr(), res.ctypes.data)
+            assert abs(float(res[0]) - 1.0) < 1e-5, f"norm after sharded normalize is {res[0]}"
             if world > 1:
                 sharding.destroy_comm(dist)
-        del dres
-        del a, b
+        del dres, a, b
         torch.cuda.empty_cache()
-        # config 4: single 4096^2 f32 product, FFMA path (and tcgen05 3xTF32 when built)
+        # config 4: single 4096^2 f32 product, FFMA path and tcgen05 3xTF32 path
         if rank == 0:
             n_ = 4096
             a, b = dev_uniform(n_ * n_, torch.float32, 6), dev_uniform(n_ * n_, torch.float32, 7)
@@ -517,33 +693,38 @@ def run_cuda(args):
             def gemm():
                 cuda.matrix_mul(va, vb, vc, n_, n_, n_, n_, n_, n_, False, False)
 
-            sl.set_sgemm_path("ffma")
-            for _ in range(2):
-                gemm()
-            torch.cuda.synchronize()
-            ts = []
-            for _ in range(5):
-                flush.zero_()  # > L2: evict the operands between timed iterations
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream); gemm(); e1.record(stream)
-                torch.cuda.synchronize()
-                ts.append(e0.elapsed_time(e1))
-            record("single 4096^2 f32 matrix_mul, FFMA path (set_sgemm_path('ffma'))", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="fp32", fma="f32")
-            try:
-                sl.set_sgemm_path("tcgen05")
+            def time_gemm():
                 for _ in range(2):
                     gemm()
                 torch.cuda.synchronize()
-                n_before = sl.launch_count()
                 ts = []
-                for _ in range(5):
-                    flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record(stream); gemm(); e1.record(stream)
-                    torch.cuda.synchronize()
-                    ts.append(e0.elapsed_time(e1))
-                record("single 4096^2 f32 matrix_mul, tcgen05 3xTF32 path (the default at this size)", float(np.median(ts)), flop=2.0 * n_ ** 3, bound="tensor",
-                       extra={"launches_per_call": (sl.launch_count() - n_before) / 5})
+                n_before = sl.launch_count()
+                with ClockSampler(local_rank) as ck:
+                    for _ in range(7):
+                        flush.zero_()  # > L2: evict the operands between timed iterations
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record(stream); gemm(); e1.record(stream)
+                        torch.cuda.synchronize()
+                        ts.append(e0.elapsed_time(e1))
+                return float(np.median(ts)), (sl.launch_count() - n_before) / 7, ck.summary()["sm_mhz"]
+
+            def freivalds():
+                """C x = A (B x) for a random x, in f64 on the harness side: the whole product, O(n^2)"""
+                x = torch.rand(n_, device=dev, dtype=torch.float64) - 0.5
+                lhs = c.view(n_, n_).double() @ x
+                rhs = a.view(n_, n_).double() @ (b.view(n_, n_).double() @ x)
+                mag = a.view(n_, n_).double().abs() @ (b.view(n_, n_).double().abs() @ x.abs())
+                return float(((lhs - rhs).abs() / (1e-5 * np.sqrt(n_) * mag)).max().item())
+
+            sl.set_sgemm_path("ffma")
+            ms_, lpc, mhz = time_gemm()
+            rec("sgemm4096_ffma", ms_, "single 4096^2 f32 matrix_mul, FFMA path (every C element an ascending-k fp32 chain)",
+                flop=2.0 * n_ ** 3, bound="fp32", extra={"launches_per_call": lpc, "sm_mhz": mhz, "parity_error_over_bar": freivalds()})
+            try:
+                sl.set_sgemm_path("tcgen05")
+                ms_, lpc, mhz = time_gemm()
+                rec("sgemm4096_tcgen05", ms_, "single 4096^2 f32 matrix_mul, tcgen05 3xTF32 path (the default at this size), split pass included",
+                    flop=2.0 * n_ ** 3, bound="tensor", extra={"launches_per_call": lpc, "sm_mhz": mhz, "parity_error_over_bar": freivalds()})
             finally:
                 sl.set_sgemm_path("auto")
             del a, b, c, va, vb, vc, flush
@@ -553,7 +734,7 @@ def run_cuda(args):
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r = cpu_reference_4x4(min(args.batch_log2, 22), 3, 1)
+        r = cpu_reference_4x4(min(args.batch_log2, CPU_SAMPLE_LOG2), 5, 1)
         cpu = {"value": r["gflops_1t"], "unit": "GFLOP/s", "cores": 1, "kind": "port", "sample": r["sample"],
                "all_cores_value": r["gflops_all_cores"], "cores_available": r["cores_available"]}
         if not args.no_others:
@@ -565,16 +746,16 @@ def run_cuda(args):
             "metric": "batched matrix_mul GFLOP/s", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batched static 4x4 f32 matrix_mul, batch 2^{args.batch_log2} per GPU (BASELINE configs[1])",
-                       "layout": "[[f32; 16]; batch] contiguous row-major, no transposes", "parallelism": f"batch-index shards x{world}, no collective",
-                       "l2": "working set 3 GiB per GPU >> 126 MB L2 (no flush needed)"},
+            "config": workload_config(args.batch_log2, world),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": achieved_gbs / peak_gbs,
                          "traffic": (traffic or {}).get("bytes") if batch == 1 << 24 else None,
                          "traffic_source": (traffic or {}).get("source"),
                          "peak_source": peak_src, "kernel": "gemm_small_kernel<float, 4x4x4>",
-                         "algorithmic_bytes_per_launch": BYTES_PER_4X4 * batch},
+                         "algorithmic_bytes_per_launch": BYTES_PER_4X4 * batch,
+                         "parity_error_over_bar": headline_parity,
+                         "fma_peak_tflops_measured": fma_peak, "tf32_peak_measured": tf32_peak,
+                         "configs": configs},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "fma_peak_tflops_measured": fma_peak if not args.no_others else None, "others": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

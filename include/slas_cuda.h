@@ -75,6 +75,18 @@ int slas_cuda_get_tunable(const char *name, long *value);
 /* Roofline denominator measured on the box: sustained FMA TFLOP/s of a register-only 8x8
  * outer-product loop (the GEMM kernels' instruction mix), f32 (is_double = 0) or f64. */
 int slas_cuda_bench_fma_peak(int is_double, double *tflops);
+/* Tensor-pipe denominator measured on the box: back-to-back tcgen05.mma.kind::tf32 (M128 N256 K8) from resident
+ * shared-memory tiles, one CTA per SM, no memory traffic -> dense TF32 TFLOP/s at the clocks the chip sustains.
+ * The 3xTF32 product executes three such MMAs per useful one. */
+int slas_cuda_bench_tf32_peak(double *tflops);
+/* BASELINE configs[0] (the reference's own dot_product bench, tests/src/main.rs:589-601, is a loop of single calls):
+ * `calls` back-to-back calls of slas_cuda_sdot (op 0, results to out[i]) or slas_cuda_sadd (op 1, results to
+ * out + i * stride) on operands `stride` elements apart, issued from C -- the launch-bound loop without an
+ * interpreter between the calls.  Device pointers. */
+int slas_cuda_bench_call_loop(int op, size_t len, const float *a, const float *b, float *out, int calls, size_t stride);
+/* With the tunable "reduce_phases" = 1 the dot / norm kernel stamps %globaltimer (ns): [0] start, [1] block 0's
+ * loads + FMAs done, [2] its block sum done, [3] grid combine done, [4] result written. */
+int slas_cuda_get_reduce_phases(uint64_t *ns5);
 
 /* ---- device-resident storage (what `CudaVec<T, LEN>` / `CudaBatch` own) --------- */
 int slas_cuda_malloc(void **dptr, size_t bytes);

@@ -256,7 +256,72 @@ def g_misc():
     report("dot 2^20 x 256 calls, slas_cuda_graph replay", timed(own.launch, 5, 2), nbytes=8.0 * 256 * l20)
 
 
+def g_small():
+    """BASELINE configs[0]: single dot / add calls at LEN 2^16 .. 2^22, 256 distinct pairs, replayed from one CUDA graph
+    (per-call time without the interpreter), over the small-vector geometry knobs: CTA size, CTAs per SM, tail protocol
+    (flagged words polled by block 0 vs ticket + last block), against the round-1 tiled geometry (reduce_small = 1)."""
+    import ctypes as C
+    ncalls = 256
+    for log2 in (20, 16, 18, 22):
+        n = 1 << log2
+        per = max(n, 1 << 20)  # distinct operands, >= 2 GiB in total for the 2^20 case
+        (ta, _), (tb, _), (tc, _) = uniform(ncalls * per, np.float32, 1), uniform(ncalls * per, np.float32, 2), uniform(ncalls * per, np.float32, 3)
+        out = torch.zeros(ncalls, device=dev, dtype=torch.float32)
+
+        def loop(op):
+            _lib.call("slas_cuda_bench_call_loop", op, n, ta.data_ptr(), tb.data_ptr(), (out if op == 0 else tc).data_ptr(), ncalls, per)
+
+        def graph_time(op):
+            loop(op)
+            with sl.Graph() as g:
+                loop(op)
+            ms = timed(g.launch, 10, 3)
+            del g
+            return ms / ncalls
+
+        variants = [("round-1 tiled geometry + ticket", {"reduce_small": 1}),
+                    ("balanced 1024 x 1/SM, flagged words", {}),
+                    ("balanced 1024 x 1/SM, ticket", {"reduce_small_tail": 1}),
+                    ("balanced 512 x 2/SM, flagged words", {"reduce_small_threads": 512}),
+                    ("balanced 512 x 1/SM, flagged words", {"reduce_small_threads": 512, "reduce_small_cps": 1}),
+                    ("balanced 512 x 2/SM, ticket", {"reduce_small_threads": 512, "reduce_small_tail": 1}),
+                    ("balanced 256 x 4/SM, flagged words", {"reduce_small_threads": 256}),
+                    ("balanced 256 x 2/SM, flagged words", {"reduce_small_threads": 256, "reduce_small_cps": 2}),
+                    ("balanced 1024 x 2/SM, flagged words", {"reduce_small_cps": 2})]
+        for name, knobs in variants:
+            for k, v in knobs.items():
+                set_tunable(k, v)
+            ms = graph_time(0)
+            ms_c = timed(lambda: loop(0), 5, 2) / ncalls
+            # phases of one cold kernel
+            set_tunable("reduce_phases", 1)
+            ph = (C.c_uint64 * 5)()
+            st = []
+            for i in range(8):
+                _lib.lib().slas_cuda_sdot(n, ta.data_ptr() + 4 * (i + 64) * per, tb.data_ptr() + 4 * (i + 64) * per, out.data_ptr())
+                _lib.call("slas_cuda_get_reduce_phases", ph)
+                st.append([int(ph[j]) - int(ph[0]) for j in range(5)])
+            set_tunable("reduce_phases", 0)
+            med = [int(np.median([x[j] for x in st])) for j in range(1, 5)]
+            for k in knobs:
+                set_tunable(k, 0)
+            report(f"dot 2^{log2} f32 single call [{name}] graph {ms * 1e3:.2f} us/call, C loop {ms_c * 1e3:.2f} us/call, "
+                   f"phases ns (loads, block sum, partials in, written) {med}", ms, nbytes=8.0 * n)
+        for name, knobs in (("round-1 tiled 256 x 1024 vec", {"ewise_small": 1}), ("balanced 256 x 8/SM", {}),
+                            ("balanced 512 x 4/SM", {"ewise_small": 2}), ("balanced 1024 x 2/SM", {"ewise_small": 3})):
+            for k, v in knobs.items():
+                set_tunable(k, v)
+            ms = graph_time(1)
+            ms_c = timed(lambda: loop(1), 5, 2) / ncalls
+            for k in knobs:
+                set_tunable(k, 0)
+            report(f"add 2^{log2} f32 single call [{name}] graph {ms * 1e3:.2f} us/call, C loop {ms_c * 1e3:.2f} us/call", ms, nbytes=12.0 * n)
+        del ta, tb, tc, out
+        torch.cuda.empty_cache()
+
+
 GROUPS = {
+    "small": g_small,
     "misc": g_misc,
     "rect": g_rect,
     "gemv": g_gemv,

@@ -56,6 +56,9 @@ SIGNATURES = {
     "slas_cuda_set_tunable": [C.c_char_p, C.c_long],
     "slas_cuda_get_tunable": [C.c_char_p, C.POINTER(C.c_long)],
     "slas_cuda_bench_fma_peak": [_i, C.POINTER(C.c_double)],
+    "slas_cuda_bench_tf32_peak": [C.POINTER(C.c_double)],
+    "slas_cuda_bench_call_loop": [_i, _sz, _vp, _vp, _vp, _i, _sz],
+    "slas_cuda_get_reduce_phases": [C.POINTER(C.c_uint64)],
     "slas_cuda_malloc": [C.POINTER(_vp), _sz],
     "slas_cuda_free": [_vp],
     "slas_cuda_malloc_host": [C.POINTER(_vp), _sz],

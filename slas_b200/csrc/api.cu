@@ -89,7 +89,13 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
                 SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], (const char *)ops[i].host + done * ops[i].unit_bytes,
                                               cnt * ops[i].unit_bytes, cudaMemcpyHostToDevice, st));
         }
+        // The kernels of consecutive chunks run on different streams but share the context's scratch (the grow-only
+        // workspace: pre-transposed operands, the 3xTF32 split, gemv / segmented-reduction partials; the reduction
+        // ticket).  Chunk i + 1's kernels therefore wait for chunk i's -- they would queue for the same SMs anyway;
+        // its H2D copy above and chunk i's D2H copy below still overlap with them.
+        if (ci > 0) SLAS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->copy_events[(ci - 1) % 3], 0));
         SLAS_TRY(launch(dev, cnt, st));
+        SLAS_CUDA_TRY(cudaEventRecord(ctx->copy_events[ci % 3], st));
         for (int i = 0; i < n; ++i)
             if (ops[i].dir & OUT)
                 SLAS_CUDA_TRY(cudaMemcpyAsync((char *)const_cast<void *>(ops[i].host) + done * ops[i].unit_bytes, dev[i],
@@ -145,21 +151,30 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
         db = kind == 1 ? da : (const T *)d[1];
     }
     bool need_collective = sharded && comm_nranks() > 1;
-    // fused collective: the reduction kernel itself exchanges the partial over NVLink peer memory
-    PeerExchange px;
-    const bool fused = need_collective && comm_next_peer_exchange(&px);
-    if (fused) need_collective = false;
     // a device-resident result pointer is written by the kernel itself: one launch, no copy, no sync
     bool out_dev = false;
     if (out) SLAS_TRY(pointer_is_device(out, &out_dev));
+    // a collective's epoch / NCCL call is not replayable: sharded ops stay out of recorded graphs
+    if (need_collective && ctx->capturing)
+        return fail(SLAS_ERR_INVALID, "sharded reductions cannot be recorded in a graph (the exchange epoch is per call)");
+    // fused collective: the reduction kernel itself exchanges the partial over NVLink peer memory.  The epoch is taken
+    // last, after every check that can fail, and given back if the launch itself fails: a rank whose epoch ran ahead
+    // of its peers would make every later collective spin.
+    PeerExchange px;
+    const bool fused = need_collective && comm_next_peer_exchange(&px);
+    if (fused) need_collective = false;
     if (out_dev && (len > 0 || fused)) typed = out;
     if (len == 0 && !fused) {
         // the reference returns the empty sum: 0 (and sqrt(0) = 0)
         SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
     } else {
         // (a rank with an empty slice still takes part in the fused exchange: its partial is 0)
-        SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0,
-                                  fused ? &px : nullptr));
+        const int r = launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0,
+                                       fused ? &px : nullptr);
+        if (r != SLAS_OK) {
+            if (fused) comm_rollback_peer_exchange(px.epoch);
+            return r;
+        }
     }
     if (need_collective) {
         SLAS_TRY(comm_allreduce_f64(res, nres, ctx->stream));
@@ -190,12 +205,20 @@ static int api_normalize(size_t len, T *a, bool sharded) {
         da = (T *)d[0];
     }
     bool need_collective = sharded && comm_nranks() > 1;
+    if (need_collective && ctx->capturing)
+        return fail(SLAS_ERR_INVALID, "sharded reductions cannot be recorded in a graph (the exchange epoch is per call)");
     PeerExchange px;
-    const bool fused = need_collective && comm_next_peer_exchange(&px);
+    const bool fused = need_collective && comm_next_peer_exchange(&px);  // after every check that can fail
     if (fused) need_collective = false;
     if (len == 0 && !fused) SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
-    else SLAS_TRY(launch_reduce<T>(ctx, ctx->stream, 1, len, da, da, res, need_collective ? nullptr : typed, 1, 0,
-                                   fused ? &px : nullptr));
+    else {
+        const int r = launch_reduce<T>(ctx, ctx->stream, 1, len, da, da, res, need_collective ? nullptr : typed, 1, 0,
+                                       fused ? &px : nullptr);
+        if (r != SLAS_OK) {
+            if (fused) comm_rollback_peer_exchange(px.epoch);
+            return r;
+        }
+    }
     if (need_collective) {
         SLAS_TRY(comm_allreduce_f64(res, 1, ctx->stream));
         SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, 1));

@@ -79,6 +79,10 @@ bool comm_next_peer_exchange(PeerExchange *out) {
     return true;
 }
 
+void comm_rollback_peer_exchange(unsigned long long epoch) {
+    if (g_comm.p2p && g_comm.epoch == epoch) --g_comm.epoch;
+}
+
 int comm_allreduce_f64(double *dev_inout, size_t count, cudaStream_t st) {
     if (!g_comm.comm || g_comm.nranks == 1) return SLAS_OK;  // single rank: the local partial is the sum
     const int r = g_nccl.AllReduce(dev_inout, dev_inout, count, kNcclFloat64, kNcclSum, g_comm.comm, st);

@@ -10,4 +10,7 @@ int comm_nranks();
 int comm_allreduce_f64(double *dev_inout, size_t count, cudaStream_t st);
 // Peer-memory exchange (p2p.cuh): true + a descriptor with a fresh epoch when the NVLink mailboxes are mapped.
 bool comm_next_peer_exchange(PeerExchange *out);
+// The launch that was to use `epoch` failed before reaching the GPU: give the epoch back so that this rank stays
+// in step with its peers.
+void comm_rollback_peer_exchange(unsigned long long epoch);
 }  // namespace slas

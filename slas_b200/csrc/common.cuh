@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/slas_cuda.h"
 
@@ -39,7 +40,7 @@ int fail(int code, const char *fmt, ...);
 
 // ---- context -------------------------------------------------------------------
 struct Context {
-    int device = -1;
+    std::atomic<int> device{-1};         // -1 until init_context has finished (acquire / release: see get_context)
     int sm_count = 0;
     size_t l2_bytes = 0;
     size_t hbm_bytes = 0;
@@ -50,14 +51,21 @@ struct Context {
     double *partials = nullptr;          // [kMaxPartials * 2]
     unsigned int *ticket = nullptr;      // [4]
     double *scalars = nullptr;           // [16] device scalars (norm, sharded partial, ...)
-    // Grow-only device workspace (transpose_inplace temp, tcgen05 hi/lo split, host staging).
+    void *ll_slots = nullptr;            // [3 * kMaxPartials] 16-byte flagged partial slots (reduce.cuh), zero between launches
+    unsigned long long *phases = nullptr;  // [8] %globaltimer stamps of the last reduction (tunable "reduce_phases")
+    // Grow-only device workspace (transpose_inplace temp, tcgen05 hi/lo split, host staging).  A block that is
+    // outgrown is RETIRED, not freed, while a stream capture is open or an instantiated graph may still hold
+    // its address in a kernel argument (slas_cuda_graph_*); retired blocks are freed once no graph is alive.
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
+    std::vector<void *> retired;
+    int live_graphs = 0;
+    bool capturing = false;              // between slas_cuda_graph_begin and _end
     // Host-pointer path: staging area in HBM, copy streams + events, pinned bounce scalars.
     void *staging = nullptr;
     size_t staging_bytes = 0;
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};   // kernels of chunk i done (orders the shared scratch)
     double *pinned_scalars = nullptr;    // [16]
     std::mutex mu;                       // serialises enqueue + scratch use
 };

@@ -32,7 +32,9 @@ int fail(int code, const char *fmt, ...) {
 struct Tunable { const char *name; long value; };
 static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0}, {"gemm32s_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
-                               {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0}};
+                               {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
+                               {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
+                               {"reduce_phases", 0}, {"ewise_small", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;
@@ -43,7 +45,34 @@ constexpr int kMaxDevices = 32;
 static Context g_ctx[kMaxDevices];
 static std::mutex g_init_mu;
 
-static int init_context(Context *c, int dev) {
+static void release_context(Context *c) {
+    cudaFree(c->partials);
+    cudaFree(c->ticket);
+    cudaFree(c->scalars);
+    cudaFree(c->ll_slots);
+    cudaFree(c->phases);
+    c->ll_slots = nullptr; c->phases = nullptr;
+    cudaFree(c->workspace);
+    for (void *p : c->retired) cudaFree(p);
+    c->retired.clear();
+    cudaFree(c->staging);
+    if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
+    for (int i = 0; i < 3; ++i) {
+        if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
+        if (c->copy_events[i]) cudaEventDestroy(c->copy_events[i]);
+        c->copy_streams[i] = nullptr;
+        c->copy_events[i] = nullptr;
+    }
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    c->own_stream = c->stream = nullptr;
+    c->partials = nullptr; c->ticket = nullptr; c->scalars = nullptr;
+    c->workspace = nullptr; c->workspace_bytes = 0; c->pinned_scalars = nullptr;
+    c->staging = nullptr; c->staging_bytes = 0;
+    c->live_graphs = 0; c->capturing = false;
+    cudaGetLastError();
+}
+
+static int init_context_resources(Context *c, int dev) {
     cudaDeviceProp prop;
     SLAS_CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
     if (prop.major < 10)
@@ -57,16 +86,32 @@ static int init_context(Context *c, int dev) {
     SLAS_CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     SLAS_CUDA_TRY(cudaMalloc(&c->partials, sizeof(double) * kMaxPartials * 2));
+    SLAS_CUDA_TRY(cudaMemset(c->partials, 0, sizeof(double) * kMaxPartials * 2));
     SLAS_CUDA_TRY(cudaMalloc(&c->ticket, sizeof(unsigned int) * 4));
     SLAS_CUDA_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned int) * 4));
     SLAS_CUDA_TRY(cudaMalloc(&c->scalars, sizeof(double) * 16));
     SLAS_CUDA_TRY(cudaMemset(c->scalars, 0, sizeof(double) * 16));
+    SLAS_CUDA_TRY(cudaMalloc(&c->ll_slots, (size_t)16 * 3 * kMaxPartials));
+    SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * 3 * kMaxPartials));
+    SLAS_CUDA_TRY(cudaMalloc(&c->phases, sizeof(unsigned long long) * 8));
+    SLAS_CUDA_TRY(cudaMemset(c->phases, 0, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaMallocHost(&c->pinned_scalars, sizeof(double) * 16));
     for (int i = 0; i < 3; ++i) {
         SLAS_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking));
         SLAS_CUDA_TRY(cudaEventCreateWithFlags(&c->copy_events[i], cudaEventDisableTiming));
     }
-    c->device = dev;
+    SLAS_CUDA_TRY(cudaDeviceSynchronize());
+    return SLAS_OK;
+}
+
+// Called under g_init_mu.  A failure part-way gives back what was already made, so a retry starts clean.
+static int init_context(Context *c, int dev) {
+    const int r = init_context_resources(c, dev);
+    if (r != SLAS_OK) {
+        release_context(c);
+        return r;
+    }
+    c->device.store(dev, std::memory_order_release);  // publishes every field written above
     return SLAS_OK;
 }
 
@@ -80,24 +125,40 @@ int get_context(Context **out) {
     }
     if (dev < 0 || dev >= kMaxDevices) return fail(SLAS_ERR_CUDA, "device index %d out of range", dev);
     Context *c = &g_ctx[dev];
-    if (c->device != dev) {
+    // double-checked: the acquire load pairs with init_context's release store (libtest calls in concurrently)
+    if (c->device.load(std::memory_order_acquire) != dev) {
         std::lock_guard<std::mutex> lk(g_init_mu);
-        if (c->device != dev) SLAS_TRY(init_context(c, dev));
+        if (c->device.load(std::memory_order_relaxed) != dev) SLAS_TRY(init_context(c, dev));
     }
     *out = c;
     return SLAS_OK;
 }
 
+// Blocks retired by ensure_workspace are only needed by instantiated graphs (and an open capture).
+static void free_retired(Context *ctx) {
+    if (ctx->retired.empty() || ctx->live_graphs > 0 || ctx->capturing) return;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return; }
+    for (void *p : ctx->retired) cudaFree(p);
+    ctx->retired.clear();
+}
+
 int ensure_workspace(Context *ctx, size_t bytes, void **out) {
     if (bytes > ctx->workspace_bytes) {
+        // Kernels already enqueued -- and kernel nodes of recorded graphs -- hold the old address.  While a capture
+        // is open (no synchronising call is legal there) or a graph is alive the old block is retired, not freed.
         if (ctx->workspace) {
-            SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-            SLAS_CUDA_TRY(cudaFree(ctx->workspace));
+            if (ctx->capturing || ctx->live_graphs > 0) {
+                ctx->retired.push_back(ctx->workspace);
+            } else {
+                SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                for (int i = 0; i < 3; ++i) SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_streams[i]));
+                SLAS_CUDA_TRY(cudaFree(ctx->workspace));
+            }
             ctx->workspace = nullptr;
             ctx->workspace_bytes = 0;
         }
         size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
-        SLAS_CUDA_TRY(cudaMalloc(&ctx->workspace, want));
+        SLAS_CUDA_TRY(cudaMalloc(&ctx->workspace, want));  // legal during a relaxed-mode capture
         ctx->workspace_bytes = want;
     }
     *out = ctx->workspace;
@@ -105,6 +166,10 @@ int ensure_workspace(Context *ctx, size_t bytes, void **out) {
 }
 
 int ensure_staging(Context *ctx, size_t bytes, void **out) {
+    // host operands need synchronising copies: they cannot be part of a recorded graph (include/slas_cuda.h)
+    if (ctx->capturing)
+        return fail(SLAS_ERR_INVALID, "host operands cannot be recorded in a graph: pass device pointers between "
+                                      "slas_cuda_graph_begin and slas_cuda_graph_end");
     if (bytes > ctx->staging_bytes) {
         if (ctx->staging) {
             SLAS_CUDA_TRY(cudaDeviceSynchronize());
@@ -153,6 +218,9 @@ int deliver_scalar(Context *ctx, const void *dev_src, void *out, size_t bytes) {
         SLAS_CUDA_TRY(cudaMemcpyAsync(out, dev_src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         return SLAS_OK;
     }
+    if (ctx->capturing)
+        return fail(SLAS_ERR_INVALID, "a host result pointer needs a synchronising copy and cannot be recorded in a graph: "
+                                      "pass a device pointer for the result");
     SLAS_CUDA_TRY(cudaMemcpyAsync(ctx->pinned_scalars, dev_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     memcpy(out, ctx->pinned_scalars, bytes);
@@ -190,26 +258,12 @@ int slas_cuda_shutdown(void) {
     cudaGetDevice(&cur);
     for (int d = 0; d < kMaxDevices; ++d) {
         Context *c = &g_ctx[d];
-        if (c->device != d) continue;
+        if (c->device.load(std::memory_order_acquire) != d) continue;
         cudaSetDevice(d);
         cudaDeviceSynchronize();
-        cudaFree(c->partials);
-        cudaFree(c->ticket);
-        cudaFree(c->scalars);
-        cudaFree(c->workspace);
-        cudaFree(c->staging);
-        cudaFreeHost(c->pinned_scalars);
-        for (int i = 0; i < 3; ++i) {
-            if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
-            if (c->copy_events[i]) cudaEventDestroy(c->copy_events[i]);
-        }
-        if (c->own_stream) cudaStreamDestroy(c->own_stream);
-        c->device = -1;
-        c->own_stream = c->stream = nullptr;
-        c->partials = nullptr; c->ticket = nullptr; c->scalars = nullptr;
-        c->workspace = nullptr; c->workspace_bytes = 0; c->pinned_scalars = nullptr;
-        c->staging = nullptr; c->staging_bytes = 0;
-        for (int i = 0; i < 3; ++i) { c->copy_streams[i] = nullptr; c->copy_events[i] = nullptr; }
+        std::lock_guard<std::mutex> ck(c->mu);
+        c->device.store(-1, std::memory_order_release);
+        release_context(c);
     }
     if (cur >= 0) cudaSetDevice(cur);
     return SLAS_OK;
@@ -243,14 +297,24 @@ int slas_cuda_set_stream(void *cuda_stream) {
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    SLAS_REQUIRE(!c->capturing, "set_stream inside graph_begin / graph_end");
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    if (next != c->stream) {
+        // ops share the context's scratch (reduction slots, workspace): work queued on the new stream must not
+        // overtake what is still running on the old one
+        SLAS_CUDA_TRY(cudaEventRecord(c->copy_events[0], c->stream));
+        SLAS_CUDA_TRY(cudaStreamWaitEvent(next, c->copy_events[0], 0));
+        c->stream = next;
+    }
     return SLAS_OK;
 }
 
 int slas_cuda_synchronize(void) {
     Context *c;
     SLAS_TRY(get_context(&c));
-    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaStream_t st;
+    { std::lock_guard<std::mutex> lk(c->mu); st = c->stream; }
+    SLAS_CUDA_TRY(cudaStreamSynchronize(st));
     return SLAS_OK;
 }
 
@@ -261,7 +325,9 @@ int slas_cuda_graph_begin(void) {
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);
+    SLAS_REQUIRE(!c->capturing, "graph_begin: a capture is already open on this device");
     SLAS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+    c->capturing = true;
     return SLAS_OK;
 }
 
@@ -270,12 +336,15 @@ int slas_cuda_graph_end(void **graph_exec) {
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);
+    SLAS_REQUIRE(c->capturing, "graph_end without graph_begin");
+    c->capturing = false;
     cudaGraph_t graph = nullptr;
     SLAS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
     cudaGraphExec_t exec = nullptr;
     const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     SLAS_CUDA_TRY(e);
+    ++c->live_graphs;  // from here on the scratch blocks its kernel nodes point at must stay allocated
     *graph_exec = exec;
     return SLAS_OK;
 }
@@ -291,7 +360,13 @@ int slas_cuda_graph_launch(void *graph_exec) {
 
 int slas_cuda_graph_destroy(void *graph_exec) {
     if (!graph_exec) return SLAS_OK;
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
+    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));  // a replay may still be running
     SLAS_CUDA_TRY(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    if (c->live_graphs > 0) --c->live_graphs;
+    free_retired(c);
     return SLAS_OK;
 }
 
@@ -354,7 +429,7 @@ int slas_cuda_malloc_host(void **hptr, size_t bytes) {
     cpu_set_t before, local;
     bool moved = false;
     const char *env = getenv("SLAS_CUDA_HOST_NUMA");
-    if (!(env && env[0] == '0') && sched_getaffinity(0, sizeof(before), &before) == 0 && device_local_cpus(c->device, &local)) {
+    if (!(env && env[0] == '0') && sched_getaffinity(0, sizeof(before), &before) == 0 && device_local_cpus(c->device.load(), &local)) {
         cpu_set_t want;
         CPU_AND(&want, &before, &local);  // never leave the cpuset the process was given
         if (CPU_COUNT(&want) > 0) moved = sched_setaffinity(0, sizeof(want), &want) == 0;
@@ -376,8 +451,10 @@ static int copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind ki
     SLAS_REQUIRE(dst && src, "null pointer in memcpy");
     Context *c;
     SLAS_TRY(get_context(&c));
-    SLAS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
-    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    cudaStream_t st;
+    { std::lock_guard<std::mutex> lk(c->mu); st = c->stream; }
+    SLAS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, st));
+    SLAS_CUDA_TRY(cudaStreamSynchronize(st));
     return SLAS_OK;
 }
 
@@ -392,6 +469,7 @@ int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes) {
     SLAS_REQUIRE(dst && src, "null pointer in memcpy");
     Context *c;
     SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
     SLAS_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
     return SLAS_OK;
 }
@@ -400,6 +478,7 @@ int slas_cuda_memset(void *dst, int byte, size_t bytes) {
     SLAS_REQUIRE(dst, "null pointer in memset");
     Context *c;
     SLAS_TRY(get_context(&c));
+    std::lock_guard<std::mutex> lk(c->mu);
     SLAS_CUDA_TRY(cudaMemsetAsync(dst, byte, bytes, c->stream));
     return SLAS_OK;
 }

@@ -648,4 +648,86 @@ int launch_sgemm_3xtf32(Context *ctx, cudaStream_t st, const float *a, const flo
     return SLAS_OK;
 }
 
+// ---- tensor-pipe roofline denominator, measured on the box -----------------------------------------------------
+// One CTA per SM issues back-to-back tcgen05.mma.kind::tf32 (M128 N256 K8) from two resident shared-memory tiles into
+// its two TMEM accumulators: no TMA, no HBM traffic, no epilogue -- the dense TF32 rate the chip holds at the clocks it
+// sustains under that load.  The 3xTF32 GEMM executes 3 such MMAs per useful one.
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(uint32_t iters, float *sink) {
+    using namespace tc;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + A_TILE_BYTES + B_TILE_BYTES);
+    uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // operands: small finite values (a zero tile would flatter the clocks)
+    float *f = reinterpret_cast<float *>(smem);
+    for (int i = threadIdx.x; i < (A_TILE_BYTES + B_TILE_BYTES) / 4; i += blockDim.x)
+        f[i] = 1e-3f * (float)(((uint32_t)i * 2654435761u >> 20) & 1023u) - 0.5f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 1 && lane == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    if (warp == 2) tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+    if (warp == 1 && lane == 0) {
+        const uint32_t sa = smem_u32(smem);
+        const uint64_t da = umma_desc_k_sw128(sa), db = umma_desc_k_sw128(sa + A_TILE_BYTES);
+        const uint32_t idesc = umma_idesc_tf32(BM, BN);
+        for (uint32_t it = 0; it < iters; ++it) {
+#pragma unroll
+            for (uint32_t k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 4) >> 4);
+                umma_tf32(tmem_base + (it & 1) * BN, da + adv, db + adv, idesc, it > 1);
+            }
+        }
+        umma_commit(bar);
+        mbar_wait(bar, 0);
+        tc_fence_after();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base, v);
+        tmem_ld_wait();
+        if (__uint_as_float(v[lane]) == 123456.789f) sink[0] = __uint_as_float(v[0]);  // never true: keeps the work alive
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
 }  // namespace slas
+
+extern "C" int slas_cuda_bench_tf32_peak(double *tflops) {
+    using namespace slas;
+    SLAS_REQUIRE(tflops, "null output");
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const int smem = tc::A_TILE_BYTES + tc::B_TILE_BYTES + 1024 + 64;
+    SLAS_CUDA_TRY(cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const uint32_t iters = 16384;  // x 4 MMAs of 128 x 256 x 8: ~2 ms per launch
+    float *sink = reinterpret_cast<float *>(ctx->scalars + 8);
+    cudaEvent_t e0, e1;
+    SLAS_CUDA_TRY(cudaEventCreate(&e0));
+    SLAS_CUDA_TRY(cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)ctx->sm_count;
+    for (int w = 0; w < 2; ++w) tf32_peak_kernel<<<grid, 128, smem, ctx->stream>>>(iters, sink);
+    SLAS_CUDA_TRY(cudaEventRecord(e0, ctx->stream));
+    const int reps = 5;
+    for (int r = 0; r < reps; ++r) tf32_peak_kernel<<<grid, 128, smem, ctx->stream>>>(iters, sink);
+    SLAS_CUDA_TRY(cudaEventRecord(e1, ctx->stream));
+    SLAS_CUDA_TRY(cudaEventSynchronize(e1));
+    count_launch(reps + 2);
+    float ms = 0;
+    SLAS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flop = 2.0 * tc::BM * tc::BN * tc::BK * (double)iters * grid * reps;
+    *tflops = flop / (ms * 1e-3) / 1e12;
+    return SLAS_OK;
+}

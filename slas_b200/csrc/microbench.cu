@@ -2,7 +2,8 @@
 // FFMA-peak microbench on the box and record it").  Not part of the reference interface.
 //   slas_cuda_bench_fma_peak: register-only 8x8 outer-product FMA loop (the instruction mix of the
 //   GEMM inner loops, no memory traffic) -> sustained FP32 / FP64 FMA TFLOP/s at the clocks the
-//   chip actually holds under that load.
+//   chip actually holds under that load.  (The tensor-pipe counterpart, slas_cuda_bench_tf32_peak, lives in
+//   gemm_tcgen05.cu next to the PTX it shares.)
 #include "common.cuh"
 
 namespace slas {
@@ -56,7 +57,8 @@ static int bench_fma(Context *ctx, double *tflops, double *ms_out) {
     SLAS_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    const double flop = 2.0 * 64 * 4 * (double)iters * 256.0 * blocks * reps;  // the 8 bookkeeping FMAs per round are not counted
+    // per round: 64 FMAs of the outer product + the 8 FMAs that keep the operands moving (a*0.999 + 1e-4) = 72 issued
+    const double flop = 2.0 * 72 * 4 * (double)iters * 256.0 * blocks * reps;
     *tflops = flop / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms / reps;
     return SLAS_OK;
@@ -72,4 +74,31 @@ extern "C" int slas_cuda_bench_fma_peak(int is_double, double *tflops) {
     SLAS_TRY(get_context(&ctx));
     std::lock_guard<std::mutex> lk(ctx->mu);
     return is_double ? bench_fma<double>(ctx, tflops, nullptr) : bench_fma<float>(ctx, tflops, nullptr);
+}
+
+// The launch-bound loop of BASELINE configs[0] driven from C (no interpreter between the calls): `calls` back-to-back
+// calls of the public entry points on consecutive operands `stride` elements apart.  op 0: slas_cuda_sdot (results to
+// out[i]); op 1: slas_cuda_sadd (results to out + i * stride).  All pointers device pointers.
+extern "C" int slas_cuda_bench_call_loop(int op, size_t len, const float *a, const float *b, float *out, int calls,
+                                         size_t stride) {
+    SLAS_REQUIRE(op == 0 || op == 1, "call_loop: op must be 0 (dot) or 1 (add)");
+    for (int i = 0; i < calls; ++i) {
+        const size_t off = (size_t)i * stride;
+        if (op == 0) SLAS_TRY(slas_cuda_sdot(len, a + off, b + off, out + i));
+        else SLAS_TRY(slas_cuda_sadd(len, a + off, b + off, out + off));
+    }
+    return SLAS_OK;
+}
+
+// %globaltimer stamps of the last dot / norm kernel when the tunable "reduce_phases" is set: ns[0] kernel start
+// (block 0), ns[1] block 0's loads and FMAs done, ns[2] its block sum done, ns[3] grid combine done (all partials
+// in), ns[4] result written.  Synchronises the stream.
+extern "C" int slas_cuda_get_reduce_phases(uint64_t *ns5) {
+    SLAS_REQUIRE(ns5, "null output");
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    SLAS_CUDA_TRY(cudaMemcpy(ns5, ctx->phases, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SLAS_OK;
 }

@@ -1,0 +1,256 @@
+// reduce.cu -- grid-wide reductions of the vector half of the hot path:
+//   dot / complex dotu   (replaces src/backends/rust.rs:20-41, src/backends/blas.rs:15-52)
+//   norm                 (replaces src/backends/rust.rs:116-121, 129-140, src/backends/blas.rs:156-170)
+// 128-bit coalesced streaming loads, four independent 16-byte loads per operand in flight per thread, fp
+// accumulators flushed into f64, warp shuffles + block reduction, and a deterministic single-launch grid combine
+// (reduce.cuh).  No float atomics anywhere: same input + same launch geometry => same bits.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "reduce.cuh"
+
+namespace slas {
+
+// ---- geometry (shared with fused_chain.cu) -------------------------------------------------------------------------
+RedGeom reduce_geometry(const Context *ctx, size_t work, bool vectorised) {
+    RedGeom g;
+    const size_t sms = (size_t)ctx->sm_count;
+    const size_t tile = (size_t)256 * kRedUnroll;
+    // balanced single-wave geometry while the tiled one would not yet fill its cap of 8 CTAs per SM
+    const long mode = tunable("reduce_small");          // 0 default, 1 = tiled everywhere (the round-1 geometry)
+    const bool small = vectorised && mode != 1 && work < sms * 8 * tile;
+    if (!small) {
+        size_t blocks = (work + tile - 1) / tile;
+        size_t cap = sms * 8;
+        if (cap > 1536) cap = 1536;                      // 3 results x cap partials fit the scratch (2 * kMaxPartials)
+        if (blocks > cap) blocks = cap;
+        if (blocks == 0) blocks = 1;
+        g.blocks = (unsigned)blocks;
+        g.threads = 256;
+        return g;
+    }
+    long threads = tunable("reduce_small_threads");      // 256 / 512 / 1024; 0 = default
+    if (threads != 256 && threads != 512 && threads != 1024) threads = 1024;
+    long cps = tunable("reduce_small_cps");              // CTAs per SM; 0 = as many as keep 1024 threads per SM
+    if (cps <= 0) cps = 1024 / threads;
+    if (cps * threads > 2048) cps = 2048 / threads;
+    g.threads = (unsigned)threads;
+    g.balanced = 1;
+    g.poll = tunable("reduce_small_tail") == 1 ? 0 : 1;  // 1 = ticket tail (for the comparison), default flagged words
+    // at least one full group of loads per thread before another block is worth its cross-block step
+    size_t blocks = (work + (size_t)threads * 2 - 1) / ((size_t)threads * 2);
+    const size_t wave = sms * (size_t)cps;
+    if (blocks >= wave) blocks = wave;
+    if (blocks == 0) blocks = 1;
+    size_t per = (work + blocks - 1) / blocks;
+    per = (per + 7) / 8 * 8;                             // block ranges start on 128-byte lines
+    if (per == 0) per = 8;                               // an empty vector still launches one block (it writes the zero)
+    blocks = (work + per - 1) / per;
+    if (blocks == 0) blocks = 1;
+    g.blocks = (unsigned)blocks;
+    g.per = per;
+    return g;
+}
+
+RedScratch reduce_scratch(Context *ctx) {
+    RedScratch sc;
+    sc.partials = ctx->partials;
+    sc.ticket = ctx->ticket;
+    sc.ll = reinterpret_cast<LLSlot *>(ctx->ll_slots);
+    sc.phases = tunable("reduce_phases") ? ctx->phases : nullptr;
+    return sc;
+}
+
+// result[0] (and result[1] for KIND 2) receive the f64 sums; typed_out (may be null) receives
+// mode 0: (T)sum [, (T)sum_im]   mode 1: (T)sqrt(sum).  If accumulate != 0 the previous
+// content of result[] is added first (chunked host vectors).
+template <typename T, int KIND, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised, const RedGeom g,
+              const RedScratch sc, double *__restrict__ result, T *__restrict__ typed_out, int mode, int accumulate,
+              const PeerExchange px, unsigned head) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    constexpr int NRES = KIND == 2 ? 2 : 1;
+    __shared__ double red[THREADS / 32];
+    __shared__ double peer_vals[2 * kMaxPeers];
+    __shared__ bool is_last;
+    const bool stamp = sc.phases != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    if (stamp) sc.phases[0] = red_timer_ns();
+    Reducer<T, KIND> r;
+    r.clear();
+    const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * THREADS;
+    if (vectorised) {
+        // operands that share a misalignment (views at an odd offset): `head` elements up to the first 16-byte boundary
+        // are scalar work like the tail, the body starts on the boundary
+        const V *av = reinterpret_cast<const V *>(a + head);
+        const V *bv = reinterpret_cast<const V *>(b + head);
+        size_t i, end, stride;
+        red_range<THREADS>(g, nvec, i, end, stride);
+        int since_flush = 0;
+        // full groups: all kRedUnroll vectors of this thread are in range
+        for (; i + (size_t)(kRedUnroll - 1) * THREADS < end; i += stride) {
+            V x[kRedUnroll], y[kRedUnroll];
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) x[u] = ld_stream(av + i + (size_t)u * THREADS);
+            if (KIND != 1) {
+#pragma unroll
+                for (int u = 0; u < kRedUnroll; ++u) y[u] = ld_stream(bv + i + (size_t)u * THREADS);
+            }
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
+            if (++since_flush == kFlushEvery) { r.flush(); since_flush = 0; }
+        }
+        // ragged last group: every load is issued before the first use (this IS the whole body of a short vector)
+        {
+            V x[kRedUnroll], y[kRedUnroll];
+            bool ok[kRedUnroll];
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u) {
+                const size_t j = i + (size_t)u * THREADS;
+                ok[u] = j < end;
+                x[u] = ok[u] ? ld_stream(av + j) : vzero((V *)nullptr);
+            }
+            if (KIND != 1) {
+#pragma unroll
+                for (int u = 0; u < kRedUnroll; ++u) {
+                    const size_t j = i + (size_t)u * THREADS;
+                    y[u] = ok[u] ? ld_stream(bv + j) : vzero((V *)nullptr);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kRedUnroll; ++u)
+                if (ok[u]) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
+        }
+        r.flush();
+        // scalar tail: the len % N elements past the last whole vector (N is even, so a complex
+        // pair is never split: the complex tail is whole (re, im) pairs)
+        if (KIND != 2) {
+            const size_t j = head + nvec * N + tid;
+            if (j < len) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+            if (tid < head) r.add_scalar(a[tid], KIND == 1 ? a[tid] : b[tid]);
+        } else {
+            const size_t j = head + nvec * N + 2 * tid;
+            if (j + 1 < len) {
+                const double ar = a[j], ai = a[j + 1], br = b[j], bi = b[j + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
+            if (2 * tid + 1 < head) {
+                const double ar = a[2 * tid], ai = a[2 * tid + 1], br = b[2 * tid], bi = b[2 * tid + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
+        }
+    } else {
+        // unaligned operands: scalar grid-stride loop, f64 accumulation
+        if (KIND == 2) {
+            for (size_t j = tid; j < len / 2; j += nthreads) {
+                const double ar = a[2 * j], ai = a[2 * j + 1], br = b[2 * j], bi = b[2 * j + 1];
+                r.sum += ar * br - ai * bi;
+                r.sum_im += ar * bi + ai * br;
+            }
+        } else {
+            // operands with different misalignments: coalesced 4-byte / 8-byte loads, four in flight per thread, T
+            // accumulators flushed into f64 like the vector body (one DFMA per element was 0.35 of HBM peak)
+            size_t j = tid;
+            int since_flush = 0;
+            for (; j + 3 * nthreads < len; j += 4 * nthreads) {
+                T x[4], y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = a[j + u * nthreads];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = KIND == 1 ? x[u] : b[j + u * nthreads];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) r.acc[u] = fma(x[u], y[u], r.acc[u]);
+                if (++since_flush == kFlushEvery * 4) { r.flush(); since_flush = 0; }
+            }
+            r.flush();
+            for (; j < len; j += nthreads) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
+        }
+    }
+    if (stamp) sc.phases[1] = red_timer_ns();
+    double s[NRES], p[NRES];
+    s[0] = block_sum<THREADS>(r.sum, red);
+    if (KIND == 2) s[NRES - 1] = block_sum<THREADS>(r.sum_im, red);
+    if (stamp) sc.phases[2] = red_timer_ns();
+    if (!grid_combine<THREADS, NRES>(g, sc, s, p, red, &is_last)) return;
+    const bool stamp_end = sc.phases != nullptr && threadIdx.x == 0;
+    if (stamp_end) sc.phases[3] = red_timer_ns();
+    double pr = p[0], pi = KIND == 2 ? p[NRES - 1] : 0.0;
+    // multi-GPU: exchange the rank-local partial with the peers over NVLink and add in rank order
+    if (px.nranks > 1) peer_allreduce_sum(px, pr, pi, peer_vals);
+    if (threadIdx.x == 0) {
+        if (accumulate) { pr += result[0]; if (KIND == 2) pi += result[1]; }
+        result[0] = pr;
+        if (KIND == 2) result[1] = pi;
+        if (typed_out) {
+            if (mode == 1) typed_out[0] = (T)sqrt(pr);
+            else {
+                typed_out[0] = (T)pr;
+                if (KIND == 2) typed_out[1] = (T)pi;
+            }
+        }
+        if (stamp_end) sc.phases[4] = red_timer_ns();
+    }
+}
+
+template <typename T, int KIND>
+static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b,
+                              double *result, T *typed_out, int mode, int accumulate, const PeerExchange &px) {
+    constexpr int N = Vec16<T>::N;
+    // vector body when the operands are aligned, or share one misalignment that is whole elements (for complex: whole
+    // pairs) away from a 16-byte boundary
+    const uintptr_t ma = (uintptr_t)a % 16, mb = (uintptr_t)(KIND == 1 ? a : b) % 16;
+    const size_t unit = sizeof(T) * (KIND == 2 ? 2 : 1);
+    const bool vec = ma == mb && ma % unit == 0;
+    size_t head = vec && ma ? (16 - ma) / sizeof(T) : 0;
+    if (head > len) head = len;
+    const size_t nvec = vec ? (len - head) / N : 0;
+    const RedGeom g = reduce_geometry(ctx, vec ? nvec : len, vec);
+    const RedScratch sc = reduce_scratch(ctx);
+    const T *bb = KIND == 1 ? a : b;
+#define SLAS_REDUCE_LAUNCH(THREADS)                                                                                       \
+    reduce_kernel<T, KIND, THREADS><<<g.blocks, THREADS, 0, st>>>(a, bb, len, nvec, vec ? 1 : 0, g, sc, result, typed_out, \
+                                                                  mode, accumulate, px, (unsigned)head)
+    if (g.threads == 1024) SLAS_REDUCE_LAUNCH(1024);
+    else if (g.threads == 512) SLAS_REDUCE_LAUNCH(512);
+    else SLAS_REDUCE_LAUNCH(256);
+#undef SLAS_REDUCE_LAUNCH
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+template <typename T>
+int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
+                  T *typed_out, int mode, int accumulate, const PeerExchange *peers) {
+    const PeerExchange px = peers ? *peers : PeerExchange{};
+    switch (kind) {
+    case 0: return launch_reduce_kind<T, 0>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
+    case 1: return launch_reduce_kind<T, 1>(ctx, st, len, a, a, result, typed_out, mode, accumulate, px);
+    case 2: return launch_reduce_kind<T, 2>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
+    }
+    return fail(SLAS_ERR_INVALID, "unknown reduction kind %d", kind);
+}
+template int launch_reduce<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, double *,
+                                  float *, int, int, const PeerExchange *);
+template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const double *, const double *,
+                                   double *, double *, int, int, const PeerExchange *);
+
+// f64 sum -> typed scalar (used after the NCCL allreduce of the sharded ops)
+template <typename T>
+__global__ void finish_scalar_kernel(const double *in, T *out, int mode) {
+    out[0] = mode == 1 ? (T)sqrt(in[0]) : (T)in[0];
+}
+template <typename T>
+int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode) {
+    finish_scalar_kernel<T><<<1, 1, 0, st>>>(in, out, mode);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+template int launch_finish_scalar<float>(cudaStream_t, const double *, float *, int);
+template int launch_finish_scalar<double>(cudaStream_t, const double *, double *, int);
+
+}  // namespace slas

@@ -1,33 +1,21 @@
 // vector_ops.cu -- the bandwidth-bound vector half of the hot path:
 //   element-wise add/sub/mul/div   (replaces src/backends/rust.rs:45-73)
-//   dot / complex dotu             (replaces src/backends/rust.rs:20-41, src/backends/blas.rs:15-52)
-//   norm / normalize               (replaces src/backends/rust.rs:116-147, src/backends/blas.rs:156-170)
-// plus their batched forms over [[T; LEN]; batch].
+//   the normalize scale pass       (replaces src/backends/rust.rs:122-127, src/backends/blas.rs:163-169)
+//   batched dot / norm / normalize over [[T; LEN]; batch]
+// (the grid-wide dot / norm reductions live in reduce.cu, the fused chains in fused_chain.cu).
 //
-// Design (B200): 128-bit coalesced streaming loads (ld.global.cs), several independent
-// loads in flight per thread, fp32/fp64 register accumulators flushed into f64, warp-shuffle
-// + block reduction, and a deterministic single-launch grid reduction: every block writes
-// its partial to partials[blockIdx], the last block to finish (self-resetting ticket) adds
-// the partials in index order.  No float atomics anywhere => same input, same launch
-// geometry, same bits.  Element-wise ops and the normalize divide are single IEEE
-// operations (no fast-math, true division) => bit-exact against the reference.
+// Design (B200): 128-bit coalesced streaming loads (ld.global.cs), several independent loads in flight per
+// thread.  Element-wise ops and the normalize divide are single IEEE operations (no fast-math, true
+// division) => bit-exact against the reference.
 #include <algorithm>
 
 #include "async.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
 #include "p2p.cuh"
+#include "reduce.cuh"
 
 namespace slas {
-
-// ---------------------------------------------------------------------------------------
-// vector types: 16 bytes per load
-template <typename T> struct Vec16;
-template <> struct Vec16<float> { using type = float4; static constexpr int N = 4; };
-template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
-
-template <typename V> __device__ __forceinline__ V ld_stream(const V *p) { return __ldcs(p); }
-template <typename V> __device__ __forceinline__ void st_stream(V *p, V v) { __stcs(p, v); }
 
 template <int OP, typename T> __device__ __forceinline__ T apply_op(T a, T b) {
     if (OP == 0) return a + b;
@@ -84,6 +72,44 @@ ewise_scalar_kernel(const T *a, const T *b, T *c, size_t len) {
         c[i] = apply_op<OP>(a[i], b[i]);
 }
 
+// Short vectors (LEN <= ~2^22: one call is a few microseconds of HBM time): ONE wave of CTAs, a multiple of the SM
+// count, block c owns the contiguous vectors [c*per, (c+1)*per) so that every SM moves the same number of bytes
+// (256 CTAs of 1024 vectors on 148 SMs left 40 SMs with half the work of the others); all loads of a thread are
+// issued before its first store.
+template <typename T, int OP, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+ewise_balanced_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t nvec, size_t len, size_t per) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    constexpr int U = 4;
+    const V *av = reinterpret_cast<const V *>(a);
+    const V *bv = reinterpret_cast<const V *>(b);
+    V *cv = reinterpret_cast<V *>(c);
+    size_t lo = (size_t)blockIdx.x * per;
+    if (lo > nvec) lo = nvec;
+    const size_t end = lo + per < nvec ? lo + per : nvec;
+    for (size_t i = lo + threadIdx.x; i < end; i += (size_t)THREADS * U) {
+        V ra[U], rb[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t j = i + (size_t)u * THREADS;
+            ok[u] = j < end;
+            if (ok[u]) ra[u] = ld_stream(av + j);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) rb[u] = ld_stream(bv + i + (size_t)u * THREADS);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (ok[u]) st_stream(cv + i + (size_t)u * THREADS, apply_vec<OP>(ra[u], rb[u]));
+    }
+    if (blockIdx.x == 0) {
+        const size_t i = nvec * N + threadIdx.x;
+        if (i < len) c[i] = apply_op<OP>(a[i], b[i]);
+    }
+}
+
 template <typename T, int OP>
 static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b, T *c) {
     constexpr int N = Vec16<T>::N;
@@ -100,6 +126,24 @@ static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a
     }
     if (aligned16(a) && aligned16(b) && aligned16(c)) {
         const size_t nvec = len / N;
+        const size_t sms = (size_t)ctx->sm_count;
+        const long small = tunable("ewise_small");  // 0 default, 1 = the tiled kernel everywhere, 2 / 3 = 512 / 1024-thread CTAs
+        if (small != 1 && nvec < sms * 8 * (size_t)kEwThreads * UNROLL) {
+            const int threads = small == 3 ? 1024 : (small == 2 ? 512 : 256);
+            const size_t wave = sms * (size_t)(2048 / threads);
+            size_t blocks = (nvec + (size_t)threads * 2 - 1) / ((size_t)threads * 2);
+            if (blocks > wave) blocks = wave;
+            if (blocks == 0) blocks = 1;
+            size_t per = (nvec + blocks - 1) / blocks;
+            per = (per + 7) / 8 * 8;  // block ranges start on 128-byte lines
+            blocks = per ? (nvec + per - 1) / per : 1;
+            if (blocks == 0) blocks = 1;
+            if (threads == 1024) ewise_balanced_kernel<T, OP, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, b, c, nvec, len, per);
+            else if (threads == 512) ewise_balanced_kernel<T, OP, 512><<<(unsigned)blocks, 512, 0, st>>>(a, b, c, nvec, len, per);
+            else ewise_balanced_kernel<T, OP, 256><<<(unsigned)blocks, 256, 0, st>>>(a, b, c, nvec, len, per);
+            SLAS_LAUNCH_CHECK();
+            return SLAS_OK;
+        }
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
         if (blocks == 0) blocks = 1;
         SLAS_REQUIRE(blocks <= 0x7fffffffu, "ewise: vector too long (%zu elements)", len);
@@ -126,241 +170,6 @@ int launch_ewise(Context *ctx, cudaStream_t st, int op, size_t len, const T *a, 
 }
 template int launch_ewise<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, float *);
 template int launch_ewise<double>(Context *, cudaStream_t, int, size_t, const double *, const double *, double *);
-
-// ---- reductions --------------------------------------------------------------------------
-// KIND: 0 = dot (sum a*b), 1 = squared norm (sum a*a, one stream), 2 = complex dotu
-// (two sums: re, im over interleaved pairs).
-constexpr int kRedThreads = 256;
-constexpr int kRedUnroll = 4;
-constexpr int kFlushEvery = 16;  // outer iterations between flushes of the fp accumulators into f64
-
-template <typename T, int KIND>
-struct Reducer {
-    T acc[kRedUnroll];
-    T acc_im[kRedUnroll];
-    double sum = 0.0, sum_im = 0.0;
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int u = 0; u < kRedUnroll; ++u) { acc[u] = T(0); acc_im[u] = T(0); }
-    }
-    __device__ __forceinline__ void flush() {
-        T s = (acc[0] + acc[1]) + (acc[2] + acc[3]);
-        sum += (double)s;
-        if (KIND == 2) {
-            T t = (acc_im[0] + acc_im[1]) + (acc_im[2] + acc_im[3]);
-            sum_im += (double)t;
-        }
-        clear();
-    }
-    // one 16-byte vector from each operand
-    __device__ __forceinline__ void add(int u, float4 x, float4 y) {
-        if (KIND == 2) {
-            acc[u] = fmaf(x.x, y.x, acc[u]); acc[u] = fmaf(-x.y, y.y, acc[u]);
-            acc[u] = fmaf(x.z, y.z, acc[u]); acc[u] = fmaf(-x.w, y.w, acc[u]);
-            acc_im[u] = fmaf(x.x, y.y, acc_im[u]); acc_im[u] = fmaf(x.y, y.x, acc_im[u]);
-            acc_im[u] = fmaf(x.z, y.w, acc_im[u]); acc_im[u] = fmaf(x.w, y.z, acc_im[u]);
-        } else {
-            acc[u] = fmaf(x.x, y.x, acc[u]); acc[u] = fmaf(x.y, y.y, acc[u]);
-            acc[u] = fmaf(x.z, y.z, acc[u]); acc[u] = fmaf(x.w, y.w, acc[u]);
-        }
-    }
-    __device__ __forceinline__ void add(int u, double2 x, double2 y) {
-        if (KIND == 2) {
-            acc[u] = fma(x.x, y.x, acc[u]); acc[u] = fma(-x.y, y.y, acc[u]);
-            acc_im[u] = fma(x.x, y.y, acc_im[u]); acc_im[u] = fma(x.y, y.x, acc_im[u]);
-        } else {
-            acc[u] = fma(x.x, y.x, acc[u]); acc[u] = fma(x.y, y.y, acc[u]);
-        }
-    }
-    __device__ __forceinline__ void add_scalar(T x, T y) { sum += (double)x * (double)y; }
-};
-
-// result[0] (and result[1] for KIND 2) receive the f64 sums; typed_out (may be null) receives
-// mode 0: (T)sum [, (T)sum_im]   mode 1: (T)sqrt(sum).  If accumulate != 0 the previous
-// content of result[] is added first (chunked host vectors).
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kRedThreads)
-reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised,
-              double *__restrict__ partials, unsigned int *__restrict__ ticket, double *__restrict__ result,
-              T *__restrict__ typed_out, int mode, int accumulate, const PeerExchange px, unsigned head) {
-    using V = typename Vec16<T>::type;
-    constexpr int N = Vec16<T>::N;
-    __shared__ double red[kRedThreads / 32];
-    __shared__ double peer_vals[2 * kMaxPeers];
-    __shared__ bool is_last;
-    Reducer<T, KIND> r;
-    r.clear();
-    const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
-    const size_t nthreads = (size_t)gridDim.x * kRedThreads;
-    if (vectorised) {
-        // operands that share a misalignment (views at an odd offset): `head` elements up to the first 16-byte boundary
-        // are scalar work like the tail, the body starts on the boundary
-        const V *av = reinterpret_cast<const V *>(a + head);
-        const V *bv = reinterpret_cast<const V *>(b + head);
-        const size_t stride = nthreads * kRedUnroll;
-        size_t i = (size_t)blockIdx.x * (kRedThreads * kRedUnroll) + threadIdx.x;
-        int since_flush = 0;
-        // full tiles: every thread of the block has all kRedUnroll vectors in range
-        for (; i + (size_t)(kRedUnroll - 1) * kRedThreads < nvec; i += stride) {
-            V x[kRedUnroll], y[kRedUnroll];
-#pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) x[u] = ld_stream(av + i + (size_t)u * kRedThreads);
-            if (KIND != 1) {
-#pragma unroll
-                for (int u = 0; u < kRedUnroll; ++u) y[u] = ld_stream(bv + i + (size_t)u * kRedThreads);
-            }
-#pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
-            if (++since_flush == kFlushEvery) { r.flush(); since_flush = 0; }
-        }
-        // ragged remainder of this thread's last tile
-#pragma unroll
-        for (int u = 0; u < kRedUnroll; ++u) {
-            const size_t j = i + (size_t)u * kRedThreads;
-            if (j < nvec) {
-                V x = ld_stream(av + j);
-                V y = KIND == 1 ? x : ld_stream(bv + j);
-                r.add(u, x, y);
-            }
-        }
-        r.flush();
-        // scalar tail: the len % N elements past the last whole vector (N is even, so a complex
-        // pair is never split: the complex tail is whole (re, im) pairs)
-        if (KIND != 2) {
-            const size_t j = head + nvec * N + tid;
-            if (j < len) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
-            if (tid < head) r.add_scalar(a[tid], KIND == 1 ? a[tid] : b[tid]);
-        } else {
-            const size_t j = head + nvec * N + 2 * tid;
-            if (j + 1 < len) {
-                const double ar = a[j], ai = a[j + 1], br = b[j], bi = b[j + 1];
-                r.sum += ar * br - ai * bi;
-                r.sum_im += ar * bi + ai * br;
-            }
-            if (2 * tid + 1 < head) {
-                const double ar = a[2 * tid], ai = a[2 * tid + 1], br = b[2 * tid], bi = b[2 * tid + 1];
-                r.sum += ar * br - ai * bi;
-                r.sum_im += ar * bi + ai * br;
-            }
-        }
-    } else {
-        // unaligned operands: scalar grid-stride loop, f64 accumulation
-        if (KIND == 2) {
-            for (size_t j = tid; j < len / 2; j += nthreads) {
-                const double ar = a[2 * j], ai = a[2 * j + 1], br = b[2 * j], bi = b[2 * j + 1];
-                r.sum += ar * br - ai * bi;
-                r.sum_im += ar * bi + ai * br;
-            }
-        } else {
-            // operands with different misalignments: coalesced 4-byte / 8-byte loads, four in flight per thread, T
-            // accumulators flushed into f64 like the vector body (one DFMA per element was 0.35 of HBM peak)
-            size_t j = tid;
-            int since_flush = 0;
-            for (; j + 3 * nthreads < len; j += 4 * nthreads) {
-                T x[4], y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = a[j + u * nthreads];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) y[u] = KIND == 1 ? x[u] : b[j + u * nthreads];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) r.acc[u] = fma(x[u], y[u], r.acc[u]);
-                if (++since_flush == kFlushEvery * 4) { r.flush(); since_flush = 0; }
-            }
-            r.flush();
-            for (; j < len; j += nthreads) r.add_scalar(a[j], KIND == 1 ? a[j] : b[j]);
-        }
-    }
-    double s = block_sum<kRedThreads>(r.sum, red);
-    double s_im = 0.0;
-    if (KIND == 2) s_im = block_sum<kRedThreads>(r.sum_im, red);
-    if (threadIdx.x == 0) {
-        partials[blockIdx.x] = s;
-        if (KIND == 2) partials[kMaxPartials + blockIdx.x] = s_im;
-        __threadfence();
-        const unsigned int t = atomicInc(ticket, gridDim.x - 1);  // wraps to 0 after the last block
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last block: add the partials in index order (fixed stride pattern => deterministic)
-    double p = 0.0, p_im = 0.0;
-    for (unsigned int j = threadIdx.x; j < gridDim.x; j += kRedThreads) {
-        p += __ldcg(partials + j);
-        if (KIND == 2) p_im += __ldcg(partials + kMaxPartials + j);
-    }
-    p = block_sum<kRedThreads>(p, red);
-    if (KIND == 2) p_im = block_sum<kRedThreads>(p_im, red);
-    // multi-GPU: exchange the rank-local partial with the peers over NVLink and add in rank order
-    if (px.nranks > 1) peer_allreduce_sum(px, p, p_im, peer_vals);
-    if (threadIdx.x == 0) {
-        if (accumulate) { p += result[0]; if (KIND == 2) p_im += result[1]; }
-        result[0] = p;
-        if (KIND == 2) result[1] = p_im;
-        if (typed_out) {
-            if (mode == 1) typed_out[0] = (T)sqrt(p);
-            else {
-                typed_out[0] = (T)p;
-                if (KIND == 2) typed_out[1] = (T)p_im;
-            }
-        }
-    }
-}
-
-template <typename T, int KIND>
-static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b,
-                              double *result, T *typed_out, int mode, int accumulate, const PeerExchange &px) {
-    constexpr int N = Vec16<T>::N;
-    // vector body when the operands are aligned, or share one misalignment that is whole elements (for complex: whole
-    // pairs) away from a 16-byte boundary
-    const uintptr_t ma = (uintptr_t)a % 16, mb = (uintptr_t)(KIND == 1 ? a : b) % 16;
-    const size_t unit = sizeof(T) * (KIND == 2 ? 2 : 1);
-    const bool vec = ma == mb && ma % unit == 0;
-    size_t head = vec && ma ? (16 - ma) / sizeof(T) : 0;
-    if (head > len) head = len;
-    const size_t nvec = vec ? (len - head) / N : 0;
-    const size_t work = vec ? nvec : len;
-    size_t blocks = (work + (size_t)kRedThreads * kRedUnroll - 1) / ((size_t)kRedThreads * kRedUnroll);
-    const size_t cap = (size_t)ctx->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks > (size_t)kMaxPartials) blocks = kMaxPartials;
-    if (blocks == 0) blocks = 1;
-    reduce_kernel<T, KIND><<<(unsigned)blocks, kRedThreads, 0, st>>>(
-        a, KIND == 1 ? a : b, len, nvec, vec ? 1 : 0, ctx->partials, ctx->ticket, result, typed_out, mode,
-        accumulate, px, (unsigned)head);
-    SLAS_LAUNCH_CHECK();
-    return SLAS_OK;
-}
-
-template <typename T>
-int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
-                  T *typed_out, int mode, int accumulate, const PeerExchange *peers) {
-    const PeerExchange px = peers ? *peers : PeerExchange{};
-    switch (kind) {
-    case 0: return launch_reduce_kind<T, 0>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
-    case 1: return launch_reduce_kind<T, 1>(ctx, st, len, a, a, result, typed_out, mode, accumulate, px);
-    case 2: return launch_reduce_kind<T, 2>(ctx, st, len, a, b, result, typed_out, mode, accumulate, px);
-    }
-    return fail(SLAS_ERR_INVALID, "unknown reduction kind %d", kind);
-}
-template int launch_reduce<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, double *,
-                                  float *, int, int, const PeerExchange *);
-template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const double *, const double *,
-                                   double *, double *, int, int, const PeerExchange *);
-
-// f64 sum -> typed scalar (used after the NCCL allreduce of the sharded ops)
-template <typename T>
-__global__ void finish_scalar_kernel(const double *in, T *out, int mode) {
-    out[0] = mode == 1 ? (T)sqrt(in[0]) : (T)in[0];
-}
-template <typename T>
-int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode) {
-    finish_scalar_kernel<T><<<1, 1, 0, st>>>(in, out, mode);
-    SLAS_LAUNCH_CHECK();
-    return SLAS_OK;
-}
-template int launch_finish_scalar<float>(cudaStream_t, const double *, float *, int);
-template int launch_finish_scalar<double>(cudaStream_t, const double *, double *, int);
 
 // ---- normalize scale pass: a[i] = a[i] / *norm (true division, rust.rs:125) --------------------
 template <typename T, int UNROLL>
@@ -429,142 +238,6 @@ int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, const T *in, T *
 }
 template int launch_scale_div<float>(Context *, cudaStream_t, size_t, const float *, float *, const float *);
 template int launch_scale_div<double>(Context *, cudaStream_t, size_t, const double *, double *, const double *);
-
-// ---- fused chains: sequences a slas user writes as separate ops, in one pass over HBM ----------
-// Same launch geometry, vector tiling, accumulator layout and partial order as reduce_kernel, and the element-wise
-// step is the same single IEEE operation => the results carry the same bits as the unfused chain on this backend.
-//
-// CHAIN 0..3: x = a (+,-,*,/) b  [written to c when WRITE_C]; result = sum x*d      (add -> dot)
-// CHAIN 4:    results = sum a*b, sum a*a, sum b*b                                  (dot + both norms: cosine)
-template <typename T, int CHAIN, bool WRITE_C>
-__global__ void __launch_bounds__(kRedThreads)
-fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, const T *__restrict__ d, size_t len,
-                   size_t nvec, int vectorised, double *__restrict__ partials, unsigned int *__restrict__ ticket,
-                   T *__restrict__ typed_out) {
-    using V = typename Vec16<T>::type;
-    constexpr int N = Vec16<T>::N;
-    constexpr int NRES = CHAIN == 4 ? 3 : 1;
-    constexpr int OP = CHAIN < 4 ? CHAIN : 0;
-    __shared__ double red[kRedThreads / 32];
-    __shared__ bool is_last;
-    Reducer<T, 0> r0, r1, r2;
-    r0.clear(); r1.clear(); r2.clear();
-    const size_t tid = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
-    const size_t nthreads = (size_t)gridDim.x * kRedThreads;
-    if (vectorised) {
-        const V *av = reinterpret_cast<const V *>(a);
-        const V *bv = reinterpret_cast<const V *>(b);
-        const V *dv = reinterpret_cast<const V *>(d);
-        V *cv = reinterpret_cast<V *>(c);
-        const size_t stride = nthreads * kRedUnroll;
-        size_t i = (size_t)blockIdx.x * (kRedThreads * kRedUnroll) + threadIdx.x;
-        int since_flush = 0;
-        auto step = [&](int u, size_t j) {
-            const V x = ld_stream(av + j), y = ld_stream(bv + j);
-            if (CHAIN == 4) {
-                r0.add(u, x, y); r1.add(u, x, x); r2.add(u, y, y);
-            } else {
-                const V e = apply_vec<OP>(x, y);
-                if (WRITE_C) st_stream(cv + j, e);
-                r0.add(u, e, ld_stream(dv + j));
-            }
-        };
-        for (; i + (size_t)(kRedUnroll - 1) * kRedThreads < nvec; i += stride) {
-#pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) step(u, i + (size_t)u * kRedThreads);
-            if (++since_flush == kFlushEvery) {
-                r0.flush();
-                if (CHAIN == 4) { r1.flush(); r2.flush(); }
-                since_flush = 0;
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < kRedUnroll; ++u) {
-            const size_t j = i + (size_t)u * kRedThreads;
-            if (j < nvec) step(u, j);
-        }
-        r0.flush();
-        if (CHAIN == 4) { r1.flush(); r2.flush(); }
-        const size_t j = nvec * N + tid;
-        if (j < len) {
-            if (CHAIN == 4) {
-                r0.add_scalar(a[j], b[j]); r1.add_scalar(a[j], a[j]); r2.add_scalar(b[j], b[j]);
-            } else {
-                const T e = apply_op<OP>(a[j], b[j]);
-                if (WRITE_C) c[j] = e;
-                r0.add_scalar(e, d[j]);
-            }
-        }
-    } else {
-        for (size_t j = tid; j < len; j += nthreads) {
-            if (CHAIN == 4) {
-                r0.add_scalar(a[j], b[j]); r1.add_scalar(a[j], a[j]); r2.add_scalar(b[j], b[j]);
-            } else {
-                const T e = apply_op<OP>(a[j], b[j]);
-                if (WRITE_C) c[j] = e;
-                r0.add_scalar(e, d[j]);
-            }
-        }
-    }
-    double s[3];
-    s[0] = block_sum<kRedThreads>(r0.sum, red);
-    if (CHAIN == 4) { s[1] = block_sum<kRedThreads>(r1.sum, red); s[2] = block_sum<kRedThreads>(r2.sum, red); }
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < NRES; ++q) partials[(size_t)q * gridDim.x + blockIdx.x] = s[q];
-        __threadfence();
-        const unsigned int t = atomicInc(ticket, gridDim.x - 1);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-#pragma unroll
-    for (int q = 0; q < NRES; ++q) {
-        double p = 0.0;
-        for (unsigned int j = threadIdx.x; j < gridDim.x; j += kRedThreads) p += __ldcg(partials + (size_t)q * gridDim.x + j);
-        p = block_sum<kRedThreads>(p, red);
-        if (threadIdx.x == 0) typed_out[q] = (CHAIN == 4 && q > 0) ? (T)sqrt(p) : (T)p;
-    }
-}
-
-template <typename T, int CHAIN>
-static int launch_fused_chain_kind(Context *ctx, cudaStream_t st, size_t len, const T *a, const T *b, T *c, const T *d,
-                                   T *typed_out) {
-    constexpr int N = Vec16<T>::N;
-    const bool vec = aligned16(a) && aligned16(b) && (CHAIN == 4 || aligned16(d)) && (c == nullptr || aligned16(c));
-    const size_t nvec = vec ? len / N : 0;
-    const size_t work = vec ? nvec : len;
-    size_t blocks = (work + (size_t)kRedThreads * kRedUnroll - 1) / ((size_t)kRedThreads * kRedUnroll);
-    const size_t cap = (size_t)ctx->sm_count * 8;  // 3 * cap <= 2 * kMaxPartials
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) blocks = 1;
-    if (c)
-        fused_chain_kernel<T, CHAIN, true><<<(unsigned)blocks, kRedThreads, 0, st>>>(a, b, c, d, len, nvec, vec ? 1 : 0,
-                                                                                      ctx->partials, ctx->ticket, typed_out);
-    else
-        fused_chain_kernel<T, CHAIN, false><<<(unsigned)blocks, kRedThreads, 0, st>>>(a, b, c, d, len, nvec, vec ? 1 : 0,
-                                                                                       ctx->partials, ctx->ticket, typed_out);
-    SLAS_LAUNCH_CHECK();
-    return SLAS_OK;
-}
-
-template <typename T>
-int launch_fused_chain(Context *ctx, cudaStream_t st, int chain, size_t len, const T *a, const T *b, T *c, const T *d,
-                       T *typed_out) {
-    switch (chain) {
-    case 0: return launch_fused_chain_kind<T, 0>(ctx, st, len, a, b, c, d, typed_out);
-    case 1: return launch_fused_chain_kind<T, 1>(ctx, st, len, a, b, c, d, typed_out);
-    case 2: return launch_fused_chain_kind<T, 2>(ctx, st, len, a, b, c, d, typed_out);
-    case 3: return launch_fused_chain_kind<T, 3>(ctx, st, len, a, b, c, d, typed_out);
-    case 4: return launch_fused_chain_kind<T, 4>(ctx, st, len, a, b, nullptr, nullptr, typed_out);
-    }
-    return fail(SLAS_ERR_INVALID, "unknown fused chain %d", chain);
-}
-template int launch_fused_chain<float>(Context *, cudaStream_t, int, size_t, const float *, const float *, float *, const float *,
-                                       float *);
-template int launch_fused_chain<double>(Context *, cudaStream_t, int, size_t, const double *, const double *, double *,
-                                        const double *, double *);
 
 // ---- batched dot / norm / normalize over [[T; len]; batch] -----------------------------------
 // One group of GROUP threads per vector (GROUP = 32: a warp per vector, several vectors per

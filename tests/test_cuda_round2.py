@@ -1,0 +1,151 @@
+"""GPU tests added in round 2 (run on the B200 box: `pytest -m gpu`): scratch ownership across the host
+pipeline's streams, graphs that outlive a workspace growth, and the newer entry points.  Same bars as
+tests/test_cuda_parity.py: bit-exact for data movement, f32 1e-5 * sqrt(K) / f64 1e-13 * sqrt(K) relative to
+sum|a_i b_i| for reductions, against the oracle or an f64 / long-double truth."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from slas_b200 import _lib as L
+from slas_b200.backends import Cuda, Graph, device_count, launch_count, set_sgemm_path, set_tunable
+from slas_b200.static_vec import CudaBatch, CudaVec
+
+pytestmark = pytest.mark.gpu
+cuda = Cuda()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    assert device_count() > 0, "the gpu-marked tests need a CUDA device (there is no CPU fallback)"
+    before = launch_count()
+    yield
+    assert launch_count() > before, "no kernel of libslas_cuda was launched"
+
+
+def _rand(rng, n, dt, lo=-1.0, hi=1.0):
+    return (rng.random(n) * (hi - lo) + lo).astype(dt)
+
+
+class Pinned:
+    """numpy view of page-locked host memory from slas_cuda_malloc_host."""
+
+    def __init__(self, n, dt):
+        self.p = C.c_void_p()
+        self.nbytes = n * np.dtype(dt).itemsize
+        L.call("slas_cuda_malloc_host", C.byref(self.p), self.nbytes)
+        ctype = {np.dtype(np.float32): C.c_float, np.dtype(np.float64): C.c_double, np.dtype(np.uint8): C.c_uint8}[np.dtype(dt)]
+        self.a = np.ctypeslib.as_array((ctype * n).from_address(self.p.value))
+
+    def free(self):
+        del self.a
+        L.call("slas_cuda_free_host", self.p.value)
+
+
+def _gemm_truth(A, B, m, n, k):
+    a = A.reshape(m, k).astype(np.float64)
+    b = B.reshape(k, n).astype(np.float64)
+    return (a @ b).ravel(), (np.abs(a) @ np.abs(b)).ravel()
+
+
+# ---- consecutive chunks of the host pipeline run on different streams but share the workspace ----------
+@pytest.mark.parametrize("dt,size,path", [(np.float32, 512, "tcgen05"), (np.float32, 1024, "ffma"), (np.float64, 1024, "auto")])
+def test_host_pipeline_one_object_per_chunk_keeps_its_scratch(dt, size, path):
+    """pinned host operands, one product per chunk (slot smaller than an object), every product uses the shared
+    workspace (3xTF32 split / pre-transposed operands): chunk i + 1 must not overwrite it under chunk i's kernel"""
+    rng = np.random.default_rng(31)
+    batch, e = 6, size * size
+    hA, hB, hC = Pinned(batch * e, dt), Pinned(batch * e, dt), Pinned(batch * e, dt)
+    hA.a[:] = _rand(rng, batch * e, dt)
+    hB.a[:] = _rand(rng, batch * e, dt)
+    hC.a[:] = 0
+    set_tunable("host_slot_mb", 1)
+    set_sgemm_path(path)
+    try:
+        for rep in range(3):
+            cuda.matrix_mul_batched(hA.a, hB.a, hC.a, size, size, size, True, False)  # a_trans: f64 path pre-transposes A
+            for i in range(batch):
+                ref, mag = _gemm_truth(np.ascontiguousarray(hA.a[i * e:(i + 1) * e].reshape(size, size).T).ravel(),
+                                       hB.a[i * e:(i + 1) * e], size, size, size)
+                tol = (1e-5 if dt == np.float32 else 1e-13) * np.sqrt(size)
+                assert np.all(np.abs(hC.a[i * e:(i + 1) * e] - ref) <= tol * mag), (rep, i)
+    finally:
+        set_tunable("host_slot_mb", 0)
+        set_sgemm_path("auto")
+        for h in (hA, hB, hC):
+            h.free()
+
+
+# ---- the workspace a recorded graph points at must survive later growth --------------------------------
+def test_graph_survives_a_later_workspace_growth_and_growth_inside_a_capture():
+    rng = np.random.default_rng(32)
+    n0, n1, n2 = 512, 1024, 1536
+    A0, B0 = _rand(rng, n0 * n0, np.float32), _rand(rng, n0 * n0, np.float32)
+    a0, b0, c0 = CudaVec.from_host(A0), CudaVec.from_host(B0), CudaVec(n0 * n0, np.float32)
+    ref0, mag0 = _gemm_truth(A0, B0, n0, n0, n0)
+
+    def small():
+        cuda.matrix_mul(a0, b0, c0, n0, n0, n0, n0, n0, n0, False, False)  # tcgen05: hi/lo split in the workspace
+
+    set_sgemm_path("tcgen05")
+    try:
+        small()  # eager once: workspace at the 512^3 size
+        with Graph() as g0:
+            small()
+        # a bigger product grows the workspace while g0 is alive: the old block must be retired, not freed
+        A1, B1 = _rand(rng, n1 * n1, np.float32), _rand(rng, n1 * n1, np.float32)
+        a1, b1, c1 = CudaVec.from_host(A1), CudaVec.from_host(B1), CudaVec(n1 * n1, np.float32)
+        cuda.matrix_mul(a1, b1, c1, n1, n1, n1, n1, n1, n1, False, False)
+        ref1, mag1 = _gemm_truth(A1, B1, n1, n1, n1)
+        assert np.all(np.abs(c1.to_host() - ref1) <= 1e-5 * np.sqrt(n1) * mag1)
+        # scribble over whatever a freed-and-reused block would now hold, then replay
+        junk = [CudaVec(1 << 22, np.float32).zero_() for _ in range(4)]
+        c0.zero_()
+        g0.launch()
+        assert np.all(np.abs(c0.to_host() - ref0) <= 1e-5 * np.sqrt(n0) * mag0), "replay read a freed workspace"
+        del junk
+        # growth INSIDE a capture: allocated then, no synchronising call, the capture stays valid
+        A2, B2 = _rand(rng, n2 * n2, np.float32), _rand(rng, n2 * n2, np.float32)
+        a2, b2, c2 = CudaVec.from_host(A2), CudaVec.from_host(B2), CudaVec(n2 * n2, np.float32)
+        with Graph() as g2:
+            cuda.matrix_mul(a2, b2, c2, n2, n2, n2, n2, n2, n2, False, False)
+        g2.launch()
+        ref2, mag2 = _gemm_truth(A2, B2, n2, n2, n2)
+        assert np.all(np.abs(c2.to_host() - ref2) <= 1e-5 * np.sqrt(n2) * mag2)
+        c0.zero_()
+        g0.launch()  # still fine after two growths
+        assert np.all(np.abs(c0.to_host() - ref0) <= 1e-5 * np.sqrt(n0) * mag0)
+    finally:
+        set_sgemm_path("auto")
+
+
+def test_graph_refuses_host_operands_and_stays_usable():
+    a = _rand(np.random.default_rng(33), 4096, np.float32)
+    da, dc = CudaVec.from_host(a), CudaVec(4096, np.float32)
+    with pytest.raises(Exception, match="graph"):
+        with Graph():
+            cuda.add(a, a, np.empty_like(a))  # host operands need synchronising copies
+    cuda.add(da, da, dc)
+    assert np.array_equal(dc.to_host(), a + a)
+
+
+# ---- the automatic switch to 3xTF32 at 2^27 multiply-adds, straddled with tiny-magnitude operands ------
+@pytest.mark.parametrize("scale_log2", [0, -100, -120])
+def test_sgemm_auto_threshold_straddled_with_tiny_operands(scale_log2):
+    """just below the threshold the product is the fp32 FMA chain, at it the tensor-core 3xTF32 path: both sides stay
+    inside the 1e-5 * sqrt(K) bar, also when A is so small that the lo parts of its split are denormal (the TF32 MMA
+    flushes them: the compensation term of A is lost, an error of <= 2^-12 |a||b| per product)"""
+    rng = np.random.default_rng(34)
+    for (m, n, k), tensor_cores in (((512, 512, 511), False), ((512, 512, 512), True)):
+        A = (_rand(rng, m * k, np.float32) * np.float32(2.0 ** scale_log2)).astype(np.float32)
+        B = _rand(rng, k * n, np.float32)
+        c = CudaVec(m * n, np.float32)
+        n0 = launch_count()
+        cuda.matrix_mul(CudaVec.from_host(A), CudaVec.from_host(B), c, m, n, k, k, n, n, False, False)
+        assert (launch_count() - n0 >= 2) == tensor_cores  # the 3xTF32 path is the split pass + the tcgen05 kernel
+        ref, mag = _gemm_truth(A, B, m, n, k)
+        got = c.to_host().astype(np.float64)
+        # results that are denormal in f32 carry an absolute rounding error of half the smallest denormal per operation
+        floor = 2.0 ** -149 * k
+        assert np.all(np.abs(got - ref) <= 1e-5 * np.sqrt(k) * mag + floor), (m, n, k, scale_log2)
