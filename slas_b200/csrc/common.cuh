@@ -67,8 +67,23 @@ struct Context {
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};   // kernels of chunk i done (orders the shared scratch)
     double *pinned_scalars = nullptr;    // [16]
+    // Programmatic dependent launch of the launch-bound vector ops (reduce.cuh): what the previous kernel of this
+    // library read and wrote, so that the next one knows whether it may load its operands before that kernel is done.
+    struct Span { const char *lo, *hi; };
+    struct Hazard {
+        uint64_t seq = ~0ull;            // g_launches right after the recorded launch; anything launched since voids it
+        cudaStream_t stream = nullptr;
+        Span reads[4], writes[4];
+        int nreads = 0, nwrites = 0;
+    } hazard;
     std::mutex mu;                       // serialises enqueue + scratch use
 };
+
+// True when a kernel reading `reads` and writing `writes` may start its loads / stores while the previously recorded
+// kernel of this context is still running (no RAW, WAR or WAW overlap with it, nothing else launched in between).
+bool hazard_early_ok(const Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw);
+// Call right after the launch (after SLAS_LAUNCH_CHECK) of a kernel that triggers its dependents early.
+void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw);
 
 constexpr int kMaxPartials = 148 * 16;
 

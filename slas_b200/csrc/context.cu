@@ -34,7 +34,7 @@ static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
                                {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
                                {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
-                               {"reduce_phases", 0}, {"ewise_small", 0}};
+                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;
@@ -140,6 +140,38 @@ static void free_retired(Context *ctx) {
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { cudaGetLastError(); return; }
     for (void *p : ctx->retired) cudaFree(p);
     ctx->retired.clear();
+}
+
+static inline bool spans_overlap(const Context::Span &a, const Context::Span &b) {
+    return a.lo < b.hi && b.lo < a.hi;
+}
+
+bool hazard_early_ok(const Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw) {
+    const Context::Hazard &h = ctx->hazard;
+    // Nothing recorded, another stream, or some other kernel of the library launched since: the predecessor on the
+    // stream is unknown.  (Copies / memsets / foreign kernels in between do not trigger early, so the dependent
+    // launch degenerates to a full dependency and early loads are trivially safe -- but then they gain nothing either.)
+    if (h.seq != g_launches.load(std::memory_order_relaxed) || h.stream != st || tunable("pdl") == 1) return false;
+    for (int i = 0; i < nr; ++i)
+        for (int j = 0; j < h.nwrites; ++j)
+            if (spans_overlap(reads[i], h.writes[j])) return false;  // RAW
+    for (int i = 0; i < nw; ++i) {
+        for (int j = 0; j < h.nwrites; ++j)
+            if (spans_overlap(writes[i], h.writes[j])) return false;  // WAW
+        for (int j = 0; j < h.nreads; ++j)
+            if (spans_overlap(writes[i], h.reads[j])) return false;  // WAR
+    }
+    return true;
+}
+
+void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw) {
+    Context::Hazard &h = ctx->hazard;
+    h.seq = g_launches.load(std::memory_order_relaxed);
+    h.stream = st;
+    h.nreads = nr < 4 ? nr : 4;
+    h.nwrites = nw < 4 ? nw : 4;
+    for (int i = 0; i < h.nreads; ++i) h.reads[i] = reads[i];
+    for (int i = 0; i < h.nwrites; ++i) h.writes[i] = writes[i];
 }
 
 int ensure_workspace(Context *ctx, size_t bytes, void **out) {

@@ -69,13 +69,17 @@ template <typename T, int KIND, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised, const RedGeom g,
               const RedScratch sc, double *__restrict__ result, T *__restrict__ typed_out, int mode, int accumulate,
-              const PeerExchange px, unsigned head) {
+              const PeerExchange px, unsigned head, int early) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     constexpr int NRES = KIND == 2 ? 2 : 1;
     __shared__ double red[THREADS / 32];
     __shared__ double peer_vals[2 * kMaxPeers];
     __shared__ bool is_last;
+    // programmatic dependent launch (reduce.cuh): the successor may be scheduled from here on; this kernel's own
+    // loads wait for its predecessor unless the host found no overlap with that kernel's operands (`early`)
+    pdl_trigger();
+    if (!early) pdl_wait();
     const bool stamp = sc.phases != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) sc.phases[0] = red_timer_ns();
     Reducer<T, KIND> r;
@@ -176,6 +180,7 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
     s[0] = block_sum<THREADS>(r.sum, red);
     if (KIND == 2) s[NRES - 1] = block_sum<THREADS>(r.sum_im, red);
     if (stamp) sc.phases[2] = red_timer_ns();
+    if (early) pdl_wait();  // the scratch below is shared with the predecessor: only now is it ours
     if (!grid_combine<THREADS, NRES>(g, sc, s, p, red, &is_last)) return;
     const bool stamp_end = sc.phases != nullptr && threadIdx.x == 0;
     if (stamp_end) sc.phases[3] = red_timer_ns();
@@ -212,14 +217,32 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
     const RedGeom g = reduce_geometry(ctx, vec ? nvec : len, vec);
     const RedScratch sc = reduce_scratch(ctx);
     const T *bb = KIND == 1 ? a : b;
-#define SLAS_REDUCE_LAUNCH(THREADS)                                                                                       \
-    reduce_kernel<T, KIND, THREADS><<<g.blocks, THREADS, 0, st>>>(a, bb, len, nvec, vec ? 1 : 0, g, sc, result, typed_out, \
-                                                                  mode, accumulate, px, (unsigned)head)
+    // what this kernel reads and writes, for the early-start decision of it and of its successor
+    const Context::Span reads[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)bb, (const char *)(bb + len)}};
+    const Context::Span writes[2] = {{(const char *)result, (const char *)(result + 2)},
+                                     {(const char *)typed_out, (const char *)(typed_out ? typed_out + 2 : typed_out)}};
+    // overlap with the predecessor only on a stream nobody else enqueues kernels on (the library's own, or one the
+    // caller vouches for: tunable "pdl" = 2), without the accumulate / multi-GPU forms, and when nothing overlaps
+    const bool own = st == ctx->own_stream || tunable("pdl") == 2;
+    // (only the loads run ahead of the wait: every write of this kernel comes after it, so only RAW matters here)
+    const int early = g.balanced && own && !accumulate && px.nranks <= 1 && hazard_early_ok(ctx, st, reads, 2, nullptr, 0) ? 1 : 0;
+    cudaError_t le = cudaSuccess;
+#define SLAS_REDUCE_LAUNCH(THREADS)                                                                                         \
+    do {                                                                                                                    \
+        if (g.balanced && tunable("pdl") != 1)                                                                              \
+            le = launch_pdl(reduce_kernel<T, KIND, THREADS>, g.blocks, THREADS, st, a, bb, len, nvec, vec ? 1 : 0, g, sc,    \
+                            result, typed_out, mode, accumulate, px, (unsigned)head, early);                                \
+        else                                                                                                                \
+            reduce_kernel<T, KIND, THREADS><<<g.blocks, THREADS, 0, st>>>(a, bb, len, nvec, vec ? 1 : 0, g, sc, result,      \
+                                                                          typed_out, mode, accumulate, px, (unsigned)head, 0); \
+    } while (0)
     if (g.threads == 1024) SLAS_REDUCE_LAUNCH(1024);
     else if (g.threads == 512) SLAS_REDUCE_LAUNCH(512);
     else SLAS_REDUCE_LAUNCH(256);
 #undef SLAS_REDUCE_LAUNCH
+    SLAS_CUDA_TRY(le);
     SLAS_LAUNCH_CHECK();
+    hazard_record(ctx, st, reads, 2, writes, 2);
     return SLAS_OK;
 }
 

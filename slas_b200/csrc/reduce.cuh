@@ -97,6 +97,34 @@ struct RedScratch {
 RedGeom reduce_geometry(const Context *ctx, size_t work, bool vectorised);
 RedScratch reduce_scratch(Context *ctx);
 
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
+// The launch-bound vector kernels (one call = a few microseconds) are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: each lets its successor on the stream be scheduled as soon as
+// all of its own blocks are running (pdl_trigger at kernel start), so the successor's launch latency, and -- when the
+// host-side hazard check (common.cuh) found no overlap with this kernel's operands -- its loads and FMAs overlap
+// this kernel's cross-block tail.  pdl_wait blocks until the predecessor grid has completed and its writes are visible;
+// every block executes it before touching shared scratch / dependent data and before it exits (so completion order
+// stays the stream order).  Without the launch attribute both are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+// Launch `kern` with the programmatic-serialization attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), unsigned blocks, unsigned threads, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long red_timer_ns() {
     unsigned long long t;

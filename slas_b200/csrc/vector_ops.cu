@@ -78,10 +78,15 @@ ewise_scalar_kernel(const T *a, const T *b, T *c, size_t len) {
 // issued before its first store.
 template <typename T, int OP, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-ewise_balanced_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t nvec, size_t len, size_t per) {
+ewise_balanced_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ c, size_t nvec, size_t len, size_t per,
+                      int early) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     constexpr int U = 4;
+    // programmatic dependent launch (reduce.cuh): let the successor be scheduled; wait for the predecessor first unless
+    // the host found that nothing of ours overlaps its operands
+    pdl_trigger();
+    if (!early) pdl_wait();
     const V *av = reinterpret_cast<const V *>(a);
     const V *bv = reinterpret_cast<const V *>(b);
     V *cv = reinterpret_cast<V *>(c);
@@ -108,6 +113,7 @@ ewise_balanced_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
         const size_t i = nvec * N + threadIdx.x;
         if (i < len) c[i] = apply_op<OP>(a[i], b[i]);
     }
+    if (early) pdl_wait();  // no block leaves before the predecessor is done: completion order stays the stream order
 }
 
 template <typename T, int OP>
@@ -138,10 +144,22 @@ static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a
             per = (per + 7) / 8 * 8;  // block ranges start on 128-byte lines
             blocks = per ? (nvec + per - 1) / per : 1;
             if (blocks == 0) blocks = 1;
-            if (threads == 1024) ewise_balanced_kernel<T, OP, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, b, c, nvec, len, per);
-            else if (threads == 512) ewise_balanced_kernel<T, OP, 512><<<(unsigned)blocks, 512, 0, st>>>(a, b, c, nvec, len, per);
-            else ewise_balanced_kernel<T, OP, 256><<<(unsigned)blocks, 256, 0, st>>>(a, b, c, nvec, len, per);
+            const Context::Span reads[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)b, (const char *)(b + len)}};
+            const Context::Span writes[1] = {{(const char *)c, (const char *)(c + len)}};
+            const bool own = st == ctx->own_stream || tunable("pdl") == 2;
+            const int early = own && hazard_early_ok(ctx, st, reads, 2, writes, 1) ? 1 : 0;
+            cudaError_t le;
+            if (tunable("pdl") == 1) {
+                le = cudaSuccess;
+                if (threads == 1024) ewise_balanced_kernel<T, OP, 1024><<<(unsigned)blocks, 1024, 0, st>>>(a, b, c, nvec, len, per, 0);
+                else if (threads == 512) ewise_balanced_kernel<T, OP, 512><<<(unsigned)blocks, 512, 0, st>>>(a, b, c, nvec, len, per, 0);
+                else ewise_balanced_kernel<T, OP, 256><<<(unsigned)blocks, 256, 0, st>>>(a, b, c, nvec, len, per, 0);
+            } else if (threads == 1024) le = launch_pdl(ewise_balanced_kernel<T, OP, 1024>, (unsigned)blocks, 1024u, st, a, b, c, nvec, len, per, early);
+            else if (threads == 512) le = launch_pdl(ewise_balanced_kernel<T, OP, 512>, (unsigned)blocks, 512u, st, a, b, c, nvec, len, per, early);
+            else le = launch_pdl(ewise_balanced_kernel<T, OP, 256>, (unsigned)blocks, 256u, st, a, b, c, nvec, len, per, early);
+            SLAS_CUDA_TRY(le);
             SLAS_LAUNCH_CHECK();
+            hazard_record(ctx, st, reads, 2, writes, 1);
             return SLAS_OK;
         }
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);

@@ -3,6 +3,10 @@
 // CUDA kernels).  Each case cites the reference test it mirrors; expectations are the reference's own
 // literals (exact equality where the reference uses assert_eq!).  Needs a GPU: built by
 // __graft_entry__.build(), run by tests/test_cpp_reference_suite.py under `pytest -m gpu`.
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
 #include <cmath>
 #include <cstdio>
 #include <functional>
@@ -35,7 +39,18 @@ template <class T, std::size_t N> static bool eq(const std::array<T, N> &a, std:
     return i == N;
 }
 
+// a crash inside the library must name its frame in the pytest log (the box has no debugger)
+static void on_fatal_signal(int sig) {
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    dprintf(2, "fatal signal %d, backtrace:\n", sig);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main() {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
+    for (int sig : {SIGFPE, SIGSEGV, SIGBUS, SIGILL}) signal(sig, on_fatal_signal);
     check(slas_cuda_init(-1));
 
     // ---- mod thin_blas (tests/src/main.rs:37-96), on Cuda instead of Blas ----
