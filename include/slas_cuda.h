@@ -207,6 +207,28 @@ int slas_cuda_dnrm2_batched(size_t batch, size_t len, const double *a, double *o
 int slas_cuda_snormalize_batched(size_t batch, size_t len, float *a);
 int slas_cuda_dnormalize_batched(size_t batch, size_t len, double *a);
 
+/* ---- several GPUs inside ONE process ---------------------------------------------------------
+ * A slas backend is a zero-sized type made by `B::default()` in an ordinary program (src/static_vec.rs:76,219,
+ * src/backends/rust.rs:2-3): no launcher, no ranks.  slas_cuda_init_devices(n) (n <= 0: every visible device; the
+ * environment variable SLAS_CUDA_DEVICES=n does the same at the first op) initialises devices 0..n-1 with peer
+ * access between them.  From then on
+ *  - an op on DEVICE operands runs on the device that owns them (the pointer says which);
+ *  - element-wise ops and every *_batched entry on HOST operands of >= 64 MB are split over the devices by element
+ *    range / batch index, each device running its own copy pipeline on its own worker thread;
+ *  - dot / norm / normalize on HOST operands are split by vector slice; the f64 partials are added in device order;
+ *  - the *_multi entries below take ONE DEVICE-RESIDENT SLICE PER DEVICE (slice i on its own GPU, any lengths) and
+ *    do the exchange inside the reduction kernels over NVLink peer memory: the in-process form of the *_sharded ops
+ *    further down (same kernels, same rank-ordered f64 sum, peer access instead of CUDA IPC). */
+int slas_cuda_init_devices(int ndev);
+int slas_cuda_devices(int *ndev, int *peer_exchange /* 1: the *_multi ops exchange over peer memory */);
+int slas_cuda_malloc_on(int device, void **dptr, size_t bytes);
+int slas_cuda_sdot_multi(int nslices, const size_t *lens, const float *const *a, const float *const *b, float *out);
+int slas_cuda_ddot_multi(int nslices, const size_t *lens, const double *const *a, const double *const *b, double *out);
+int slas_cuda_snrm2_multi(int nslices, const size_t *lens, const float *const *a, float *out);
+int slas_cuda_dnrm2_multi(int nslices, const size_t *lens, const double *const *a, double *out);
+int slas_cuda_snormalize_multi(int nslices, const size_t *lens, float *const *a);
+int slas_cuda_dnormalize_multi(int nslices, const size_t *lens, double *const *a);
+
 /* ---- multi-GPU: one process per GPU, this rank owns one contiguous slice -----------------
  * Batched ops shard by batch index and need no collective (call the *_batched entry on the
  * local slice).  A single huge dot / norm / normalize shards by vector slice: local

@@ -262,7 +262,7 @@ def g_small():
     (flagged words polled by block 0 vs ticket + last block), against the round-1 tiled geometry (reduce_small = 1)."""
     import ctypes as C
     ncalls = 256
-    for log2 in (20, 16, 18, 22):
+    for log2 in (20, 16, 22):
         n = 1 << log2
         per = max(n, 1 << 20)  # distinct operands, >= 2 GiB in total for the 2^20 case
         (ta, _), (tb, _), (tc, _) = uniform(ncalls * per, np.float32, 1), uniform(ncalls * per, np.float32, 2), uniform(ncalls * per, np.float32, 3)
@@ -279,15 +279,19 @@ def g_small():
             del g
             return ms / ncalls
 
-        variants = [("round-1 tiled geometry + ticket", {"reduce_small": 1}),
-                    ("balanced 1024 x 1/SM, flagged words", {}),
-                    ("balanced 1024 x 1/SM, ticket", {"reduce_small_tail": 1}),
-                    ("balanced 512 x 2/SM, flagged words", {"reduce_small_threads": 512}),
-                    ("balanced 512 x 1/SM, flagged words", {"reduce_small_threads": 512, "reduce_small_cps": 1}),
-                    ("balanced 512 x 2/SM, ticket", {"reduce_small_threads": 512, "reduce_small_tail": 1}),
-                    ("balanced 256 x 4/SM, flagged words", {"reduce_small_threads": 256}),
-                    ("balanced 256 x 2/SM, flagged words", {"reduce_small_threads": 256, "reduce_small_cps": 2}),
-                    ("balanced 1024 x 2/SM, flagged words", {"reduce_small_cps": 2})]
+        # "pdl": 1 = plain launches, 0 = dependent launch with the wait at the kernel top (a stream shared with other
+        # libraries), 2 = the caller vouches for the stream: loads run ahead of the predecessor's tail (what the library's
+        # own stream gets by default)
+        variants = [("round-1 tiled geometry + ticket, plain launch", {"reduce_small": 1, "pdl": 1}),
+                    ("balanced 512 x 2/SM, flagged words, plain launch", {"reduce_small_threads": 512, "pdl": 1}),
+                    ("balanced 512 x 2/SM, flagged words, PDL wait-at-top", {"reduce_small_threads": 512}),
+                    ("balanced 512 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 512, "pdl": 2}),
+                    ("balanced 512 x 1/SM, flagged words, PDL early loads", {"reduce_small_threads": 512, "reduce_small_cps": 1, "pdl": 2}),
+                    ("balanced 1024 x 1/SM, flagged words, plain launch", {"pdl": 1}),
+                    ("balanced 1024 x 1/SM, flagged words, PDL early loads", {"pdl": 2}),
+                    ("balanced 256 x 4/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "pdl": 2}),
+                    ("balanced 256 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "reduce_small_cps": 2, "pdl": 2}),
+                    ("balanced 512 x 2/SM, ticket, PDL early loads", {"reduce_small_threads": 512, "reduce_small_tail": 1, "pdl": 2})]
         for name, knobs in variants:
             for k, v in knobs.items():
                 set_tunable(k, v)
@@ -307,8 +311,9 @@ def g_small():
                 set_tunable(k, 0)
             report(f"dot 2^{log2} f32 single call [{name}] graph {ms * 1e3:.2f} us/call, C loop {ms_c * 1e3:.2f} us/call, "
                    f"phases ns (loads, block sum, partials in, written) {med}", ms, nbytes=8.0 * n)
-        for name, knobs in (("round-1 tiled 256 x 1024 vec", {"ewise_small": 1}), ("balanced 256 x 8/SM", {}),
-                            ("balanced 512 x 4/SM", {"ewise_small": 2}), ("balanced 1024 x 2/SM", {"ewise_small": 3})):
+        for name, knobs in (("round-1 tiled 256 x 1024 vec", {"ewise_small": 1}), ("balanced 256 x 8/SM, plain launch", {"pdl": 1}),
+                            ("balanced 256 x 8/SM, PDL wait-at-top", {}), ("balanced 256 x 8/SM, PDL early", {"pdl": 2}),
+                            ("balanced 512 x 4/SM, PDL early", {"ewise_small": 2, "pdl": 2}), ("balanced 1024 x 2/SM, PDL early", {"ewise_small": 3, "pdl": 2})):
             for k, v in knobs.items():
                 set_tunable(k, v)
             ms = graph_time(1)

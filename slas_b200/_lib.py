@@ -108,6 +108,15 @@ SIGNATURES = {
     "slas_cuda_dnrm2_batched": [_sz, _sz, _vp, _vp],
     "slas_cuda_snormalize_batched": [_sz, _sz, _vp],
     "slas_cuda_dnormalize_batched": [_sz, _sz, _vp],
+    "slas_cuda_init_devices": [_i],
+    "slas_cuda_devices": [_ip, _ip],
+    "slas_cuda_malloc_on": [_i, C.POINTER(_vp), _sz],
+    "slas_cuda_sdot_multi": [_i, _szp, C.POINTER(_vp), C.POINTER(_vp), _vp],
+    "slas_cuda_ddot_multi": [_i, _szp, C.POINTER(_vp), C.POINTER(_vp), _vp],
+    "slas_cuda_snrm2_multi": [_i, _szp, C.POINTER(_vp), _vp],
+    "slas_cuda_dnrm2_multi": [_i, _szp, C.POINTER(_vp), _vp],
+    "slas_cuda_snormalize_multi": [_i, _szp, C.POINTER(_vp)],
+    "slas_cuda_dnormalize_multi": [_i, _szp, C.POINTER(_vp)],
     "slas_cuda_nccl_unique_id": [_vp],
     "slas_cuda_comm_init": [_i, _i, _vp],
     "slas_cuda_comm_destroy": [],

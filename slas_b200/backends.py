@@ -238,6 +238,34 @@ class Cuda:
         _lib.call(f"slas_cuda_{prefix(dt)}normalize_sharded", la, pa)
 
 
+    # -- one process, several GPUs: slice i device-resident on its own GPU, exchange inside the kernels ---------
+    @staticmethod
+    def _slices(vs, dt=None):
+        ops = [operand(v, dt) for v in vs]
+        dt = ops[0][2]
+        lens = (C.c_size_t * len(ops))(*[o[1] for o in ops])
+        ptrs = (C.c_void_p * len(ops))(*[o[0] for o in ops])
+        return len(ops), lens, ptrs, dt
+
+    def dot_multi(self, a_slices, b_slices):
+        n, lens, pa, dt = self._slices(a_slices)
+        nb, lens_b, pb, _ = self._slices(b_slices, dt)
+        assert n == nb and list(lens) == list(lens_b), "dot_multi: slices of different lengths"
+        out = np.zeros(1, dtype=dt)
+        _lib.call(f"slas_cuda_{prefix(dt)}dot_multi", n, lens, pa, pb, out.ctypes.data)
+        return out[0]
+
+    def norm_multi(self, a_slices):
+        n, lens, pa, dt = self._slices(a_slices)
+        out = np.zeros(1, dtype=dt)
+        _lib.call(f"slas_cuda_{prefix(dt)}nrm2_multi", n, lens, pa, out.ctypes.data)
+        return out[0]
+
+    def normalize_multi(self, a_slices) -> None:
+        n, lens, pa, dt = self._slices(a_slices)
+        _lib.call(f"slas_cuda_{prefix(dt)}normalize_multi", n, lens, pa)
+
+
 class WithStaticBackend:
     """`WithStaticBackend<T, U, B, LEN>` (src/backends.rs:185-249, 306-331): data + backend."""
 
@@ -283,6 +311,15 @@ def device_count() -> int:
     except _lib.SlasCudaError:
         return 0
     return n.value
+
+
+def init_devices(n: int = 0) -> int:
+    """Several GPUs inside this one process (include/slas_cuda.h, "several GPUs inside ONE process"): initialise
+    devices 0..n-1 (0 = all visible).  Returns how many are active."""
+    _lib.call("slas_cuda_init_devices", int(n))
+    nd, px = C.c_int(), C.c_int()
+    _lib.call("slas_cuda_devices", C.byref(nd), C.byref(px))
+    return nd.value
 
 
 def device_info() -> dict:
@@ -349,4 +386,4 @@ def set_sgemm_path(path: str) -> None:
 
 
 __all__ = ["Cuda", "WithStaticBackend", "CudaVec", "CudaBatch", "device_count", "device_info", "set_stream",
-           "synchronize", "launch_count", "set_sgemm_path", "Graph"]
+           "synchronize", "launch_count", "set_sgemm_path", "Graph", "init_devices"]

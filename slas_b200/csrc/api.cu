@@ -14,6 +14,7 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "kernels.cuh"
+#include "multi.cuh"
 
 namespace slas {
 
@@ -541,6 +542,143 @@ static int api_fill(size_t len, T *x, uint64_t seed, uint64_t offset, T lo, T hi
     return launch_fill_uniform<T>(ctx, ctx->stream, len, x, seed, offset, lo, hi);
 }
 
+
+// ---- several devices in one process (multi.cuh): host operands are split over them -----------------------------------
+// units [lo, lo + cnt) of `units`, in multiples of `granule`, one range per device, all devices at once
+template <typename F>
+static int split_units(size_t units, size_t granule, F fn) {
+    const int n = multi_ndev();
+    return multi_run(n, [&](int d) {
+        const size_t lo = units * (size_t)d / (size_t)n / granule * granule;
+        const size_t hi = d == n - 1 ? units : units * (size_t)(d + 1) / (size_t)n / granule * granule;
+        return hi > lo ? fn(lo, hi - lo) : (int)SLAS_OK;
+    });
+}
+
+template <typename T>
+static int entry_ewise(int op, size_t len, const T *a, const T *b, T *c) {
+    DevScope scope(c);
+    if (multi_split_wanted(c, 3 * len * sizeof(T)))
+        return split_units(len, 4096, [&](size_t lo, size_t cnt) { return api_ewise<T>(op, cnt, a + lo, b + lo, c + lo); });
+    return api_ewise<T>(op, len, a, b, c);
+}
+
+// dot / norm / dotu of HOST vectors over several devices: slice per device, f64 partials added in device order here
+template <typename T>
+static int entry_reduce(int kind, int mode, size_t len, const T *a, const T *b, T *out) {
+    DevScope scope(a);
+    const size_t unit = kind == 2 ? 2 : 1;  // complex: whole (re, im) pairs per slice
+    if (!(out && multi_split_wanted(a, (kind == 1 ? 1 : 2) * len * sizeof(T)))) return api_reduce<T>(kind, mode, len, a, b, out, false, nullptr);
+    const int n = multi_ndev();
+    double parts[32][2] = {};
+    SLAS_TRY(split_units(len / unit, 16, [&](size_t lo, size_t cnt) {
+        int cur = 0;
+        cudaGetDevice(&cur);  // worker d runs with device d current: parts[] is in slice order
+        return api_reduce<T>(kind, mode, cnt * unit, a + lo * unit, (kind == 1 ? a : b) + lo * unit, nullptr, false, parts[cur]);
+    }));
+    double s0 = 0.0, s1 = 0.0;
+    for (int d = 0; d < n; ++d) { s0 += parts[d][0]; s1 += parts[d][1]; }
+    bool out_dev = false;
+    SLAS_TRY(pointer_is_device(out, &out_dev));
+    T res[2] = {mode == 1 ? (T)sqrt(s0) : (T)s0, (T)s1};
+    if (out_dev) return slas_cuda_memcpy_h2d(out, res, sizeof(T) * (kind == 2 ? 2 : 1));
+    out[0] = res[0];
+    if (kind == 2) out[1] = res[1];
+    return SLAS_OK;
+}
+
+// normalize of a HOST vector over several devices: every device stages its slice once, the workers meet to add the
+// partial sums of squares in device order, then each scales its own slice (true division by the same norm bits)
+template <typename T>
+static int entry_normalize(size_t len, T *a) {
+    DevScope scope(a);
+    if (!multi_split_wanted(a, 2 * len * sizeof(T))) return api_normalize<T>(len, a, false);
+    const int n = multi_ndev();
+    double parts[32] = {};
+    Rendezvous meet(n);
+    return multi_run(n, [&](int d) {
+        const size_t lo = len * (size_t)d / (size_t)n / 16 * 16, hi = d == n - 1 ? len : len * (size_t)(d + 1) / (size_t)n / 16 * 16;
+        const size_t cnt = hi - lo;
+        Context *ctx = nullptr;
+        int st = get_context(&ctx);
+        std::unique_lock<std::mutex> lk;
+        void *dv[1] = {nullptr};
+        const Operand ops[1] = {{a + lo, sizeof(T), INOUT}};
+        const size_t sizes[1] = {cnt * sizeof(T)};
+        if (st == SLAS_OK) lk = std::unique_lock<std::mutex>(ctx->mu);
+        if (st == SLAS_OK && cnt) st = stage_all_begin(ctx, ops, sizes, 1, dv);
+        if (st == SLAS_OK && cnt) st = launch_reduce<T>(ctx, ctx->stream, 1, cnt, (const T *)dv[0], (const T *)dv[0], ctx->scalars, nullptr, 1, 0, nullptr);
+        if (st == SLAS_OK && cnt) st = deliver_scalar(ctx, ctx->scalars, &parts[d], sizeof(double));
+        if (!meet.arrive(st == SLAS_OK)) return st != SLAS_OK ? st : fail(SLAS_ERR_CUDA, "normalize: another device failed");
+        if (!cnt) return (int)SLAS_OK;
+        double sum = 0.0;
+        for (int i = 0; i < n; ++i) sum += parts[i];
+        const T nrm = (T)sqrt(sum);
+        T *typed = reinterpret_cast<T *>(ctx->scalars + 4);
+        if (cudaMemcpyAsync(typed, &nrm, sizeof(T), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(SLAS_ERR_CUDA, "normalize: cannot upload the norm");
+        }
+        SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // nrm lives on this thread's stack
+        SLAS_TRY(launch_scale_div<T>(ctx, ctx->stream, cnt, (const T *)dv[0], (T *)dv[0], typed));
+        return stage_all_finish(ctx, ops, sizes, 1, dv);
+    });
+}
+
+template <typename T>
+static int entry_gemm_batched(size_t batch, const T *a, const T *b, T *c, size_t m, size_t n, size_t k, int ta, int tb) {
+    DevScope scope(c);
+    if (multi_split_wanted(c, batch * (m * k + k * n + m * n) * sizeof(T))) {
+        size_t granule = 1;
+        while ((granule * m * k * sizeof(T)) % 16 || (granule * k * n * sizeof(T)) % 16 || (granule * m * n * sizeof(T)) % 16) granule *= 2;
+        return split_units(batch, granule, [&](size_t lo, size_t cnt) {
+            return api_gemm_batched<T>(cnt, a + lo * m * k, b + lo * k * n, c + lo * m * n, m, n, k, ta, tb);
+        });
+    }
+    return api_gemm_batched<T>(batch, a, b, c, m, n, k, ta, tb);
+}
+
+template <typename T>
+static int entry_gemv_batched(size_t batch, const T *a, const T *x, T *y, size_t m, size_t n, int ta) {
+    DevScope scope(y);
+    const size_t xlen = ta ? n : m, ylen = ta ? m : n;
+    if (multi_split_wanted(y, batch * (m * n + xlen + ylen) * sizeof(T))) {
+        size_t granule = 1;
+        while ((granule * m * n * sizeof(T)) % 16 || (granule * xlen * sizeof(T)) % 16 || (granule * ylen * sizeof(T)) % 16) granule *= 2;
+        return split_units(batch, granule, [&](size_t lo, size_t cnt) {
+            return api_gemv<T>(cnt, a + lo * m * n, x + lo * xlen, y + lo * ylen, m, n, m, ta, true);
+        });
+    }
+    return api_gemv<T>(batch, a, x, y, m, n, m, ta, true);
+}
+
+static int entry_transpose_batched(size_t batch, size_t len, size_t elem, const void *a, void *buffer, size_t columns, bool inplace) {
+    DevScope scope(a);
+    if (batch > 1 && multi_split_wanted(a, 2 * batch * len * elem)) {
+        size_t granule = 1;
+        while ((granule * len * elem) % 16) granule *= 2;
+        return split_units(batch, granule, [&](size_t lo, size_t cnt) {
+            return api_transpose(cnt, len, elem, (const char *)a + lo * len * elem, inplace ? nullptr : (char *)buffer + lo * len * elem, columns, inplace);
+        });
+    }
+    return api_transpose(batch, len, elem, a, buffer, columns, inplace);
+}
+
+template <typename T>
+static int entry_batched_reduce(int mode, size_t batch, size_t len, const T *a, const T *b, T *out, T *a_mut) {
+    const void *anchor = mode == 2 ? (const void *)a_mut : (const void *)out;
+    DevScope scope(anchor);
+    if (multi_split_wanted(anchor, batch * len * sizeof(T) * (mode == 0 ? 2 : 1))) {
+        size_t granule = 4;
+        while ((granule * len * sizeof(T)) % 16) granule *= 2;
+        return split_units(batch, granule, [&](size_t lo, size_t cnt) {
+            return api_batched_reduce<T>(mode, cnt, len, a ? a + lo * len : nullptr, b ? b + lo * len : nullptr, out ? out + lo : nullptr,
+                                         a_mut ? a_mut + lo * len : nullptr);
+        });
+    }
+    return api_batched_reduce<T>(mode, batch, len, a, b, out, a_mut);
+}
+
 }  // namespace slas
 
 using namespace slas;
@@ -548,51 +686,55 @@ using namespace slas;
 extern "C" {
 
 int slas_cuda_sfill_uniform(size_t len, float *x, uint64_t seed, uint64_t offset, float lo, float hi) {
+    DevScope scope(x);
     return api_fill<float>(len, x, seed, offset, lo, hi);
 }
 int slas_cuda_dfill_uniform(size_t len, double *x, uint64_t seed, uint64_t offset, double lo, double hi) {
+    DevScope scope(x);
     return api_fill<double>(len, x, seed, offset, lo, hi);
 }
 
 // DotProduct
 int slas_cuda_sdot(size_t len, const float *a, const float *b, float *out) {
-    return api_reduce<float>(0, 0, len, a, b, out, false, nullptr);
+    return entry_reduce<float>(0, 0, len, a, b, out);
 }
 int slas_cuda_ddot(size_t len, const double *a, const double *b, double *out) {
-    return api_reduce<double>(0, 0, len, a, b, out, false, nullptr);
+    return entry_reduce<double>(0, 0, len, a, b, out);
 }
 int slas_cuda_cdotu(size_t len, const float *a, const float *b, float *out) {
-    return api_reduce<float>(2, 0, 2 * len, a, b, out, false, nullptr);
+    return entry_reduce<float>(2, 0, 2 * len, a, b, out);
 }
 int slas_cuda_zdotu(size_t len, const double *a, const double *b, double *out) {
-    return api_reduce<double>(2, 0, 2 * len, a, b, out, false, nullptr);
+    return entry_reduce<double>(2, 0, 2 * len, a, b, out);
 }
 
 // Normalize
-int slas_cuda_snrm2(size_t len, const float *a, float *out) { return api_reduce<float>(1, 1, len, a, a, out, false, nullptr); }
-int slas_cuda_dnrm2(size_t len, const double *a, double *out) { return api_reduce<double>(1, 1, len, a, a, out, false, nullptr); }
-int slas_cuda_scnrm2(size_t len, const float *a, float *out) { return api_reduce<float>(1, 1, 2 * len, a, a, out, false, nullptr); }
-int slas_cuda_dznrm2(size_t len, const double *a, double *out) { return api_reduce<double>(1, 1, 2 * len, a, a, out, false, nullptr); }
-int slas_cuda_snormalize(size_t len, float *a) { return api_normalize<float>(len, a, false); }
-int slas_cuda_dnormalize(size_t len, double *a) { return api_normalize<double>(len, a, false); }
-int slas_cuda_cnormalize(size_t len, float *a) { return api_normalize<float>(2 * len, a, false); }
-int slas_cuda_znormalize(size_t len, double *a) { return api_normalize<double>(2 * len, a, false); }
+int slas_cuda_snrm2(size_t len, const float *a, float *out) { return entry_reduce<float>(1, 1, len, a, a, out); }
+int slas_cuda_dnrm2(size_t len, const double *a, double *out) { return entry_reduce<double>(1, 1, len, a, a, out); }
+int slas_cuda_scnrm2(size_t len, const float *a, float *out) { return entry_reduce<float>(1, 1, 2 * len, a, a, out); }
+int slas_cuda_dznrm2(size_t len, const double *a, double *out) { return entry_reduce<double>(1, 1, 2 * len, a, a, out); }
+int slas_cuda_snormalize(size_t len, float *a) { return entry_normalize<float>(len, a); }
+int slas_cuda_dnormalize(size_t len, double *a) { return entry_normalize<double>(len, a); }
+int slas_cuda_cnormalize(size_t len, float *a) { return entry_normalize<float>(2 * len, a); }
+int slas_cuda_znormalize(size_t len, double *a) { return entry_normalize<double>(2 * len, a); }
 
 // Addition / Subtraction / Multiplication / Divition
-int slas_cuda_sadd(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(0, len, a, b, c); }
-int slas_cuda_ssub(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(1, len, a, b, c); }
-int slas_cuda_smul(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(2, len, a, b, c); }
-int slas_cuda_sdiv(size_t len, const float *a, const float *b, float *c) { return api_ewise<float>(3, len, a, b, c); }
-int slas_cuda_dadd(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(0, len, a, b, c); }
-int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(1, len, a, b, c); }
-int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(2, len, a, b, c); }
-int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c) { return api_ewise<double>(3, len, a, b, c); }
+int slas_cuda_sadd(size_t len, const float *a, const float *b, float *c) { return entry_ewise<float>(0, len, a, b, c); }
+int slas_cuda_ssub(size_t len, const float *a, const float *b, float *c) { return entry_ewise<float>(1, len, a, b, c); }
+int slas_cuda_smul(size_t len, const float *a, const float *b, float *c) { return entry_ewise<float>(2, len, a, b, c); }
+int slas_cuda_sdiv(size_t len, const float *a, const float *b, float *c) { return entry_ewise<float>(3, len, a, b, c); }
+int slas_cuda_dadd(size_t len, const double *a, const double *b, double *c) { return entry_ewise<double>(0, len, a, b, c); }
+int slas_cuda_dsub(size_t len, const double *a, const double *b, double *c) { return entry_ewise<double>(1, len, a, b, c); }
+int slas_cuda_dmul(size_t len, const double *a, const double *b, double *c) { return entry_ewise<double>(2, len, a, b, c); }
+int slas_cuda_ddiv(size_t len, const double *a, const double *b, double *c) { return entry_ewise<double>(3, len, a, b, c); }
 
 #define SLAS_FUSED_DOT(NAME, CHAIN)                                                                                         \
     int slas_cuda_s##NAME##_dot(size_t len, const float *a, const float *b, float *c, const float *d, float *out) {         \
+        DevScope scope(a);                                                                                                  \
         return api_fused_chain<float>(CHAIN, len, a, b, c, d, out);                                                         \
     }                                                                                                                       \
     int slas_cuda_d##NAME##_dot(size_t len, const double *a, const double *b, double *c, const double *d, double *out) {    \
+        DevScope scope(a);                                                                                                  \
         return api_fused_chain<double>(CHAIN, len, a, b, c, d, out);                                                        \
     }
 SLAS_FUSED_DOT(add, 0)
@@ -601,36 +743,48 @@ SLAS_FUSED_DOT(mul, 2)
 SLAS_FUSED_DOT(div, 3)
 #undef SLAS_FUSED_DOT
 int slas_cuda_sdot_norms(size_t len, const float *a, const float *b, float *out3) {
+    DevScope scope(a);
     return api_fused_chain<float>(4, len, a, b, nullptr, nullptr, out3);
 }
 int slas_cuda_ddot_norms(size_t len, const double *a, const double *b, double *out3) {
+    DevScope scope(a);
     return api_fused_chain<double>(4, len, a, b, nullptr, nullptr, out3);
 }
-int slas_cuda_snormalize_into(size_t len, const float *a, float *out) { return api_normalize_into<float>(len, a, out); }
-int slas_cuda_dnormalize_into(size_t len, const double *a, double *out) { return api_normalize_into<double>(len, a, out); }
+int slas_cuda_snormalize_into(size_t len, const float *a, float *out) {
+    DevScope scope(a);
+    return api_normalize_into<float>(len, a, out);
+}
+int slas_cuda_dnormalize_into(size_t len, const double *a, double *out) {
+    DevScope scope(a);
+    return api_normalize_into<double>(len, a, out);
+}
 
 // Transpose
 int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns) {
+    DevScope scope(a);
     return api_transpose(1, len, elem_size, a, buffer, columns, false);
 }
 int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns) {
+    DevScope scope(a);
     return api_transpose(1, len, elem_size, a, nullptr, columns, true);
 }
 int slas_cuda_transpose_inplace_batched(size_t batch, size_t len, size_t elem_size, void *a, size_t columns) {
-    return api_transpose(batch, len, elem_size, a, nullptr, columns, true);
+    return entry_transpose_batched(batch, len, elem_size, a, nullptr, columns, true);
 }
 int slas_cuda_transpose_batched(size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
                                 size_t columns) {
-    return api_transpose(batch, len, elem_size, a, buffer, columns, false);
+    return entry_transpose_batched(batch, len, elem_size, a, buffer, columns, false);
 }
 
 // MatrixMul
 int slas_cuda_sgemm(const float *a, const float *b, float *c, size_t m, size_t n, size_t k, size_t lda, size_t ldb,
                     size_t ldc, int a_trans, int b_trans) {
+    DevScope scope(c);
     return api_gemm<float>(a, b, c, m, n, k, lda, ldb, ldc, a_trans, b_trans);
 }
 int slas_cuda_dgemm(const double *a, const double *b, double *c, size_t m, size_t n, size_t k, size_t lda, size_t ldb,
                     size_t ldc, int a_trans, int b_trans) {
+    DevScope scope(c);
     return api_gemm<double>(a, b, c, m, n, k, lda, ldb, ldc, a_trans, b_trans);
 }
 int slas_cuda_set_sgemm_path(int path) {
@@ -645,66 +799,74 @@ int slas_cuda_get_sgemm_path(int *path) {
 }
 int slas_cuda_sgemm_batched(size_t batch, const float *a, const float *b, float *c, size_t m, size_t n, size_t k,
                             int a_trans, int b_trans) {
-    return api_gemm_batched<float>(batch, a, b, c, m, n, k, a_trans, b_trans);
+    return entry_gemm_batched<float>(batch, a, b, c, m, n, k, a_trans, b_trans);
 }
 int slas_cuda_dgemm_batched(size_t batch, const double *a, const double *b, double *c, size_t m, size_t n, size_t k,
                             int a_trans, int b_trans) {
-    return api_gemm_batched<double>(batch, a, b, c, m, n, k, a_trans, b_trans);
+    return entry_gemm_batched<double>(batch, a, b, c, m, n, k, a_trans, b_trans);
 }
 
 // matrix_vector_mul
 int slas_cuda_sgemv(const float *a, const float *x, float *y, size_t m, size_t n, size_t lda, int a_trans) {
+    DevScope scope(y);
     return api_gemv<float>(1, a, x, y, m, n, lda, a_trans, false);
 }
 int slas_cuda_dgemv(const double *a, const double *x, double *y, size_t m, size_t n, size_t lda, int a_trans) {
+    DevScope scope(y);
     return api_gemv<double>(1, a, x, y, m, n, lda, a_trans, false);
 }
 int slas_cuda_sgemv_batched(size_t batch, const float *a, const float *x, float *y, size_t m, size_t n, int a_trans) {
-    return api_gemv<float>(batch, a, x, y, m, n, m, a_trans, true);
+    return entry_gemv_batched<float>(batch, a, x, y, m, n, a_trans);
 }
 int slas_cuda_dgemv_batched(size_t batch, const double *a, const double *x, double *y, size_t m, size_t n, int a_trans) {
-    return api_gemv<double>(batch, a, x, y, m, n, m, a_trans, true);
+    return entry_gemv_batched<double>(batch, a, x, y, m, n, a_trans);
 }
 
 // batched dot / norm / normalize
 int slas_cuda_sdot_batched(size_t batch, size_t len, const float *a, const float *b, float *out) {
-    return api_batched_reduce<float>(0, batch, len, a, b, out, nullptr);
+    return entry_batched_reduce<float>(0, batch, len, a, b, out, nullptr);
 }
 int slas_cuda_ddot_batched(size_t batch, size_t len, const double *a, const double *b, double *out) {
-    return api_batched_reduce<double>(0, batch, len, a, b, out, nullptr);
+    return entry_batched_reduce<double>(0, batch, len, a, b, out, nullptr);
 }
 int slas_cuda_snrm2_batched(size_t batch, size_t len, const float *a, float *out) {
-    return api_batched_reduce<float>(1, batch, len, a, nullptr, out, nullptr);
+    return entry_batched_reduce<float>(1, batch, len, a, nullptr, out, nullptr);
 }
 int slas_cuda_dnrm2_batched(size_t batch, size_t len, const double *a, double *out) {
-    return api_batched_reduce<double>(1, batch, len, a, nullptr, out, nullptr);
+    return entry_batched_reduce<double>(1, batch, len, a, nullptr, out, nullptr);
 }
 int slas_cuda_snormalize_batched(size_t batch, size_t len, float *a) {
-    return api_batched_reduce<float>(2, batch, len, nullptr, nullptr, nullptr, a);
+    return entry_batched_reduce<float>(2, batch, len, nullptr, nullptr, nullptr, a);
 }
 int slas_cuda_dnormalize_batched(size_t batch, size_t len, double *a) {
-    return api_batched_reduce<double>(2, batch, len, nullptr, nullptr, nullptr, a);
+    return entry_batched_reduce<double>(2, batch, len, nullptr, nullptr, nullptr, a);
 }
 
 // sharded (one slice per rank + one allreduce)
 int slas_cuda_sdot_sharded(size_t local_len, const float *a, const float *b, float *out) {
+    DevScope scope(a);
     return api_reduce<float>(0, 0, local_len, a, b, out, true, nullptr);
 }
 int slas_cuda_ddot_sharded(size_t local_len, const double *a, const double *b, double *out) {
+    DevScope scope(a);
     return api_reduce<double>(0, 0, local_len, a, b, out, true, nullptr);
 }
 int slas_cuda_snrm2_sharded(size_t local_len, const float *a, float *out) {
+    DevScope scope(a);
     return api_reduce<float>(1, 1, local_len, a, a, out, true, nullptr);
 }
 int slas_cuda_dnrm2_sharded(size_t local_len, const double *a, double *out) {
+    DevScope scope(a);
     return api_reduce<double>(1, 1, local_len, a, a, out, true, nullptr);
 }
 int slas_cuda_snormalize_sharded(size_t local_len, float *a) { return api_normalize<float>(local_len, a, true); }
 int slas_cuda_dnormalize_sharded(size_t local_len, double *a) { return api_normalize<double>(local_len, a, true); }
 int slas_cuda_sdot_partial(size_t len, const float *a, const float *b, double *partial) {
+    DevScope scope(a);
     return api_reduce<float>(0, 0, len, a, b, nullptr, false, partial);
 }
 int slas_cuda_ddot_partial(size_t len, const double *a, const double *b, double *partial) {
+    DevScope scope(a);
     return api_reduce<double>(0, 0, len, a, b, nullptr, false, partial);
 }
 

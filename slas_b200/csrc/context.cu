@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "multi.cuh"
 
 namespace slas {
 
@@ -34,7 +35,7 @@ static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
                                {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
                                {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
-                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}};
+                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;
@@ -481,6 +482,7 @@ int slas_cuda_free_host(void *hptr) {
 static int copy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
     if (bytes == 0) return SLAS_OK;
     SLAS_REQUIRE(dst && src, "null pointer in memcpy");
+    DevScope scope(kind == cudaMemcpyHostToDevice ? dst : src);  // several devices: the stream of the one that owns the memory
     Context *c;
     SLAS_TRY(get_context(&c));
     cudaStream_t st;
@@ -499,6 +501,7 @@ int slas_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes) {
 int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes) {
     if (bytes == 0) return SLAS_OK;
     SLAS_REQUIRE(dst && src, "null pointer in memcpy");
+    DevScope scope(dst);
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);
@@ -508,6 +511,7 @@ int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes) {
 int slas_cuda_memset(void *dst, int byte, size_t bytes) {
     if (bytes == 0) return SLAS_OK;
     SLAS_REQUIRE(dst, "null pointer in memset");
+    DevScope scope(dst);
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);

@@ -37,13 +37,16 @@ def prefix(dtype) -> str:
 class CudaVec:
     """Device-resident `StaticVec<T, LEN>`.  Owns its allocation unless built as a view."""
 
-    def __init__(self, length: int, dtype=np.float32, *, _ptr: int | None = None, _owner=None):
+    def __init__(self, length: int, dtype=np.float32, *, device: int | None = None, _ptr: int | None = None, _owner=None):
         self.dtype = np.dtype(dtype)  # any Copy element may be stored; arithmetic ops check the type
         self.LEN = int(length)
         self._owner = _owner
         if _ptr is None:
             p = C.c_void_p()
-            _lib.call("slas_cuda_malloc", C.byref(p), self.nbytes)
+            if device is None:
+                _lib.call("slas_cuda_malloc", C.byref(p), self.nbytes)
+            else:  # several devices in one process (backends.init_devices): storage on a chosen one
+                _lib.call("slas_cuda_malloc_on", int(device), C.byref(p), self.nbytes)
             self._ptr = p.value
             self._owns = True
         else:
@@ -71,9 +74,9 @@ class CudaVec:
 
     # -- explicit data movement -----------------------------------------------------------------
     @classmethod
-    def from_host(cls, array) -> "CudaVec":
+    def from_host(cls, array, device: int | None = None) -> "CudaVec":
         a = np.ascontiguousarray(array)
-        v = cls(a.size, a.dtype)
+        v = cls(a.size, a.dtype, device=device)
         _lib.call("slas_cuda_memcpy_h2d", v._ptr, a.ctypes.data, a.nbytes)
         return v
 

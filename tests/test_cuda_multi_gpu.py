@@ -21,3 +21,14 @@ def test_sharded_ops_across_gpus(world):
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_multi_gpu_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and f"MULTI_GPU_OK {world}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_single_process_several_devices(ndev):
+    """ONE ordinary process driving several GPUs (slas_cuda_init_devices): host-operand splits, the in-process sharded
+    reductions over peer memory, device-pointer ops on the owning device (tests/_multi_device_worker.py)"""
+    if device_count() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_multi_device_worker.py"), str(ndev)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and f"MULTI_DEVICE_OK {ndev}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

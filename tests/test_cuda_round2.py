@@ -149,3 +149,55 @@ def test_sgemm_auto_threshold_straddled_with_tiny_operands(scale_log2):
         # results that are denormal in f32 carry an absolute rounding error of half the smallest denormal per operation
         floor = 2.0 ** -149 * k
         assert np.all(np.abs(got - ref) <= 1e-5 * np.sqrt(k) * mag + floor), (m, n, k, scale_log2)
+
+
+# ---- programmatic dependent launch of the launch-bound vector ops: overlap must never reorder dependent ops --------
+@pytest.mark.parametrize("pdl", [0, 1, 2])
+@pytest.mark.parametrize("graph", [False, True])
+def test_back_to_back_small_ops_keep_stream_order(pdl, graph):
+    """short dots / adds issued back to back start while their predecessor is still in its tail (pdl = 2: the caller
+    vouches that only this library uses the stream; the library's own stream gets that by default).  Read-after-write,
+    write-after-read and write-after-write chains must behave exactly like the serial sequence, eagerly and replayed
+    from a graph; independent calls must give the bits of the same calls issued one at a time."""
+    rng = np.random.default_rng(41)
+    n, reps = 1 << 16, 48
+    a = _rand(rng, reps * n, np.float32)
+    b = _rand(rng, reps * n, np.float32)
+    d = _rand(rng, n, np.float32)
+    da, db, dd = CudaVec.from_host(a), CudaVec.from_host(b), CudaVec.from_host(d)
+    c, c2 = CudaVec(n, np.float32), CudaVec(n, np.float32)
+    out = CudaVec(4 * reps, np.float32).zero_()
+    # serial truth from this backend, one call at a time with a sync after each
+    want = np.zeros(4 * reps, np.float32)
+    for i in range(reps):
+        ai, bi = a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]
+        ci = ai + bi                                     # RAW: add -> dot of the sum
+        want[4 * i] = cuda.dot(CudaVec.from_host(ci), dd)
+        want[4 * i + 1] = cuda.dot(CudaVec.from_host(ai), CudaVec.from_host(bi))  # independent
+        want[4 * i + 2] = cuda.dot(CudaVec.from_host(ci * bi), dd)                # WAW on c2, then RAW
+        want[4 * i + 3] = cuda.norm(CudaVec.from_host(ci))
+
+    def chain():
+        for i in range(reps):
+            va, vb = da.view(i * n, n), db.view(i * n, n)
+            cuda.add(va, vb, c)                                                                     # WAR: the previous dot read c
+            L.call("slas_cuda_sdot", n, c.as_ptr(), dd.as_ptr(), out.as_ptr() + 16 * i)           # RAW on c
+            L.call("slas_cuda_sdot", n, va.as_ptr(), vb.as_ptr(), out.as_ptr() + 16 * i + 4)      # independent of everything before
+            cuda.mul(c, vb, c2)                                                                     # RAW on c, WAW on c2
+            L.call("slas_cuda_sdot", n, c2.as_ptr(), dd.as_ptr(), out.as_ptr() + 16 * i + 8)
+            L.call("slas_cuda_snrm2", n, c.as_ptr(), out.as_ptr() + 16 * i + 12)
+
+    set_tunable("pdl", pdl)
+    try:
+        for rep in range(3):
+            out.zero_()
+            if graph:
+                with Graph() as g:
+                    chain()
+                g.launch()
+                g.launch()
+            else:
+                chain()
+            assert np.array_equal(out.to_host(), want), (pdl, graph, rep)
+    finally:
+        set_tunable("pdl", 0)
