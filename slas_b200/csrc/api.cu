@@ -31,7 +31,7 @@ struct Operand {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Whole-operand staging: sizes[i] bytes each.  Fills dev[i]; caller runs the op on ctx->stream and
-// then calls stage_all_finish.
+// then calls stage_all_finish.  Pageable operands go through the pinned bounce ring (hostcopy.cu).
 static int stage_all_begin(Context *ctx, const Operand *ops, const size_t *sizes, int n, void **dev) {
     size_t total = 0;
     for (int i = 0; i < n; ++i) total += align_up(sizes[i], 256);
@@ -41,30 +41,36 @@ static int stage_all_begin(Context *ctx, const Operand *ops, const size_t *sizes
     for (int i = 0; i < n; ++i) {
         dev[i] = (char *)base + off;
         off += align_up(sizes[i], 256);
-        if ((ops[i].dir & IN) && sizes[i])
-            SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], ops[i].host, sizes[i], cudaMemcpyHostToDevice, ctx->stream));
+        if ((ops[i].dir & IN) && sizes[i]) SLAS_TRY(copy_h2d(ctx, ctx->stream, dev[i], ops[i].host, sizes[i]));
     }
     return SLAS_OK;
 }
 static int stage_all_finish(Context *ctx, const Operand *ops, const size_t *sizes, int n, void *const *dev) {
     for (int i = 0; i < n; ++i)
-        if ((ops[i].dir & OUT) && sizes[i])
-            SLAS_CUDA_TRY(cudaMemcpyAsync(const_cast<void *>(ops[i].host), dev[i], sizes[i], cudaMemcpyDeviceToHost,
-                                          ctx->stream));
+        if ((ops[i].dir & OUT) && sizes[i]) SLAS_TRY(copy_d2h(ctx, ctx->stream, const_cast<void *>(ops[i].host), dev[i], sizes[i]));
     SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     return SLAS_OK;
 }
 
 // Chunked 3-slot pipeline over `units` independent units.  `granule`: chunk sizes are multiples of
 // it (keeps every chunk's device pointers 16-byte aligned and whole objects together).
+// Pinned operands: H2D copy, kernel and D2H copy of consecutive chunks on three streams, straight from / to the
+// caller's memory.  Pageable operands (what a slas StaticVec is, static_vec.rs:126): the same pipeline with a pinned
+// bounce slot per chunk -- the copy threads fill the slot of chunk i + 1 and empty the slot of chunk i - 2 while the
+// DMA engines and the SMs work on the chunks in between.
 template <typename F>
 static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand *ops, int n, F launch) {
     if (units == 0) return SLAS_OK;
     size_t unit_total = 0;
-    for (int i = 0; i < n; ++i) unit_total += ops[i].unit_bytes;
-    // 96 MB slots by default; "host_slot_mb" is the sweep knob (profiles/tune.py e2e)
+    bool pageable = false;
+    for (int i = 0; i < n; ++i) {
+        unit_total += ops[i].unit_bytes;
+        if (!pageable && ops[i].unit_bytes && host_pointer_pageable(ops[i].host)) pageable = true;
+    }
+    if (pageable && units * unit_total < ((size_t)4 << 20)) pageable = false;  // small: the driver's own bounce is fine
+    // 96 MB slots by default (24 MB through the bounce ring); "host_slot_mb" is the sweep knob (profiles/tune.py e2e)
     const long slot_mb = tunable("host_slot_mb");
-    const size_t kSlotBytes = (size_t)(slot_mb > 0 ? slot_mb : 96) << 20;
+    const size_t kSlotBytes = (size_t)(slot_mb > 0 ? slot_mb : (pageable ? 24 : 96)) << 20;
     size_t chunk = kSlotBytes / (unit_total ? unit_total : 1);
     chunk = chunk / granule * granule;
     if (chunk == 0) chunk = granule;
@@ -74,21 +80,56 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
     const int nslots = units > chunk ? 3 : 1;
     void *base = nullptr;
     SLAS_TRY(ensure_staging(ctx, slot_bytes * nslots, &base));
+    char *ring = nullptr;
+    if (pageable) SLAS_TRY(ensure_bounce(ctx, slot_bytes * nslots, &ring));
     // the copy streams must not overtake work already queued on the op stream
     SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    struct Pending { bool live = false; size_t first = 0, cnt = 0; } pend[3];
+    // bring the results of the chunk that last used `slot` from the ring into the caller's memory
+    auto drain_slot = [&](int slot) -> int {
+        if (!pend[slot].live) return SLAS_OK;
+        SLAS_CUDA_TRY(cudaEventSynchronize(ctx->bounce_events[slot]));
+        HostCopyJob jobs[8];
+        int nj = 0;
+        size_t off = 0;
+        for (int i = 0; i < n; ++i) {
+            if (ops[i].dir & OUT)
+                jobs[nj++] = {(char *)const_cast<void *>(ops[i].host) + pend[slot].first * ops[i].unit_bytes,
+                              ring + (size_t)slot * slot_bytes + off, pend[slot].cnt * ops[i].unit_bytes};
+            off += align_up(chunk * ops[i].unit_bytes, 256);
+        }
+        parallel_memcpy(jobs, nj);
+        pend[slot].live = false;
+        return SLAS_OK;
+    };
     size_t done = 0;
     for (size_t ci = 0; done < units; ++ci) {
         const int slot = (int)(ci % nslots);
         cudaStream_t st = ctx->copy_streams[slot];
         const size_t cnt = std::min(chunk, units - done);
         void *dev[8];
+        if (pageable) {
+            SLAS_TRY(drain_slot(slot));  // also guarantees the slot's last H2D has left the ring
+            HostCopyJob jobs[8];
+            int nj = 0;
+            size_t off = 0;
+            for (int i = 0; i < n; ++i) {
+                if (ops[i].dir & IN)
+                    jobs[nj++] = {ring + (size_t)slot * slot_bytes + off, (const char *)ops[i].host + done * ops[i].unit_bytes,
+                                  cnt * ops[i].unit_bytes};
+                off += align_up(chunk * ops[i].unit_bytes, 256);
+            }
+            parallel_memcpy(jobs, nj);
+        }
         size_t off = 0;
         for (int i = 0; i < n; ++i) {
             dev[i] = (char *)base + (size_t)slot * slot_bytes + off;
+            if (ops[i].dir & IN) {
+                const void *src = pageable ? (const void *)(ring + (size_t)slot * slot_bytes + off)
+                                           : (const void *)((const char *)ops[i].host + done * ops[i].unit_bytes);
+                SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], src, cnt * ops[i].unit_bytes, cudaMemcpyHostToDevice, st));
+            }
             off += align_up(chunk * ops[i].unit_bytes, 256);
-            if (ops[i].dir & IN)
-                SLAS_CUDA_TRY(cudaMemcpyAsync(dev[i], (const char *)ops[i].host + done * ops[i].unit_bytes,
-                                              cnt * ops[i].unit_bytes, cudaMemcpyHostToDevice, st));
         }
         // The kernels of consecutive chunks run on different streams but share the context's scratch (the grow-only
         // workspace: pre-transposed operands, the 3xTF32 split, gemv / segmented-reduction partials; the reduction
@@ -97,11 +138,31 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
         if (ci > 0) SLAS_CUDA_TRY(cudaStreamWaitEvent(st, ctx->copy_events[(ci - 1) % 3], 0));
         SLAS_TRY(launch(dev, cnt, st));
         SLAS_CUDA_TRY(cudaEventRecord(ctx->copy_events[ci % 3], st));
-        for (int i = 0; i < n; ++i)
-            if (ops[i].dir & OUT)
-                SLAS_CUDA_TRY(cudaMemcpyAsync((char *)const_cast<void *>(ops[i].host) + done * ops[i].unit_bytes, dev[i],
-                                              cnt * ops[i].unit_bytes, cudaMemcpyDeviceToHost, st));
+        off = 0;
+        for (int i = 0; i < n; ++i) {
+            if (ops[i].dir & OUT) {
+                void *dst = pageable ? (void *)(ring + (size_t)slot * slot_bytes + off)
+                                     : (void *)((char *)const_cast<void *>(ops[i].host) + done * ops[i].unit_bytes);
+                SLAS_CUDA_TRY(cudaMemcpyAsync(dst, dev[i], cnt * ops[i].unit_bytes, cudaMemcpyDeviceToHost, st));
+            }
+            off += align_up(chunk * ops[i].unit_bytes, 256);
+        }
+        if (pageable) {
+            SLAS_CUDA_TRY(cudaEventRecord(ctx->bounce_events[slot], st));
+            pend[slot].live = true;
+            pend[slot].first = done;
+            pend[slot].cnt = cnt;
+        }
         done += cnt;
+    }
+    if (pageable) {
+        // the last chunks, oldest first
+        for (int q = 0; q < nslots; ++q) {
+            int oldest = -1;
+            for (int s = 0; s < nslots; ++s)
+                if (pend[s].live && (oldest < 0 || pend[s].first < pend[oldest].first)) oldest = s;
+            if (oldest >= 0) SLAS_TRY(drain_slot(oldest));
+        }
     }
     for (int s = 0; s < nslots; ++s) SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->copy_streams[s]));
     return SLAS_OK;

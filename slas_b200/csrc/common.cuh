@@ -67,6 +67,10 @@ struct Context {
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};   // kernels of chunk i done (orders the shared scratch)
     double *pinned_scalars = nullptr;    // [16]
+    // Pageable host operands (hostcopy.cu): pinned bounce ring + one event per slot
+    void *bounce = nullptr;
+    size_t bounce_bytes = 0;
+    cudaEvent_t bounce_events[4] = {nullptr, nullptr, nullptr, nullptr};
     // Programmatic dependent launch of the launch-bound vector ops (reduce.cuh): what the previous kernel of this
     // library read and wrote, so that the next one knows whether it may load its operands before that kernel is done.
     struct Span { const char *lo, *hi; };
@@ -91,6 +95,17 @@ constexpr int kMaxPartials = 148 * 16;
 int get_context(Context **out);
 int ensure_workspace(Context *ctx, size_t bytes, void **out);
 int ensure_staging(Context *ctx, size_t bytes, void **out);
+
+// hostcopy.cu -- copies that know about pageable host memory (what a slas StaticVec is)
+constexpr int kBounceSlots = 4;
+struct HostCopyJob { void *dst; const void *src; size_t bytes; };
+void parallel_memcpy(const HostCopyJob *jobs, int njobs);           // the copy-thread pool, fork-join
+bool host_pointer_pageable(const void *p);                          // neither pinned nor registered
+int ensure_bounce(Context *ctx, size_t bytes, char **out);          // grow-only pinned ring
+// enqueue-or-stage: pinned memory -> one cudaMemcpyAsync; pageable -> through the bounce ring (h2d returns with every
+// chunk enqueued and the ring idle, d2h returns with the bytes in the caller's memory)
+int copy_h2d(Context *ctx, cudaStream_t st, void *dev, const void *host, size_t bytes);
+int copy_d2h(Context *ctx, cudaStream_t st, void *host, const void *dev, size_t bytes);
 
 // Counts every kernel launch of this library (slas_cuda_launch_count).
 extern std::atomic<uint64_t> g_launches;

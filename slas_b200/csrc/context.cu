@@ -35,7 +35,7 @@ static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
                                {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
                                {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
-                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}};
+                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}, {"host_copy_threads", 0}, {"host_bounce", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;
@@ -58,6 +58,12 @@ static void release_context(Context *c) {
     c->retired.clear();
     cudaFree(c->staging);
     if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
+    if (c->bounce) cudaFreeHost(c->bounce);
+    c->bounce = nullptr; c->bounce_bytes = 0;
+    for (int i = 0; i < kBounceSlots; ++i) {
+        if (c->bounce_events[i]) cudaEventDestroy(c->bounce_events[i]);
+        c->bounce_events[i] = nullptr;
+    }
     for (int i = 0; i < 3; ++i) {
         if (c->copy_streams[i]) cudaStreamDestroy(c->copy_streams[i]);
         if (c->copy_events[i]) cudaEventDestroy(c->copy_events[i]);

@@ -201,3 +201,43 @@ def test_back_to_back_small_ops_keep_stream_order(pdl, graph):
             assert np.array_equal(out.to_host(), want), (pdl, graph, rep)
     finally:
         set_tunable("pdl", 0)
+
+
+# ---- pageable host operands (what a slas StaticVec is) go through the pinned bounce ring ---------------------------
+def test_pageable_and_pinned_host_operands_give_the_same_bytes():
+    """the reference hands a backend pageable memory ([T; LEN] / Vec, static_vec.rs:126): copy threads stage it
+    through a pinned ring; pinned operands are copied from in place.  Same kernels, same bytes -- also for ragged last
+    chunks, INOUT operands (a transpose with a tail the reference leaves untouched) and the one-slot case."""
+    rng = np.random.default_rng(51)
+    batch, e = 700_003, 16
+    A = _rand(rng, batch * e, np.float32)
+    B = _rand(rng, batch * e, np.float32)
+    hA, hB, hC = Pinned(batch * e, np.float32), Pinned(batch * e, np.float32), Pinned(batch * e, np.float32)
+    hA.a[:], hB.a[:] = A, B
+    try:
+        for slot_mb in (0, 3):  # default slots, and small ones (many chunks, every ring slot reused many times)
+            set_tunable("host_slot_mb", slot_mb)
+            Cp = np.zeros(batch * e, np.float32)
+            cuda.matrix_mul_batched(A, B, Cp, 4, 4, 4)
+            hC.a[:] = 0
+            cuda.matrix_mul_batched(hA.a, hB.a, hC.a, 4, 4, 4)
+            assert np.array_equal(Cp, hC.a), slot_mb
+            want = oracle.gemm_batched(A[:4096 * e], B[:4096 * e], 4096, 4, 4, 4)
+            assert np.max(np.abs(Cp[:4096 * e] - want)) <= 1e-5 * 2 * 16
+            # transpose with len % columns != 0: the tail of every object keeps the caller's bytes (INOUT through the ring)
+            ln, cols, nb = 37, 5, 300_001
+            src = _rand(rng, nb * ln, np.float32)
+            dst = np.full(nb * ln, 7.0, np.float32)
+            cuda.transpose_batched(src, dst, ln, cols)
+            ref = np.full((nb, ln), 7.0, np.float32)
+            rows = ln // cols
+            ref[:, :rows * cols] = src.reshape(nb, ln)[:, :rows * cols].reshape(nb, cols, rows).transpose(0, 2, 1).reshape(nb, rows * cols)
+            assert np.array_equal(dst.reshape(nb, ln), ref), slot_mb
+            x = _rand(rng, 9_000_001, np.float32)
+            y = np.empty_like(x)
+            cuda.add(x, x, y)
+            assert np.array_equal(y, x + x)
+    finally:
+        set_tunable("host_slot_mb", 0)
+        for h in (hA, hB, hC):
+            h.free()
