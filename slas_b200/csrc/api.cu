@@ -231,7 +231,10 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
         SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
     } else {
         // (a rank with an empty slice still takes part in the fused exchange: its partial is 0)
-        const int r = launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res, need_collective ? nullptr : typed, mode, 0,
+        // the f64 sums go to the context's scalars only when somebody reads them (a collective behind the kernel, the
+        // *_partial entries): every reduction writing that one slot would order all of them one behind the other
+        double *res_arg = (need_collective || partial_out) ? res : nullptr;
+        const int r = launch_reduce<T>(ctx, ctx->stream, kind, len, da, db, res_arg, need_collective ? nullptr : typed, mode, 0,
                                        fused ? &px : nullptr);
         if (r != SLAS_OK) {
             if (fused) comm_rollback_peer_exchange(px.epoch);

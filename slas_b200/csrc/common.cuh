@@ -51,7 +51,8 @@ struct Context {
     double *partials = nullptr;          // [kMaxPartials * 2]
     unsigned int *ticket = nullptr;      // [4]
     double *scalars = nullptr;           // [16] device scalars (norm, sharded partial, ...)
-    void *ll_slots = nullptr;            // [3 * kMaxPartials] 16-byte flagged partial slots (reduce.cuh), zero between launches
+    void *ll_slots = nullptr;            // [kRedScratchSets][3 * kMaxPartials] 16-byte flagged partial slots (reduce.cuh), zero between launches
+    unsigned red_seq = 0;                // rotates the scratch set: overlapping reductions never share one
     unsigned long long *phases = nullptr;  // [8] %globaltimer stamps of the last reduction (tunable "reduce_phases")
     // Grow-only device workspace (transpose_inplace temp, tcgen05 hi/lo split, host staging).  A block that is
     // outgrown is RETIRED, not freed, while a stream capture is open or an instantiated graph may still hold
@@ -71,25 +72,32 @@ struct Context {
     void *bounce = nullptr;
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_events[4] = {nullptr, nullptr, nullptr, nullptr};
-    // Programmatic dependent launch of the launch-bound vector ops (reduce.cuh): what the previous kernel of this
-    // library read and wrote, so that the next one knows whether it may load its operands before that kernel is done.
+    // Programmatic dependent launch of the launch-bound vector ops (reduce.cuh): what the kernels that may still be
+    // running read and write, so that the next one knows whether it may touch its operands before they are done.
+    // A kernel that waits for its predecessor BEFORE it lets its successor go ("early" = 0) is a barrier: everything
+    // before it has completed by the time anything after it starts.  The window holds that kernel and every "early"
+    // kernel launched since; a full window forces the next kernel to be a barrier.
     struct Span { const char *lo, *hi; };
+    struct HazardOp { Span reads[2], writes[2]; };
     struct Hazard {
-        uint64_t seq = ~0ull;            // g_launches right after the recorded launch; anything launched since voids it
+        static constexpr int kWindow = 8;   // == kRedScratchSets: a kernel of the window owns one scratch set
+        uint64_t seq = ~0ull;            // g_launches right after the last recorded launch; anything launched since voids it
         cudaStream_t stream = nullptr;
-        Span reads[4], writes[4];
-        int nreads = 0, nwrites = 0;
+        HazardOp ops[kWindow];
+        int n = 0;
     } hazard;
     std::mutex mu;                       // serialises enqueue + scratch use
 };
 
-// True when a kernel reading `reads` and writing `writes` may start its loads / stores while the previously recorded
-// kernel of this context is still running (no RAW, WAR or WAW overlap with it, nothing else launched in between).
+// True when a kernel that reads `reads` and writes `writes` BEFORE its griddepcontrol.wait may do so while the kernels
+// of the window are still running (no RAW, WAR or WAW overlap with any of them, nothing else launched in between).
 bool hazard_early_ok(const Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw);
-// Call right after the launch (after SLAS_LAUNCH_CHECK) of a kernel that triggers its dependents early.
-void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw);
+// Call right after the launch (after SLAS_LAUNCH_CHECK) of a dependent-launch kernel: `reads` / `writes` = everything it
+// touches at any time; early = what hazard_early_ok allowed (0: the kernel is a barrier, the window restarts at it).
+void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw, int early);
 
 constexpr int kMaxPartials = 148 * 16;
+constexpr int kRedScratchSets = 8;
 
 // Returns the context of the current device, initialising it on first use.
 int get_context(Context **out);

@@ -98,8 +98,8 @@ static int init_context_resources(Context *c, int dev) {
     SLAS_CUDA_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned int) * 4));
     SLAS_CUDA_TRY(cudaMalloc(&c->scalars, sizeof(double) * 16));
     SLAS_CUDA_TRY(cudaMemset(c->scalars, 0, sizeof(double) * 16));
-    SLAS_CUDA_TRY(cudaMalloc(&c->ll_slots, (size_t)16 * 3 * kMaxPartials));
-    SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * 3 * kMaxPartials));
+    SLAS_CUDA_TRY(cudaMalloc(&c->ll_slots, (size_t)16 * 3 * kMaxPartials * kRedScratchSets));
+    SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * 3 * kMaxPartials * kRedScratchSets));
     SLAS_CUDA_TRY(cudaMalloc(&c->phases, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaMemset(c->phases, 0, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaMallocHost(&c->pinned_scalars, sizeof(double) * 16));
@@ -155,30 +155,35 @@ static inline bool spans_overlap(const Context::Span &a, const Context::Span &b)
 
 bool hazard_early_ok(const Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw) {
     const Context::Hazard &h = ctx->hazard;
-    // Nothing recorded, another stream, or some other kernel of the library launched since: the predecessor on the
-    // stream is unknown.  (Copies / memsets / foreign kernels in between do not trigger early, so the dependent
-    // launch degenerates to a full dependency and early loads are trivially safe -- but then they gain nothing either.)
-    if (h.seq != g_launches.load(std::memory_order_relaxed) || h.stream != st || tunable("pdl") == 1) return false;
-    for (int i = 0; i < nr; ++i)
-        for (int j = 0; j < h.nwrites; ++j)
-            if (spans_overlap(reads[i], h.writes[j])) return false;  // RAW
-    for (int i = 0; i < nw; ++i) {
-        for (int j = 0; j < h.nwrites; ++j)
-            if (spans_overlap(writes[i], h.writes[j])) return false;  // WAW
-        for (int j = 0; j < h.nreads; ++j)
-            if (spans_overlap(writes[i], h.reads[j])) return false;  // WAR
+    // Nothing recorded, another stream, or some other kernel of the library launched since: what may still be running
+    // is unknown.  (Copies / memsets / foreign kernels in between do not trigger early, so the dependent launch
+    // degenerates to a full dependency -- the barrier kernel this returns false for costs nothing extra then.)
+    if (h.n == 0 || h.n >= Context::Hazard::kWindow || h.seq != g_launches.load(std::memory_order_relaxed) || h.stream != st ||
+        tunable("pdl") == 1)
+        return false;
+    for (int o = 0; o < h.n; ++o) {
+        const Context::HazardOp &op = h.ops[o];
+        for (int i = 0; i < nr; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (spans_overlap(reads[i], op.writes[j])) return false;  // RAW
+        for (int i = 0; i < nw; ++i)
+            for (int j = 0; j < 2; ++j)
+                if (spans_overlap(writes[i], op.writes[j]) || spans_overlap(writes[i], op.reads[j])) return false;  // WAW, WAR
     }
     return true;
 }
 
-void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw) {
+void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw, int early) {
     Context::Hazard &h = ctx->hazard;
+    if (!early || h.n >= Context::Hazard::kWindow) h.n = 0;  // a barrier kernel: everything before it is done when its successors start
+    Context::HazardOp &op = h.ops[h.n++];
+    const Context::Span none = {nullptr, nullptr};
+    for (int i = 0; i < 2; ++i) {
+        op.reads[i] = i < nr ? reads[i] : none;
+        op.writes[i] = i < nw ? writes[i] : none;
+    }
     h.seq = g_launches.load(std::memory_order_relaxed);
     h.stream = st;
-    h.nreads = nr < 4 ? nr : 4;
-    h.nwrites = nw < 4 ? nw : 4;
-    for (int i = 0; i < h.nreads; ++i) h.reads[i] = reads[i];
-    for (int i = 0; i < h.nwrites; ++i) h.writes[i] = writes[i];
 }
 
 int ensure_workspace(Context *ctx, size_t bytes, void **out) {
@@ -402,7 +407,8 @@ int slas_cuda_graph_destroy(void *graph_exec) {
     Context *c;
     SLAS_TRY(get_context(&c));
     std::lock_guard<std::mutex> lk(c->mu);
-    SLAS_CUDA_TRY(cudaStreamSynchronize(c->stream));  // a replay may still be running
+    // (a garbage-collected handle may be destroyed while another capture is open: no synchronising call then; the
+    // driver defers the destruction of an exec that is still running, and retired scratch is freed later)
     SLAS_CUDA_TRY(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
     if (c->live_graphs > 0) --c->live_graphs;
     free_retired(c);

@@ -57,7 +57,9 @@ RedScratch reduce_scratch(Context *ctx) {
     RedScratch sc;
     sc.partials = ctx->partials;
     sc.ticket = ctx->ticket;
-    sc.ll = reinterpret_cast<LLSlot *>(ctx->ll_slots);
+    // consecutive launches use consecutive sets of flagged slots: kernels that overlap (dependent launch, at most
+    // Hazard::kWindow == kRedScratchSets of them between two barriers) never publish into the same set
+    sc.ll = reinterpret_cast<LLSlot *>(ctx->ll_slots) + (size_t)(ctx->red_seq++ % kRedScratchSets) * 3 * kMaxPartials;
     sc.phases = tunable("reduce_phases") ? ctx->phases : nullptr;
     return sc;
 }
@@ -78,8 +80,8 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
     __shared__ bool is_last;
     // programmatic dependent launch (reduce.cuh): the successor may be scheduled from here on; this kernel's own
     // loads wait for its predecessor unless the host found no overlap with that kernel's operands (`early`)
+    if (!early) pdl_wait();  // a barrier kernel: its successor starts only after everything before this kernel is done
     pdl_trigger();
-    if (!early) pdl_wait();
     const bool stamp = sc.phases != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
     if (stamp) sc.phases[0] = red_timer_ns();
     Reducer<T, KIND> r;
@@ -180,17 +182,26 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
     s[0] = block_sum<THREADS>(r.sum, red);
     if (KIND == 2) s[NRES - 1] = block_sum<THREADS>(r.sum_im, red);
     if (stamp) sc.phases[2] = red_timer_ns();
-    if (early) pdl_wait();  // the scratch below is shared with the predecessor: only now is it ours
-    if (!grid_combine<THREADS, NRES>(g, sc, s, p, red, &is_last)) return;
+    // early kernels: the flagged-slot combine runs in this launch's own scratch set and the result goes to memory no
+    // running kernel touches (host-checked), so it need not wait either; only the ticket tail shares its counter.
+    // Every block still waits for the predecessor before it exits: completion order stays the stream order.
+    const bool wait_before_combine = early && !g.poll;
+    if (wait_before_combine) pdl_wait();
+    if (!grid_combine<THREADS, NRES>(g, sc, s, p, red, &is_last)) {
+        if (early && !wait_before_combine) pdl_wait();
+        return;
+    }
     const bool stamp_end = sc.phases != nullptr && threadIdx.x == 0;
     if (stamp_end) sc.phases[3] = red_timer_ns();
     double pr = p[0], pi = KIND == 2 ? p[NRES - 1] : 0.0;
     // multi-GPU: exchange the rank-local partial with the peers over NVLink and add in rank order
     if (px.nranks > 1) peer_allreduce_sum(px, pr, pi, peer_vals);
     if (threadIdx.x == 0) {
-        if (accumulate) { pr += result[0]; if (KIND == 2) pi += result[1]; }
-        result[0] = pr;
-        if (KIND == 2) result[1] = pi;
+        if (result) {
+            if (accumulate) { pr += result[0]; if (KIND == 2) pi += result[1]; }
+            result[0] = pr;
+            if (KIND == 2) result[1] = pi;
+        }
         if (typed_out) {
             if (mode == 1) typed_out[0] = (T)sqrt(pr);
             else {
@@ -200,6 +211,7 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
         }
         if (stamp_end) sc.phases[4] = red_timer_ns();
     }
+    if (early && !wait_before_combine) pdl_wait();
 }
 
 template <typename T, int KIND>
@@ -219,13 +231,13 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
     const T *bb = KIND == 1 ? a : b;
     // what this kernel reads and writes, for the early-start decision of it and of its successor
     const Context::Span reads[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)bb, (const char *)(bb + len)}};
-    const Context::Span writes[2] = {{(const char *)result, (const char *)(result + 2)},
+    const Context::Span writes[2] = {{(const char *)result, (const char *)(result ? result + 2 : result)},
                                      {(const char *)typed_out, (const char *)(typed_out ? typed_out + 2 : typed_out)}};
     // overlap with the predecessor only on a stream nobody else enqueues kernels on (the library's own, or one the
     // caller vouches for: tunable "pdl" = 2), without the accumulate / multi-GPU forms, and when nothing overlaps
     const bool own = st == ctx->own_stream || tunable("pdl") == 2;
-    // (only the loads run ahead of the wait: every write of this kernel comes after it, so only RAW matters here)
-    const int early = g.balanced && own && !accumulate && px.nranks <= 1 && hazard_early_ok(ctx, st, reads, 2, nullptr, 0) ? 1 : 0;
+    // (an early kernel runs to its end without waiting: loads, combine in its own scratch set, result store)
+    const int early = g.balanced && own && !accumulate && px.nranks <= 1 && hazard_early_ok(ctx, st, reads, 2, writes, 2) ? 1 : 0;
     cudaError_t le = cudaSuccess;
 #define SLAS_REDUCE_LAUNCH(THREADS)                                                                                         \
     do {                                                                                                                    \
@@ -242,7 +254,7 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
 #undef SLAS_REDUCE_LAUNCH
     SLAS_CUDA_TRY(le);
     SLAS_LAUNCH_CHECK();
-    hazard_record(ctx, st, reads, 2, writes, 2);
+    hazard_record(ctx, st, reads, 2, writes, 2, early);
     return SLAS_OK;
 }
 

@@ -100,11 +100,14 @@ RedScratch reduce_scratch(Context *ctx);
 // ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------
 // The launch-bound vector kernels (one call = a few microseconds) are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization: each lets its successor on the stream be scheduled as soon as
-// all of its own blocks are running (pdl_trigger at kernel start), so the successor's launch latency, and -- when the
-// host-side hazard check (common.cuh) found no overlap with this kernel's operands -- its loads and FMAs overlap
-// this kernel's cross-block tail.  pdl_wait blocks until the predecessor grid has completed and its writes are visible;
-// every block executes it before touching shared scratch / dependent data and before it exits (so completion order
-// stays the stream order).  Without the launch attribute both are no-ops.
+// all of its own blocks have executed pdl_trigger, so the successor's launch latency, and -- when the host-side hazard
+// check (common.cuh) found no overlap with the operands of any kernel that may still be running -- its loads and FMAs
+// overlap this kernel's cross-block tail.  pdl_wait blocks until the predecessor grid has completed and its writes are
+// visible; every block executes it before touching shared scratch / dependent data and before it exits (so completion
+// order stays the stream order).  Two kinds of kernel: "early" ones trigger first and wait late; the others wait
+// first and trigger afterwards, which makes them barriers (nothing launched before them is still running when their
+// successors start) -- that bounds the set of kernels an early one can overlap with to the host's hazard window.
+// Without the launch attribute both instructions are no-ops.
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

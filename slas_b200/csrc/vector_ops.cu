@@ -85,8 +85,8 @@ ewise_balanced_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
     constexpr int U = 4;
     // programmatic dependent launch (reduce.cuh): let the successor be scheduled; wait for the predecessor first unless
     // the host found that nothing of ours overlaps its operands
+    if (!early) pdl_wait();  // a barrier kernel: its successor starts only after everything before this kernel is done
     pdl_trigger();
-    if (!early) pdl_wait();
     const V *av = reinterpret_cast<const V *>(a);
     const V *bv = reinterpret_cast<const V *>(b);
     V *cv = reinterpret_cast<V *>(c);
@@ -159,7 +159,7 @@ static int launch_ewise_op(Context *ctx, cudaStream_t st, size_t len, const T *a
             else le = launch_pdl(ewise_balanced_kernel<T, OP, 256>, (unsigned)blocks, 256u, st, a, b, c, nvec, len, per, early);
             SLAS_CUDA_TRY(le);
             SLAS_LAUNCH_CHECK();
-            hazard_record(ctx, st, reads, 2, writes, 1);
+            hazard_record(ctx, st, reads, 2, writes, 1, early);
             return SLAS_OK;
         }
         size_t blocks = (nvec + (size_t)kEwThreads * UNROLL - 1) / ((size_t)kEwThreads * UNROLL);
