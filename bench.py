@@ -237,8 +237,12 @@ def run_reference(args):
 
 # ---- GPU arm ---------------------------------------------------------------------------------------------
 def run_cuda(args):
-    # stdout carries exactly one JSON line: NCCL's version/debug banner goes to stderr
+    # stdout carries exactly one JSON line: everything else any library prints (NCCL's version banner ...) goes to
+    # stderr -- file descriptor 1 is pointed at stderr for the run and the line is written to the saved descriptor
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -757,7 +761,8 @@ def run_cuda(args):
                          "configs": configs},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -27,6 +27,8 @@ mod cuda_backend {
         "gemm_jit.cu", "gemm_generic.cu", "gemm_large.cu", "gemm_large_f64.cu", "gemm_ffma.cu", "gemm_tcgen05.cu",
         "comm.cu", "multi.cu", "hostcopy.cu", "microbench.cu",
     ];
+    // == HOSTSRCS of the Makefile
+    const HOST_SOURCES: &[&str] = &["hostcopy_pool.cpp"];
     const NVCC_FLAGS: &[&str] = &[
         "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
     ];
@@ -61,6 +63,12 @@ mod cuda_backend {
             println!("cargo:rerun-if-changed={}", path.display());
             let obj = out.join(src.replace(".cu", ".o"));
             run(Command::new(&nvcc).args(NVCC_FLAGS).arg("-I").arg(out).arg("-c").arg(&path).arg("-o").arg(&obj), src);
+            objects.push(obj);
+        }
+        // plain host C++ (Makefile: HOSTSRCS): the copy-thread pool of the pageable-operand path
+        for src in HOST_SOURCES {
+            let obj = out.join(src.replace(".cpp", ".o"));
+            run(Command::new("g++").args(["-O3", "-std=c++17", "-fPIC", "-c"]).arg(csrc.join(src)).arg("-o").arg(&obj), src);
             objects.push(obj);
         }
         // gemm_tiny.cu holds 64 kernels per element type: one object per type (Makefile: gemm_tiny_f32.o / gemm_tiny_f64.o)

@@ -3,111 +3,13 @@
 // cudaMemcpyAsync from pageable memory is a synchronous bounce inside the driver on the calling thread (measured here:
 // 11.6 GB/s, and no overlap with the kernels or the other direction), so pageable operands go through the library's own
 // pinned bounce ring instead: a small pool of copy threads moves the caller's bytes into / out of pinned slots with
-// plain memcpy while the DMA engines move the previous slots over PCIe.  Pinned (or registered) operands keep the
-// direct cudaMemcpyAsync.
+// streaming (non-temporal) stores while the DMA engines move the previous slots over PCIe (hostcopy_pool.cpp).
+// Pinned (or registered) operands keep the direct cudaMemcpyAsync.
 #include <string.h>
-
-#include <atomic>
-#include <condition_variable>
-#include <thread>
-#include <vector>
 
 #include "common.cuh"
 
 namespace slas {
-
-namespace {
-
-// ---- copy-thread pool: fork-join memcpy over fixed-size pieces ------------------------------------------------------
-struct CopyPool {
-    struct Piece { char *dst; const char *src; size_t bytes; };
-    std::vector<std::thread> threads;
-    std::mutex mu;              // pool state
-    std::mutex call_mu;         // one parallel copy at a time (it uses every thread anyway)
-    std::condition_variable cv_work, cv_done;
-    std::vector<Piece> pieces;
-    std::atomic<size_t> next{0};
-    size_t generation = 0;
-    int active = 0;
-    bool quit = false;
-
-    void worker() {
-        size_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv_work.wait(lk, [&] { return quit || generation != seen; });
-                if (quit) return;
-                seen = generation;
-            }
-            drain();
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (--active == 0) cv_done.notify_all();
-            }
-        }
-    }
-    void drain() {
-        for (;;) {
-            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
-            if (i >= pieces.size()) return;
-            memcpy(pieces[i].dst, pieces[i].src, pieces[i].bytes);
-        }
-    }
-    void start(int n) {
-        for (int i = 0; i < n; ++i) threads.emplace_back([this] { worker(); });
-    }
-    ~CopyPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            quit = true;
-            cv_work.notify_all();
-        }
-        for (auto &t : threads)
-            if (t.joinable()) t.join();
-    }
-} g_pool;
-std::once_flag g_pool_once;
-
-int pool_threads() {
-    const long knob = tunable("host_copy_threads");
-    if (knob > 0) return (int)(knob > 64 ? 64 : knob);
-    const unsigned hw = std::thread::hardware_concurrency();
-    int n = hw ? (int)hw / 2 : 4;
-    if (n < 2) n = 2;
-    if (n > 8) n = 8;
-    return n;
-}
-
-}  // namespace
-
-void parallel_memcpy(const HostCopyJob *jobs, int njobs) {
-    size_t total = 0;
-    for (int j = 0; j < njobs; ++j) total += jobs[j].bytes;
-    if (total < ((size_t)1 << 20)) {  // not worth waking anybody
-        for (int j = 0; j < njobs; ++j)
-            if (jobs[j].bytes) memcpy(jobs[j].dst, jobs[j].src, jobs[j].bytes);
-        return;
-    }
-    std::call_once(g_pool_once, [] { g_pool.start(pool_threads() - 1); });  // the caller is the last copier
-    std::lock_guard<std::mutex> call_lk(g_pool.call_mu);
-    constexpr size_t kPiece = (size_t)1 << 20;
-    {
-        std::lock_guard<std::mutex> lk(g_pool.mu);
-        g_pool.pieces.clear();
-        for (int j = 0; j < njobs; ++j)
-            for (size_t off = 0; off < jobs[j].bytes; off += kPiece)
-                g_pool.pieces.push_back({(char *)jobs[j].dst + off, (const char *)jobs[j].src + off,
-                                         jobs[j].bytes - off < kPiece ? jobs[j].bytes - off : kPiece});
-        g_pool.next.store(0, std::memory_order_relaxed);
-        g_pool.active = (int)g_pool.threads.size();
-        ++g_pool.generation;
-        g_pool.cv_work.notify_all();
-    }
-    g_pool.drain();
-    std::unique_lock<std::mutex> lk(g_pool.mu);
-    g_pool.cv_done.wait(lk, [&] { return g_pool.active == 0; });
-}
 
 bool host_pointer_pageable(const void *p) {
     if (!p || tunable("host_bounce") == 1) return false;

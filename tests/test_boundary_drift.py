@@ -123,6 +123,9 @@ def test_build_rs_compiles_what_the_makefile_compiles():
     listed = re.search(r"KERNEL_SOURCES:\s*&\[&str\]\s*=\s*&\[(.*?)\];", rs, flags=re.S).group(1)
     rs_srcs = re.findall(r'"([a-z_0-9]+\.cu)"', listed)
     assert sorted(rs_srcs) == sorted(srcs), f"build.rs KERNEL_SOURCES != Makefile SRCS: {sorted(set(srcs) ^ set(rs_srcs))}"
+    host = re.search(r"^HOSTSRCS\s*:=\s*(.*)$", mk, flags=re.M).group(1).split()
+    rs_host = re.findall(r'"([a-z_0-9]+\.cpp)"', re.search(r"HOST_SOURCES:\s*&\[&str\]\s*=\s*&\[(.*?)\];", rs, flags=re.S).group(1))
+    assert sorted(rs_host) == sorted(host), f"build.rs HOST_SOURCES != Makefile HOSTSRCS: {host} vs {rs_host}"
     # the pieces of the Makefile that are not plain `nvcc -c file.cu`: gemm_tiny.cu once per element type, and the
     # kernel text gemm_jit.cu embeds for NVRTC
     assert "gemm_tiny.cu" in rs and "SLAS_TINY_F64" in rs, "build.rs must compile gemm_tiny.cu twice (f32 and -DSLAS_TINY_F64)"
