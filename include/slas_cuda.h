@@ -158,7 +158,8 @@ int slas_cuda_dnormalize_into(size_t len, const double *a, double *out);
 /* ---- Transpose::{transpose, transpose_inplace}  (src/backends.rs:152-154;
  *      Rust: src/backends/rust.rs:151-177).  buffer[columns*row + column] =
  *      a[(len/columns)*column + row]; `columns` is the column count of the OUTPUT.
- *      Generic over any Copy element: elem_size in {1, 2, 4, 8, 16} bytes.  Bit-exact. --- */
+ *      Generic over any Copy element like the reference (`Transpose<T: Copy>`): any elem_size (1/2/4/8/16 bytes on
+ *      the vector kernels, anything else -- a 12-byte [f32; 3] ... -- on a granule kernel).  Bit-exact. --- */
 int slas_cuda_transpose(size_t len, size_t elem_size, const void *a, void *buffer, size_t columns);
 int slas_cuda_transpose_inplace(size_t len, size_t elem_size, void *a, size_t columns);
 

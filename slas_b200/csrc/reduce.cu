@@ -231,8 +231,9 @@ static int launch_reduce_kind(Context *ctx, cudaStream_t st, size_t len, const T
     const T *bb = KIND == 1 ? a : b;
     // what this kernel reads and writes, for the early-start decision of it and of its successor
     const Context::Span reads[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)bb, (const char *)(bb + len)}};
-    const Context::Span writes[2] = {{(const char *)result, (const char *)(result ? result + 2 : result)},
-                                     {(const char *)typed_out, (const char *)(typed_out ? typed_out + 2 : typed_out)}};
+    constexpr int NRES = KIND == 2 ? 2 : 1;
+    const Context::Span writes[2] = {{(const char *)result, (const char *)(result ? result + NRES : result)},
+                                     {(const char *)typed_out, (const char *)(typed_out ? typed_out + NRES : typed_out)}};
     // overlap with the predecessor only on a stream nobody else enqueues kernels on (the library's own, or one the
     // caller vouches for: tunable "pdl" = 2), without the accumulate / multi-GPU forms, and when nothing overlaps
     const bool own = st == ctx->own_stream || tunable("pdl") == 2;

@@ -6,7 +6,8 @@
 // i.e. the input is read as `columns` x `rows` row-major and written `rows` x `columns`
 // row-major; `columns` is the column count of the OUTPUT.  Elements past rows*columns (when
 // columns does not divide len) are never written, exactly like the reference's loop.
-// Pure data movement on opaque 1/2/4/8/16-byte elements => bit-exact for any Copy type.
+// Pure data movement on opaque elements => bit-exact for any Copy type: 1/2/4/8/16-byte elements on the vector / tiled /
+// staged kernels, any other size (a 12-byte [f32; 3] ...) on the granule kernel at the end of the file.
 //
 // Kernels: (1) big matrices: 32x32 element tiles through padded shared memory, both sides
 // coalesced; (2) many small objects: one warp per object, coalesced read into a padded
@@ -776,6 +777,68 @@ static int launch_transpose_inplace_typed(Context *ctx, cudaStream_t st, size_t 
     return SLAS_OK;
 }
 
+// ---- any other element size (`Transpose<T: Copy>` is generic over T, rust.rs:151: a 12-byte [f32; 3], a 24-byte
+// struct ...): the element is W granules of the widest power-of-two size G that divides it and that both pointers are
+// aligned to; 32 x 32 element tiles go through shared memory as rows of 32 * W granules, so both sides move contiguous
+// runs.  Same index map as above: out[(row * columns + column) * W + j] = in[(column * rows + row) * W + j].
+template <typename G>
+__global__ void __launch_bounds__(256)
+transpose_granules_kernel(const G *__restrict__ a, G *__restrict__ out, size_t batch, size_t len, unsigned rows, unsigned columns,
+                          unsigned w) {
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    G *tile = reinterpret_cast<G *>(tile_raw);            // [32][32 * w + 1]
+    const unsigned seg = 32 * w, pitch = seg + 1;
+    const unsigned c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (size_t obj = blockIdx.z; obj < batch; obj += gridDim.z) {
+        const G *src = a + obj * len * w;
+        G *dst = out + obj * len * w;
+        for (unsigned idx = threadIdx.x; idx < 32 * seg; idx += 256) {
+            const unsigned ic = idx / seg, q = idx - ic * seg;
+            if (c0 + ic < columns && r0 + q / w < rows) tile[ic * pitch + q] = src[((size_t)(c0 + ic) * rows + r0) * w + q];
+        }
+        __syncthreads();
+        for (unsigned idx = threadIdx.x; idx < 32 * seg; idx += 256) {
+            const unsigned orow = idx / seg, q = idx - orow * seg;
+            const unsigned oc = q / w, j = q - oc * w;
+            if (r0 + orow < rows && c0 + oc < columns) dst[((size_t)(r0 + orow) * columns + c0) * w + q] = tile[oc * pitch + orow * w + j];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename G>
+static int launch_transpose_granules(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
+                                     size_t columns) {
+    const size_t rows = len / columns, w = elem_size / sizeof(G);
+    if (rows == 0 || batch == 0) return SLAS_OK;
+    SLAS_REQUIRE(rows <= 0x7fffffffu && columns <= 0x7fffffffu, "transpose: object too large");
+    const size_t smem = (size_t)32 * (32 * w + 1) * sizeof(G);
+    SLAS_REQUIRE(smem <= 200 * 1024, "transpose: element size %zu is too large (the 32 x 32 element tile must fit shared memory)", elem_size);
+    const size_t gx = (columns + 31) / 32, gy = (rows + 31) / 32;
+    SLAS_REQUIRE(gy <= 65535, "transpose: more than 2^21 rows of a generic-size element");
+    auto kern = transpose_granules_kernel<G>;
+    if (smem > 48 * 1024) SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t gz = batch;
+    const size_t cap = std::max<size_t>(1, (size_t)ctx->sm_count * 16 / (gx * gy));
+    if (gz > cap) gz = cap;
+    if (gz > 65535) gz = 65535;
+    kern<<<dim3((unsigned)gx, (unsigned)gy, (unsigned)gz), 256, smem, st>>>((const G *)a, (G *)buffer, batch, len, (unsigned)rows,
+                                                                            (unsigned)columns, (unsigned)w);
+    SLAS_LAUNCH_CHECK();
+    return SLAS_OK;
+}
+
+static int launch_transpose_any_size(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a, void *buffer,
+                                     size_t columns) {
+    SLAS_REQUIRE(elem_size > 0, "transpose: element size 0");
+    const uintptr_t bits = (uintptr_t)a | (uintptr_t)buffer | (uintptr_t)elem_size;
+    if (bits % 16 == 0) return launch_transpose_granules<Elem16>(ctx, st, batch, len, elem_size, a, buffer, columns);
+    if (bits % 8 == 0) return launch_transpose_granules<uint64_t>(ctx, st, batch, len, elem_size, a, buffer, columns);
+    if (bits % 4 == 0) return launch_transpose_granules<uint32_t>(ctx, st, batch, len, elem_size, a, buffer, columns);
+    if (bits % 2 == 0) return launch_transpose_granules<uint16_t>(ctx, st, batch, len, elem_size, a, buffer, columns);
+    return launch_transpose_granules<uint8_t>(ctx, st, batch, len, elem_size, a, buffer, columns);
+}
+
 int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, void *a,
                              size_t columns, bool *handled) {
     SLAS_REQUIRE(columns != 0, "transpose: columns == 0 (the reference divides by it, rust.rs:169)");
@@ -786,7 +849,8 @@ int launch_transpose_inplace(Context *ctx, cudaStream_t st, size_t batch, size_t
     case 8: return launch_transpose_inplace_typed<uint64_t>(ctx, st, batch, len, (uint64_t *)a, columns, handled);
     case 16: return launch_transpose_inplace_typed<Elem16>(ctx, st, batch, len, (Elem16 *)a, columns, handled);
     }
-    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 1, 2, 4, 8, 16)", elem_size);
+    *handled = false;  // any other element size: through the temporary, like the reference (rust.rs:152-160)
+    return SLAS_OK;
 }
 
 int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, size_t elem_size, const void *a,
@@ -800,7 +864,7 @@ int launch_transpose(Context *ctx, cudaStream_t st, size_t batch, size_t len, si
     case 8: return launch_transpose_typed<uint64_t>(ctx, st, batch, len, (const uint64_t *)a, (uint64_t *)buffer, columns);
     case 16: return launch_transpose_typed<Elem16>(ctx, st, batch, len, (const Elem16 *)a, (Elem16 *)buffer, columns);
     }
-    return fail(SLAS_ERR_UNSUPPORTED, "transpose: element size %zu (supported: 1, 2, 4, 8, 16)", elem_size);
+    return launch_transpose_any_size(ctx, st, batch, len, elem_size, a, buffer, columns);
 }
 
 }  // namespace slas

@@ -241,3 +241,40 @@ def test_pageable_and_pinned_host_operands_give_the_same_bytes():
         set_tunable("host_slot_mb", 0)
         for h in (hA, hB, hC):
             h.free()
+
+
+# ---- Transpose<T: Copy> for any element size (rust.rs:151): 12-byte [f32; 3], 24-byte, 6-byte, 3-byte elements --------
+@pytest.mark.parametrize("elem", [12, 24, 6, 3, 20, 48])
+@pytest.mark.parametrize("rows,cols,batch", [(1, 1, 1), (3, 5, 1), (33, 65, 1), (100, 257, 1), (16, 16, 300), (7, 3, 1001), (64, 40, 9)])
+def test_transpose_elements_of_any_size(elem, rows, cols, batch):
+    rng = np.random.default_rng(elem * 1000 + rows)
+    dt = np.dtype((np.void, elem))
+    raw = rng.integers(0, 256, batch * rows * cols * elem, dtype=np.uint8)
+    a = raw.view(dt)                                   # batch * rows * cols opaque elements
+    n = rows * cols
+    want = raw.reshape(batch, cols, rows, elem).transpose(0, 2, 1, 3).reshape(-1)   # input read as cols x rows, written rows x cols
+    for src in (a, CudaVec.from_host(a)):
+        out = np.zeros(batch * n, dt) if isinstance(src, np.ndarray) else CudaVec(batch * n, dt).zero_()
+        if batch == 1:
+            cuda.transpose(src, out, cols)
+        else:
+            cuda.transpose_batched(src, out, n, cols)
+        got = (out if isinstance(out, np.ndarray) else out.to_host()).view(np.uint8)
+        assert np.array_equal(got, want), (elem, rows, cols, batch)
+        # in place (Matrix::deref_mut): through the zeroed temporary, like the reference
+        ip = a.copy() if isinstance(src, np.ndarray) else CudaVec.from_host(a)
+        if batch == 1:
+            cuda.transpose_inplace(ip, cols)
+        else:
+            cuda.transpose_inplace_batched(ip, n, cols)
+        got = (ip if isinstance(ip, np.ndarray) else ip.to_host()).view(np.uint8)
+        assert np.array_equal(got, want), ("inplace", elem, rows, cols, batch)
+    # ragged: len % columns != 0 -- the tail is never written (rust.rs:168-175)
+    if batch == 1 and rows * cols > 2:
+        ln = n + 2
+        raw2 = rng.integers(0, 256, ln * elem, dtype=np.uint8)
+        out = np.full(ln * elem, 0xAB, np.uint8).view(dt)
+        cuda.transpose(raw2.view(dt), out, cols)
+        r2 = ln // cols
+        w2 = raw2[:cols * r2 * elem].reshape(cols, r2, elem).transpose(1, 0, 2).reshape(-1)
+        assert np.array_equal(out.view(np.uint8)[:r2 * cols * elem], w2) and np.all(out.view(np.uint8)[r2 * cols * elem:] == 0xAB)
