@@ -183,6 +183,42 @@ def g_e2e():
         _lib.call("slas_cuda_free_host", p.value)
 
 
+def g_pageable():
+    """host-pointer pipeline with PAGEABLE operands (what a slas StaticVec is): copy-thread count (environment, read once
+    per process: one subprocess per setting), ring slot size, streaming stores on / off; plus the bare copy pool rate"""
+    import subprocess
+    import time
+    if os.environ.get("SLAS_TUNE_PAGEABLE_CHILD"):
+        b = 1 << 24
+        A, B = np.full(b * 16, 0.5, np.float32), np.full(b * 16, 0.25, np.float32)
+        Cm = np.zeros(b * 16, np.float32)
+        for nt in (0, 1):
+            set_tunable("host_copy_nt", nt)
+            for mb in (8, 24, 64):
+                set_tunable("host_slot_mb", mb)
+                cuda.matrix_mul_batched(A, B, Cm, 4, 4, 4)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    cuda.matrix_mul_batched(A, B, Cm, 4, 4, 4)
+                ms = (time.perf_counter() - t0) * 1e3 / 3
+                report(f"e2e 4x4 f32 2^24 PAGEABLE host operands, {os.environ.get('SLAS_CUDA_HOST_COPY_THREADS')} copy threads, slot {mb} MB, "
+                       f"{'cached' if nt else 'streaming'} stores", ms, nbytes=3.0 * b * 64, flop=128.0 * b)
+        set_tunable("host_slot_mb", 0)
+        set_tunable("host_copy_nt", 0)
+        # a plain 1 GiB numpy copy on one thread, for scale
+        t0 = time.perf_counter()
+        Cm[:] = A
+        report("numpy 1 GiB copy, one thread", (time.perf_counter() - t0) * 1e3, nbytes=2.0 * b * 64)
+        return
+    for threads in (4, 8, 12, 16):
+        env = dict(os.environ, SLAS_TUNE_PAGEABLE_CHILD="1", SLAS_CUDA_HOST_COPY_THREADS=str(threads))
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "pageable"], env=env, capture_output=True, text=True)
+        sys.stdout.write(r.stdout)
+        if r.returncode:
+            sys.stdout.write(r.stderr[-2000:])
+        sys.stdout.flush()
+
+
 def g_gemv():
     for size, dt, log2 in ((4, np.float32, 24), (16, np.float32, 20), (32, np.float32, 20), (16, np.float64, 20), (32, np.float64, 20),
                            (64, np.float32, 18)):
@@ -287,8 +323,9 @@ def g_small():
                     ("balanced 512 x 2/SM, flagged words, PDL wait-at-top", {"reduce_small_threads": 512}),
                     ("balanced 512 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 512, "pdl": 2}),
                     ("balanced 512 x 1/SM, flagged words, PDL early loads", {"reduce_small_threads": 512, "reduce_small_cps": 1, "pdl": 2}),
-                    ("balanced 1024 x 1/SM, flagged words, plain launch", {"pdl": 1}),
-                    ("balanced 1024 x 1/SM, flagged words, PDL early loads", {"pdl": 2}),
+                    ("balanced 1024 x 1/SM, flagged words, plain launch", {"reduce_small_threads": 1024, "pdl": 1}),
+                    ("balanced 1024 x 1/SM, flagged words, PDL early loads", {"reduce_small_threads": 1024, "pdl": 2}),
+                    ("default geometry, PDL early loads", {"pdl": 2}),
                     ("balanced 256 x 4/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "pdl": 2}),
                     ("balanced 256 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "reduce_small_cps": 2, "pdl": 2}),
                     ("balanced 512 x 2/SM, ticket, PDL early loads", {"reduce_small_threads": 512, "reduce_small_tail": 1, "pdl": 2})]
@@ -327,6 +364,7 @@ def g_small():
 
 GROUPS = {
     "small": g_small,
+    "pageable": g_pageable,
     "misc": g_misc,
     "rect": g_rect,
     "gemv": g_gemv,

@@ -80,7 +80,7 @@ struct Context {
     struct Span { const char *lo, *hi; };
     struct HazardOp { Span reads[2], writes[2]; };
     struct Hazard {
-        static constexpr int kWindow = 8;   // == kRedScratchSets: a kernel of the window owns one scratch set
+        static constexpr int kWindow = 32;  // == kRedScratchSets: a kernel of the window owns one scratch set
         uint64_t seq = ~0ull;            // g_launches right after the last recorded launch; anything launched since voids it
         cudaStream_t stream = nullptr;
         HazardOp ops[kWindow];
@@ -97,7 +97,7 @@ bool hazard_early_ok(const Context *ctx, cudaStream_t st, const Context::Span *r
 void hazard_record(Context *ctx, cudaStream_t st, const Context::Span *reads, int nr, const Context::Span *writes, int nw, int early);
 
 constexpr int kMaxPartials = 148 * 16;
-constexpr int kRedScratchSets = 8;
+constexpr int kRedScratchSets = 32;
 
 // Returns the context of the current device, initialising it on first use.
 int get_context(Context **out);

@@ -5,6 +5,7 @@
 // more DRAM traffic on a path that is host-memory-bandwidth bound.
 #include <immintrin.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -42,8 +43,8 @@ __attribute__((target("avx2"))) void stream_copy_avx2(char *dst, const char *src
 }
 
 void copy_piece(char *dst, const char *src, size_t bytes) {
-    static const bool avx2 = __builtin_cpu_supports("avx2") && tunable("host_copy_nt") != 1;
-    if (avx2 && bytes >= 4096) stream_copy_avx2(dst, src, bytes);
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && bytes >= 4096 && tunable("host_copy_nt") != 1) stream_copy_avx2(dst, src, bytes);
     else memcpy(dst, src, bytes);
 }
 
@@ -99,7 +100,11 @@ struct CopyPool {
 std::once_flag g_pool_once;
 
 int pool_threads() {
-    const long knob = tunable("host_copy_threads");
+    long knob = tunable("host_copy_threads");
+    if (knob <= 0) {
+        const char *env = getenv("SLAS_CUDA_HOST_COPY_THREADS");  // run-time knob in the style of SLAS_CUDA_DEVICES
+        if (env) knob = atol(env);
+    }
     if (knob > 0) return (int)(knob > 64 ? 64 : knob);
     const unsigned hw = std::thread::hardware_concurrency();
     int n = hw ? (int)hw / 2 : 4;

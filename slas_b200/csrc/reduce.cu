@@ -30,10 +30,14 @@ RedGeom reduce_geometry(const Context *ctx, size_t work, bool vectorised) {
         g.threads = 256;
         return g;
     }
+    // Measured on B200 (profiles/r2d_tune_small.log, 256 distinct 2^20-element pairs replayed from a graph): back-to-back
+    // calls overlap (dependent launch), and the smaller a kernel's footprint per SM the more of its successor fits next
+    // to it -- 256 threads x 2 CTAs per SM: 2.85 us per call, 512 x 1: 3.05, 512 x 2: 3.33, 1024 x 1: 3.58 (an isolated
+    // kernel is fastest the other way round: 1024 x 1 writes its result 3.3 us after it starts, 256 x 2 after 5.3 us).
     long threads = tunable("reduce_small_threads");      // 256 / 512 / 1024; 0 = default
-    if (threads != 256 && threads != 512 && threads != 1024) threads = 1024;
-    long cps = tunable("reduce_small_cps");              // CTAs per SM; 0 = as many as keep 1024 threads per SM
-    if (cps <= 0) cps = 1024 / threads;
+    if (threads != 256 && threads != 512 && threads != 1024) threads = 256;
+    long cps = tunable("reduce_small_cps");              // CTAs per SM; 0 = default
+    if (cps <= 0) cps = threads == 256 ? 2 : 1024 / threads;
     if (cps * threads > 2048) cps = 2048 / threads;
     g.threads = (unsigned)threads;
     g.balanced = 1;
