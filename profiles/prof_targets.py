@@ -72,6 +72,19 @@ def vector_ops():
     synchronize()
 
 
+def vector_small():
+    """BASELINE configs[0] as written: single dot / add calls at LEN 2^20 on distinct operands (balanced one-wave
+    geometry, flagged-word combine, dependent launch)"""
+    n, calls = 1 << 20, 24
+    a, b, c = uniform(calls * n, np.float32, 3, 0, 1), uniform(calls * n, np.float32, 4, 0, 1), CudaVec(calls * n, np.float32)
+    out = CudaVec(calls, np.float32)
+    for i in range(calls):
+        _lib.call("slas_cuda_sdot", n, a.as_ptr() + 4 * i * n, b.as_ptr() + 4 * i * n, out.as_ptr() + 4 * i)
+    for i in range(calls):
+        _lib.call("slas_cuda_sadd", n, a.as_ptr() + 4 * i * n, b.as_ptr() + 4 * i * n, c.as_ptr() + 4 * i * n)
+    synchronize()
+
+
 def gemm_large(path):
     n = 4096
     a, b, c = uniform(n * n, np.float32, 5), uniform(n * n, np.float32, 6), CudaVec(n * n, np.float32)
@@ -95,6 +108,7 @@ TARGETS = {
     "tr_i16": lambda: transpose_single(8192, np.int16),
     "small_odd": small_odd,
     "vector": vector_ops,
+    "vector_small": vector_small,
     "gemm4096_ffma": lambda: gemm_large("ffma"),
     "gemm4096_tc": lambda: gemm_large("tcgen05"),
 }
