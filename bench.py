@@ -376,6 +376,17 @@ def run_cuda(args):
         pC = np.zeros_like(pA)
         pageable_ms = time_host_steps(pA, pB, pC)
         assert np.array_equal(pC, hC), "pageable-operand result differs from the pinned-operand result"
+        # the same pageable arrays page-locked IN PLACE once (slas_cuda_host_register): what a program does with a
+        # long-lived Vec it wants the DMA engines to read directly
+        t_reg = time.perf_counter()
+        for arr in (pA, pB, pC):
+            _lib.call("slas_cuda_host_register", arr.ctypes.data, arr.nbytes)
+        t_reg = time.perf_counter() - t_reg
+        pC[:] = 0
+        registered_ms = time_host_steps(pA, pB, pC)
+        assert np.array_equal(pC, hC), "registered-operand result differs from the pinned-operand result"
+        for arr in (pA, pB, pC):
+            _lib.call("slas_cuda_host_unregister", arr.ctypes.data)
         del pA, pB, pC
         # the PCIe roofline of that step, measured here: pinned copies on their own (torch pinned buffers + cudaMemcpyAsync,
         # nothing of the library), one direction and both at once, all ranks at the same time (N > 1: the host-side
@@ -410,7 +421,11 @@ def run_cuda(args):
                "h2d_gbs_in_step": 2 * nbytes / (e2e_ms * 1e-3) / 1e9,
                "pageable": {"value": FLOP_PER_4X4 * batch * world / (pageable_ms * 1e-3) / 1e9, "ms_per_step": pageable_ms,
                             "frac_of_pinned": e2e_ms / pageable_ms,
-                            "how": "pageable numpy operands: copy threads stage them through a pinned bounce ring"},
+                            "how": "pageable numpy operands: copy threads stage them through a pinned bounce ring (3 passes over host "
+                                   "memory per byte instead of 1: host-DRAM bound)"},
+               "registered_in_place": {"value": FLOP_PER_4X4 * batch * world / (registered_ms * 1e-3) / 1e9, "ms_per_step": registered_ms,
+                                       "frac_of_pinned": e2e_ms / registered_ms, "one_time_register_s": t_reg,
+                                       "how": "the same pageable arrays after slas_cuda_host_register (page-locked in place, once)"},
                "copy_only": {"ranks_copying_at_once": world, "h2d_gbs_per_gpu": h2d_gbs, "d2h_gbs_per_gpu": d2h_gbs,
                              "bidir_gbs_each_way_per_gpu": nbytes / bidir_s / 1e9,
                              "step_floor_ms": max(2 * nbytes / (h2d_gbs * 1e9), nbytes / (d2h_gbs * 1e9)) * 1e3,
@@ -732,7 +747,71 @@ def run_cuda(args):
             finally:
                 sl.set_sgemm_path("auto")
             del a, b, c, va, vb, vc, flush
+        # ONE process driving all N GPUs (what a slas program is: a backend is a ZST made by B::default(), no launcher):
+        # rank 0 alone, the other ranks wait at the barrier below with their HBM released
         if world > 1:
+            torch.cuda.empty_cache()
+            dist.barrier()
+            if rank == 0:
+                from slas_b200.backends import init_devices
+                ndev = init_devices(world)
+                total = 1 << 32
+                sa, sb = [], []
+                for r in range(ndev):
+                    lo_, hi_ = sharding.shard_range(total, 4, ndev, r)
+                    va_, vb_ = CudaVec(hi_ - lo_, np.float32, device=r), CudaVec(hi_ - lo_, np.float32, device=r)
+                    _lib.call("slas_cuda_sfill_uniform", hi_ - lo_, va_.as_ptr(), 4, lo_, 0.0, 1.0)
+                    _lib.call("slas_cuda_sfill_uniform", hi_ - lo_, vb_.as_ptr(), 5, lo_, 0.0, 1.0)
+                    sa.append(va_)
+                    sb.append(vb_)
+                part = np.zeros(1, np.float64)
+                sum_parts = 0.0
+                for r in range(ndev):  # slice order, like the exchange inside the kernels
+                    _lib.call("slas_cuda_sdot_partial", sa[r].LEN, sa[r].as_ptr(), sb[r].as_ptr(), part.ctypes.data)
+                    sum_parts += float(part[0])
+
+                def wall(fn, reps=5):
+                    fn()
+                    ts = []
+                    for _ in range(reps):
+                        t0 = time.perf_counter()
+                        fn()
+                        ts.append((time.perf_counter() - t0) * 1e3)
+                    return float(np.median(ts))
+
+                got = cuda.dot_multi(sa, sb)
+                assert np.float32(got).tobytes() == np.float32(sum_parts).tobytes(), f"in-process sharded dot {got} != f32(sum of partials) {sum_parts}"
+                assert float(got) == configs["sharded_dot_p2p"]["result"], "one process / N processes disagree on the 2^32-element dot"
+                ms_ = wall(lambda: cuda.dot_multi(sa, sb))
+                rec("inproc_sharded_dot", ms_, f"ONE process, {ndev} GPUs (slas_cuda_init_devices): dot f32 over 2^32 elements, one device-resident slice per "
+                    f"GPU, exchange inside the kernels over peer memory, scalar returned to the host (wall clock of the call)",
+                    flop=2.0 * total, bytes_=8.0 * total, ranks=ndev,
+                    extra={"result": float(got), "parity": "== f32(slice-ordered sum of the f64 partials) == the N-process result"})
+                ms_ = wall(lambda: cuda.normalize_multi(sa))
+                rec("inproc_sharded_normalize", ms_, f"ONE process, {ndev} GPUs: normalize f32 over 2^32 elements (wall clock incl. a final synchronize per device)",
+                    bytes_=12.0 * total, ranks=ndev)
+                assert abs(float(cuda.norm_multi(sa)) - 1.0) < 1e-5
+                del sa, sb
+                # host operands (pinned) split over the devices by batch index: N PCIe links from one process
+                hb = 1 << 24
+                hp = [C.c_void_p() for _ in range(3)]
+                for p_ in hp:
+                    _lib.call("slas_cuda_malloc_host", C.byref(p_), hb * 64)
+                hA, hB, hC = [np.ctypeslib.as_array((C.c_float * (hb * 16)).from_address(p_.value)) for p_ in hp]
+                rng_ = np.random.default_rng(3)
+                hA[:] = rng_.random(hb * 16, dtype=np.float32)
+                hB[:] = rng_.random(hb * 16, dtype=np.float32)
+                ms_ = wall(lambda: cuda.matrix_mul_batched(hA, hB, hC, 4, 4, 4), reps=3)
+                want = oracle.gemm_batched(hA[-4096 * 16:], hB[-4096 * 16:], 4096, 4, 4, 4)
+                assert np.max(np.abs(hC[-4096 * 16:] - want)) <= 1e-5 * 2 * 4, "in-process split of the host batch differs from the oracle"
+                configs["inproc_mm4_host_e2e"] = {
+                    "what": f"ONE process, {ndev} GPUs: batched 4x4 f32 matrix_mul, 2^24 pairs in pinned HOST memory split over the devices by "
+                            f"batch index (per-device worker thread + 3-slot copy pipeline), wall clock of the call",
+                    "ms": ms_, "bound": "pcie / host memory", "achieved": 3.0 * hb * 64 / (ms_ * 1e-3) / 1e9, "unit": "GB/s over all links",
+                    "gflops": FLOP_PER_4X4 * hb / (ms_ * 1e-3) / 1e9,
+                    "n_process_e2e_ms_for_2^24_pairs_per_gpu": e2e["ms_per_step"] if e2e else None}
+                for p_ in hp:
+                    _lib.call("slas_cuda_free_host", p_.value)
             dist.barrier()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----

@@ -93,6 +93,14 @@ int slas_cuda_malloc(void **dptr, size_t bytes);
 int slas_cuda_free(void *dptr);
 int slas_cuda_malloc_host(void **hptr, size_t bytes);   /* pinned */
 int slas_cuda_free_host(void *hptr);
+/* Host operands.  What a slas StaticVec hands over is PAGEABLE memory ([T; LEN] / Vec, src/static_vec.rs:126): the
+ * library stages it through its own pinned bounce ring with a pool of copy threads (streaming stores), overlapped with
+ * the DMA engines -- three passes over host memory per byte instead of one, so it runs at ~0.73 of the pinned rate on
+ * a host whose DRAM is the limit.  Memory from slas_cuda_malloc_host, or a caller's own long-lived allocation
+ * registered in place with slas_cuda_host_register (unregister before freeing it), is read / written by the DMA
+ * engines directly. */
+int slas_cuda_host_register(void *hptr, size_t bytes);
+int slas_cuda_host_unregister(void *hptr);
 int slas_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int slas_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes);
 int slas_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes);

@@ -50,6 +50,8 @@ extern "C" {
     fn slas_cuda_free(dptr: *mut c_void) -> c_int;
     fn slas_cuda_malloc_host(hptr: *mut *mut c_void, bytes: usize) -> c_int;
     fn slas_cuda_free_host(hptr: *mut c_void) -> c_int;
+    fn slas_cuda_host_register(hptr: *mut c_void, bytes: usize) -> c_int;
+    fn slas_cuda_host_unregister(hptr: *mut c_void) -> c_int;
     fn slas_cuda_memcpy_h2d(dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     fn slas_cuda_memcpy_d2h(dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     fn slas_cuda_memcpy_d2d(dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
@@ -492,6 +494,10 @@ impl_cuda_sharded!(f32, slas_cuda_sdot_sharded, slas_cuda_snrm2_sharded, slas_cu
 impl_cuda_sharded!(f64, slas_cuda_ddot_sharded, slas_cuda_dnrm2_sharded, slas_cuda_dnormalize_sharded, slas_cuda_ddot_multi, slas_cuda_dnrm2_multi, slas_cuda_dnormalize_multi);
 
 impl Cuda {
+    /// Page-lock a long-lived host allocation in place (a `Vec`, a `Box<[T; LEN]>`): its operands are then copied by the
+    /// DMA engines directly instead of through the library's bounce ring.  Call `host_unregister` before freeing it.
+    pub unsafe fn host_register<T>(data: &mut [T]) { check(slas_cuda_host_register(data.as_mut_ptr() as *mut c_void, std::mem::size_of_val(data))); }
+    pub unsafe fn host_unregister<T>(data: &mut [T]) { check(slas_cuda_host_unregister(data.as_mut_ptr() as *mut c_void)); }
     /// Drive `n` GPUs from this one process (0 = every visible device); same as `SLAS_CUDA_DEVICES=n` in the environment.
     pub fn init_devices(n: usize) -> usize {
         check(unsafe { slas_cuda_init_devices(n as c_int) });

@@ -63,6 +63,8 @@ SIGNATURES = {
     "slas_cuda_free": [_vp],
     "slas_cuda_malloc_host": [C.POINTER(_vp), _sz],
     "slas_cuda_free_host": [_vp],
+    "slas_cuda_host_register": [_vp, _sz],
+    "slas_cuda_host_unregister": [_vp],
     "slas_cuda_memcpy_h2d": [_vp, _vp, _sz],
     "slas_cuda_memcpy_d2h": [_vp, _vp, _sz],
     "slas_cuda_memcpy_d2d": [_vp, _vp, _sz],

@@ -68,9 +68,10 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
         if (!pageable && ops[i].unit_bytes && host_pointer_pageable(ops[i].host)) pageable = true;
     }
     if (pageable && units * unit_total < ((size_t)4 << 20)) pageable = false;  // small: the driver's own bounce is fine
-    // 96 MB slots by default (24 MB through the bounce ring); "host_slot_mb" is the sweep knob (profiles/tune.py e2e)
+    // 96 MB slots by default (64 MB through the bounce ring: measured 58.7 ms per 3 GiB step against 66.6 at 24 MB and
+    // 99 at 8 MB, profiles/r2e_tune_pageable.log); "host_slot_mb" is the sweep knob (profiles/tune.py e2e / pageable)
     const long slot_mb = tunable("host_slot_mb");
-    const size_t kSlotBytes = (size_t)(slot_mb > 0 ? slot_mb : (pageable ? 24 : 96)) << 20;
+    const size_t kSlotBytes = (size_t)(slot_mb > 0 ? slot_mb : (pageable ? 64 : 96)) << 20;
     size_t chunk = kSlotBytes / (unit_total ? unit_total : 1);
     chunk = chunk / granule * granule;
     if (chunk == 0) chunk = granule;

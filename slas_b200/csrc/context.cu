@@ -485,6 +485,21 @@ int slas_cuda_malloc_host(void **hptr, size_t bytes) {
     return SLAS_OK;
 }
 
+// Page-lock memory the caller already owns (a Vec / Box / numpy array), in place: from then on it is a pinned operand
+// -- copied from directly by the DMA engines instead of through the bounce ring.  The caller unregisters before freeing.
+int slas_cuda_host_register(void *hptr, size_t bytes) {
+    SLAS_REQUIRE(hptr && bytes, "host_register: null pointer or zero size");
+    Context *c;
+    SLAS_TRY(get_context(&c));
+    SLAS_CUDA_TRY(cudaHostRegister(hptr, bytes, cudaHostRegisterPortable));
+    return SLAS_OK;
+}
+int slas_cuda_host_unregister(void *hptr) {
+    if (!hptr) return SLAS_OK;
+    SLAS_CUDA_TRY(cudaHostUnregister(hptr));
+    return SLAS_OK;
+}
+
 int slas_cuda_free_host(void *hptr) {
     if (!hptr) return SLAS_OK;
     SLAS_CUDA_TRY(cudaFreeHost(hptr));

@@ -106,10 +106,12 @@ int pool_threads() {
         if (env) knob = atol(env);
     }
     if (knob > 0) return (int)(knob > 64 ? 64 : knob);
+    // measured on the 16-core B200 host (profiles/r2e_tune_pageable.log): 4 threads 92 ms, 8 threads 66 ms, 12 threads
+    // 58.7 ms, 16 threads 60 ms per 3 GiB step -- at 12 the host DRAM is the limit (9 GiB cross it per step)
     const unsigned hw = std::thread::hardware_concurrency();
-    int n = hw ? (int)hw / 2 : 4;
+    int n = hw ? (int)(hw * 3 / 4) : 4;
     if (n < 2) n = 2;
-    if (n > 8) n = 8;
+    if (n > 12) n = 12;
     return n;
 }
 

@@ -278,3 +278,21 @@ def test_transpose_elements_of_any_size(elem, rows, cols, batch):
         r2 = ln // cols
         w2 = raw2[:cols * r2 * elem].reshape(cols, r2, elem).transpose(1, 0, 2).reshape(-1)
         assert np.array_equal(out.view(np.uint8)[:r2 * cols * elem], w2) and np.all(out.view(np.uint8)[r2 * cols * elem:] == 0xAB)
+
+
+def test_host_register_makes_a_callers_array_a_pinned_operand():
+    rng = np.random.default_rng(61)
+    n = 6_000_011
+    a, b = _rand(rng, n, np.float32), _rand(rng, n, np.float32)
+    want = np.empty_like(a)
+    cuda.add(a, b, want)                      # pageable: through the bounce ring
+    c = np.zeros_like(a)
+    for arr in (a, b, c):
+        L.call("slas_cuda_host_register", arr.ctypes.data, arr.nbytes)
+    try:
+        cuda.add(a, b, c)                     # registered in place: direct DMA
+        assert np.array_equal(c, want) and np.array_equal(c, a + b)
+        assert float(cuda.dot(a, b)) == float(cuda.dot(CudaVec.from_host(a), CudaVec.from_host(b)))
+    finally:
+        for arr in (a, b, c):
+            L.call("slas_cuda_host_unregister", arr.ctypes.data)
