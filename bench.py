@@ -570,6 +570,9 @@ def run_cuda(args):
         rec("dot_2^20x1024", ms_, "dot f32 LEN=2^20 x 1024 distinct pairs (one batched launch, 8 GiB)", flop=2.0 * 1024 * l20, bytes_=8.0 * 1024 * l20)
         del a4, b4
 
+        # Back-to-back short calls overlap (programmatic dependent launch) when nothing but this library enqueues on the
+        # stream between them: automatic on the library's own stream; on a stream shared with another library (here:
+        # torch's, for the events) the caller vouches for it with the tunable "pdl" = 2.  Both are reported.
         ncalls = 256
         for opname, opid, bytes_per in (("dot", 0, 8.0), ("add", 1, 12.0)):
             dst = out if opid == 0 else c
@@ -584,17 +587,27 @@ def run_cuda(args):
             def c_loop():
                 _lib.call("slas_cuda_bench_call_loop", opid, l20, a.data_ptr(), b.data_ptr(), dst.data_ptr(), ncalls, l20)
 
+            ms_py0, _ = timed(py_loop, 3, 1)
+            ms_c0, _ = timed(c_loop, 5, 2)
+            with sl.Graph() as g:
+                c_loop()
+            ms_g0, _ = timed(g.launch, 10, 3)
+            del g
+            _lib.call("slas_cuda_set_tunable", b"pdl", 2)
             ms_py, _ = timed(py_loop, 3, 1)
             ms_c, _ = timed(c_loop, 5, 2)
             with sl.Graph() as g:
                 c_loop()
             ms_g, _ = timed(g.launch, 10, 3)
             del g
+            _lib.call("slas_cuda_set_tunable", b"pdl", 0)
             rec(f"{opname}_2^20_single", ms_g / ncalls, f"{opname} f32 LEN=2^20, one call per pair, {ncalls} distinct pairs (2-3 GiB >> L2), replayed from one "
-                f"CUDA graph (slas_cuda_graph_*): per-call time", bytes_=bytes_per * l20,
+                f"CUDA graph (slas_cuda_graph_*), back-to-back calls overlapping (dependent launch): per-call time", bytes_=bytes_per * l20,
                 extra={"us_per_call_graph": ms_g * 1e3 / ncalls, "us_per_call_c_loop": ms_c * 1e3 / ncalls,
                        "us_per_call_python_loop": ms_py * 1e3 / ncalls,
                        "frac_c_loop": bytes_per * l20 / (ms_c * 1e-3 / ncalls) / 1e9 / peak_gbs,
+                       "shared_stream_no_overlap": {"us_per_call_graph": ms_g0 * 1e3 / ncalls, "us_per_call_c_loop": ms_c0 * 1e3 / ncalls,
+                                                    "us_per_call_python_loop": ms_py0 * 1e3 / ncalls},
                        "hbm_floor_us": bytes_per * l20 / (peak_gbs * 1e9) * 1e6})
         # phases of one cold 2^20 dot kernel (%globaltimer inside the kernel)
         _lib.call("slas_cuda_set_tunable", b"reduce_phases", 1)

@@ -325,7 +325,9 @@ def g_small():
                     ("balanced 512 x 1/SM, flagged words, PDL early loads", {"reduce_small_threads": 512, "reduce_small_cps": 1, "pdl": 2}),
                     ("balanced 1024 x 1/SM, flagged words, plain launch", {"reduce_small_threads": 1024, "pdl": 1}),
                     ("balanced 1024 x 1/SM, flagged words, PDL early loads", {"reduce_small_threads": 1024, "pdl": 2}),
+                    ("balanced 1024 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 1024, "reduce_small_cps": 2, "pdl": 2}),
                     ("default geometry, PDL early loads", {"pdl": 2}),
+                    ("default geometry, plain launch", {"pdl": 1}),
                     ("balanced 256 x 4/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "pdl": 2}),
                     ("balanced 256 x 2/SM, flagged words, PDL early loads", {"reduce_small_threads": 256, "reduce_small_cps": 2, "pdl": 2}),
                     ("balanced 512 x 2/SM, ticket, PDL early loads", {"reduce_small_threads": 512, "reduce_small_tail": 1, "pdl": 2})]

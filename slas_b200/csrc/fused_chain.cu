@@ -33,6 +33,7 @@ fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restri
     constexpr int N = Vec16<T>::N;
     constexpr int NRES = CHAIN == 4 ? 3 : 1;
     constexpr int OP = CHAIN < 4 ? CHAIN : 0;
+    constexpr int U = RedTile<THREADS>::U;  // reduce_kernel's tiling: same element-to-accumulator map, same bits
     __shared__ double red[THREADS / 32];
     __shared__ bool is_last;
     Reducer<T, 0> r0, r1, r2;
@@ -56,17 +57,17 @@ fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restri
                 r0.add(u, e, z);
             }
         };
-        for (; i + (size_t)(kRedUnroll - 1) * THREADS < end; i += stride) {
-            V x[kRedUnroll], y[kRedUnroll], z[kRedUnroll];
+        for (; i + (size_t)(U - 1) * THREADS < end; i += stride) {
+            V x[U], y[U], z[U];
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const size_t j = i + (size_t)u * THREADS;
                 x[u] = ld_stream(av + j);
                 y[u] = ld_stream(bv + j);
                 z[u] = CHAIN == 4 ? x[u] : ld_stream(dv + j);
             }
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) use(u, i + (size_t)u * THREADS, x[u], y[u], z[u]);
+            for (int u = 0; u < U; ++u) use(u, i + (size_t)u * THREADS, x[u], y[u], z[u]);
             if (++since_flush == kFlushEvery) {
                 r0.flush();
                 if (CHAIN == 4) { r1.flush(); r2.flush(); }
@@ -74,10 +75,10 @@ fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restri
             }
         }
         {
-            V x[kRedUnroll], y[kRedUnroll], z[kRedUnroll];
-            bool ok[kRedUnroll];
+            V x[U], y[U], z[U];
+            bool ok[U];
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const size_t j = i + (size_t)u * THREADS;
                 ok[u] = j < end;
                 x[u] = ok[u] ? ld_stream(av + j) : vzero((V *)nullptr);
@@ -85,7 +86,7 @@ fused_chain_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restri
                 z[u] = (CHAIN != 4 && ok[u]) ? ld_stream(dv + j) : x[u];
             }
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u)
+            for (int u = 0; u < U; ++u)
                 if (ok[u]) use(u, i + (size_t)u * THREADS, x[u], y[u], z[u]);
         }
         r0.flush();

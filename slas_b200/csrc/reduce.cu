@@ -72,13 +72,14 @@ RedScratch reduce_scratch(Context *ctx) {
 // mode 0: (T)sum [, (T)sum_im]   mode 1: (T)sqrt(sum).  If accumulate != 0 the previous
 // content of result[] is added first (chunked host vectors).
 template <typename T, int KIND, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, RedTile<THREADS>::MINB)
 reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size_t nvec, int vectorised, const RedGeom g,
               const RedScratch sc, double *__restrict__ result, T *__restrict__ typed_out, int mode, int accumulate,
               const PeerExchange px, unsigned head, int early) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     constexpr int NRES = KIND == 2 ? 2 : 1;
+    constexpr int U = RedTile<THREADS>::U;
     __shared__ double red[THREADS / 32];
     __shared__ double peer_vals[2 * kMaxPeers];
     __shared__ bool is_last;
@@ -100,38 +101,38 @@ reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t len, size
         size_t i, end, stride;
         red_range<THREADS>(g, nvec, i, end, stride);
         int since_flush = 0;
-        // full groups: all kRedUnroll vectors of this thread are in range
-        for (; i + (size_t)(kRedUnroll - 1) * THREADS < end; i += stride) {
-            V x[kRedUnroll], y[kRedUnroll];
+        // full groups: all U (RedTile) vectors of this thread are in range
+        for (; i + (size_t)(U - 1) * THREADS < end; i += stride) {
+            V x[U], y[U];
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) x[u] = ld_stream(av + i + (size_t)u * THREADS);
+            for (int u = 0; u < U; ++u) x[u] = ld_stream(av + i + (size_t)u * THREADS);
             if (KIND != 1) {
 #pragma unroll
-                for (int u = 0; u < kRedUnroll; ++u) y[u] = ld_stream(bv + i + (size_t)u * THREADS);
+                for (int u = 0; u < U; ++u) y[u] = ld_stream(bv + i + (size_t)u * THREADS);
             }
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
+            for (int u = 0; u < U; ++u) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
             if (++since_flush == kFlushEvery) { r.flush(); since_flush = 0; }
         }
         // ragged last group: every load is issued before the first use (this IS the whole body of a short vector)
         {
-            V x[kRedUnroll], y[kRedUnroll];
-            bool ok[kRedUnroll];
+            V x[U], y[U];
+            bool ok[U];
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const size_t j = i + (size_t)u * THREADS;
                 ok[u] = j < end;
                 x[u] = ok[u] ? ld_stream(av + j) : vzero((V *)nullptr);
             }
             if (KIND != 1) {
 #pragma unroll
-                for (int u = 0; u < kRedUnroll; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const size_t j = i + (size_t)u * THREADS;
                     y[u] = ok[u] ? ld_stream(bv + j) : vzero((V *)nullptr);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kRedUnroll; ++u)
+            for (int u = 0; u < U; ++u)
                 if (ok[u]) r.add(u, x[u], KIND == 1 ? x[u] : y[u]);
         }
         r.flush();

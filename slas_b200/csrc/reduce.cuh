@@ -30,6 +30,10 @@ __device__ __forceinline__ double2 vzero(double2 *) { return make_double2(0.0, 0
 
 constexpr int kRedUnroll = 4;
 constexpr int kFlushEvery = 16;  // outer iterations between flushes of the fp accumulators into f64
+// Loads in flight per thread and operand: 4 x 16 bytes for the 256- / 512-thread CTAs; the 1024-thread CTA keeps 2 (the
+// same bytes in flight per SM) so that reduce_kernel fits 32 registers per thread and TWO of them -- a kernel and its
+// dependent-launch successor -- are resident on an SM at once.
+template <int THREADS> struct RedTile { static constexpr int U = THREADS == 1024 ? 2 : kRedUnroll, MINB = THREADS == 1024 ? 2 : 1; };
 
 // KIND: 0 = dot (sum a*b), 1 = squared norm (sum a*a, one stream), 2 = complex dotu (two sums over interleaved pairs)
 template <typename T, int KIND>
@@ -158,7 +162,7 @@ __device__ __forceinline__ double ll_wait(LLSlot *slot) {
     return __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
 }
 
-// The range of 16-byte vectors this thread walks: i, i + THREADS, ... in groups of kRedUnroll, up to `end`.
+// The range of 16-byte vectors this thread walks: i, i + THREADS, ... in groups of RedTile<THREADS>::U, up to `end`.
 template <int THREADS>
 __device__ __forceinline__ void red_range(const RedGeom &g, size_t nvec, size_t &i, size_t &end, size_t &stride) {
     if (g.balanced) {
@@ -166,11 +170,11 @@ __device__ __forceinline__ void red_range(const RedGeom &g, size_t nvec, size_t 
         if (lo > nvec) lo = nvec;
         end = lo + g.per < nvec ? lo + (size_t)g.per : nvec;
         i = lo + threadIdx.x;
-        stride = (size_t)THREADS * kRedUnroll;
+        stride = (size_t)THREADS * RedTile<THREADS>::U;
     } else {
-        i = (size_t)blockIdx.x * (THREADS * kRedUnroll) + threadIdx.x;
+        i = (size_t)blockIdx.x * (THREADS * RedTile<THREADS>::U) + threadIdx.x;
         end = nvec;
-        stride = (size_t)gridDim.x * (THREADS * kRedUnroll);
+        stride = (size_t)gridDim.x * (THREADS * RedTile<THREADS>::U);
     }
 }
 
