@@ -257,8 +257,10 @@ def run_cuda(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")  # a barrier that keeps the GPUs idle (the one-process rows below)
     stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream shared by torch's events and the library
     torch.cuda.set_stream(stream)
     sl.set_stream(stream.cuda_stream)
@@ -764,7 +766,8 @@ def run_cuda(args):
         # rank 0 alone, the other ranks wait at the barrier below with their HBM released
         if world > 1:
             torch.cuda.empty_cache()
-            dist.barrier()
+            barrier()
+            dist.barrier(group=host_group)
             if rank == 0:
                 from slas_b200.backends import init_devices
                 ndev = init_devices(world)
@@ -800,7 +803,12 @@ def run_cuda(args):
                     f"GPU, exchange inside the kernels over peer memory, scalar returned to the host (wall clock of the call)",
                     flop=2.0 * total, bytes_=8.0 * total, ranks=ndev,
                     extra={"result": float(got), "parity": "== f32(slice-ordered sum of the f64 partials) == the N-process result"})
-                ms_ = wall(lambda: cuda.normalize_multi(sa))
+                def normalize_all():
+                    cuda.normalize_multi(sa)
+                    for r_ in range(ndev):
+                        torch.cuda.synchronize(r_)
+
+                ms_ = wall(normalize_all)
                 rec("inproc_sharded_normalize", ms_, f"ONE process, {ndev} GPUs: normalize f32 over 2^32 elements (wall clock incl. a final synchronize per device)",
                     bytes_=12.0 * total, ranks=ndev)
                 assert abs(float(cuda.norm_multi(sa)) - 1.0) < 1e-5
@@ -825,7 +833,7 @@ def run_cuda(args):
                     "n_process_e2e_ms_for_2^24_pairs_per_gpu": e2e["ms_per_step"] if e2e else None}
                 for p_ in hp:
                     _lib.call("slas_cuda_free_host", p_.value)
-            dist.barrier()
+            dist.barrier(group=host_group)  # CPU-side wait: no NCCL kernel spins on the GPUs rank 0 is driving
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None

@@ -20,6 +20,7 @@ def test_sharded_ops_across_gpus(world):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_multi_gpu_worker.py")],
                        capture_output=True, text=True, timeout=600)
+    print(r.stdout[-600:])  # `pytest -s` keeps the MULTI_GPU_OK line (with the observed error / bar ratios) in the log
     assert r.returncode == 0 and f"MULTI_GPU_OK {world}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
@@ -31,4 +32,5 @@ def test_single_process_several_devices(ndev):
         pytest.skip(f"needs {ndev} GPUs")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_multi_device_worker.py"), str(ndev)],
                        capture_output=True, text=True, timeout=600)
+    print(r.stdout[-600:])
     assert r.returncode == 0 and f"MULTI_DEVICE_OK {ndev}" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
