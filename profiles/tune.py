@@ -364,7 +364,21 @@ def g_small():
         torch.cuda.empty_cache()
 
 
+def g_vec3():
+    """3-vector dot / norm / normalize (bulk-TMA staged, a thread per vector): stage size (CTAs per SM)"""
+    b = 1 << 24
+    (_, x), (_, y) = uniform(b * 3, np.float32, 1), uniform(b * 3, np.float32, 2)
+    (_, o) = uniform(b, np.float32, 3)
+    for kb in (0, 4, 8, 12, 24, 32):
+        set_tunable("bdot_stage_kb", kb)
+        report(f"batched 3-vector f32 dot, 2^24, stage {kb or 16} KB", timed(lambda: cuda.dot_batched(x, y, o, 3)), nbytes=28.0 * b)
+        report(f"batched 3-vector f32 norm, 2^24, stage {kb or 16} KB", timed(lambda: cuda.norm_batched(x, o, 3)), nbytes=16.0 * b)
+        report(f"batched 3-vector f32 normalize, 2^24, stage {kb or 16} KB", timed(lambda: cuda.normalize_batched(x, 3)), nbytes=24.0 * b)
+    set_tunable("bdot_stage_kb", 0)
+
+
 GROUPS = {
+    "vec3": g_vec3,
     "small": g_small,
     "pageable": g_pageable,
     "misc": g_misc,

@@ -652,7 +652,8 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    size_t G = (16 * 1024 / vbytes) / galign * galign;
+    const long stage_kb = tunable("bdot_stage_kb") > 0 ? tunable("bdot_stage_kb") : 16;
+    size_t G = ((size_t)stage_kb * 1024 / vbytes) / galign * galign;
     if (G > 1024) G = 1024 / galign * galign;
     if (G < galign) G = galign;
     const size_t stage_bytes = (G * vbytes + 127) / 128 * 128;
