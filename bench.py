@@ -435,6 +435,10 @@ def run_cuda(args):
                                      "host-memory ceiling of the e2e step, which moves 2 GiB down and 1 GiB up per GPU"},
                "api": "slas_cuda_sgemm_batched with host pointers (3-slot H2D/kernel/D2H pipeline)"}
         e2e["frac_of_copy_floor"] = e2e["copy_only"]["step_floor_ms"] / e2e_ms
+        # all links together: what the step moves per second over the whole box against what bare copies reach
+        e2e["aggregate_gbs_in_step"] = 3 * nbytes * world / (e2e_ms * 1e-3) / 1e9
+        e2e["copy_only"]["aggregate_gbs"] = {"h2d_alone": h2d_gbs * world, "d2h_alone": d2h_gbs * world,
+                                             "both_directions_at_once": 2 * nbytes / bidir_s / 1e9 * world}
         _lib.call("slas_cuda_free_host", hp[2].value)
         del hC
 
