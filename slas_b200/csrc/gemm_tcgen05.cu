@@ -1,7 +1,9 @@
 // gemm_tcgen05.cu -- the tensor-core path for ONE large dense f32 MatrixMul::matrix_mul
 // (the cblas_sgemm call of src/backends/blas.rs:94-109 at BASELINE config 4, 4096^3):
-// 3xTF32 on the 5th-generation tensor cores.  Selected with slas_cuda_set_sgemm_path(1); the
-// default for f32 stays the reference-faithful FFMA kernel (gemm_large.cu).
+// 3xTF32 on the 5th-generation tensor cores.  This IS the default for f32 products of >= 2^27 multiply-adds whose
+// padding to whole tiles adds <= 60 % work (api.cu, slas_cuda_set_sgemm_path(2) = auto); path 0 forces the
+// reference-faithful FFMA kernel (gemm_large.cu: every C element an ascending-k fp32 chain), path 1 this kernel wherever
+// its tiling applies.
 //
 // Numerics.  Every f32 operand x is split as x = hi + lo + e with hi = rna_tf32(x),
 // lo = rna_tf32(x - hi), |e| <= 2^-22 |x|, and
