@@ -108,17 +108,18 @@ def test_dot_add_len_2_28():
 
 
 def test_host_pointer_pipeline_crosses_chunk_boundaries():
-    """The reference's calling convention is HOST pointers; large host operands go through the 3-slot
-    H2D / kernel / D2H pipeline in chunks of ~96 MB.  Every byte must land where the one-shot device path puts it,
-    including ragged final chunks (bit-exact: same kernels, same per-object arithmetic)."""
+    """The reference's calling convention is HOST pointers -- pageable ones (numpy arrays here, [T; LEN] / Vec there):
+    large host operands go through the 3-slot H2D / kernel / D2H pipeline in chunks of ~64 MB, staged through the pinned
+    bounce ring by the copy threads.  Every byte must land where the one-shot device path puts it, including ragged
+    final chunks (bit-exact: same kernels, same per-object arithmetic)."""
     rng = np.random.default_rng(77)
-    # element-wise: 3 operands x 4 B -> 8M-element chunks; 20M + 5 elements = 3 chunks, ragged tail
+    # element-wise: 3 operands x 4 B -> ~5.6M-element chunks; 20M + 5 elements = 4 chunks, ragged tail
     n = 20_000_005
     a, b = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32) + 0.5
     c = np.empty_like(a)
     cuda.div(a, b, c)
     assert np.array_equal(c, a / b)
-    # batched 4x4 product: 192 B per pair -> 524288-pair chunks; 1.3M + 3 pairs = 3 chunks
+    # batched 4x4 product: 192 B per pair -> ~350K-pair chunks; 1.3M + 3 pairs = 4 chunks
     batch = 1_300_003
     A = rng.integers(-4, 5, batch * 16).astype(np.float32)
     B = rng.integers(-4, 5, batch * 16).astype(np.float32)
