@@ -397,7 +397,7 @@ GROUPS = {
     "gemm64": lambda: (g_gemm("gemm32s_variant", 64, np.float32, (0,), 18), g_gemm("gemm32d_variant", 64, np.float64, (0,), 17),
                        g_gemm("gemm4s_variant", 8, np.float32, (0,), 22), g_gemm("gemm4s_variant", 8, np.float64, (0,), 22),
                        g_gemm("gemm4s_variant", 4, np.float64, (0,), 24)),
-    "large": lambda: g_large("ffma", "gemm_large_variant", (0, 4, 1, 2)),  # 0 interior BK=16 kernel, 4 general BK=8 kernel, 1 cp.async ring, 2 no pre-transposition
+    "large": lambda: g_large("ffma", "gemm_large_variant", (0, 2)),  # 0 default, 2 no pre-transposition of the operands
     "tc": lambda: g_large("tcgen05", "tc_variant", (0, 1, 2, 3)),
 }
 

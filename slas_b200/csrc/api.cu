@@ -429,12 +429,6 @@ static int gemm_device(Context *ctx, cudaStream_t st, size_t batch, const T *a, 
                                               ldc, ta, tb);
             if (r != SLAS_ERR_UNSUPPORTED) return r;
         }
-        // measured on B200 (profiles/r1b_tune.log): the register-staged kernel of gemm_large.cu holds 43.4
-        // TFLOP/s at 4096^3, the cp.async ring of gemm_ffma.cu 41.8 -- the latter stays a benchmark variant
-        if (sizeof(T) == 4 && tunable("gemm_large_variant") == 1) {
-            const int r = launch_sgemm_ffma(ctx, st, (const float *)a, (const float *)b, (float *)c, m, n, k, lda, ldb, ldc, ta, tb);
-            if (r != SLAS_ERR_UNSUPPORTED) return r;
-        }
         // The FFMA kernel is fastest when A arrives k-major (a_trans) and B n-major (!b_trans): both tiles then go
         // to shared memory with 128-bit stores (measured 50.6 vs 43.4 TFLOP/s at 4096^3).  For a big enough dense
         // f32 product it pays to put the operands into that form first with the HBM-speed transpose kernels

@@ -372,6 +372,7 @@ int slas_cuda_graph_begin(void) {
     SLAS_REQUIRE(!c->capturing, "graph_begin: a capture is already open on this device");
     SLAS_CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
     c->capturing = true;
+    c->hazard.n = 0;  // the first recorded kernel is a barrier kernel: a replay may follow anything
     return SLAS_OK;
 }
 
@@ -382,6 +383,7 @@ int slas_cuda_graph_end(void **graph_exec) {
     std::lock_guard<std::mutex> lk(c->mu);
     SLAS_REQUIRE(c->capturing, "graph_end without graph_begin");
     c->capturing = false;
+    c->hazard.n = 0;  // recorded kernels have not run: nothing of them is in flight
     cudaGraph_t graph = nullptr;
     SLAS_CUDA_TRY(cudaStreamEndCapture(c->stream, &graph));
     cudaGraphExec_t exec = nullptr;

@@ -10,6 +10,14 @@
 //   memory, double buffered, with the next tile's global loads in flight during the FMAs.
 // Any m, n, k, leading dimensions and op(A)/op(B) are accepted: interior tiles use 128-bit
 // loads, edge tiles fall back to guarded scalar loads with zero fill.
+//
+// Where the time goes at 4096^3 (ncu --set full, profiles/r2i_ncu_summary.csv, r2i_ffma_stalls.txt): FMA pipe 69 %
+// busy, 84 % of the loop's instructions are FFMA, the schedulers issue on ~90 % of the cycles (stall_dispatch 10 %,
+// barrier 7 %); shared memory is conflict-free (wavefronts == ideal).  Two rewrites were measured and dropped
+// (profiles/r2j_tune_large.log, r1b_tune.log): an interior-only kernel with 16 k-steps per stage and no guards (90.6 %
+// FFMA in the loop) ran 48.0 TFLOP/s against this kernel's 49.6, a cp.async multi-stage ring 41.8 -- the kernel is not
+// bound by its bookkeeping instructions; it sits at 0.80 of what a register-only FFMA loop reaches on this chip
+// (60.9 TFLOP/s, microbench.cu).
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -152,80 +160,6 @@ gemm_large_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restric
         }
 }
 
-// ---- interior fast path (f32): the layout api.cu puts big dense products into -- A k-major (a[p*lda + i]), B n-major
-// (b[p*ldb + j]) -- with m, n multiples of 128, k a multiple of 16 and every pointer / leading dimension 16-byte
-// aligned.  Same CTA tile and the same 8 x 8 register tile (so the same ascending-k fp32 FMA chain per C element) as
-// gemm_large_kernel, but 16 k-steps per shared-memory stage and no bounds checks: ncu on the general kernel
-// (profiles/r2i_ncu_summary.csv, r2i_ffma_source.csv) showed the FMA pipe 69 % busy with 16 % of the issue slots going to
-// guards / address arithmetic and 8 % of the warp samples parked behind the per-stage barrier -- one barrier and one set
-// of global loads per 1024 FMAs instead of per 512 halves both.
-constexpr int kFastBK = 16;
-__global__ void __launch_bounds__(256, 2)
-sgemm_kn_interior_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ c, unsigned k, size_t lda,
-                         size_t ldb, size_t ldc) {
-    constexpr int BM = 128, BN = 128, BK = kFastBK, PAD = 4;
-    __shared__ __align__(16) float As[2][BK][BM + PAD];
-    __shared__ __align__(16) float Bs[2][BK][BN + PAD];
-    const size_t m0 = (size_t)blockIdx.y * BM, n0 = (size_t)blockIdx.x * BN;
-    const int t = threadIdx.x, tx = t % 16, ty = t / 16;
-    // this thread's two vectors of each operand tile: k rows kr and kr + 8, columns 4 * (t % 32)
-    const int kr = t / 32, cv = (t % 32) * 4;
-    const float *ap = a + (size_t)kr * lda + m0 + cv;
-    const float *bp = b + (size_t)kr * ldb + n0 + cv;
-    float acc[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    float4 ra0 = *reinterpret_cast<const float4 *>(ap), ra1 = *reinterpret_cast<const float4 *>(ap + 8 * lda);
-    float4 rb0 = *reinterpret_cast<const float4 *>(bp), rb1 = *reinterpret_cast<const float4 *>(bp + 8 * ldb);
-    *reinterpret_cast<float4 *>(&As[0][kr][cv]) = ra0;
-    *reinterpret_cast<float4 *>(&As[0][kr + 8][cv]) = ra1;
-    *reinterpret_cast<float4 *>(&Bs[0][kr][cv]) = rb0;
-    *reinterpret_cast<float4 *>(&Bs[0][kr + 8][cv]) = rb1;
-    __syncthreads();
-    const unsigned ktiles = k / BK;
-    for (unsigned kt = 0; kt < ktiles; ++kt) {
-        const int cur = (int)(kt & 1);
-        const bool more = kt + 1 < ktiles;
-        if (more) {
-            ap += (size_t)BK * lda;
-            bp += (size_t)BK * ldb;
-            ra0 = *reinterpret_cast<const float4 *>(ap);
-            ra1 = *reinterpret_cast<const float4 *>(ap + 8 * lda);
-            rb0 = *reinterpret_cast<const float4 *>(bp);
-            rb1 = *reinterpret_cast<const float4 *>(bp + 8 * ldb);
-        }
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            float av[8], bv[8];
-            *reinterpret_cast<float4 *>(&av[0]) = *reinterpret_cast<const float4 *>(&As[cur][kk][ty * 4]);
-            *reinterpret_cast<float4 *>(&av[4]) = *reinterpret_cast<const float4 *>(&As[cur][kk][BM / 2 + ty * 4]);
-            *reinterpret_cast<float4 *>(&bv[0]) = *reinterpret_cast<const float4 *>(&Bs[cur][kk][tx * 4]);
-            *reinterpret_cast<float4 *>(&bv[4]) = *reinterpret_cast<const float4 *>(&Bs[cur][kk][BN / 2 + tx * 4]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        if (more) {
-            *reinterpret_cast<float4 *>(&As[cur ^ 1][kr][cv]) = ra0;
-            *reinterpret_cast<float4 *>(&As[cur ^ 1][kr + 8][cv]) = ra1;
-            *reinterpret_cast<float4 *>(&Bs[cur ^ 1][kr][cv]) = rb0;
-            *reinterpret_cast<float4 *>(&Bs[cur ^ 1][kr + 8][cv]) = rb1;
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int hi = 0; hi < 2; ++hi)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float *dst = c + (m0 + hi * (BM / 2) + ty * 4 + i) * ldc + n0 + tx * 4;
-            *reinterpret_cast<float4 *>(dst) = *reinterpret_cast<const float4 *>(&acc[hi * 4 + i][0]);
-            *reinterpret_cast<float4 *>(dst + BN / 2) = *reinterpret_cast<const float4 *>(&acc[hi * 4 + i][4]);
-        }
-}
-
 template <typename T>
 static int launch_gemm_large_z(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
                                size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb, size_t stride_a, size_t stride_b,
@@ -263,15 +197,6 @@ int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *
         // at least one full wave of 128 x 128 tiles: the big-tile DFMA kernel (gemm_large_f64.cu)
         if (((m + 127) / 128) * ((n + 127) / 128) >= (size_t)ctx->sm_count && tunable("gemm_large_variant") != 3)
             return launch_dgemm_big(ctx, st, a, b, c, m, n, k, lda, ldb, ldc, ta, tb);
-    }
-    if constexpr (sizeof(T) == 4) {
-        if (ta && !tb && m % 128 == 0 && n % 128 == 0 && k % kFastBK == 0 && k >= kFastBK && k <= 0xffffffffu && aligned16(a) &&
-            aligned16(b) && aligned16(c) && lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && n / 128 <= 0x7fffffffu && m / 128 <= 65535 &&
-            tunable("gemm_large_variant") != 4) {
-            sgemm_kn_interior_kernel<<<dim3((unsigned)(n / 128), (unsigned)(m / 128)), 256, 0, st>>>(a, b, c, (unsigned)k, lda, ldb, ldc);
-            SLAS_LAUNCH_CHECK();
-            return SLAS_OK;
-        }
     }
     return launch_gemm_large_z<T>(ctx, st, 1, a, b, c, m, n, k, lda, ldb, ldc, ta, tb, 0, 0, 0);
 }

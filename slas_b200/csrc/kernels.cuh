@@ -64,10 +64,6 @@ template <typename T>
 int launch_gemm_large(Context *ctx, cudaStream_t st, const T *a, const T *b, T *c, size_t m, size_t n, size_t k,
                       size_t lda, size_t ldb, size_t ldc, int ta, int tb);
 
-// gemm_ffma.cu -- cp.async multi-stage FFMA kernel (aligned f32 operands); SLAS_ERR_UNSUPPORTED otherwise
-int launch_sgemm_ffma(Context *ctx, cudaStream_t st, const float *a, const float *b, float *c, size_t m, size_t n,
-                      size_t k, size_t lda, size_t ldb, size_t ldc, int ta, int tb);
-
 // gemm_tcgen05.cu -- 3xTF32 on the 5th-gen tensor cores (TMA + TMEM); SLAS_ERR_UNSUPPORTED
 // when the shape does not fit its tiles.
 // gemm_large.cu -- a batch of medium-sized products on the register-tiled FFMA / DFMA kernel, one grid layer per object
