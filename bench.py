@@ -615,6 +615,18 @@ def run_cuda(args):
                        "shared_stream_no_overlap": {"us_per_call_graph": ms_g0 * 1e3 / ncalls, "us_per_call_c_loop": ms_c0 * 1e3 / ncalls,
                                                     "us_per_call_python_loop": ms_py0 * 1e3 / ncalls},
                        "hbm_floor_us": bytes_per * l20 / (peak_gbs * 1e9) * 1e6})
+        # the reference's own calling pattern: `let x = a.dot(&b)` -- the scalar comes back to the host after EVERY call
+        # (tests/src/main.rs:589-601 benches exactly this loop).  Device-resident operands, distinct pairs, C loop.
+        def sync_loop():
+            _lib.call("slas_cuda_bench_call_loop", 2, l20, a.data_ptr(), b.data_ptr(), None, ncalls, l20)
+
+        ms_sync, _ = timed(sync_loop, 5, 2)
+        _lib.call("slas_cuda_set_tunable", b"host_result", 1)   # the round-1 way: device scalar + D2H copy + stream sync
+        ms_sync_copy, _ = timed(sync_loop, 5, 2)
+        _lib.call("slas_cuda_set_tunable", b"host_result", 0)
+        rec("dot_2^20_single_host_result", ms_sync / ncalls, f"dot f32 LEN=2^20 returning its scalar to the HOST after every call (`a.dot(&b)`), {ncalls} distinct "
+            f"device-resident pairs, C loop: per-call latency; the kernel stores the scalar into mapped pinned memory and the host spins on it",
+            bytes_=8.0 * l20, extra={"us_per_call": ms_sync * 1e3 / ncalls, "us_per_call_with_d2h_copy_and_stream_sync": ms_sync_copy * 1e3 / ncalls})
         # phases of one cold 2^20 dot kernel (%globaltimer inside the kernel)
         _lib.call("slas_cuda_set_tunable", b"reduce_phases", 1)
         ph = (C.c_uint64 * 5)()

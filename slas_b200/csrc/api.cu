@@ -227,6 +227,11 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
     const bool fused = need_collective && comm_next_peer_exchange(&px);
     if (fused) need_collective = false;
     if (out_dev && (len > 0 || fused)) typed = out;
+    // a scalar bound for the HOST (`let x = a.dot(&b)`): the kernel stores it into mapped pinned memory and the host
+    // spins on that word -- no device scalar, no D2H copy, no stream synchronisation
+    const bool direct_host = out && !out_dev && len > 0 && !need_collective && !fused && !partial_out && !ctx->capturing &&
+                             tunable("host_result") != 1;
+    if (direct_host) typed = static_cast<T *>(host_result_arm(ctx, sizeof(T) * nres));
     if (len == 0 && !fused) {
         // the reference returns the empty sum: 0 (and sqrt(0) = 0)
         SLAS_CUDA_TRY(cudaMemsetAsync(ctx->scalars, 0, sizeof(double) * 8, ctx->stream));
@@ -242,6 +247,7 @@ static int api_reduce(int kind, int mode, size_t len, const T *a, const T *b, T 
             return r;
         }
     }
+    if (direct_host) return host_result_wait(ctx, ctx->stream, out, sizeof(T), nres);
     if (need_collective) {
         SLAS_TRY(comm_allreduce_f64(res, nres, ctx->stream));
         SLAS_TRY(launch_finish_scalar<T>(ctx->stream, res, typed, mode));
@@ -314,7 +320,11 @@ static int api_fused_chain(int chain, size_t len, const T *a, const T *b, T *c, 
     bool dev = false;
     SLAS_TRY(operands_side(ptrs, 4, &dev));
     if (dev) {
+        // device operands, host-bound scalars: stored by the kernel into mapped pinned memory, the host spins (as api_reduce)
+        const bool direct_host = !out_dev && !ctx->capturing && tunable("host_result") != 1;
+        if (direct_host) typed = static_cast<T *>(host_result_arm(ctx, sizeof(T) * nres));
         SLAS_TRY(launch_fused_chain<T>(ctx, ctx->stream, chain, len, a, b, c, dd, out_dev ? out : typed));
+        if (direct_host) return host_result_wait(ctx, ctx->stream, out, sizeof(T), nres);
         return out_dev ? SLAS_OK : deliver_scalar(ctx, typed, out, sizeof(T) * nres);
     }
     const Operand ops[4] = {{a, sizeof(T), IN}, {b, sizeof(T), IN}, {dd, sizeof(T), IN}, {c, sizeof(T), OUT}};

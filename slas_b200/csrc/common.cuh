@@ -67,7 +67,8 @@ struct Context {
     size_t staging_bytes = 0;
     cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t copy_events[3] = {nullptr, nullptr, nullptr};   // kernels of chunk i done (orders the shared scratch)
-    double *pinned_scalars = nullptr;    // [16]
+    double *pinned_scalars = nullptr;    // [16]; mapped: [8..11] is the slot reductions write a host-bound scalar into directly
+    double *pinned_scalars_dev = nullptr;  // the same memory as the device sees it
     // Pageable host operands (hostcopy.cu): pinned bounce ring + one event per slot
     void *bounce = nullptr;
     size_t bounce_bytes = 0;
@@ -134,6 +135,13 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
 int pointer_is_device(const void *p, bool *is_dev);
 // Classify all data operands of a call; fails on a mix.
 int operands_side(const void *const *ptrs, int n, bool *is_dev);
+
+// A reduction whose scalar goes back to the HOST (`let x = a.dot(&b)`: the reference's own calling pattern) lets the
+// kernel store it straight into mapped pinned memory and the host spin on that word, instead of a device scalar + a
+// D2H copy + a stream synchronisation.  host_result_arm fills the slot with a sentinel and returns the device view;
+// host_result_wait returns once every word has changed (or the stream has drained) and copies the slot to `out`.
+void *host_result_arm(Context *ctx, size_t bytes);
+int host_result_wait(Context *ctx, cudaStream_t st, void *out, size_t elem_bytes, int count);
 
 // Write a device scalar (value computed on ctx->stream) to `out`, which may be a host or a
 // device pointer.  Host: copies through the pinned bounce buffer and synchronises the stream.

@@ -35,7 +35,7 @@ static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
                                {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
                                {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
-                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}, {"host_copy_threads", 0}, {"host_bounce", 0}, {"host_copy_nt", 0}, {"bdot_stage_kb", 0}};
+                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}, {"host_copy_threads", 0}, {"host_bounce", 0}, {"host_copy_nt", 0}, {"bdot_stage_kb", 0}, {"host_result", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;
@@ -73,7 +73,7 @@ static void release_context(Context *c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     c->own_stream = c->stream = nullptr;
     c->partials = nullptr; c->ticket = nullptr; c->scalars = nullptr;
-    c->workspace = nullptr; c->workspace_bytes = 0; c->pinned_scalars = nullptr;
+    c->workspace = nullptr; c->workspace_bytes = 0; c->pinned_scalars = nullptr; c->pinned_scalars_dev = nullptr;
     c->staging = nullptr; c->staging_bytes = 0;
     c->live_graphs = 0; c->capturing = false;
     cudaGetLastError();
@@ -102,7 +102,8 @@ static int init_context_resources(Context *c, int dev) {
     SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * 3 * kMaxPartials * kRedScratchSets));
     SLAS_CUDA_TRY(cudaMalloc(&c->phases, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaMemset(c->phases, 0, sizeof(unsigned long long) * 8));
-    SLAS_CUDA_TRY(cudaMallocHost(&c->pinned_scalars, sizeof(double) * 16));
+    SLAS_CUDA_TRY(cudaHostAlloc(&c->pinned_scalars, sizeof(double) * 16, cudaHostAllocMapped | cudaHostAllocPortable));
+    SLAS_CUDA_TRY(cudaHostGetDevicePointer(&c->pinned_scalars_dev, c->pinned_scalars, 0));
     for (int i = 0; i < 3; ++i) {
         SLAS_CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_streams[i], cudaStreamNonBlocking));
         SLAS_CUDA_TRY(cudaEventCreateWithFlags(&c->copy_events[i], cudaEventDisableTiming));
@@ -251,6 +252,44 @@ int operands_side(const void *const *ptrs, int n, bool *is_dev) {
             return fail(SLAS_ERR_INVALID, "operands mix host and device pointers (operand %d)", i);
     }
     *is_dev = first;
+    return SLAS_OK;
+}
+
+constexpr uint32_t kHostResultSentinel = 0x7fc5a5a5u;  // a quiet NaN with a payload no arithmetic produces
+
+void *host_result_arm(Context *ctx, size_t bytes) {
+    volatile uint32_t *slot = reinterpret_cast<volatile uint32_t *>(ctx->pinned_scalars + 8);
+    for (size_t w = 0; w < bytes / 4; ++w) slot[w] = kHostResultSentinel;
+    __sync_synchronize();
+    return ctx->pinned_scalars_dev + 8;
+}
+
+int host_result_wait(Context *ctx, cudaStream_t st, void *out, size_t elem_bytes, int count) {
+    volatile uint32_t *slot = reinterpret_cast<volatile uint32_t *>(ctx->pinned_scalars + 8);
+    const size_t wpe = elem_bytes / 4;  // words per element: 1 (f32) or 2 (f64); each element is ONE store of the kernel
+    for (unsigned spins = 0;; ++spins) {
+        bool all = true;
+        for (int e = 0; e < count && all; ++e) {
+            bool changed = false;  // (one word of a 64-bit result may legitimately equal the sentinel)
+            for (size_t w = 0; w < wpe; ++w) changed = changed || slot[e * wpe + w] != kHostResultSentinel;
+            all = changed;
+        }
+        if (all) break;
+        if ((spins & 0x3ff) == 0x3ff) {
+            // a result that IS the sentinel, or a kernel that died: the stream tells
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q == cudaSuccess) break;  // drained: whatever the kernel wrote is in the slot
+            if (q != cudaErrorNotReady) {
+                cudaGetLastError();
+                return fail(SLAS_ERR_CUDA, "reduction failed: %s", cudaGetErrorString(q));
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+    __sync_synchronize();
+    memcpy(out, (const void *)slot, elem_bytes * (size_t)count);
     return SLAS_OK;
 }
 

@@ -296,3 +296,30 @@ def test_host_register_makes_a_callers_array_a_pinned_operand():
     finally:
         for arr in (a, b, c):
             L.call("slas_cuda_host_unregister", arr.ctypes.data)
+
+
+# ---- host-bound scalars: the kernel stores them into mapped pinned memory, the host spins on the word ---------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64, np.complex128])
+def test_host_result_direct_store_matches_the_copy_path(dt):
+    rng = np.random.default_rng(71)
+    for n in (1, 5, 4097, (1 << 20) + 3):
+        if np.dtype(dt).kind == "c":
+            rdt = np.float32 if dt == np.complex64 else np.float64
+            a = (_rand(rng, n, rdt) + 1j * _rand(rng, n, rdt)).astype(dt)
+        else:
+            a = _rand(rng, n, dt)
+        da = CudaVec.from_host(a)
+        direct = (cuda.dot(da, da), cuda.norm(da))
+        set_tunable("host_result", 1)
+        try:
+            copied = (cuda.dot(da, da), cuda.norm(da))
+        finally:
+            set_tunable("host_result", 0)
+        assert direct[0].tobytes() == copied[0].tobytes() and direct[1].tobytes() == copied[1].tobytes(), (dt, n)
+    # results that ARE special values come back intact (the wait falls back to the stream when a word never changes)
+    z = CudaVec.from_host(np.zeros(1000, np.float32))
+    assert cuda.dot(z, z) == 0.0 and cuda.norm(z) == 0.0
+    nanv = CudaVec.from_host(np.array([np.nan, 1.0], np.float32))
+    assert np.isnan(cuda.dot(nanv, nanv))
+    inf = CudaVec.from_host(np.array([np.inf, 1.0], np.float32))
+    assert np.isposinf(cuda.dot(inf, inf))
