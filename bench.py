@@ -784,7 +784,9 @@ def run_cuda(args):
             torch.cuda.empty_cache()
             barrier()
             dist.barrier(group=host_group)
-            if rank == 0:
+            if rank == 0 and torch.cuda.device_count() < world:
+                configs["inproc_skipped"] = {"what": f"one-process rows skipped: this rank sees {torch.cuda.device_count()} device(s), not {world}"}
+            elif rank == 0:
                 from slas_b200.backends import init_devices
                 ndev = init_devices(world)
                 total = 1 << 32

@@ -185,7 +185,7 @@ def test_bad_arguments_of_the_newer_entry_points():
     assert L.slas_cuda_sadd_dot(8, p(a), p(a), None, p(a), None) == _lib.SLAS_ERR_INVALID             # no result pointer
     assert L.slas_cuda_sdot_norms(8, p(a), None, p(out)) == _lib.SLAS_ERR_INVALID                      # null operand
     assert L.slas_cuda_snormalize_into(8, p(a), p(a)) == _lib.SLAS_ERR_INVALID                         # aliasing: use normalize
-    assert L.slas_cuda_transpose_inplace_batched(2, 4, 3, p(a), 2) == _lib.SLAS_ERR_INVALID           # element size
+    assert L.slas_cuda_transpose_inplace_batched(2, 4, 0, p(a), 2) == _lib.SLAS_ERR_INVALID           # element size 0 (any other size is a valid Copy type)
     assert L.slas_cuda_transpose_inplace_batched(2, 4, 4, p(a), 0) == _lib.SLAS_ERR_INVALID           # columns == 0
     assert L.slas_cuda_transpose_inplace_batched(0, 4, 4, p(a), 2) == _lib.SLAS_OK                     # empty batch: nothing to do
     g = C.c_void_p()
