@@ -20,6 +20,8 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 #include <type_traits>
 
 #include "slas_cuda.h"
@@ -225,6 +227,38 @@ struct Cuda {
     void matrix_vector_mul(const A &a, const B &b, C &buffer, std::size_t m, std::size_t n, std::size_t lda, bool a_trans) const {
         if constexpr (std::is_same_v<elem_t<A>, float>) check(slas_cuda_sgemv(ptr_of(a), ptr_of(b), mut_ptr_of(buffer), m, n, lda, a_trans));
         else check(slas_cuda_dgemv(ptr_of(a), ptr_of(b), mut_ptr_of(buffer), m, n, lda, a_trans));
+    }
+    // -- process-level knobs (not trait methods: a backend is a ZST, the state lives in the library) --------------------
+    // Drive `n` GPUs from this one process (0 = all visible; same as SLAS_CUDA_DEVICES=n): host operands are split over
+    // them, device operands run where they live.  Returns the number of active devices.
+    static int init_devices(int n = 0) {
+        check(slas_cuda_init_devices(n));
+        int nd = 1, px = 0;
+        check(slas_cuda_devices(&nd, &px));
+        return nd;
+    }
+    // Page-lock a long-lived host allocation in place: its operands are then read by the DMA engines directly instead
+    // of through the library's bounce ring (unregister before freeing it).
+    static void host_register(void *p, std::size_t bytes) { check(slas_cuda_host_register(p, bytes)); }
+    static void host_unregister(void *p) { check(slas_cuda_host_unregister(p)); }
+    // 0 = exact fp32 FMA chains for every f32 matrix_mul, 1 = tcgen05 3xTF32 wherever it applies, 2 = auto (default:
+    // 3xTF32 from 2^27 multiply-adds -- an fp32-class result, not the ascending-k fp32 sum of Rust / Blas)
+    static void set_sgemm_path(int path) { check(slas_cuda_set_sgemm_path(path)); }
+    // dot / norm of ONE vector whose slices live on different GPUs of this process (slice i on its own device): the
+    // exchange runs inside the reduction kernels over NVLink peer memory
+    template <class T> static T dot_multi(const std::vector<std::pair<const T *, std::size_t>> &a, const std::vector<std::pair<const T *, std::size_t>> &b) {
+        static_assert(std::is_same_v<T, float> || std::is_same_v<T, double>, "dot_multi: f32 / f64");
+        if (a.size() != b.size()) throw Panic("dot_multi: different numbers of slices");
+        std::vector<std::size_t> lens;
+        std::vector<const T *> pa, pb;
+        for (std::size_t i = 0; i < a.size(); ++i) {
+            if (a[i].second != b[i].second) throw Panic("dot_multi: slices of different lengths");
+            lens.push_back(a[i].second); pa.push_back(a[i].first); pb.push_back(b[i].first);
+        }
+        T out{};
+        if constexpr (std::is_same_v<T, float>) check(slas_cuda_sdot_multi((int)a.size(), lens.data(), pa.data(), pb.data(), &out));
+        else check(slas_cuda_ddot_multi((int)a.size(), lens.data(), pa.data(), pb.data(), &out));
+        return out;
     }
 };
 

@@ -152,23 +152,26 @@ def test_sgemm_auto_threshold_straddled_with_tiny_operands(scale_log2):
 
 
 # ---- programmatic dependent launch of the launch-bound vector ops: overlap must never reorder dependent ops --------
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("pdl", [0, 1, 2])
 @pytest.mark.parametrize("graph", [False, True])
-def test_back_to_back_small_ops_keep_stream_order(pdl, graph):
+def test_back_to_back_small_ops_keep_stream_order(pdl, graph, dt):
     """short dots / adds issued back to back start while their predecessor is still in its tail (pdl = 2: the caller
     vouches that only this library uses the stream; the library's own stream gets that by default).  Read-after-write,
     write-after-read and write-after-write chains must behave exactly like the serial sequence, eagerly and replayed
     from a graph; independent calls must give the bits of the same calls issued one at a time."""
     rng = np.random.default_rng(41)
     n, reps = 1 << 16, 48
-    a = _rand(rng, reps * n, np.float32)
-    b = _rand(rng, reps * n, np.float32)
-    d = _rand(rng, n, np.float32)
+    es = np.dtype(dt).itemsize
+    t = "s" if dt == np.float32 else "d"
+    a = _rand(rng, reps * n, dt)
+    b = _rand(rng, reps * n, dt)
+    d = _rand(rng, n, dt)
     da, db, dd = CudaVec.from_host(a), CudaVec.from_host(b), CudaVec.from_host(d)
-    c, c2 = CudaVec(n, np.float32), CudaVec(n, np.float32)
-    out = CudaVec(4 * reps, np.float32).zero_()
+    c, c2 = CudaVec(n, dt), CudaVec(n, dt)
+    out = CudaVec(4 * reps, dt).zero_()
     # serial truth from this backend, one call at a time with a sync after each
-    want = np.zeros(4 * reps, np.float32)
+    want = np.zeros(4 * reps, dt)
     for i in range(reps):
         ai, bi = a[i * n:(i + 1) * n], b[i * n:(i + 1) * n]
         ci = ai + bi                                     # RAW: add -> dot of the sum
@@ -198,7 +201,7 @@ def test_back_to_back_small_ops_keep_stream_order(pdl, graph):
                 g.launch()
             else:
                 chain()
-            assert np.array_equal(out.to_host(), want), (pdl, graph, rep)
+            assert np.array_equal(out.to_host(), want), (pdl, graph, rep, dt)
     finally:
         set_tunable("pdl", 0)
 
