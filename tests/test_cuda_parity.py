@@ -214,7 +214,7 @@ def test_bad_arguments_fail_loudly_not_fatally():
     assert b"mix" in L.slas_cuda_last_error()
     assert L.slas_cuda_sdot(6, p(a), p(a), None) == _lib.SLAS_ERR_INVALID                  # no result pointer
     assert L.slas_cuda_transpose(6, 4, p(a), p(a), 0) == _lib.SLAS_ERR_INVALID             # columns == 0 (rust.rs:169 divides)
-    assert L.slas_cuda_transpose(6, 3, p(a), p(out), 2) == _lib.SLAS_ERR_INVALID           # element size
+    assert L.slas_cuda_transpose(6, 0, p(a), p(out), 2) == _lib.SLAS_ERR_INVALID           # element size 0 (every other size is a valid Copy type)
     c = np.zeros(4, np.float32)
     assert L.slas_cuda_sgemm(p(a), p(a), p(c), 2, 2, 3, 2, 2, 2, 0, 0) == _lib.SLAS_ERR_INVALID   # lda < k
     assert L.slas_cuda_sgemm(p(a), p(a), p(c), 2, 2, 3, 3, 2, 1, 0, 0) == _lib.SLAS_ERR_INVALID   # ldc < n

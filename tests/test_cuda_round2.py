@@ -184,11 +184,11 @@ def test_back_to_back_small_ops_keep_stream_order(pdl, graph, dt):
         for i in range(reps):
             va, vb = da.view(i * n, n), db.view(i * n, n)
             cuda.add(va, vb, c)                                                                     # WAR: the previous dot read c
-            L.call("slas_cuda_sdot", n, c.as_ptr(), dd.as_ptr(), out.as_ptr() + 16 * i)           # RAW on c
-            L.call("slas_cuda_sdot", n, va.as_ptr(), vb.as_ptr(), out.as_ptr() + 16 * i + 4)      # independent of everything before
+            L.call(f"slas_cuda_{t}dot", n, c.as_ptr(), dd.as_ptr(), out.as_ptr() + es * 4 * i)           # RAW on c
+            L.call(f"slas_cuda_{t}dot", n, va.as_ptr(), vb.as_ptr(), out.as_ptr() + es * (4 * i + 1))      # independent of everything before
             cuda.mul(c, vb, c2)                                                                     # RAW on c, WAW on c2
-            L.call("slas_cuda_sdot", n, c2.as_ptr(), dd.as_ptr(), out.as_ptr() + 16 * i + 8)
-            L.call("slas_cuda_snrm2", n, c.as_ptr(), out.as_ptr() + 16 * i + 12)
+            L.call(f"slas_cuda_{t}dot", n, c2.as_ptr(), dd.as_ptr(), out.as_ptr() + es * (4 * i + 2))
+            L.call(f"slas_cuda_{t}nrm2", n, c.as_ptr(), out.as_ptr() + es * (4 * i + 3))
 
     set_tunable("pdl", pdl)
     try:
