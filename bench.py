@@ -627,6 +627,22 @@ def run_cuda(args):
         rec("dot_2^20_single_host_result", ms_sync / ncalls, f"dot f32 LEN=2^20 returning its scalar to the HOST after every call (`a.dot(&b)`), {ncalls} distinct "
             f"device-resident pairs, C loop: per-call latency; the kernel stores the scalar into mapped pinned memory and the host spins on it",
             bytes_=8.0 * l20, extra={"us_per_call": ms_sync * 1e3 / ncalls, "us_per_call_with_d2h_copy_and_stream_sync": ms_sync_copy * 1e3 / ncalls})
+        # ... and with the operands where a StaticCowVec keeps them: in pageable HOST memory (8 MiB down per call)
+        ha_, hb_ = a[:8 * l20].cpu().numpy(), b[:8 * l20].cpu().numpy()
+        hres = np.zeros(1, np.float32)
+
+        def host_operand_loop():
+            for i in range(8):
+                L.slas_cuda_sdot(l20, ha_.ctypes.data + 4 * i * l20, hb_.ctypes.data + 4 * i * l20, hres.ctypes.data)
+
+        host_operand_loop()
+        t0_ = time.perf_counter()
+        for _ in range(5):
+            host_operand_loop()
+        us_host = (time.perf_counter() - t0_) / 40 * 1e6
+        configs["dot_2^20_single_host_result"]["us_per_call_host_resident_pageable_operands"] = us_host
+        configs["dot_2^20_single_host_result"]["host_operands_gbs"] = 8.0 * l20 / (us_host * 1e-6) / 1e9
+        del ha_, hb_
         # phases of one cold 2^20 dot kernel (%globaltimer inside the kernel)
         _lib.call("slas_cuda_set_tunable", b"reduce_phases", 1)
         ph = (C.c_uint64 * 5)()

@@ -278,3 +278,16 @@ def test_run_time_specialised_kernel_text_compiles_for_sm_100a():
     assert os.path.exists(inc), "build the library first (__graft_entry__.build())"
     r = subprocess.run([sys.executable, "-c", _NVRTC_CHECK, inc], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_c99_program_links_and_runs(tmp_path):
+    """include/slas_cuda.h is C99-clean and libslas_cuda.so links from plain C (the reference is compiled code: a C / Rust
+    / C++ host must be able to bind the boundary without a C++ compiler)"""
+    import subprocess
+    exe = tmp_path / "abi_smoke"
+    src = os.path.join(ROOT, "tests", "c", "abi_smoke.c")
+    libdir = os.path.join(ROOT, "slas_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-o", str(exe),
+                    "-L", libdir, "-lslas_cuda", f"-Wl,-rpath,{libdir}"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "C_ABI_OK" in r.stdout, (r.returncode, r.stdout, r.stderr)
