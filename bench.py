@@ -615,6 +615,27 @@ def run_cuda(args):
                        "shared_stream_no_overlap": {"us_per_call_graph": ms_g0 * 1e3 / ncalls, "us_per_call_c_loop": ms_c0 * 1e3 / ncalls,
                                                     "us_per_call_python_loop": ms_py0 * 1e3 / ncalls},
                        "hbm_floor_us": bytes_per * l20 / (peak_gbs * 1e9) * 1e6})
+        # normalize of LEN 2^20 vectors, one call each: one launch with the vector held in registers between the norm and
+        # the division (8 B per element), against the two-pass path (reduce + scale: 12 B per element, two launches)
+        def norm_loop():
+            _lib.call("slas_cuda_bench_call_loop", 3, l20, a.data_ptr(), b.data_ptr(), c.data_ptr(), ncalls, l20)
+
+        c.copy_(a)
+        _lib.call("slas_cuda_set_tunable", b"pdl", 2)
+        with sl.Graph() as g:
+            norm_loop()
+        ms_n, _ = timed(g.launch, 10, 3)
+        del g
+        _lib.call("slas_cuda_set_tunable", b"normalize_fused", 1)
+        with sl.Graph() as g:
+            norm_loop()
+        ms_n2, _ = timed(g.launch, 10, 3)
+        del g
+        _lib.call("slas_cuda_set_tunable", b"normalize_fused", 0)
+        _lib.call("slas_cuda_set_tunable", b"pdl", 0)
+        rec("normalize_2^20_single", ms_n / ncalls, f"normalize f32 LEN=2^20, one call per vector, {ncalls} distinct vectors, replayed from one CUDA graph: "
+            f"single-launch kernel (vector in registers between norm and division), 8 B per element", bytes_=8.0 * l20,
+            extra={"us_per_call": ms_n * 1e3 / ncalls, "us_per_call_two_pass": ms_n2 * 1e3 / ncalls})
         # the reference's own calling pattern: `let x = a.dot(&b)` -- the scalar comes back to the host after EVERY call
         # (tests/src/main.rs:589-601 benches exactly this loop).  Device-resident operands, distinct pairs, C loop.
         def sync_loop():

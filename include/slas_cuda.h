@@ -82,8 +82,8 @@ int slas_cuda_bench_tf32_peak(double *tflops);
 /* BASELINE configs[0] (the reference's own dot_product bench, tests/src/main.rs:589-601, is a loop of single calls):
  * `calls` back-to-back calls of slas_cuda_sdot (op 0, results to out[i]), slas_cuda_sadd (op 1, results to
  * out + i * stride) or slas_cuda_sdot with its scalar returned to the HOST after every call (op 2: what `a.dot(&b)` does
- * in the reference) on operands `stride` elements apart, issued from C -- the launch-bound loop without an interpreter
- * between the calls.  a, b device pointers. */
+ * in the reference) or slas_cuda_snormalize in place on out + i * stride (op 3), on operands `stride` elements apart,
+ * issued from C -- the launch-bound loop without an interpreter between the calls.  a, b device pointers. */
 int slas_cuda_bench_call_loop(int op, size_t len, const float *a, const float *b, float *out, int calls, size_t stride);
 /* With the tunable "reduce_phases" = 1 the dot / norm kernel stamps %globaltimer (ns): [0] start, [1] block 0's
  * loads + FMAs done, [2] its block sum done, [3] grid combine done, [4] result written. */

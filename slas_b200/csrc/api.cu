@@ -279,6 +279,15 @@ static int api_normalize(size_t len, T *a, bool sharded) {
     bool need_collective = sharded && comm_nranks() > 1;
     if (need_collective && ctx->capturing)
         return fail(SLAS_ERR_INVALID, "sharded reductions cannot be recorded in a graph (the exchange epoch is per call)");
+    if (!need_collective && len > 0) {
+        // a short vector: one launch, the vector stays in registers between the norm and the division
+        bool handled = false;
+        SLAS_TRY(launch_normalize_fused<T>(ctx, ctx->stream, len, da, typed, &handled));
+        if (handled) {
+            if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
+            return SLAS_OK;
+        }
+    }
     PeerExchange px;
     const bool fused = need_collective && comm_next_peer_exchange(&px);  // after every check that can fail
     if (fused) need_collective = false;

@@ -14,6 +14,9 @@ template <typename T>
 int launch_reduce(Context *ctx, cudaStream_t st, int kind, size_t len, const T *a, const T *b, double *result,
                   T *typed_out, int mode, int accumulate, const PeerExchange *peers = nullptr);
 template <typename T> int launch_finish_scalar(cudaStream_t st, const double *in, T *out, int mode);
+// normalize of a short vector in one launch (registers hold the vector between the two phases); *handled = false: not
+// applicable (too long for one wave's registers, misaligned), use launch_reduce + launch_scale_div
+template <typename T> int launch_normalize_fused(Context *ctx, cudaStream_t st, size_t len, T *a, T *norm_out, bool *handled);
 template <typename T> int launch_scale_div(Context *ctx, cudaStream_t st, size_t len, const T *in, T *a, const T *norm_dev);
 // fused chains: 0..3 = (add, sub, mul, div) -> dot with d (c optional), 4 = dot(a,b), |a|, |b|; results to typed_out (device)
 template <typename T>

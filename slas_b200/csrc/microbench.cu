@@ -80,15 +80,16 @@ extern "C" int slas_cuda_bench_fma_peak(int is_double, double *tflops) {
 // calls of the public entry points on consecutive operands `stride` elements apart.  op 0: slas_cuda_sdot (results to
 // out[i]); op 1: slas_cuda_sadd (results to out + i * stride); op 2: slas_cuda_sdot returning its scalar to the HOST
 // after every call, the way `a.dot(&b)` does in the reference (out may be NULL; the last value is stored to out[0] when it
-// is a host pointer).  a, b device pointers.
+// is a host pointer); op 3: slas_cuda_snormalize in place on out + i * stride.  a, b device pointers.
 extern "C" int slas_cuda_bench_call_loop(int op, size_t len, const float *a, const float *b, float *out, int calls,
                                          size_t stride) {
-    SLAS_REQUIRE(op >= 0 && op <= 2, "call_loop: op must be 0 (dot), 1 (add) or 2 (dot, scalar to the host)");
+    SLAS_REQUIRE(op >= 0 && op <= 3, "call_loop: op must be 0 (dot), 1 (add), 2 (dot, scalar to the host) or 3 (normalize)");
     float host_result = 0.f;
     for (int i = 0; i < calls; ++i) {
         const size_t off = (size_t)i * stride;
         if (op == 0) SLAS_TRY(slas_cuda_sdot(len, a + off, b + off, out + i));
         else if (op == 1) SLAS_TRY(slas_cuda_sadd(len, a + off, b + off, out + off));
+        else if (op == 3) SLAS_TRY(slas_cuda_snormalize(len, out + off));  // in place on out + i * stride
         else SLAS_TRY(slas_cuda_sdot(len, a + off, b + off, &host_result));
     }
     if (op == 2 && out) {

@@ -280,6 +280,120 @@ template int launch_reduce<float>(Context *, cudaStream_t, int, size_t, const fl
 template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const double *, const double *,
                                    double *, double *, int, int, const PeerExchange *);
 
+// ---- normalize of a short vector in ONE launch ------------------------------------------------------------------------
+// (rust.rs:122-127: a[i] /= norm(a).)  For vectors that fit the registers of one CTA wave (<= 4 vectors of 16 bytes per
+// thread: LEN <= ~1.2 M f32) the two passes collapse: every thread keeps its part of the vector in registers, the blocks
+// combine their partial sums of squares exactly like reduce_kernel<T, 1> does (same geometry, accumulators and order:
+// the norm carries the bits slas_cuda_?nrm2 returns), block 0 publishes the norm as flagged words, every block picks it
+// up and divides its registers (IEEE div.rn) -- 8 bytes per element instead of 12, one launch instead of two.  All
+// blocks are resident at once (one wave by construction), so waiting for block 0 cannot deadlock.  Always a barrier
+// kernel for the dependent-launch scheme: it waits for its predecessor first.
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+normalize_fused_kernel(T *__restrict__ a, size_t len, size_t nvec, const RedGeom g, const RedScratch sc, LLSlot *bcast,
+                       unsigned int *ack, T *__restrict__ norm_out) {
+    using V = typename Vec16<T>::type;
+    constexpr int N = Vec16<T>::N;
+    constexpr int U = RedTile<THREADS>::U;
+    __shared__ double red[THREADS / 32];
+    __shared__ bool is_last;
+    __shared__ T nrm_s;
+    pdl_wait();
+    pdl_trigger();
+    Reducer<T, 1> r;
+    r.clear();
+    V *av = reinterpret_cast<V *>(a);
+    size_t i, end, stride;
+    red_range<THREADS>(g, nvec, i, end, stride);
+    V x[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const size_t j = i + (size_t)u * THREADS;
+        ok[u] = j < end;
+        x[u] = ok[u] ? ld_stream(av + j) : vzero((V *)nullptr);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (ok[u]) r.add(u, x[u], x[u]);
+    r.flush();
+    const size_t tid = (size_t)blockIdx.x * THREADS + threadIdx.x;
+    const size_t jt = nvec * N + tid;  // the len % N elements past the last whole vector
+    T tail = T(0);
+    if (jt < len) { tail = a[jt]; r.add_scalar(tail, tail); }
+    double s[1], p[1];
+    s[0] = block_sum<THREADS>(r.sum, red);
+    const bool combiner = grid_combine<THREADS, 1>(g, sc, s, p, red, &is_last);
+    if (combiner && threadIdx.x == 0) {
+        const T nrm = (T)sqrt(p[0]);
+        if (norm_out) norm_out[0] = nrm;
+        nrm_s = nrm;
+        if (gridDim.x > 1) ll_store(bcast, (double)nrm);  // exact: T -> double -> T
+    }
+    if (!combiner && threadIdx.x == 0) {
+        // every block but the combiner waits for the norm (without consuming the slot: the last reader resets it)
+        unsigned long long w0, w1;
+        const unsigned long long t0 = red_timer_ns();
+        unsigned spins = 0;
+        for (;;) {
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w0) : "l"(&bcast->w[0]) : "memory");
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w1) : "l"(&bcast->w[1]) : "memory");
+            if ((unsigned)(w0 >> 32) == kLLFlag && (unsigned)(w1 >> 32) == kLLFlag) break;
+            if ((++spins & 0xfff) == 0 && red_timer_ns() - t0 > 20000000000ull) __trap();
+        }
+        nrm_s = (T)__longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+    }
+    __syncthreads();
+    const T nrm = nrm_s;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+            T *e = reinterpret_cast<T *>(&x[u]);
+#pragma unroll
+            for (int q = 0; q < N; ++q) e[q] = e[q] / nrm;  // IEEE div.rn: a true division, not a reciprocal multiply
+            st_stream(av + i + (size_t)u * THREADS, x[u]);
+        }
+    }
+    if (jt < len) a[jt] = tail / nrm;
+    // the last block to have read the norm clears the slot for the next launch
+    if (gridDim.x > 1 && threadIdx.x == 0) {
+        const unsigned int t = atomicInc(ack, gridDim.x - 1);
+        if (t == gridDim.x - 1) {
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&bcast->w[0]), "l"(0ull) : "memory");
+            asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&bcast->w[1]), "l"(0ull) : "memory");
+        }
+    }
+}
+
+// *handled = false: the vector does not fit one wave's registers (or is a misaligned view): use the two-pass path
+template <typename T>
+int launch_normalize_fused(Context *ctx, cudaStream_t st, size_t len, T *a, T *norm_out, bool *handled) {
+    constexpr int N = Vec16<T>::N;
+    *handled = false;
+    if (len == 0 || !aligned16(a) || tunable("normalize_fused") == 1) return SLAS_OK;
+    const size_t nvec = len / N;
+    const RedGeom g = reduce_geometry(ctx, nvec, true);
+    if (!g.balanced || !g.poll) return SLAS_OK;
+    // every thread must hold its whole share in one group of loads
+    if (g.per > (unsigned long long)g.threads * (g.threads == 1024 ? 2 : kRedUnroll)) return SLAS_OK;
+    const RedScratch sc = reduce_scratch(ctx);
+    LLSlot *bcast = reinterpret_cast<LLSlot *>(ctx->ll_slots) + (size_t)kRedScratchSets * 3 * kMaxPartials;  // one slot past the sets
+    unsigned int *ack = ctx->ticket + 1;
+    cudaError_t le;
+    if (g.threads == 1024) le = launch_pdl(normalize_fused_kernel<T, 1024>, g.blocks, 1024u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
+    else if (g.threads == 512) le = launch_pdl(normalize_fused_kernel<T, 512>, g.blocks, 512u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
+    else le = launch_pdl(normalize_fused_kernel<T, 256>, g.blocks, 256u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
+    SLAS_CUDA_TRY(le);
+    SLAS_LAUNCH_CHECK();
+    const Context::Span rw[1] = {{(const char *)a, (const char *)(a + len)}};
+    const Context::Span w2[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)norm_out, (const char *)(norm_out ? norm_out + 1 : norm_out)}};
+    hazard_record(ctx, st, rw, 1, w2, 2, 0);
+    *handled = true;
+    return SLAS_OK;
+}
+template int launch_normalize_fused<float>(Context *, cudaStream_t, size_t, float *, float *, bool *);
+template int launch_normalize_fused<double>(Context *, cudaStream_t, size_t, double *, double *, bool *);
+
 // f64 sum -> typed scalar (used after the NCCL allreduce of the sharded ops)
 template <typename T>
 __global__ void finish_scalar_kernel(const double *in, T *out, int mode) {
