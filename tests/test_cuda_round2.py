@@ -326,3 +326,43 @@ def test_host_result_direct_store_matches_the_copy_path(dt):
     assert np.isnan(cuda.dot(nanv, nanv))
     inf = CudaVec.from_host(np.array([np.inf, 1.0], np.float32))
     assert np.isposinf(cuda.dot(inf, inf))
+
+
+# ---- normalize of a short vector in one launch: same bits as norm + true division ------------------------------------
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.complex64])
+@pytest.mark.parametrize("n", [1, 3, 4, 1000, 4097, 65536, (1 << 20), (1 << 20) + 3, 1_200_000, 1_300_000])
+def test_single_launch_normalize_matches_the_two_pass_path(dt, n):
+    rng = np.random.default_rng(n)
+    if np.dtype(dt).kind == "c":
+        a = (_rand(rng, n, np.float32) + 1j * _rand(rng, n, np.float32)).astype(dt)
+    else:
+        a = _rand(rng, n, dt)
+    one, two = CudaVec.from_host(a), CudaVec.from_host(a)
+    nrm = cuda.norm(one)
+    cuda.normalize(one)
+    set_tunable("normalize_fused", 1)
+    try:
+        cuda.normalize(two)
+    finally:
+        set_tunable("normalize_fused", 0)
+    assert np.array_equal(one.to_host(), two.to_host()), (dt, n)
+    assert np.array_equal(one.to_host(), (a / nrm).astype(dt)), (dt, n)      # true division by the backend's own norm
+    h = a.copy()
+    cuda.normalize(h)                                                           # host operand: staged, same kernel
+    assert np.array_equal(h, one.to_host())
+    # back to back on distinct vectors, replayed from a graph
+    if n >= 4096 and np.dtype(dt).kind != "c":
+        vs = [CudaVec.from_host(a * (i + 1)) for i in range(6)]
+        t = "s" if dt == np.float32 else "d"
+        with Graph() as g:
+            for v in vs:
+                L.call(f"slas_cuda_{t}normalize", n, v.as_ptr())
+        g.launch()
+        for i, v in enumerate(vs):
+            ref = CudaVec.from_host(a * (i + 1))
+            set_tunable("normalize_fused", 1)
+            try:
+                cuda.normalize(ref)
+            finally:
+                set_tunable("normalize_fused", 0)
+            assert np.array_equal(v.to_host(), ref.to_host()), (dt, n, i)
