@@ -83,8 +83,10 @@ static int run_chunked(Context *ctx, size_t units, size_t granule, const Operand
     SLAS_TRY(ensure_staging(ctx, slot_bytes * nslots, &base));
     char *ring = nullptr;
     if (pageable) SLAS_TRY(ensure_bounce(ctx, slot_bytes * nslots, &ring));
-    // the copy streams must not overtake work already queued on the op stream
+    // the copy streams must not overtake work already queued on the op stream (this also drains whatever the
+    // whole-operand copies left in flight in the bounce ring, which is laid out differently below)
     SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < kBounceSlots; ++i) ctx->bounce_pending[i] = false;
     struct Pending { bool live = false; size_t first = 0, cnt = 0; } pend[3];
     // bring the results of the chunk that last used `slot` from the ring into the caller's memory
     auto drain_slot = [&](int slot) -> int {
@@ -282,7 +284,7 @@ static int api_normalize(size_t len, T *a, bool sharded) {
     if (!need_collective && len > 0) {
         // a short vector: one launch, the vector stays in registers between the norm and the division
         bool handled = false;
-        SLAS_TRY(launch_normalize_fused<T>(ctx, ctx->stream, len, da, typed, &handled));
+        SLAS_TRY(launch_normalize_fused<T>(ctx, ctx->stream, len, da, (T *)nullptr, &handled));  // nobody reads the norm itself
         if (handled) {
             if (!dev) SLAS_TRY(stage_all_finish(ctx, ops, sizes, 1, d));
             return SLAS_OK;

@@ -73,6 +73,8 @@ struct Context {
     void *bounce = nullptr;
     size_t bounce_bytes = 0;
     cudaEvent_t bounce_events[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool bounce_pending[4] = {false, false, false, false};  // a DMA out of / into that slot may still be running
+    unsigned bounce_next = 0;                                 // round-robin slot of the whole-operand copies
     // Programmatic dependent launch of the launch-bound vector ops (reduce.cuh): what the kernels that may still be
     // running read and write, so that the next one knows whether it may touch its operands before they are done.
     // A kernel that waits for its predecessor BEFORE it lets its successor go ("early" = 0) is a barrier: everything

@@ -98,9 +98,9 @@ static int init_context_resources(Context *c, int dev) {
     SLAS_CUDA_TRY(cudaMemset(c->ticket, 0, sizeof(unsigned int) * 4));
     SLAS_CUDA_TRY(cudaMalloc(&c->scalars, sizeof(double) * 16));
     SLAS_CUDA_TRY(cudaMemset(c->scalars, 0, sizeof(double) * 16));
-    // + 16 slots past the sets: the norm broadcast of normalize_fused_kernel
-    SLAS_CUDA_TRY(cudaMalloc(&c->ll_slots, (size_t)16 * (3 * kMaxPartials * kRedScratchSets + 16)));
-    SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * (3 * kMaxPartials * kRedScratchSets + 16)));
+    // + past the sets: per set one norm-broadcast slot and one acknowledge counter of normalize_fused_kernel
+    SLAS_CUDA_TRY(cudaMalloc(&c->ll_slots, (size_t)16 * (3 * kMaxPartials * kRedScratchSets + 2 * kRedScratchSets)));
+    SLAS_CUDA_TRY(cudaMemset(c->ll_slots, 0, (size_t)16 * (3 * kMaxPartials * kRedScratchSets + 2 * kRedScratchSets)));
     SLAS_CUDA_TRY(cudaMalloc(&c->phases, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaMemset(c->phases, 0, sizeof(unsigned long long) * 8));
     SLAS_CUDA_TRY(cudaHostAlloc(&c->pinned_scalars, sizeof(double) * 16, cudaHostAllocMapped | cudaHostAllocPortable));

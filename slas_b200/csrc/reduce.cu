@@ -286,19 +286,21 @@ template int launch_reduce<double>(Context *, cudaStream_t, int, size_t, const d
 // combine their partial sums of squares exactly like reduce_kernel<T, 1> does (same geometry, accumulators and order:
 // the norm carries the bits slas_cuda_?nrm2 returns), block 0 publishes the norm as flagged words, every block picks it
 // up and divides its registers (IEEE div.rn) -- 8 bytes per element instead of 12, one launch instead of two.  All
-// blocks are resident at once (one wave by construction), so waiting for block 0 cannot deadlock.  Always a barrier
-// kernel for the dependent-launch scheme: it waits for its predecessor first.
+// blocks are resident at once (one wave by construction), so waiting for block 0 cannot deadlock.  Dependent launch as
+// for reduce_kernel: the partial slots, the broadcast slot and the acknowledge counter belong to this launch's scratch
+// set, so an "early" kernel (no overlap with what may still be running: it reads AND writes its vector) runs to its end
+// without waiting for its predecessor.
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 normalize_fused_kernel(T *__restrict__ a, size_t len, size_t nvec, const RedGeom g, const RedScratch sc, LLSlot *bcast,
-                       unsigned int *ack, T *__restrict__ norm_out) {
+                       unsigned int *ack, T *__restrict__ norm_out, int early) {
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     constexpr int U = RedTile<THREADS>::U;
     __shared__ double red[THREADS / 32];
     __shared__ bool is_last;
     __shared__ T nrm_s;
-    pdl_wait();
+    if (!early) pdl_wait();
     pdl_trigger();
     Reducer<T, 1> r;
     r.clear();
@@ -363,6 +365,7 @@ normalize_fused_kernel(T *__restrict__ a, size_t len, size_t nvec, const RedGeom
             asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(&bcast->w[1]), "l"(0ull) : "memory");
         }
     }
+    if (early) pdl_wait();  // completion order stays the stream order
 }
 
 // *handled = false: the vector does not fit one wave's registers (or is a misaligned view): use the two-pass path
@@ -376,18 +379,23 @@ int launch_normalize_fused(Context *ctx, cudaStream_t st, size_t len, T *a, T *n
     if (!g.balanced || !g.poll) return SLAS_OK;
     // every thread must hold its whole share in one group of loads
     if (g.per > (unsigned long long)g.threads * (g.threads == 1024 ? 2 : kRedUnroll)) return SLAS_OK;
+    // this launch's scratch set: partial slots (reduce_scratch rotates), one broadcast slot and one acknowledge counter
+    const unsigned set = ctx->red_seq % kRedScratchSets;
     const RedScratch sc = reduce_scratch(ctx);
-    LLSlot *bcast = reinterpret_cast<LLSlot *>(ctx->ll_slots) + (size_t)kRedScratchSets * 3 * kMaxPartials;  // one slot past the sets
-    unsigned int *ack = ctx->ticket + 1;
-    cudaError_t le;
-    if (g.threads == 1024) le = launch_pdl(normalize_fused_kernel<T, 1024>, g.blocks, 1024u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
-    else if (g.threads == 512) le = launch_pdl(normalize_fused_kernel<T, 512>, g.blocks, 512u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
-    else le = launch_pdl(normalize_fused_kernel<T, 256>, g.blocks, 256u, st, a, len, nvec, g, sc, bcast, ack, norm_out);
-    SLAS_CUDA_TRY(le);
-    SLAS_LAUNCH_CHECK();
+    LLSlot *tail = reinterpret_cast<LLSlot *>(ctx->ll_slots) + (size_t)kRedScratchSets * 3 * kMaxPartials;  // past the sets
+    LLSlot *bcast = tail + set;
+    unsigned int *ack = reinterpret_cast<unsigned int *>(tail + kRedScratchSets) + set;
     const Context::Span rw[1] = {{(const char *)a, (const char *)(a + len)}};
     const Context::Span w2[2] = {{(const char *)a, (const char *)(a + len)}, {(const char *)norm_out, (const char *)(norm_out ? norm_out + 1 : norm_out)}};
-    hazard_record(ctx, st, rw, 1, w2, 2, 0);
+    const bool own = st == ctx->own_stream || tunable("pdl") == 2;
+    const int early = own && hazard_early_ok(ctx, st, rw, 1, w2, 2) ? 1 : 0;
+    cudaError_t le;
+    if (g.threads == 1024) le = launch_pdl(normalize_fused_kernel<T, 1024>, g.blocks, 1024u, st, a, len, nvec, g, sc, bcast, ack, norm_out, early);
+    else if (g.threads == 512) le = launch_pdl(normalize_fused_kernel<T, 512>, g.blocks, 512u, st, a, len, nvec, g, sc, bcast, ack, norm_out, early);
+    else le = launch_pdl(normalize_fused_kernel<T, 256>, g.blocks, 256u, st, a, len, nvec, g, sc, bcast, ack, norm_out, early);
+    SLAS_CUDA_TRY(le);
+    SLAS_LAUNCH_CHECK();
+    hazard_record(ctx, st, rw, 1, w2, 2, early);
     *handled = true;
     return SLAS_OK;
 }
