@@ -120,14 +120,14 @@ int pool_threads() {
 void parallel_memcpy(const HostCopyJob *jobs, int njobs) {
     size_t total = 0;
     for (int j = 0; j < njobs; ++j) total += jobs[j].bytes;
-    if (total < ((size_t)1 << 20)) {  // not worth waking anybody
+    if (total < ((size_t)512 << 10)) {  // not worth waking anybody
         for (int j = 0; j < njobs; ++j)
             if (jobs[j].bytes) memcpy(jobs[j].dst, jobs[j].src, jobs[j].bytes);
         return;
     }
     std::call_once(g_pool_once, [] { g_pool.start(pool_threads() - 1); });  // the caller is the last copier
     std::lock_guard<std::mutex> call_lk(g_pool.call_mu);
-    constexpr size_t kPiece = (size_t)1 << 20;
+    constexpr size_t kPiece = (size_t)256 << 10;  // a 4 MiB operand still keeps every copy thread busy
     {
         std::lock_guard<std::mutex> lk(g_pool.mu);
         g_pool.pieces.clear();
