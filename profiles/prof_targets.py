@@ -95,7 +95,18 @@ def gemm_large(path):
     set_sgemm_path("auto")
 
 
+def odd_normalize():
+    """batched normalize of vectors that are not whole 16-byte words: LEN 3 (built-in constant) and LEN 30 (NVRTC)"""
+    for length, log2 in ((3, 24), (30, 21)):
+        b = 1 << log2
+        x = uniform(b * length, np.float32, 2)
+        for _ in range(2):
+            cuda.normalize_batched(x, length)
+    synchronize()
+
+
 TARGETS = {
+    "odd_normalize": odd_normalize,
     "gemm4_f32": lambda: gemm_batched(4, np.float32, 24),
     "gemm16_f32": lambda: gemm_batched(16, np.float32, 20),
     "gemm32_f32": lambda: gemm_batched(32, np.float32, 20),

@@ -377,7 +377,138 @@ def g_vec3():
     set_tunable("bdot_stage_kb", 0)
 
 
+def g_odd():
+    """small objects that are not whole 16-byte words (bulk-TMA staged kernels): shape as a run-time argument (staged_jit 2)
+    against shape as a compile-time constant (0: built in for LEN <= 8 / 3x3, NVRTC for the rest); same bits required"""
+    for length, log2, dt in ((3, 24, np.float32), (3, 24, np.float64), (2, 24, np.float32), (5, 23, np.float32), (7, 23, np.float32),
+                             (7, 22, np.float64), (9, 22, np.float32), (13, 22, np.float32), (30, 21, np.float32), (19, 21, np.float64),
+                             (38, 21, np.float32), (127, 19, np.float32)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (ta, a), (_, bb), (to, o) = uniform(b * length, dt, 1), uniform(b * length, dt, 2), uniform(b, dt, 3)
+        keep = ta.clone()
+        for name, fn, nbytes in (("dot", lambda: cuda.dot_batched(a, bb, o, length), (2.0 * length + 1) * b * es),
+                                 ("norm", lambda: cuda.norm_batched(a, o, length), (length + 1.0) * b * es),
+                                 ("normalize", lambda: cuda.normalize_batched(a, length), 2.0 * length * b * es)):
+            res = []
+            for mode in (2, 0):
+                set_tunable("staged_jit", mode)
+                ta.copy_(keep)
+                fn()
+                res.append((ta if name == "normalize" else to).clone())
+                ta.copy_(keep)
+                report(f"batched LEN {length} {np.dtype(dt).name} {name}, 2^{log2}, shape {'run-time' if mode else 'compile-time'}",
+                       timed(fn), nbytes=nbytes)
+            assert torch.equal(res[0].view(torch.uint8), res[1].view(torch.uint8)), (name, length)
+            ta.copy_(keep)
+        del ta, a, bb, to, o, keep
+        torch.cuda.empty_cache()
+    for rows, cols, log2, dt in ((3, 3, 24, np.float32), (3, 3, 23, np.float64), (2, 3, 24, np.float32), (5, 5, 22, np.float32),
+                                 (3, 5, 23, np.float32), (6, 6, 22, np.float32), (7, 7, 21, np.float32), (9, 9, 21, np.float32),
+                                 (5, 3, 22, np.float64), (10, 10, 20, np.float32), (30, 30, 18, np.float32), (100, 100, 14, np.float32)):
+        b, es, e = 1 << log2, np.dtype(dt).itemsize, rows * cols
+        (ta, a), (tc, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
+        res = []
+        for mode in (2, 0):
+            set_tunable("staged_jit", mode)
+            cuda.transpose_batched(a, c, e, cols)
+            res.append(tc.clone())
+            report(f"transpose {rows}x{cols} {np.dtype(dt).name}, 2^{log2}, shape {'run-time' if mode else 'compile-time'}",
+                   timed(lambda: cuda.transpose_batched(a, c, e, cols)), nbytes=2.0 * b * e * es)
+        assert torch.equal(res[0].view(torch.uint8), res[1].view(torch.uint8)), (rows, cols)
+        set_tunable("staged_jit", 0)
+        keep = ta.clone()
+        cuda.transpose_inplace_batched(a, e, cols)
+        assert torch.equal(ta.view(torch.uint8), res[0].view(torch.uint8)), ("in place", rows, cols)
+        ta.copy_(keep)
+        report(f"transpose_inplace {rows}x{cols} {np.dtype(dt).name}, 2^{log2}, compile-time",
+               timed(lambda: cuda.transpose_inplace_batched(a, e, cols)), nbytes=2.0 * b * e * es)
+        del ta, a, tc, c, keep
+        torch.cuda.empty_cache()
+    set_tunable("staged_jit", 0)
+
+
+def g_oddsweep():
+    """stage size of the staged small-object kernels (CTAs per SM against bytes per bulk copy)"""
+    b = 1 << 24
+    (_, x), (_, y), (_, o) = uniform(b * 3, np.float32, 1), uniform(b * 3, np.float32, 2), uniform(b, np.float32, 3)
+    set_tunable("bdot_gcap", 8192)
+    for kb in (4, 8, 12, 16, 24, 32, 48):
+        set_tunable("bdot_stage_kb", kb)
+        report(f"batched 3-vector f32 dot, 2^24, stage {kb} KB", timed(lambda: cuda.dot_batched(x, y, o, 3)), nbytes=28.0 * b)
+        report(f"batched 3-vector f32 norm, 2^24, stage {kb} KB", timed(lambda: cuda.norm_batched(x, o, 3)), nbytes=16.0 * b)
+        report(f"batched 3-vector f32 normalize, 2^24, stage {kb} KB", timed(lambda: cuda.normalize_batched(x, 3)), nbytes=24.0 * b)
+    del x, y, o
+    b = 1 << 21
+    (_, x), (_, y), (_, o) = uniform(b * 30, np.float32, 1), uniform(b * 30, np.float32, 2), uniform(b, np.float32, 3)
+    for kb in (4, 8, 12, 16, 24, 32, 48):
+        set_tunable("bdot_stage_kb", kb)
+        report(f"batched 30-vector f32 dot, 2^21, stage {kb} KB", timed(lambda: cuda.dot_batched(x, y, o, 30)), nbytes=244.0 * b)
+        report(f"batched 30-vector f32 normalize, 2^21, stage {kb} KB", timed(lambda: cuda.normalize_batched(x, 30)), nbytes=240.0 * b)
+    set_tunable("bdot_stage_kb", 0)
+    set_tunable("bdot_gcap", 0)
+    del x, y, o
+    torch.cuda.empty_cache()
+    for rows, cols, log2, dt in ((3, 3, 24, np.float32), (3, 3, 23, np.float64), (9, 9, 21, np.float32), (30, 30, 18, np.float32)):
+        b, es, e = 1 << log2, np.dtype(dt).itemsize, rows * cols
+        (ta, a), (tc, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
+        for mode in (2, 0):
+            set_tunable("staged_jit", mode)
+            for kb in (4, 8, 12, 16, 24, 32, 40):
+                set_tunable("transpose_stage_kb", kb)
+                report(f"transpose {rows}x{cols} {np.dtype(dt).name}, 2^{log2}, shape {'run-time' if mode else 'compile-time'}, stage {kb} KB",
+                       timed(lambda: cuda.transpose_batched(a, c, e, cols)), nbytes=2.0 * b * e * es)
+        del ta, a, tc, c
+        torch.cuda.empty_cache()
+    set_tunable("staged_jit", 0)
+    set_tunable("transpose_stage_kb", 0)
+
+
+def g_oddsweep2():
+    """small stages x CTAs per SM for the compile-time-shape staged kernels"""
+    cases = []
+    b = 1 << 24
+    (_, x), (_, y), (_, o) = uniform(b * 3, np.float32, 1), uniform(b * 3, np.float32, 2), uniform(b, np.float32, 3)
+    (_, m), (_, c) = uniform(b * 9, np.float32, 4), uniform(b * 9, np.float32, 5)
+    b7 = 1 << 23
+    (_, x7) = uniform(b7 * 7, np.float32, 6)
+    (_, md), (_, cd) = uniform(b7 * 9, np.float64, 4), uniform(b7 * 9, np.float64, 5)
+    set_tunable("bdot_gcap", 8192)
+    for cap in (4, 5, 6, 7):
+        set_tunable("staged_cta_cap", cap)
+        for kb in (2, 3, 4, 6, 8, 12, 16):
+            set_tunable("bdot_stage_kb", kb)
+            set_tunable("transpose_stage_kb", kb)
+            tag = f"cap {cap}, stage {kb} KB"
+            report(f"3-vector f32 dot, {tag}", timed(lambda: cuda.dot_batched(x, y, o, 3)), nbytes=28.0 * b)
+            report(f"3-vector f32 norm, {tag}", timed(lambda: cuda.norm_batched(x, o, 3)), nbytes=16.0 * b)
+            report(f"3-vector f32 normalize, {tag}", timed(lambda: cuda.normalize_batched(x, 3)), nbytes=24.0 * b)
+            report(f"7-vector f32 normalize, {tag}", timed(lambda: cuda.normalize_batched(x7, 7)), nbytes=56.0 * b7)
+            report(f"transpose 3x3 f32, {tag}", timed(lambda: cuda.transpose_batched(m, c, 9, 3)), nbytes=72.0 * b)
+            report(f"transpose 3x3 f64, {tag}", timed(lambda: cuda.transpose_batched(md, cd, 9, 3)), nbytes=144.0 * b7)
+    for k in ("bdot_gcap", "staged_cta_cap", "bdot_stage_kb", "transpose_stage_kb"):
+        set_tunable(k, 0)
+
+
+def g_oddsweep3():
+    """stage size for the staged normalize (two more shared tiles than dot: CTAs per SM against bytes per bulk copy)"""
+    for length, log2, dt in ((3, 24, np.float32), (7, 23, np.float32), (9, 22, np.float32), (13, 22, np.float32), (30, 21, np.float32),
+                             (38, 21, np.float32), (127, 19, np.float32), (3, 23, np.float64), (7, 22, np.float64), (19, 21, np.float64)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, x) = uniform(b * length, dt, 1)
+        for kb in (6, 8, 12, 16, 24):
+            set_tunable("bdot_stage_kb", kb)
+            report(f"batched LEN {length} {np.dtype(dt).name} normalize, 2^{log2}, stage {kb} KB",
+                   timed(lambda: cuda.normalize_batched(x, length)), nbytes=2.0 * length * b * es)
+        del x
+        torch.cuda.empty_cache()
+    set_tunable("bdot_stage_kb", 0)
+
+
 GROUPS = {
+    "oddsweep3": g_oddsweep3,
+    "oddsweep2": g_oddsweep2,
+    "oddsweep": g_oddsweep,
+    "odd": g_odd,
     "vec3": g_vec3,
     "small": g_small,
     "pageable": g_pageable,

@@ -24,7 +24,7 @@ mod cuda_backend {
     // == SRCS of slas_b200/csrc/Makefile
     const KERNEL_SOURCES: &[&str] = &[
         "context.cu", "api.cu", "vector_ops.cu", "reduce.cu", "fused_chain.cu", "transpose.cu", "gemm_small.cu",
-        "gemm_jit.cu", "gemm_generic.cu", "gemm_large.cu", "gemm_large_f64.cu", "gemm_tcgen05.cu",
+        "gemm_jit.cu", "staged_jit.cu", "gemm_generic.cu", "gemm_large.cu", "gemm_large_f64.cu", "gemm_tcgen05.cu",
         "comm.cu", "multi.cu", "hostcopy.cu", "microbench.cu",
     ];
     // == HOSTSRCS of the Makefile
@@ -57,6 +57,11 @@ mod cuda_backend {
         run(Command::new("python3").arg(csrc.join("embed_jit_source.py")).arg(&inc)
                 .args(["async.cuh", "gemm_small_kernel.cuh", "gemm_tiny_kernel.cuh"].map(|h| csrc.join(h))),
             "embed_jit_source.py");
+        // staged_jit.cu does the same for the staged small-object kernels (Makefile: staged_jit_src.inc)
+        let inc = out.join("staged_jit_src.inc");
+        run(Command::new("python3").arg(csrc.join("embed_jit_source.py")).arg(&inc)
+                .args(["async.cuh", "divby.cuh", "staged_objects_kernel.cuh"].map(|h| csrc.join(h))),
+            "embed_jit_source.py (staged objects)");
 
         for src in KERNEL_SOURCES {
             let path = csrc.join(src);

@@ -21,6 +21,7 @@
 #include <tuple>
 
 #include "common.cuh"
+#include "jit.cuh"
 #include "kernels.cuh"
 
 namespace slas {
@@ -222,20 +223,15 @@ using JitKey = std::tuple<int, int, size_t, size_t, size_t, int, int>;  // devic
 static std::map<JitKey, JitKernel> g_cache;
 static std::mutex g_cache_mu;
 
-static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, int tb, JitKernel *kern) {
-    const char *tname = elem == 4 ? "float" : "double";
-    char expr[256];
-    if (kern->cfg.tiny == 1)
-        snprintf(expr, sizeof(expr), "slas::gemm_tiny_kernel<%s, %zu, %zu, %zu, %d>", tname, m, n, k, kern->cfg.g);
-    else if (kern->cfg.tiny == 2)
-        snprintf(expr, sizeof(expr), "slas::gemm_rect_kernel<%s, %zu, %zu, %zu, %d, %d, %d>", tname, m, n, k, kern->cfg.tm, kern->cfg.tn,
-                 kern->cfg.g);
-    else
-        snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>",
-                 tname, tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages,
-                 ta ? "true" : "false", tb ? "true" : "false");
+bool jit_ready() {
+    std::call_once(g_api_once, bind_api);
+    return g_api.ok;
+}
+
+bool jit_compile(const char *source, const char *file_name, const char *expr, size_t smem, CUfunction *fn) {
+    if (!jit_ready()) return false;
     nvrtcProgram prog = nullptr;
-    if (g_api.CreateProgram(&prog, kKernelSource, "gemm_small_jit.cu", 0, nullptr, nullptr) != NVRTC_SUCCESS) return false;
+    if (g_api.CreateProgram(&prog, source, file_name, 0, nullptr, nullptr) != NVRTC_SUCCESS) return false;
     bool ok = g_api.AddNameExpression(prog, expr) == NVRTC_SUCCESS;
     const char *opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
     if (ok && g_api.CompileProgram(prog, 3, opts) != NVRTC_SUCCESS) {
@@ -258,18 +254,39 @@ static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, in
     }
     CUmodule mod = nullptr;
     ok = ok && g_api.ModuleLoadData(&mod, cubin.data()) == CUDA_SUCCESS;  // the module lives as long as the process
-    ok = ok && g_api.ModuleGetFunction(&kern->fn, mod, lowered) == CUDA_SUCCESS;
-    ok = ok && g_api.FuncSetAttribute(kern->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)kern->cfg.smem) == CUDA_SUCCESS;
+    ok = ok && g_api.ModuleGetFunction(fn, mod, lowered) == CUDA_SUCCESS;
+    ok = ok && g_api.FuncSetAttribute(*fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) == CUDA_SUCCESS;
     g_api.DestroyProgram(&prog);
     return ok;
+}
+
+int jit_launch(CUfunction fn, unsigned grid, unsigned block, size_t smem, cudaStream_t st, void **params) {
+    const CUresult r = g_api.LaunchKernel(fn, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr);
+    if (r != CUDA_SUCCESS) return fail(SLAS_ERR_CUDA, "launch of a run-time specialised kernel failed (CUresult %d)", (int)r);
+    count_launch();
+    return SLAS_OK;
+}
+
+static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, int tb, JitKernel *kern) {
+    const char *tname = elem == 4 ? "float" : "double";
+    char expr[256];
+    if (kern->cfg.tiny == 1)
+        snprintf(expr, sizeof(expr), "slas::gemm_tiny_kernel<%s, %zu, %zu, %zu, %d>", tname, m, n, k, kern->cfg.g);
+    else if (kern->cfg.tiny == 2)
+        snprintf(expr, sizeof(expr), "slas::gemm_rect_kernel<%s, %zu, %zu, %zu, %d, %d, %d>", tname, m, n, k, kern->cfg.tm, kern->cfg.tn,
+                 kern->cfg.g);
+    else
+        snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>",
+                 tname, tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages,
+                 ta ? "true" : "false", tb ? "true" : "false");
+    return jit_compile(kKernelSource, "gemm_small_jit.cu", expr, kern->cfg.smem, &kern->fn);
 }
 
 template <typename T>
 int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
                             size_t k, int ta, int tb) {
     if (tunable("gemm_jit") == 1 || batch < 64) return SLAS_ERR_UNSUPPORTED;
-    std::call_once(g_api_once, bind_api);
-    if (!g_api.ok) return SLAS_ERR_UNSUPPORTED;
+    if (!jit_ready()) return SLAS_ERR_UNSUPPORTED;
     JitKernel kern;
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -304,11 +321,7 @@ int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T
                       (void *)&ta_arg, (void *)&tb_arg, (void *)&stage_arg, (void *)&cstage_arg};
     if (kern.cfg.tiny && ((batch * m * k * sizeof(T)) % 16 || (batch * k * n * sizeof(T)) % 16))
         return SLAS_ERR_UNSUPPORTED;  // its ragged last chunk is copied in whole 16-byte words
-    const CUresult r = g_api.LaunchKernel(kern.fn, (unsigned)grid, 1, 1, (unsigned)kern.cfg.cons + 32, 1, 1, (unsigned)kern.cfg.smem,
-                                          (CUstream)st, params, nullptr);
-    if (r != CUDA_SUCCESS) return fail(SLAS_ERR_CUDA, "launch of the run-time specialised GEMM kernel failed (CUresult %d)", (int)r);
-    count_launch();
-    return SLAS_OK;
+    return jit_launch(kern.fn, (unsigned)grid, (unsigned)kern.cfg.cons + 32, kern.cfg.smem, st, params);
 }
 template int launch_gemm_jit_batched<float>(Context *, cudaStream_t, size_t, const float *, const float *, float *, size_t, size_t,
                                             size_t, int, int);

@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "divby.cuh"
 #include "kernels.cuh"
 #include "reduce.cuh"
 
@@ -346,17 +347,18 @@ normalize_fused_kernel(T *__restrict__ a, size_t len, size_t nvec, const RedGeom
         nrm_s = (T)__longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
     }
     __syncthreads();
-    const T nrm = nrm_s;
+    DivBy<T> by;
+    by.init(nrm_s);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         if (ok[u]) {
             T *e = reinterpret_cast<T *>(&x[u]);
 #pragma unroll
-            for (int q = 0; q < N; ++q) e[q] = e[q] / nrm;  // IEEE div.rn: a true division, not a reciprocal multiply
+            for (int q = 0; q < N; ++q) e[q] = by.div(e[q]);  // the bits of IEEE div.rn (divby.cuh): not a reciprocal multiply
             st_stream(av + i + (size_t)u * THREADS, x[u]);
         }
     }
-    if (jt < len) a[jt] = tail / nrm;
+    if (jt < len) a[jt] = by.div(tail);
     // the last block to have read the norm clears the slot for the next launch
     if (gridDim.x > 1 && threadIdx.x == 0) {
         const unsigned int t = atomicInc(ack, gridDim.x - 1);

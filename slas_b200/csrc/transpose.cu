@@ -18,7 +18,9 @@
 
 #include "async.cuh"
 #include "common.cuh"
+#include "jit.cuh"
 #include "kernels.cuh"
+#include "staged_objects_kernel.cuh"
 
 namespace slas {
 
@@ -220,84 +222,22 @@ transpose_small_kernel(const E *in, E *out, size_t batch, unsigned len, unsigned
     }
 }
 
-// ---- (2b) many small objects of any shape: bulk-TMA staging, element gather in shared memory ------------------------
+// ---- (2b) many small objects of any shape: bulk-TMA staging, transposed in shared memory --------------------------------
 // The warp-per-object kernel above leaves most of a warp idle on objects of a few elements (3x3 f32: 0.07 of HBM
-// peak).  Here HBM only ever sees 1-D bulk copies: a producer warp streams chunks of G consecutive objects into a
-// three-stage shared-memory ring (cp.async.bulk + mbarrier, as in the batched GEMM), the 256 consumers walk the OUTPUT
-// elements of the chunk linearly -- thread t takes elements t, t + 256, ... and keeps (object, row, column) up to date
-// with additions only -- gather each from its transposed position in the stage, write the output chunk to a
-// double-buffered shared tile (consecutive threads, consecutive elements: conflict-free), and one bulk store per chunk
-// takes it to HBM.  Works in place too (a chunk is read completely before it is stored).  Objects with
-// len == rows * columns only (a bulk store would overwrite a never-written tail).
+// peak).  transpose_staged_kernel (staged_objects_kernel.cuh): HBM only ever sees 1-D bulk copies, the transposition
+// happens between two shared-memory tiles.  <E, 0, 0, 0, false> takes the shape as run-time arguments; for small objects
+// of 8- and 16-byte elements the shape is a template constant and a thread moves a whole object (3x3 built in, other
+// shapes specialised by NVRTC at run time, staged_jit.cu) -- see the launcher for the measurements behind the split.
 template <typename E>
-__global__ void __launch_bounds__(288)
-transpose_staged_kernel(const E *in, E *out, size_t batch, size_t nchunks, unsigned len, unsigned rows, unsigned columns,
-                        unsigned G, unsigned stage_bytes) {
-    constexpr int CONSUMERS = 256, STAGES = 3;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(STAGES + 2) * stage_bytes);
-    uint64_t *empty = full + STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
-        mbar_fence_init();
+using StagedTransposeKernel = void (*)(const E *, E *, size_t, size_t, unsigned, unsigned, unsigned, unsigned, unsigned);
+template <typename E>
+static StagedTransposeKernel<E> staged_transpose_builtin(size_t rows, size_t columns) {
+    if constexpr (sizeof(E) == 8) {
+        if (rows == 3 && columns == 3) return transpose_staged_kernel<E, 9, 3, 3, true>;
     }
-    __syncthreads();
-    if (warp == CONSUMERS / 32) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-                const uint32_t s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
-                const size_t first = ch * G;
-                const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
-                // ragged final chunk: whole 16-byte words (the array ends on one: checked by the launcher)
-                const uint32_t bytes = (cnt * len * (uint32_t)sizeof(E) + 15u) & ~15u;
-                mbar_expect_tx(full + s, bytes);
-                bulk_g2s(smem_raw + (size_t)s * stage_bytes, in + first * len, bytes, full + s);
-            }
-        }
-        return;
-    }
-    // how (object, row, column) of the output element move when the linear index advances by 256
-    const unsigned step_obj = CONSUMERS / len, step_o = CONSUMERS % len;
-    const unsigned step_row = step_o / columns, step_col = step_o % columns;
-    uint32_t it = 0;
-    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-        const uint32_t s = it % STAGES, use = it / STAGES;
-        const size_t first = ch * G;
-        const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
-        const E *src = reinterpret_cast<const E *>(smem_raw + (size_t)s * stage_bytes);
-        E *cst = reinterpret_cast<E *>(smem_raw + (size_t)(STAGES + (it & 1)) * stage_bytes);
-        mbar_wait(full + s, use & 1);
-        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");  // the bulk store that read this output tile is done
-        unsigned obj = threadIdx.x / len, o = threadIdx.x % len;
-        unsigned orow = o / columns, ocol = o % columns;
-        const unsigned total = cnt * len;
-        for (unsigned e = threadIdx.x; e < total; e += CONSUMERS) {
-            cst[e] = src[obj * len + ocol * rows + orow];  // buffer[columns*row + column] = a[rows*column + row]
-            obj += step_obj; o += step_o; orow += step_row; ocol += step_col;
-            if (ocol >= columns) { ocol -= columns; ++orow; }
-            if (o >= len) { o -= len; ++obj; orow -= rows; }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 2, %0;" ::"n"(CONSUMERS) : "memory");
-        if (threadIdx.x == 0) {
-            const size_t cbytes = (size_t)total * sizeof(E);
-            const uint32_t whole = (uint32_t)(cbytes & ~(size_t)15);
-            if (whole)
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + first * len), "r"(smem_u32(cst)),
-                             "r"(whole)
-                             : "memory");
-            for (size_t e = whole / sizeof(E); e < total; ++e) out[first * len + e] = cst[e];
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        }
-    }
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return nullptr;
 }
+static unsigned gcd_u(unsigned a, unsigned b) { return b ? gcd_u(b, a % b) : a; }
 
 // launcher shared by the out-of-place and in-place paths; *handled = false when the shape does not qualify
 template <typename E>
@@ -342,18 +282,41 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    size_t G = (16 * 1024 / obj_bytes) / galign * galign;
+    const size_t stage_kb = tunable("transpose_stage_kb") > 0 ? (size_t)tunable("transpose_stage_kb") : 16;
+    size_t G = (stage_kb * 1024 / obj_bytes) / galign * galign;
     if (G < galign) G = galign;
     const size_t stage_bytes = (G * obj_bytes + 127) / 128 * 128;
     const size_t smem = 5 * stage_bytes + 6 * sizeof(uint64_t);
     if (smem > 200 * 1024) return SLAS_OK;
     const size_t nchunks = (batch + G - 1) / G;
     int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    const int cta_cap = tunable("staged_cta_cap") > 0 ? (int)tunable("staged_cta_cap") : 4;
+    if (per_sm > cta_cap) per_sm = cta_cap;
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)ctx->sm_count * per_sm;
     if (grid > nchunks) grid = nchunks;
-    auto kern = transpose_staged_kernel<E>;
+    // Shape as a compile-time constant, a thread per object (built in for 3x3, else specialised by NVRTC): for 8- and
+    // 16-byte elements whose objects fit a thread's registers and start in different shared-memory banks (an odd number
+    // of elements, or sharing only a factor 2 with the 16 / 8 accesses of a shared-memory phase).  Measured, fraction of
+    // HBM peak, run-time walk -> thread per object: 3x3 f64 0.85 -> 0.92, 5x3 f64 0.85 -> 0.94.  For 4-byte elements the
+    // run-time walk already runs at 0.93-0.96 and neither a thread per object (3x3 0.92, 5x5 0.92) nor the walk with
+    // constant indices (9x9 0.89, 10x10 0.89) beat it (profiles/r2t_tune_odd.log) -- what is left there is the bulk-copy
+    // pipeline, not instruction issue.  tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
+    const long jit_mode = tunable("staged_jit");
+    StagedTransposeKernel<E> kern = jit_mode == 2 ? nullptr : staged_transpose_builtin<E>(rows, columns);
+    if (!kern && jit_mode == 0 && sizeof(E) >= 8 && obj_bytes <= 256 && gcd_u((unsigned)len, 128 / (unsigned)sizeof(E)) <= 2) {
+        if (CUfunction fn = staged_transpose_jit(ctx, sizeof(E), (unsigned)len, (unsigned)rows, (unsigned)columns, true)) {
+            size_t batch_arg = batch, nchunks_arg = nchunks;
+            unsigned len_arg = (unsigned)len, rows_arg = (unsigned)rows, cols_arg = (unsigned)columns, g_arg = (unsigned)G,
+                     stage_arg = (unsigned)stage_bytes;
+            void *params[] = {(void *)&a,        (void *)&buffer,   (void *)&batch_arg, (void *)&nchunks_arg, (void *)&len_arg,
+                              (void *)&rows_arg, (void *)&cols_arg, (void *)&g_arg,     (void *)&stage_arg};
+            SLAS_TRY(jit_launch(fn, (unsigned)grid, 288, smem, st, params));
+            *handled = true;
+            return SLAS_OK;
+        }
+    }
+    if (!kern) kern = transpose_staged_kernel<E, 0, 0, 0, false>;
     SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, 288, smem, st>>>(a, buffer, batch, nchunks, (unsigned)len, (unsigned)rows, (unsigned)columns, (unsigned)G,
                                             (unsigned)stage_bytes);

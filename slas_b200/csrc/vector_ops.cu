@@ -11,9 +11,12 @@
 
 #include "async.cuh"
 #include "common.cuh"
+#include "divby.cuh"
+#include "jit.cuh"
 #include "kernels.cuh"
 #include "p2p.cuh"
 #include "reduce.cuh"
+#include "staged_objects_kernel.cuh"
 
 namespace slas {
 
@@ -196,6 +199,8 @@ scale_div_vec_kernel(const T *in, T *a, size_t nvec, size_t len, const T *__rest
     using V = typename Vec16<T>::type;
     constexpr int N = Vec16<T>::N;
     const T nrm = *norm_ptr;
+    DivBy<T> by;
+    by.init(nrm);
     V *av = reinterpret_cast<V *>(a);
     const V *iv = reinterpret_cast<const V *>(in);  // == av for the in-place normalize
     const size_t base = (size_t)blockIdx.x * (kEwThreads * UNROLL) + threadIdx.x;
@@ -211,20 +216,21 @@ scale_div_vec_kernel(const T *in, T *a, size_t nvec, size_t len, const T *__rest
         if (i < nvec) {
             T *e = reinterpret_cast<T *>(&r[u]);
 #pragma unroll
-            for (int j = 0; j < N; ++j) e[j] = e[j] / nrm;  // IEEE div.rn: a true division, not a reciprocal multiply
+            for (int j = 0; j < N; ++j) e[j] = by.div(e[j]);  // the bits of IEEE div.rn (divby.cuh): not a reciprocal multiply
             st_stream(av + i, r[u]);
         }
     }
     if (blockIdx.x == 0) {
         const size_t i = nvec * N + threadIdx.x;
-        if (i < len) a[i] = in[i] / nrm;
+        if (i < len) a[i] = by.div(in[i]);
     }
 }
 template <typename T>
 __global__ void __launch_bounds__(kEwThreads) scale_div_scalar_kernel(const T *in, T *a, size_t len, const T *norm_ptr) {
-    const T nrm = *norm_ptr;
+    DivBy<T> by;
+    by.init(*norm_ptr);
     for (size_t i = (size_t)blockIdx.x * kEwThreads + threadIdx.x; i < len; i += (size_t)gridDim.x * kEwThreads)
-        a[i] = in[i] / nrm;
+        a[i] = by.div(in[i]);
 }
 
 template <typename T>
@@ -342,7 +348,8 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
         } else if (MODE == 1) {
             if (t == 0) out[v] = (T)sqrt(s);
         } else {
-            const T nrm = (T)sqrt(s);
+            DivBy<T> by;
+            by.init((T)sqrt(s));
             T *pm = a_mut + v * len;
             if (vectorised) {
                 V *mv = reinterpret_cast<V *>(pm + head);
@@ -356,7 +363,7 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
                     for (int u = 0; u < 4; ++u) {
                         T *px = reinterpret_cast<T *>(&x[u]);
 #pragma unroll
-                        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                        for (int j = 0; j < N; ++j) px[j] = by.div(px[j]);
                         st_stream(mv + i + u * GROUP, x[u]);
                     }
                 }
@@ -364,13 +371,13 @@ batched_reduce_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__res
                     V x = mv[i];
                     T *px = reinterpret_cast<T *>(&x);
 #pragma unroll
-                    for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                    for (int j = 0; j < N; ++j) px[j] = by.div(px[j]);
                     st_stream(mv + i, x);
                 }
-                for (size_t j = head + nvec * N + t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
-                if ((size_t)t < head) pm[t] = pm[t] / nrm;
+                for (size_t j = head + nvec * N + t; j < len; j += GROUP) pm[j] = by.div(pm[j]);
+                if ((size_t)t < head) pm[t] = by.div(pm[t]);
             } else {
-                for (size_t j = t; j < len; j += GROUP) pm[j] = pm[j] / nrm;
+                for (size_t j = t; j < len; j += GROUP) pm[j] = by.div(pm[j]);
             }
         }
     }
@@ -440,7 +447,8 @@ batched_reduce_subwarp_kernel(const T *__restrict__ a, const T *__restrict__ b, 
             } else if (MODE == 1) {
                 if (t == 0) out[v] = (T)sqrt(s);
             } else {
-                const T nrm = (T)sqrt(s);
+                DivBy<T> by;
+                by.init((T)sqrt(s));
                 V *mv = reinterpret_cast<V *>(a_mut + v * len);
 #pragma unroll
                 for (int p = 0; p < PER; ++p) {
@@ -448,7 +456,7 @@ batched_reduce_subwarp_kernel(const T *__restrict__ a, const T *__restrict__ b, 
                     if (i < nvec) {
                         T *px = reinterpret_cast<T *>(&x[u][p]);
 #pragma unroll
-                        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+                        for (int j = 0; j < N; ++j) px[j] = by.div(px[j]);
                         st_stream(mv + i, x[u][p]);
                     }
                 }
@@ -507,13 +515,14 @@ batched_reduce_lane_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
         } else if (MODE == 1) {
             out[v] = (T)sqrt(s);
         } else {
-            const T nrm = (T)sqrt(s);
+            DivBy<T> by;
+            by.init((T)sqrt(s));
 #pragma unroll
             for (int c = 0; c < CHMAX; ++c)
                 if (c < (int)chunks) {
                     T *px = reinterpret_cast<T *>(xa[c]);
 #pragma unroll
-                    for (int j = 0; j < E32; ++j) px[j] = px[j] / nrm;
+                    for (int j = 0; j < E32; ++j) px[j] = by.div(px[j]);
                     stg256(a_mut + v * len + c * E32, xa[c]);
                 }
         }
@@ -522,105 +531,25 @@ batched_reduce_lane_kernel(const T *__restrict__ a, const T *__restrict__ b, T *
 
 // Short vectors that are NOT whole 16-byte words (3-vectors, LEN 5, 7, 30 ...): the vector kernels above cannot load
 // them with aligned vectors and a warp per vector idles on three elements (LEN 3 f32: 0.02 of HBM peak).  Same cure as
-// for the small transposes and products: HBM only sees 1-D bulk copies.  A producer warp streams chunks of G
-// consecutive vectors of a (and b) into a three-stage shared-memory ring; each consumer thread owns whole vectors of
-// the chunk -- a plain ascending loop of FMAs in T, exactly the reference's naive loop (rust.rs:116-121) -- and writes
-// its result to consecutive out[] (dot / norm), or the scaled vector to a double-buffered shared tile that leaves with
-// one bulk store per chunk (normalize).
+// for the small transposes and products: HBM only sees 1-D bulk copies, a thread per vector works in shared memory --
+// batched_reduce_staged_kernel, staged_objects_kernel.cuh.  LEN is a template constant for the lengths built in below
+// (up to 8 elements) and for whatever else NVRTC specialises at run time (staged_jit.cu); CLEN = 0 is the run-time
+// fallback.  All forms run the same operations in the same order: the same bits.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(288)
-batched_reduce_staged_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict__ out, T *a_mut, size_t batch,
-                             size_t nchunks, unsigned len, unsigned G, unsigned stage_bytes) {
-    constexpr int CONSUMERS = 256, STAGES = 3;
-    constexpr int NIN = MODE == 0 ? 2 : 1;  // operands per stage
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned char *out_base = smem_raw + (size_t)STAGES * NIN * stage_bytes;
-    uint64_t *full = reinterpret_cast<uint64_t *>(out_base + (MODE == 2 ? 2 * (size_t)stage_bytes : 0));
-    uint64_t *empty = full + STAGES;
-    T *norms = reinterpret_cast<T *>(empty + STAGES);  // MODE 2: the chunk's G norms
-    // measured: up to 8 elements the owning thread scales its own vector (LEN 3 f32 0.72 against 0.59); longer ones are
-    // scaled by all threads over consecutive elements (LEN 38 f32 0.64 against 0.53, LEN 19 f64 0.80 against 0.67)
-    const bool coop_scale = len > 8;
-    const T *abase = MODE == 2 ? a_mut : a;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, CONSUMERS / 32); }
-        mbar_fence_init();
+using StagedReduceKernel = void (*)(const T *, const T *, T *, T *, size_t, size_t, unsigned, unsigned, unsigned);
+template <typename T, int MODE>
+static StagedReduceKernel<T, MODE> staged_reduce_builtin(size_t len) {
+    switch (len) {
+    case 1: return batched_reduce_staged_kernel<T, MODE, 1>;
+    case 3: return batched_reduce_staged_kernel<T, MODE, 3>;
+    case 5: return batched_reduce_staged_kernel<T, MODE, 5>;
+    case 7: return batched_reduce_staged_kernel<T, MODE, 7>;
     }
-    __syncthreads();
-    if (warp == CONSUMERS / 32) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-                const uint32_t s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
-                const size_t first = ch * G;
-                const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
-                const uint32_t bytes = (cnt * len * (uint32_t)sizeof(T) + 15u) & ~15u;  // the arrays end on a 16-byte word
-                mbar_expect_tx(full + s, NIN * bytes);
-                bulk_g2s(smem_raw + (size_t)s * NIN * stage_bytes, abase + first * len, bytes, full + s);
-                if (MODE == 0) bulk_g2s(smem_raw + (size_t)s * NIN * stage_bytes + stage_bytes, b + first * len, bytes, full + s);
-            }
-        }
-        return;
+    if constexpr (sizeof(T) == 4) {  // (even lengths of 8-byte elements are whole 16-byte words: never staged)
+        if (len == 2) return batched_reduce_staged_kernel<T, MODE, 2>;
+        if (len == 6) return batched_reduce_staged_kernel<T, MODE, 6>;
     }
-    uint32_t it = 0;
-    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-        const uint32_t s = it % STAGES, use = it / STAGES;
-        const size_t first = ch * G;
-        const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
-        const T *sa = reinterpret_cast<const T *>(smem_raw + (size_t)s * NIN * stage_bytes);
-        const T *sb = MODE == 0 ? reinterpret_cast<const T *>(smem_raw + (size_t)s * NIN * stage_bytes + stage_bytes) : sa;
-        T *cst = reinterpret_cast<T *>(out_base + (size_t)(it & 1) * stage_bytes);
-        mbar_wait(full + s, use & 1);
-        if (MODE == 2) asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");  // the bulk store that read this tile is done
-        for (uint32_t v = threadIdx.x; v < cnt; v += CONSUMERS) {
-            const T *pa = sa + (size_t)v * len, *pb = sb + (size_t)v * len;
-            T acc = T(0);
-            for (unsigned i = 0; i < len; ++i) acc = fma(pa[i], pb[i], acc);
-            if (MODE == 0) {
-                out[first + v] = acc;
-            } else if (MODE == 1) {
-                out[first + v] = sqrt(acc);  // correctly rounded in T (sqrt.rn): the same bits as rounding a wider sqrt
-            } else if (coop_scale) {
-                norms[v] = sqrt(acc);
-            } else {
-                const T nrm = sqrt(acc);
-                T *pc = cst + (size_t)v * len;
-                for (unsigned i = 0; i < len; ++i) pc[i] = pa[i] / nrm;
-            }
-        }
-        if (MODE == 2 && coop_scale) {
-            // scale pass over the chunk's elements, all threads, consecutive elements (no bank conflicts, no idle lanes);
-            // (vector, element) of the linear index kept up to date with additions
-            asm volatile("bar.sync 3, %0;" ::"n"(CONSUMERS) : "memory");
-            const unsigned total = cnt * len, step_v = CONSUMERS / len, step_i = CONSUMERS % len;
-            unsigned v = threadIdx.x / len, i = threadIdx.x % len;
-            for (unsigned e = threadIdx.x; e < total; e += CONSUMERS) {
-                cst[e] = sa[e] / norms[v];
-                v += step_v; i += step_i;
-                if (i >= len) { i -= len; ++v; }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
-        if (MODE == 2) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 2, %0;" ::"n"(CONSUMERS) : "memory");
-            if (threadIdx.x == 0) {
-                const size_t total = (size_t)cnt * len, cbytes = total * sizeof(T);
-                const uint32_t whole = (uint32_t)(cbytes & ~(size_t)15);
-                if (whole)
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a_mut + first * len),
-                                 "r"(smem_u32(cst)), "r"(whole)
-                                 : "memory");
-                for (size_t e = whole / sizeof(T); e < total; ++e) a_mut[first * len + e] = cst[e];
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            }
-        }
-    }
-    if (MODE == 2 && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return nullptr;
 }
 
 template <typename T, int MODE>
@@ -652,20 +581,43 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    const long stage_kb = tunable("bdot_stage_kb") > 0 ? tunable("bdot_stage_kb") : 16;
+    // measured (profiles/r2w_tune_oddsweep3.log): the cooperative scale pass of normalize (LEN > 8, two more shared tiles
+    // than dot) prefers three CTAs per SM -- 12 KB stages: LEN 13 / 30 / 38 f32 0.84 / 0.85 / 0.91 against 0.80 / 0.81 / 0.84
+    // at 16 KB, LEN 19 f64 0.92 against 0.75
+    const long stage_kb = tunable("bdot_stage_kb") > 0 ? tunable("bdot_stage_kb") : (MODE == 2 && len > 8 ? 12 : 16);
     size_t G = ((size_t)stage_kb * 1024 / vbytes) / galign * galign;
-    if (G > 1024) G = 1024 / galign * galign;
+    const size_t gcap = tunable("bdot_gcap") > 0 ? (size_t)tunable("bdot_gcap") : 4096;
+    if (G > gcap) G = gcap / galign * galign;
     if (G < galign) G = galign;
-    const size_t stage_bytes = (G * vbytes + 127) / 128 * 128;
-    const size_t smem = (3 * (MODE == 0 ? 2 : 1) + (MODE == 2 ? 2 : 0)) * stage_bytes + 6 * sizeof(uint64_t) +
-                        (MODE == 2 ? G * sizeof(T) : 0);
+    size_t stage_bytes = 0, smem = 0;
+    for (;; G = (G / 2 + galign - 1) / galign * galign) {  // (a stage-size tunable beyond what fits: halve)
+        stage_bytes = (G * vbytes + 127) / 128 * 128;
+        smem = (3 * (MODE == 0 ? 2 : 1) + (MODE == 2 ? 2 : 0)) * stage_bytes + 6 * sizeof(uint64_t) + (MODE == 2 ? G * sizeof(DivBy<T>) : 0);
+        if (smem <= 200 * 1024 || G <= galign) break;
+    }
     const size_t nchunks = (batch + G - 1) / G;
     int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    const int cta_cap = tunable("staged_cta_cap") > 0 ? (int)tunable("staged_cta_cap") : 4;
+    if (per_sm > cta_cap) per_sm = cta_cap;
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)ctx->sm_count * per_sm;
     if (grid > nchunks) grid = nchunks;
-    auto kern = batched_reduce_staged_kernel<T, MODE>;
+    // shape as a compile-time constant: built in, else specialised by NVRTC (lengths that fit a thread's unrolled loop),
+    // else the run-time-shape instantiation.  tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
+    const long jit_mode = tunable("staged_jit");
+    StagedReduceKernel<T, MODE> kern = jit_mode == 2 ? nullptr : staged_reduce_builtin<T, MODE>(len);
+    if (!kern && jit_mode == 0 && len <= 64 && smem <= kStagedJitSmem) {
+        if (CUfunction fn = staged_reduce_jit(ctx, sizeof(T), MODE, (unsigned)len)) {
+            size_t batch_arg = batch, nchunks_arg = nchunks;
+            unsigned len_arg = (unsigned)len, g_arg = (unsigned)G, stage_arg = (unsigned)stage_bytes;
+            void *params[] = {(void *)&a, (void *)&b, (void *)&out, (void *)&a_mut, (void *)&batch_arg, (void *)&nchunks_arg,
+                              (void *)&len_arg, (void *)&g_arg, (void *)&stage_arg};
+            SLAS_TRY(jit_launch(fn, (unsigned)grid, 288, smem, st, params));
+            *handled = true;
+            return SLAS_OK;
+        }
+    }
+    if (!kern) kern = batched_reduce_staged_kernel<T, MODE, 0>;
     SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, 288, smem, st>>>(a, b, out, a_mut, batch, nchunks, (unsigned)len, (unsigned)G, (unsigned)stage_bytes);
     SLAS_LAUNCH_CHECK();
@@ -743,10 +695,11 @@ batched_scale_kernel(T *__restrict__ a, const T *__restrict__ norms, size_t len,
         const size_t v = i / nvec_per, w = i - v * nvec_per;
         V *p = reinterpret_cast<V *>(a + v * len) + w;
         V x = *p;
-        const T nrm = norms[v];
+        DivBy<T> by;
+        by.init(norms[v]);
         T *px = reinterpret_cast<T *>(&x);
 #pragma unroll
-        for (int j = 0; j < N; ++j) px[j] = px[j] / nrm;
+        for (int j = 0; j < N; ++j) px[j] = by.div(px[j]);
         st_stream(p, x);
     }
 }

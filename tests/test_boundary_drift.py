@@ -130,6 +130,11 @@ def test_build_rs_compiles_what_the_makefile_compiles():
     # kernel text gemm_jit.cu embeds for NVRTC
     assert "gemm_tiny.cu" in rs and "SLAS_TINY_F64" in rs, "build.rs must compile gemm_tiny.cu twice (f32 and -DSLAS_TINY_F64)"
     assert "embed_jit_source.py" in rs and "gemm_small_jit_src.inc" in rs, "build.rs must run the embed step gemm_jit.cu needs"
+    assert "staged_jit_src.inc" in rs and "staged_jit_src.inc" in mk, "build.rs must run the embed step staged_jit.cu needs"
+    for inc in ("gemm_small_jit_src.inc", "staged_jit_src.inc"):   # ... over the same headers as the Makefile rule
+        mk_hdrs = re.search(rf"embed_jit_source\.py \$@ (.*)$", mk[mk.index(inc + ":"):], flags=re.M).group(1).split()
+        rs_hdrs = re.findall(r'"([a-z_0-9]+\.cuh)"', rs[rs.index(inc):][:400])
+        assert mk_hdrs == rs_hdrs, (inc, mk_hdrs, rs_hdrs)
     for flag in ("arch=compute_100a,code=sm_100a", "-lineinfo", "-std=c++17"):
         assert flag in rs and flag in mk, flag
     # config knobs of the reference's build script style (build.rs:7-27 there): SLAS_* environment variables

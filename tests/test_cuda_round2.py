@@ -367,3 +367,101 @@ def test_single_launch_normalize_matches_the_two_pass_path(dt, n):
             finally:
                 set_tunable("normalize_fused", 0)
             assert np.array_equal(v.to_host(), ref.to_host()), (dt, n, i)
+
+
+# ---- small objects with the shape as a compile-time constant (staged_objects_kernel.cuh: built in / NVRTC / run-time) ----
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("length,batch", [(1, 4096), (2, 5000), (3, 70001), (5, 4099), (6, 3000), (7, 2048), (9, 3001), (13, 1024),
+                                          (19, 2000), (30, 1500), (63, 700), (127, 600)])
+def test_staged_reductions_same_bits_for_every_form_of_the_shape(dt, length, batch):
+    """tunable staged_jit: 2 = the length is a run-time argument, 1 = built-in constants only, 0 = NVRTC too"""
+    rng = np.random.default_rng(length * 7 + batch)
+    a = rng.uniform(-1, 1, batch * length).astype(dt)
+    b = rng.uniform(-1, 1, batch * length).astype(dt)
+    da, db = CudaVec.from_host(a), CudaVec.from_host(b)
+    got = {}
+    try:
+        for mode in (2, 1, 0):
+            set_tunable("staged_jit", mode)
+            o1, o2, x = CudaVec(batch, dt), CudaVec(batch, dt), CudaVec.from_host(a)
+            cuda.dot_batched(da, db, o1, length)
+            cuda.norm_batched(da, o2, length)
+            cuda.normalize_batched(x, length)
+            got[mode] = (o1.to_host(), o2.to_host(), x.to_host())
+    finally:
+        set_tunable("staged_jit", 0)
+    for mode in (1, 0):
+        for r, w in zip(got[mode], got[2]):
+            assert np.array_equal(r.view(np.uint8), w.view(np.uint8)), (mode, length, batch)
+    A, B = a.reshape(batch, length).astype(np.float64), b.reshape(batch, length).astype(np.float64)
+    eps = np.finfo(dt).eps
+    assert np.allclose(got[0][0], (A * B).sum(1), rtol=0, atol=4 * length * eps)
+    nrm = np.sqrt((A * A).sum(1))
+    assert np.allclose(got[0][1], nrm, rtol=4 * length * eps, atol=0)
+    assert np.allclose(got[0][2].reshape(batch, length), A / nrm[:, None], rtol=8 * length * eps, atol=eps)
+    # normalize divides by exactly the bits norm returns (norm and normalize share a kernel)
+    assert np.array_equal(got[0][2].reshape(batch, length), a.reshape(batch, length) / got[0][1][:, None])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("rows,cols,batch", [(3, 3, 70001), (2, 3, 4096), (3, 2, 1001), (5, 5, 3000), (3, 5, 2050), (6, 6, 999), (7, 9, 1024),
+                                             (10, 10, 600), (30, 31, 300), (1, 7, 4096), (7, 1, 4096)])
+def test_staged_transposes_same_bytes_for_every_form_of_the_shape(elem, rows, cols, batch):
+    rng = np.random.default_rng(elem * 100 + rows * 10 + cols)
+    n = rows * cols
+    raw = rng.integers(0, 256, batch * n * elem, dtype=np.uint8)
+    dt = np.dtype((np.void, elem))
+    want = raw.reshape(batch, cols, rows, elem).transpose(0, 2, 1, 3).reshape(-1)
+    src = CudaVec.from_host(raw.view(dt))
+    try:
+        for mode in (2, 1, 0):
+            set_tunable("staged_jit", mode)
+            out = CudaVec(batch * n, dt).zero_()
+            cuda.transpose_batched(src, out, n, cols)
+            assert np.array_equal(out.to_host().view(np.uint8), want), (mode, elem, rows, cols, batch)
+            ip = CudaVec.from_host(raw.view(dt))
+            cuda.transpose_inplace_batched(ip, n, cols)
+            assert np.array_equal(ip.to_host().view(np.uint8), want), ("in place", mode, elem, rows, cols, batch)
+    finally:
+        set_tunable("staged_jit", 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("length,batch", [(2, 200_000), (3, 150_001), (7, 50_000), (13, 40_000), (16, 40_000), (64, 10_000), (100, 5_000),
+                                          (1000, 600), (5000, 64), (1 << 20, 1)])
+def test_normalize_divides_with_the_bits_of_an_ieee_division_over_the_whole_exponent_range(length, batch):
+    """divby.cuh hoists the reciprocal refinement of div.rn.f32 out of the per-element loop; zero / subnormal / huge
+    operands take the plain division.  Every element must equal numpy's correctly rounded a / norm."""
+    rng = np.random.default_rng(length)
+    n = batch * length
+    mant = rng.uniform(1, 2, n).astype(np.float32)
+    expo = rng.integers(-75, 30, n)
+    a = (np.ldexp(mant, expo) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    # sprinkle zeros, subnormals, the smallest normals and values that make the norm subnormal / huge / infinite
+    special = np.array([0.0, -0.0, 1e-45, -3e-42, 1.1754944e-38, -1.1754944e-38, 2e-38, 1e-30, 3e18, -2.5e19], np.float32)
+    idx = rng.integers(0, n, max(1, n // 50))
+    a[idx] = special[rng.integers(0, len(special), idx.size)]
+    if batch > 8:
+        rows = a.reshape(batch, length)
+        rows[0] = np.float32(1e-30)          # norm ~ 1e-30 * sqrt(len): squares underflow -> norm of subnormal sum
+        rows[1] = np.float32(1e-44)          # all subnormal: norm 0 -> division by zero (inf / nan like the reference)
+        rows[2] = np.float32(3e19)           # squares overflow: norm = inf
+        rows[3, :] = 0
+        rows[4] = np.float32(2.0) ** -50
+        rows[5] = np.float32(2.0) ** 59
+    d = CudaVec.from_host(a)
+    norms = CudaVec(batch, np.float32)
+    if batch == 1:
+        nrm = np.array([cuda.norm(d)], np.float32)
+        cuda.normalize(d)
+    else:
+        cuda.norm_batched(d, norms, length)
+        cuda.normalize_batched(d, length)
+        nrm = norms.to_host()
+    got = d.to_host().reshape(batch, length)
+    with np.errstate(all="ignore"):
+        want = a.reshape(batch, length) / nrm[:, None]
+    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (length, batch, np.argwhere(~same)[:5], got[~same][:5], want[~same][:5])
