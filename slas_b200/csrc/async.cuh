@@ -45,6 +45,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         if ((++spins & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
     }
 }
+// the producer's wait for a free stage is not latency-critical (two more stages are in flight): back off instead of
+// spinning on the issue slots the consumers need (ncu, profiles/r2s_*: the spin was 13 % of all instructions issued by the staged transpose / normalize kernels)
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const uint64_t t0 = global_timer_ns();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(400);
+        if ((++spins & 0x3f) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
+    }
+}
+
 // global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -75,7 +75,7 @@ gemm_small_generic_kernel(const T *__restrict__ a, const T *__restrict__ b, T *_
             uint32_t it = 0;
             for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
                 const uint32_t s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                if (use > 0) mbar_wait_backoff(empty + s, (use - 1) & 1);
                 const size_t first = ch * G;
                 const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
                 T *sa = stage_base + (size_t)s * stage_elems;

@@ -72,7 +72,7 @@ gemm_tiny_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict
             uint32_t it = 0;
             for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
                 const uint32_t s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                if (use > 0) mbar_wait_backoff(empty + s, (use - 1) & 1);
                 const size_t first = ch * G;
                 const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
                 T *sa = stage_base + (size_t)s * stage_elems;
@@ -158,7 +158,7 @@ gemm_rect_kernel(const T *__restrict__ a, const T *__restrict__ b, T *__restrict
             uint32_t it = 0;
             for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
                 const uint32_t s = it % STAGES, use = it / STAGES;
-                if (use > 0) mbar_wait(empty + s, (use - 1) & 1);
+                if (use > 0) mbar_wait_backoff(empty + s, (use - 1) & 1);
                 const size_t first = ch * G;
                 const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
                 T *sa = stage_base + (size_t)s * stage_elems;

@@ -21,18 +21,6 @@
 
 namespace slas {
 
-// the producer's wait for a free stage is not latency-critical (two more stages are in flight): back off instead of
-// spinning on the issue slots the consumers need (ncu: the spin was 13 % of all instructions issued)
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_timer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        __nanosleep(400);
-        if ((++spins & 0x3f) == 0 && global_timer_ns() - t0 > 4000000000ull) __trap();
-    }
-}
-
 // ---- batched dot (MODE 0) / norm (1) / normalize in place (2) ------------------------------------------------------------
 // Each consumer thread owns whole vectors of the chunk: a plain ascending loop of FMAs in T from 0 -- the reference's
 // naive loop (rust.rs:116-121) -- then sqrt.rn / div.rn.  The same operations in the same order for every CLEN, so the
