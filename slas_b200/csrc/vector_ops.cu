@@ -592,7 +592,7 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
     size_t stage_bytes = 0, smem = 0;
     for (;; G = (G / 2 + galign - 1) / galign * galign) {  // (a stage-size tunable beyond what fits: halve)
         stage_bytes = (G * vbytes + 127) / 128 * 128;
-        smem = (3 * (MODE == 0 ? 2 : 1) + (MODE == 2 ? 2 : 0)) * stage_bytes + 6 * sizeof(uint64_t) + (MODE == 2 ? G * sizeof(DivBy<T>) : 0);
+        smem = (3 * (MODE == 0 ? 2 : 1) + (MODE == 2 ? 2 : 0)) * stage_bytes + 6 * sizeof(uint64_t) + (MODE == 2 && len > 8 ? G * sizeof(DivBy<T>) : 0);  // (the divisors of the cooperative scale pass)
         if (smem <= 200 * 1024 || G <= galign) break;
     }
     const size_t nchunks = (batch + G - 1) / G;

@@ -429,39 +429,66 @@ def test_staged_transposes_same_bytes_for_every_form_of_the_shape(elem, rows, co
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("length,batch", [(2, 200_000), (3, 150_001), (7, 50_000), (13, 40_000), (16, 40_000), (64, 10_000), (100, 5_000),
-                                          (1000, 600), (5000, 64), (1 << 20, 1)])
-def test_normalize_divides_with_the_bits_of_an_ieee_division_over_the_whole_exponent_range(length, batch):
-    """divby.cuh hoists the reciprocal refinement of div.rn.f32 out of the per-element loop; zero / subnormal / huge
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("length,batch", [(2, 200_000), (3, 150_001), (7, 50_000), (13, 40_000), (16, 40_000), (19, 30_000), (64, 10_000),
+                                          (100, 5_000), (1000, 600), (5000, 64), (1 << 20, 1)])
+def test_normalize_divides_with_the_bits_of_an_ieee_division_over_the_whole_exponent_range(dt, length, batch):
+    """divby.cuh hoists the reciprocal refinement of div.rn out of the per-element loop; zero / subnormal / huge
     operands take the plain division.  Every element must equal numpy's correctly rounded a / norm."""
     rng = np.random.default_rng(length)
     n = batch * length
-    mant = rng.uniform(1, 2, n).astype(np.float32)
-    expo = rng.integers(-75, 30, n)
-    a = (np.ldexp(mant, expo) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    f32 = dt == np.float32
+    mant = rng.uniform(1, 2, n)
+    expo = rng.integers(-75, 30, n) if f32 else rng.integers(-530, 250, n)
+    a = (np.ldexp(mant, expo) * rng.choice([-1.0, 1.0], n)).astype(dt)
     # sprinkle zeros, subnormals, the smallest normals and values that make the norm subnormal / huge / infinite
-    special = np.array([0.0, -0.0, 1e-45, -3e-42, 1.1754944e-38, -1.1754944e-38, 2e-38, 1e-30, 3e18, -2.5e19], np.float32)
+    special = np.array([0.0, -0.0, 1e-45, -3e-42, 1.1754944e-38, -1.1754944e-38, 2e-38, 1e-30, 3e18, -2.5e19] if f32 else
+                       [0.0, -0.0, 5e-324, -3e-310, 2.2250738585072014e-308, -2.2250738585072014e-308, 1e-300, 1e-160, 1e150, -3e153], dt)
     idx = rng.integers(0, n, max(1, n // 50))
     a[idx] = special[rng.integers(0, len(special), idx.size)]
     if batch > 8:
         rows = a.reshape(batch, length)
-        rows[0] = np.float32(1e-30)          # norm ~ 1e-30 * sqrt(len): squares underflow -> norm of subnormal sum
-        rows[1] = np.float32(1e-44)          # all subnormal: norm 0 -> division by zero (inf / nan like the reference)
-        rows[2] = np.float32(3e19)           # squares overflow: norm = inf
+        rows[0] = dt(1e-30 if f32 else 1e-200)   # squares underflow: a norm that is a (sub)normal tiny number or zero
+        rows[1] = dt(1e-44 if f32 else 1e-320)   # all subnormal: norm 0 -> division by zero (inf / nan like the reference)
+        rows[2] = dt(3e19 if f32 else 1e160)     # squares overflow: norm = inf
         rows[3, :] = 0
-        rows[4] = np.float32(2.0) ** -50
-        rows[5] = np.float32(2.0) ** 59
+        rows[4] = dt(2.0) ** (-50 if f32 else -490)
+        rows[5] = dt(2.0) ** (59 if f32 else 499)
     d = CudaVec.from_host(a)
-    norms = CudaVec(batch, np.float32)
-    if batch == 1:
-        nrm = np.array([cuda.norm(d)], np.float32)
-        cuda.normalize(d)
-    else:
-        cuda.norm_batched(d, norms, length)
-        cuda.normalize_batched(d, length)
-        nrm = norms.to_host()
-    got = d.to_host().reshape(batch, length)
+    norms = CudaVec(batch, dt)
     with np.errstate(all="ignore"):
+        if batch == 1:
+            nrm = np.array([cuda.norm(d)], dt)
+            cuda.normalize(d)
+        else:
+            cuda.norm_batched(d, norms, length)
+            cuda.normalize_batched(d, length)
+            nrm = norms.to_host()
+        got = d.to_host().reshape(batch, length)
         want = a.reshape(batch, length) / nrm[:, None]
-    same = (got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))
+    u = np.uint32 if f32 else np.uint64
+    same = (got.view(u) == want.view(u)) | (np.isnan(got) & np.isnan(want))
     assert same.all(), (length, batch, np.argwhere(~same)[:5], got[~same][:5], want[~same][:5])
+
+
+@pytest.mark.gpu
+def test_a_shape_is_specialised_by_nvrtc_inside_a_graph_capture():
+    """first sight of a shape while a capture is open: NVRTC compile + module load must not invalidate the capture
+    (relaxed capture mode), and the recorded launch of the driver-API kernel must replay"""
+    rng = np.random.default_rng(77)
+    length, batch = 21, 3000                       # LEN 21 f64 vectors; 3 x 7 objects of 8-byte elements: not built in
+    a = rng.uniform(-1, 1, batch * length)
+    x, t = CudaVec.from_host(a), CudaVec(batch * length, np.float64).zero_()
+    with Graph() as g:
+        cuda.transpose_batched(x, t, length, 7)    # read as 7 x 3, written 3 x 7
+        cuda.normalize_batched(x, length)
+    want_t = a.reshape(batch, 7, 3).transpose(0, 2, 1).reshape(-1)
+    for _ in range(2):
+        x.copy_from_host(a)
+        t.zero_()
+        g.launch()
+        assert np.array_equal(t.to_host(), want_t)
+        rows = a.reshape(batch, length)
+        got = x.to_host().reshape(batch, length)
+        nrm = np.sqrt((rows * rows).sum(1))
+        assert np.allclose(got, rows / nrm[:, None], rtol=1e-13, atol=0)
