@@ -504,7 +504,31 @@ def g_oddsweep3():
     set_tunable("bdot_stage_kb", 0)
 
 
+def g_bnorm():
+    """batched norm / normalize of medium vectors (8 KB .. 512 KB): CTA per vector (bnorm_cluster = 1) against a thread-block
+    cluster per vector with the vector in registers (0), CTAs per SM swept"""
+    for length, log2, dt in ((2048, 17, np.float32), (4096, 16, np.float32), (8192, 15, np.float32), (16384, 14, np.float32),
+                             (32768, 13, np.float32), (65536, 12, np.float32), (131072, 11, np.float32), (20000, 14, np.float32),
+                             (2048, 16, np.float64), (16384, 13, np.float64), (65536, 11, np.float64)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, a), (_, o) = uniform(b * length, dt, 1), uniform(b, dt, 3)
+        for off, caps in ((1, (0,)), (0, (0, 3, 6))):
+            set_tunable("bnorm_cluster", off)
+            for cap in caps:
+                set_tunable("bnorm_cluster_ctas", cap)
+                tag = "CTA per vector" if off else f"cluster per vector, {cap or 'default'} CTAs per SM"
+                report(f"norm_batched len {length} x 2^{log2} {np.dtype(dt).name} [{tag}]", timed(lambda: cuda.norm_batched(a, o, length)),
+                       nbytes=1.0 * b * length * es)
+                report(f"normalize_batched len {length} x 2^{log2} {np.dtype(dt).name} [{tag}]", timed(lambda: cuda.normalize_batched(a, length)),
+                       nbytes=2.0 * b * length * es)
+        del a, o
+        torch.cuda.empty_cache()
+    set_tunable("bnorm_cluster", 0)
+    set_tunable("bnorm_cluster_ctas", 0)
+
+
 GROUPS = {
+    "bnorm": g_bnorm,
     "oddsweep3": g_oddsweep3,
     "oddsweep2": g_oddsweep2,
     "oddsweep": g_oddsweep,

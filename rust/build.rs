@@ -23,7 +23,7 @@ mod cuda_backend {
 
     // == SRCS of slas_b200/csrc/Makefile
     const KERNEL_SOURCES: &[&str] = &[
-        "context.cu", "api.cu", "vector_ops.cu", "reduce.cu", "fused_chain.cu", "transpose.cu", "gemm_small.cu",
+        "context.cu", "api.cu", "vector_ops.cu", "batched_cluster.cu", "reduce.cu", "fused_chain.cu", "transpose.cu", "gemm_small.cu",
         "gemm_jit.cu", "staged_jit.cu", "gemm_generic.cu", "gemm_large.cu", "gemm_large_f64.cu", "gemm_tcgen05.cu",
         "comm.cu", "multi.cu", "hostcopy.cu", "microbench.cu",
     ];

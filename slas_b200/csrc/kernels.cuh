@@ -26,6 +26,10 @@ int launch_fused_chain(Context *ctx, cudaStream_t st, int chain, size_t len, con
 template <typename T>
 int launch_batched_reduce(Context *ctx, cudaStream_t st, int mode, size_t batch, size_t len, const T *a,
                           const T *b, T *out, T *a_mut);
+// batched_cluster.cu -- norm (MODE 1) / normalize (MODE 2) of medium vectors, a thread-block cluster per vector;
+// *handled = false: not a length for it
+template <typename T, int MODE>
+int launch_batched_norm_cluster(Context *ctx, cudaStream_t st, size_t batch, size_t len, const T *a, T *out, T *a_mut, bool *handled);
 template <typename T>
 int launch_fill_uniform(Context *ctx, cudaStream_t st, size_t len, T *x, uint64_t seed, uint64_t offset, T lo, T hi);
 

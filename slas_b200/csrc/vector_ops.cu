@@ -763,6 +763,13 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
         SLAS_TRY((launch_batched_reduce_staged<T, MODE>(ctx, st, batch, len, a, b, out, a_mut, &staged)));
         if (staged) return SLAS_OK;
     }
+    if constexpr (MODE != 0) {
+        // 8 KB .. 512 KB per vector: a thread-block cluster per vector, the vector in registers between norm and division
+        // (norm switches with normalize: normalize divides by the bits norm returns)
+        bool clustered = false;
+        SLAS_TRY((launch_batched_norm_cluster<T, MODE>(ctx, st, batch, len, a, out, a_mut, &clustered)));
+        if (clustered) return SLAS_OK;
+    }
     if (vec && len >= (size_t)N && len / N <= 32 * 8) {
         // tiny: sub-warp groups, registers only
         const size_t pieces = len / N;

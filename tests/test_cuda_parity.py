@@ -1046,7 +1046,10 @@ def test_gemv_batched_small_odd_shapes(dt, rows, cols, ta):
                                           # warp / CTA per vector with ragged piece counts, more vectors than groups in
                                           # the grid, and the lengths either side of every kernel switch
                                           (1028, 77), (2052, 19), (4092, 3000), (8192, 11), (8196, 7), (12004, 1500),
-                                          (32768, 5), (32772, 3), (65536, 3)])
+                                          (32768, 5), (32772, 3), (65536, 3),
+                                          # 8 KB .. 512 KB: a thread-block cluster per vector (1 / 2 / 4 / 8 CTAs, 4 / 8 / 16
+                                          # vectors per thread), more vectors than resident clusters, either side of its range
+                                          (2052, 700), (2560, 2000), (6000, 900), (49152, 300), (98304, 40), (131072, 3), (131076, 2)])
 def test_batched_reductions(dt, length, batch):
     rng = np.random.default_rng(length + batch)
     a, b = _rand(rng, batch * length, dt), _rand(rng, batch * length, dt)
