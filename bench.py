@@ -439,6 +439,10 @@ def run_cuda(args):
         e2e["aggregate_gbs_in_step"] = 3 * nbytes * world / (e2e_ms * 1e-3) / 1e9
         e2e["copy_only"]["aggregate_gbs"] = {"h2d_alone": h2d_gbs * world, "d2h_alone": d2h_gbs * world,
                                              "both_directions_at_once": 2 * nbytes / bidir_s / 1e9 * world}
+        # with several ranks the host's memory system, not a link, is the limit: bare copies in both directions at once
+        # reach less than the two directions alone add up to, and the floor above (directions alone) overstates what a
+        # step can do.  >= 1.0 here means the step moves bytes at least as fast as bare bidirectional copies do.
+        e2e["vs_bare_copies_both_directions"] = e2e["aggregate_gbs_in_step"] / e2e["copy_only"]["aggregate_gbs"]["both_directions_at_once"]
         _lib.call("slas_cuda_free_host", hp[2].value)
         del hC
 
