@@ -441,7 +441,9 @@ def run_cuda(args):
                                              "both_directions_at_once": 2 * nbytes / bidir_s / 1e9 * world}
         # with several ranks the host's memory system, not a link, is the limit: bare copies in both directions at once
         # reach less than the two directions alone add up to, and the floor above (directions alone) overstates what a
-        # step can do.  >= 1.0 here means the step moves bytes at least as fast as bare bidirectional copies do.
+        # step can do.  >= 1.0 here means the step moves bytes at least as fast as bare bidirectional copies do.  (On ONE
+        # GPU the step's 2 : 1 mix of directions is bound by the down direction -- frac_of_copy_floor is the figure there --
+        # and cannot reach the 1 : 1 aggregate: ~0.8.)
         e2e["vs_bare_copies_both_directions"] = e2e["aggregate_gbs_in_step"] / e2e["copy_only"]["aggregate_gbs"]["both_directions_at_once"]
         _lib.call("slas_cuda_free_host", hp[2].value)
         del hC
