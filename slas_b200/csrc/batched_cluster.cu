@@ -14,6 +14,8 @@
 // Summation order (fixed => deterministic): a thread adds its vectors p = 0 .. PER-1 into accumulator p & 3 by FMA in T,
 // the four accumulators are added in f64, block_sum (fixed butterfly) gives the CTA partial, the CL partials are added
 // in rank order in f64, sqrt.rn in f64, rounded to T.
+#include <atomic>
+
 #include "common.cuh"
 #include "divby.cuh"
 #include "kernels.cuh"
@@ -140,9 +142,13 @@ static int launch_cluster_per(Context *ctx, cudaStream_t st, size_t batch, size_
     cfg.numAttrs = 1;
     // as many clusters as can be resident at once (persistent: a cluster strides over the vectors)
     cfg.gridDim = dim3(cl);
-    int resident = 0;
-    SLAS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&resident, kern, &cfg));
-    if (resident < 1) return fail(SLAS_ERR_CUDA, "no cluster of %u CTAs fits the device", cl);
+    static std::atomic<int> resident_cache[9];  // per instantiation and cluster size (every device of a box is the same part)
+    int resident = resident_cache[cl].load(std::memory_order_relaxed);
+    if (resident == 0) {
+        SLAS_CUDA_TRY(cudaOccupancyMaxActiveClusters(&resident, kern, &cfg));
+        if (resident < 1) return fail(SLAS_ERR_CUDA, "no cluster of %u CTAs fits the device", cl);
+        resident_cache[cl].store(resident, std::memory_order_relaxed);
+    }
     const long cap = tunable("bnorm_cluster_ctas") > 0 ? tunable("bnorm_cluster_ctas") : ClusterOcc<MODE, PER>::kMinBlocks;  // CTAs per SM
     size_t clusters = (size_t)resident;
     const size_t by_cap = (size_t)ctx->sm_count * (size_t)cap / cl;
