@@ -527,7 +527,26 @@ def g_bnorm():
     set_tunable("bnorm_cluster_ctas", 0)
 
 
+def g_trsmall():
+    """small transposes, a thread per object: stage size sweep over shapes"""
+    for rows, cols, log2, dt in ((2, 3, 24, np.float32), (3, 3, 24, np.float32), (3, 5, 23, np.float32), (5, 5, 22, np.float32), (7, 7, 21, np.float32),
+                                 (3, 7, 22, np.float32), (2, 3, 23, np.float64), (3, 3, 23, np.float64), (5, 3, 22, np.float64), (5, 5, 21, np.float64)):
+        b, es, e = 1 << log2, np.dtype(dt).itemsize, rows * cols
+        (_, a), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
+        for mode in (2, 0):   # 2: the run-time walk, 0: a thread per object where the shape qualifies
+            set_tunable("staged_jit", mode)
+            for kb in (0, 2, 3, 4, 5, 6, 8, 12, 16):
+                set_tunable("transpose_stage_kb", kb)
+                report(f"transpose {rows}x{cols} {np.dtype(dt).name} 2^{log2}, {'run-time walk' if mode else 'thread per object'}, stage {kb or 'default'} KB",
+                       timed(lambda: cuda.transpose_batched(a, c, e, cols)), nbytes=2.0 * b * e * es)
+        del a, c
+        torch.cuda.empty_cache()
+    set_tunable("staged_jit", 0)
+    set_tunable("transpose_stage_kb", 0)
+
+
 GROUPS = {
+    "trsmall": g_trsmall,
     "bnorm": g_bnorm,
     "oddsweep3": g_oddsweep3,
     "oddsweep2": g_oddsweep2,

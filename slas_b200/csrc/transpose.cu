@@ -232,7 +232,7 @@ template <typename E>
 using StagedTransposeKernel = void (*)(const E *, E *, size_t, size_t, unsigned, unsigned, unsigned, unsigned, unsigned);
 template <typename E>
 static StagedTransposeKernel<E> staged_transpose_builtin(size_t rows, size_t columns) {
-    if constexpr (sizeof(E) == 8) {
+    if constexpr (sizeof(E) == 4 || sizeof(E) == 8) {
         if (rows == 3 && columns == 3) return transpose_staged_kernel<E, 9, 3, 3, true>;
     }
     return nullptr;
@@ -282,7 +282,26 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    const size_t stage_kb = tunable("transpose_stage_kb") > 0 ? (size_t)tunable("transpose_stage_kb") : 16;
+    // A thread per object (shape a compile-time constant: built in for 3x3, else specialised by NVRTC) when the object fits a
+    // thread's registers and consecutive objects start in different shared-memory banks: 4-byte elements up to 120 bytes
+    // per object (word stride sharing at most a factor 2 with the 32 banks), 8- / 16-byte elements up to 256 bytes (element
+    // count sharing at most a factor 2 with the 16 / 8 accesses of a shared-memory phase).  Objects of up to 120 bytes then
+    // take 4 KB stages, four CTAs per SM -- measured, fraction of HBM peak, run-time walk at 16 KB -> thread per object at
+    // 4 KB: 2x3 / 3x3 / 3x5 / 3x7 f32 0.93 / 0.94 / 0.94 / 0.95 -> 0.98 / 0.97 / 0.99 / 0.97, 2x3 / 3x3 / 5x3 f64 0.88 / 0.85 /
+    // 0.84 -> 0.99 / 0.98 / 1.00; the optimum is sharp (3 or 5 KB: 0.86-0.92) and the same wherever the output array lies
+    // (profiles/r3c_tune_trsmall.log, r3c_tune_tr3place.log).  Bigger objects leave too few per 4 KB chunk (7x7 f32 0.60) and
+    // keep 16 KB stages: per object for 8-byte elements (5x5 f64 0.93), the run-time walk for 4-byte ones (7x7 0.94, 9x9
+    // 0.95, where neither a thread per object nor the walk with constant indices beat it, profiles/r2t_tune_odd.log).
+    // tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
+    const long jit_mode = tunable("staged_jit");
+    const bool banks_ok = sizeof(E) == 4 ? gcd_u((unsigned)len, 32) <= 2 : gcd_u((unsigned)len, 128 / (unsigned)sizeof(E)) <= 2;
+    bool per_object = jit_mode != 2 && sizeof(E) >= 4 && banks_ok && obj_bytes <= (sizeof(E) == 4 ? 120 : 256);
+    // the specialised kernel first: without one (no NVRTC, compile failure) the run-time walk keeps its own stage size
+    StagedTransposeKernel<E> kern = per_object ? staged_transpose_builtin<E>(rows, columns) : nullptr;
+    CUfunction jit_fn = nullptr;
+    if (!kern && per_object && jit_mode == 0) jit_fn = staged_transpose_jit(ctx, sizeof(E), (unsigned)len, (unsigned)rows, (unsigned)columns, true);
+    if (!kern && !jit_fn) per_object = false;
+    const size_t stage_kb = tunable("transpose_stage_kb") > 0 ? (size_t)tunable("transpose_stage_kb") : (per_object && obj_bytes <= 120 ? 4 : 16);
     size_t G = (stage_kb * 1024 / obj_bytes) / galign * galign;
     if (G < galign) G = galign;
     const size_t stage_bytes = (G * obj_bytes + 127) / 128 * 128;
@@ -295,26 +314,15 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     if (per_sm < 1) per_sm = 1;
     size_t grid = (size_t)ctx->sm_count * per_sm;
     if (grid > nchunks) grid = nchunks;
-    // Shape as a compile-time constant, a thread per object (built in for 3x3, else specialised by NVRTC): for 8- and
-    // 16-byte elements whose objects fit a thread's registers and start in different shared-memory banks (an odd number
-    // of elements, or sharing only a factor 2 with the 16 / 8 accesses of a shared-memory phase).  Measured, fraction of
-    // HBM peak, run-time walk -> thread per object: 3x3 f64 0.85 -> 0.92, 5x3 f64 0.85 -> 0.94.  For 4-byte elements the
-    // run-time walk already runs at 0.93-0.96 and neither a thread per object (3x3 0.92, 5x5 0.92) nor the walk with
-    // constant indices (9x9 0.89, 10x10 0.89) beat it (profiles/r2t_tune_odd.log) -- what is left there is the bulk-copy
-    // pipeline, not instruction issue.  tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
-    const long jit_mode = tunable("staged_jit");
-    StagedTransposeKernel<E> kern = jit_mode == 2 ? nullptr : staged_transpose_builtin<E>(rows, columns);
-    if (!kern && jit_mode == 0 && sizeof(E) >= 8 && obj_bytes <= 256 && gcd_u((unsigned)len, 128 / (unsigned)sizeof(E)) <= 2) {
-        if (CUfunction fn = staged_transpose_jit(ctx, sizeof(E), (unsigned)len, (unsigned)rows, (unsigned)columns, true)) {
-            size_t batch_arg = batch, nchunks_arg = nchunks;
-            unsigned len_arg = (unsigned)len, rows_arg = (unsigned)rows, cols_arg = (unsigned)columns, g_arg = (unsigned)G,
-                     stage_arg = (unsigned)stage_bytes;
-            void *params[] = {(void *)&a,        (void *)&buffer,   (void *)&batch_arg, (void *)&nchunks_arg, (void *)&len_arg,
-                              (void *)&rows_arg, (void *)&cols_arg, (void *)&g_arg,     (void *)&stage_arg};
-            SLAS_TRY(jit_launch(fn, (unsigned)grid, 288, smem, st, params));
-            *handled = true;
-            return SLAS_OK;
-        }
+    if (jit_fn) {
+        size_t batch_arg = batch, nchunks_arg = nchunks;
+        unsigned len_arg = (unsigned)len, rows_arg = (unsigned)rows, cols_arg = (unsigned)columns, g_arg = (unsigned)G,
+                 stage_arg = (unsigned)stage_bytes;
+        void *params[] = {(void *)&a,        (void *)&buffer,   (void *)&batch_arg, (void *)&nchunks_arg, (void *)&len_arg,
+                          (void *)&rows_arg, (void *)&cols_arg, (void *)&g_arg,     (void *)&stage_arg};
+        SLAS_TRY(jit_launch(jit_fn, (unsigned)grid, 288, smem, st, params));
+        *handled = true;
+        return SLAS_OK;
     }
     if (!kern) kern = transpose_staged_kernel<E, 0, 0, 0, false>;
     SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -492,3 +492,40 @@ def test_a_shape_is_specialised_by_nvrtc_inside_a_graph_capture():
         got = x.to_host().reshape(batch, length)
         nrm = np.sqrt((rows * rows).sum(1))
         assert np.allclose(got, rows / nrm[:, None], rtol=1e-13, atol=0)
+
+
+@pytest.mark.gpu
+def test_concurrent_first_sight_of_shapes_from_several_threads():
+    """libtest-style concurrency (SURVEY 8b 'Threading') on the run-time specialisation: several threads meet new shapes at
+    once -- the same one and different ones -- and every result is exact"""
+    import threading
+    errors = []
+
+    def worker(seed):
+        try:
+            rng = np.random.default_rng(seed)
+            for length in (11 + seed % 3, 23, 45):                      # two shared lengths, one per-thread group
+                batch = 2048
+                a = rng.integers(-4, 5, batch * length).astype(np.float64)
+                a[::length] = 3.0                                       # no zero vectors
+                x = CudaVec.from_host(a)
+                o = CudaVec(batch, np.float64)
+                cuda.norm_batched(x, o, length)
+                rows = a.reshape(batch, length)
+                assert np.array_equal(o.to_host(), np.sqrt((rows * rows).sum(1)))      # exact: small integers, sqrt.rn
+                cuda.normalize_batched(x, length)
+                assert np.array_equal(x.to_host().reshape(batch, length), rows / o.to_host()[:, None])
+            r, c = 3 + seed % 2, 5
+            m = rng.integers(0, 1 << 30, 1024 * r * c).astype(np.int64)
+            t = CudaVec(m.size, np.int64)
+            cuda.transpose_batched(CudaVec.from_host(m), t, r * c, c)
+            assert np.array_equal(t.to_host(), m.reshape(1024, c, r).transpose(0, 2, 1).reshape(-1))
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
