@@ -545,7 +545,26 @@ def g_trsmall():
     set_tunable("transpose_stage_kb", 0)
 
 
+def g_oddsweep4():
+    """stage size for the staged dot / norm over vector lengths"""
+    for length, log2, dt in ((2, 24, np.float32), (3, 24, np.float32), (5, 23, np.float32), (7, 23, np.float32), (9, 22, np.float32),
+                             (13, 22, np.float32), (30, 21, np.float32), (38, 21, np.float32), (127, 19, np.float32),
+                             (3, 23, np.float64), (7, 22, np.float64), (19, 21, np.float64)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, x), (_, y), (_, o) = uniform(b * length, dt, 1), uniform(b * length, dt, 2), uniform(b, dt, 3)
+        for kb in (4, 6, 8, 12, 16, 24):
+            set_tunable("bdot_stage_kb", kb)
+            report(f"batched LEN {length} {np.dtype(dt).name} dot, 2^{log2}, stage {kb} KB",
+                   timed(lambda: cuda.dot_batched(x, y, o, length)), nbytes=(2.0 * length + 1) * b * es)
+            report(f"batched LEN {length} {np.dtype(dt).name} norm, 2^{log2}, stage {kb} KB",
+                   timed(lambda: cuda.norm_batched(x, o, length)), nbytes=(length + 1.0) * b * es)
+        del x, y, o
+        torch.cuda.empty_cache()
+    set_tunable("bdot_stage_kb", 0)
+
+
 GROUPS = {
+    "oddsweep4": g_oddsweep4,
     "trsmall": g_trsmall,
     "bnorm": g_bnorm,
     "oddsweep3": g_oddsweep3,

@@ -584,7 +584,12 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
     // measured (profiles/r2w_tune_oddsweep3.log): the cooperative scale pass of normalize (LEN > 8, two more shared tiles
     // than dot) prefers three CTAs per SM -- 12 KB stages: LEN 13 / 30 / 38 f32 0.84 / 0.85 / 0.91 against 0.80 / 0.81 / 0.84
     // at 16 KB, LEN 19 f64 0.92 against 0.75
-    const long stage_kb = tunable("bdot_stage_kb") > 0 ? tunable("bdot_stage_kb") : (MODE == 2 && len > 8 ? 12 : 16);
+    // ... and for vectors of up to 160 bytes dot prefers 4 KB stages per operand and norm 8 KB (four CTAs per SM either
+    // way: profiles/r3e_tune_oddsweep4.log -- LEN 2 / 3 / 30 f32 norm 0.87 / 0.90 / 0.91 at 16 KB, 0.96 / 0.96 / 0.95 at 8 KB;
+    // dot 0.93 / 0.98 / 0.98 -> 0.98 / 1.01 / 1.00); longer ones lose at small stages (LEN 127: 0.95 -> 0.61)
+    const long small_kb = MODE == 0 ? 4 : 8;
+    const long stage_kb = tunable("bdot_stage_kb") > 0 ? tunable("bdot_stage_kb")
+                          : (MODE == 2 ? (len > 8 ? 12 : 16) : (vbytes <= 160 ? small_kb : 16));
     size_t G = ((size_t)stage_kb * 1024 / vbytes) / galign * galign;
     const size_t gcap = tunable("bdot_gcap") > 0 ? (size_t)tunable("bdot_gcap") : 4096;
     if (G > gcap) G = gcap / galign * galign;
