@@ -611,7 +611,7 @@ static int launch_batched_reduce_staged(Context *ctx, cudaStream_t st, size_t ba
     // else the run-time-shape instantiation.  tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
     const long jit_mode = tunable("staged_jit");
     StagedReduceKernel<T, MODE> kern = jit_mode == 2 ? nullptr : staged_reduce_builtin<T, MODE>(len);
-    if (!kern && jit_mode == 0 && len <= 64 && smem <= kStagedJitSmem) {
+    if (!kern && jit_mode == 0 && smem <= kStagedJitSmem) {
         if (CUfunction fn = staged_reduce_jit(ctx, sizeof(T), MODE, (unsigned)len)) {
             size_t batch_arg = batch, nchunks_arg = nchunks;
             unsigned len_arg = (unsigned)len, g_arg = (unsigned)G, stage_arg = (unsigned)stage_bytes;
