@@ -105,7 +105,29 @@ def odd_normalize():
     synchronize()
 
 
+def odd_final():
+    """the shipped small-object kernels: 3x3 f32 / f64 transposes (a thread per object, 4 KB stages), 3-vector dot / norm /
+    normalize, LEN 30 normalize (NVRTC), batched normalize of 8192- and 65536-element vectors (CTA / cluster per vector)"""
+    b = 1 << 24
+    a, c = uniform(b * 9, np.float32, 1), CudaVec(b * 9, np.float32)
+    x, y, o = uniform(b * 3, np.float32, 2), uniform(b * 3, np.float32, 3), CudaVec(b, np.float32)
+    ad, cd = uniform(b // 2 * 9, np.float64, 4), CudaVec(b // 2 * 9, np.float64)
+    x30 = uniform((1 << 21) * 30, np.float32, 5)
+    m8, m64 = uniform((1 << 15) * 8192, np.float32, 6), uniform((1 << 12) * 65536, np.float32, 7)
+    for _ in range(2):
+        cuda.transpose_batched(a, c, 9, 3)
+        cuda.transpose_batched(ad, cd, 9, 3)
+        cuda.dot_batched(x, y, o, 3)
+        cuda.norm_batched(x, o, 3)
+        cuda.normalize_batched(x, 3)
+        cuda.normalize_batched(x30, 30)
+        cuda.normalize_batched(m8, 8192)
+        cuda.normalize_batched(m64, 65536)
+    synchronize()
+
+
 TARGETS = {
+    "odd_final": odd_final,
     "odd_normalize": odd_normalize,
     "gemm4_f32": lambda: gemm_batched(4, np.float32, 24),
     "gemm16_f32": lambda: gemm_batched(16, np.float32, 20),
