@@ -85,6 +85,11 @@ int slas_cuda_bench_tf32_peak(double *tflops);
  * in the reference) or slas_cuda_snormalize in place on out + i * stride (op 3), on operands `stride` elements apart,
  * issued from C -- the launch-bound loop without an interpreter between the calls.  a, b device pointers. */
 int slas_cuda_bench_call_loop(int op, size_t len, const float *a, const float *b, float *out, int calls, size_t stride);
+/* Self-check of the hoisted division normalize uses (csrc/divby.cuh: the reciprocal refinement of div.rn.f32 runs once per
+ * divisor, each numerator costs three FMAs; operands outside [2^-60, 2^60] take the plain division): for each of the
+ * `count` divisors (host array) EVERY one of the 2^32 float bit patterns is divided both ways on the device;
+ * *mismatches = how many quotients differ in their bits from `x / n` (NaN == NaN).  0 is the only acceptable answer. */
+int slas_cuda_bench_divby_mismatches(const float *divisors, size_t count, uint64_t *mismatches);
 /* With the tunable "reduce_phases" = 1 the dot / norm kernel stamps %globaltimer (ns): [0] start, [1] block 0's
  * loads + FMAs done, [2] its block sum done, [3] grid combine done, [4] result written. */
 int slas_cuda_get_reduce_phases(uint64_t *ns5);

@@ -563,7 +563,24 @@ def g_oddsweep4():
     set_tunable("bdot_stage_kb", 0)
 
 
+def g_trmid():
+    """batched transposes across object sizes and aspect ratios, out of place and in place (which kernel takes what)"""
+    for rows, cols, dt in ((12, 12, np.float32), (20, 20, np.float32), (24, 8, np.float32), (8, 24, np.float32), (33, 31, np.float32),
+                           (31, 33, np.float32), (64, 40, np.float32), (100, 3, np.float32), (3, 100, np.float32), (50, 50, np.float32),
+                           (96, 96, np.float32), (128, 128, np.float32), (200, 200, np.float32), (12, 12, np.float64), (48, 5, np.float64),
+                           (33, 31, np.float64), (100, 100, np.float64)):
+        e, es = rows * cols, np.dtype(dt).itemsize
+        b = max(256, (1 << 28) // (e * es))
+        (_, a), (_, c) = uniform(b * e, dt, 1), uniform(b * e, dt, 2)
+        report(f"transpose {rows}x{cols} {np.dtype(dt).name} batch {b}", timed(lambda: cuda.transpose_batched(a, c, e, cols)), nbytes=2.0 * b * e * es)
+        report(f"transpose_inplace {rows}x{cols} {np.dtype(dt).name} batch {b}", timed(lambda: cuda.transpose_inplace_batched(a, e, cols)),
+               nbytes=2.0 * b * e * es)
+        del a, c
+        torch.cuda.empty_cache()
+
+
 GROUPS = {
+    "trmid": g_trmid,
     "oddsweep4": g_oddsweep4,
     "trsmall": g_trsmall,
     "bnorm": g_bnorm,

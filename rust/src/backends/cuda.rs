@@ -45,6 +45,7 @@ extern "C" {
     fn slas_cuda_bench_fma_peak(is_double: c_int, tflops: *mut f64) -> c_int;
     fn slas_cuda_bench_tf32_peak(tflops: *mut f64) -> c_int;
     fn slas_cuda_bench_call_loop(op: c_int, len: usize, a: *const f32, b: *const f32, out: *mut f32, calls: c_int, stride: usize) -> c_int;
+    fn slas_cuda_bench_divby_mismatches(divisors: *const f32, count: usize, mismatches: *mut u64) -> c_int;
     fn slas_cuda_get_reduce_phases(ns5: *mut u64) -> c_int;
     fn slas_cuda_malloc(dptr: *mut *mut c_void, bytes: usize) -> c_int;
     fn slas_cuda_free(dptr: *mut c_void) -> c_int;

@@ -58,6 +58,7 @@ SIGNATURES = {
     "slas_cuda_bench_fma_peak": [_i, C.POINTER(C.c_double)],
     "slas_cuda_bench_tf32_peak": [C.POINTER(C.c_double)],
     "slas_cuda_bench_call_loop": [_i, _sz, _vp, _vp, _vp, _i, _sz],
+    "slas_cuda_bench_divby_mismatches": [_vp, _sz, C.POINTER(C.c_uint64)],
     "slas_cuda_get_reduce_phases": [C.POINTER(C.c_uint64)],
     "slas_cuda_malloc": [C.POINTER(_vp), _sz],
     "slas_cuda_free": [_vp],

@@ -5,6 +5,7 @@
 //   chip actually holds under that load.  (The tensor-pipe counterpart, slas_cuda_bench_tf32_peak, lives in
 //   gemm_tcgen05.cu next to the PTX it shares.)
 #include "common.cuh"
+#include "divby.cuh"
 
 namespace slas {
 
@@ -109,5 +110,46 @@ extern "C" int slas_cuda_get_reduce_phases(uint64_t *ns5) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     SLAS_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
     SLAS_CUDA_TRY(cudaMemcpy(ns5, ctx->phases, 5 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return SLAS_OK;
+}
+
+// ---- exhaustive self-check of divby.cuh (see include/slas_cuda.h) ----------------------------------------------------
+namespace slas {
+__global__ void __launch_bounds__(256) divby_check_kernel(const float *divisors, unsigned long long *mismatches) {
+    const float n = divisors[blockIdx.y];
+    DivBy<float> by;
+    by.init(n);
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < (1ull << 32); i += (unsigned long long)gridDim.x * 256) {
+        const float x = __uint_as_float((unsigned)i);
+        const float q = by.div(x), r = x / n;
+        if (__float_as_uint(q) != __float_as_uint(r) && !(q != q && r != r)) ++bad;
+        // the branch-free form the kernels use: fast() where ok(), else the plain division
+        const float f = by.ok(x) ? by.fast(x) : r;
+        if (__float_as_uint(f) != __float_as_uint(r) && !(f != f && r != r)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace slas
+
+extern "C" int slas_cuda_bench_divby_mismatches(const float *divisors, size_t count, uint64_t *mismatches) {
+    using namespace slas;
+    SLAS_REQUIRE(divisors && mismatches && count > 0 && count <= 65535, "divby self-check: 1 .. 65535 divisors");
+    Context *ctx;
+    SLAS_TRY(get_context(&ctx));
+    float *d = nullptr;
+    unsigned long long *m = nullptr;
+    SLAS_CUDA_TRY(cudaMalloc(&d, count * sizeof(float)));
+    cudaError_t e = cudaMalloc(&m, sizeof(unsigned long long));
+    if (e != cudaSuccess) { cudaFree(d); return fail(SLAS_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    cudaMemcpy(d, divisors, count * sizeof(float), cudaMemcpyHostToDevice);
+    cudaMemset(m, 0, sizeof(unsigned long long));
+    divby_check_kernel<<<dim3((unsigned)ctx->sm_count * 8, (unsigned)count), 256, 0, ctx->stream>>>(d, m);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(mismatches, m, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    cudaFree(m);
+    if (e != cudaSuccess) return fail(SLAS_ERR_CUDA, "divby self-check: %s", cudaGetErrorString(e));
     return SLAS_OK;
 }

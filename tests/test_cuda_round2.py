@@ -529,3 +529,21 @@ def test_concurrent_first_sight_of_shapes_from_several_threads():
     for t in threads:
         t.join()
     assert not errors, errors[:3]
+
+
+@pytest.mark.gpu
+def test_hoisted_division_matches_ieee_division_for_every_float_numerator():
+    """csrc/divby.cuh, exhaustively: for each divisor, all 2^32 float bit patterns as numerators, both forms the kernels
+    use (div, and fast where ok) against the device's own `x / n`; divisors span the exponent range, both edges of the
+    fast range [2^-60, 2^60], subnormals, zero, infinities, NaN"""
+    rng = np.random.default_rng(5)
+    mant = rng.uniform(1, 2, 40)
+    rnd = (np.ldexp(mant, rng.integers(-126, 127, 40)) * rng.choice([-1.0, 1.0], 40)).astype(np.float32)
+    edge = np.array([1.0, -1.0, 3.0, 0.1, 7.0e-5, np.float32(2.0) ** -60, np.nextafter(np.float32(2.0) ** -60, np.float32(0)),
+                     np.nextafter(np.float32(2.0) ** -60, np.float32(1)), np.float32(2.0) ** 60, np.nextafter(np.float32(2.0) ** 60, np.float32(np.inf)),
+                     np.nextafter(np.float32(2.0) ** 60, np.float32(0)), 1.1754944e-38, 1e-45, 5e-40, 0.0, -0.0, np.inf, -np.inf, np.nan,
+                     3.4028235e38, 1.9999999, 0.99999994, 1.0000001, 16777216.0], np.float32)
+    divisors = np.ascontiguousarray(np.concatenate([edge, rnd]))
+    bad = C.c_uint64(123)
+    L.call("slas_cuda_bench_divby_mismatches", divisors.ctypes.data, divisors.size, C.byref(bad))
+    assert bad.value == 0, f"{bad.value} quotients differ from x / n"
