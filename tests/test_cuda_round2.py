@@ -547,3 +547,20 @@ def test_hoisted_division_matches_ieee_division_for_every_float_numerator():
     bad = C.c_uint64(123)
     L.call("slas_cuda_bench_divby_mismatches", divisors.ctypes.data, divisors.size, C.byref(bad))
     assert bad.value == 0, f"{bad.value} quotients differ from x / n"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64, np.int16])
+@pytest.mark.parametrize("n,batch", [(66, 7), (68, 3), (96, 40), (100, 9), (130, 2), (200, 5), (256, 3), (1000, 1), (72, 300)])
+def test_transpose_inplace_square_of_any_size(dt, n, batch):
+    """square objects too big for the register / staged kernels: vector tiles with predicated edges when rows are whole
+    16-byte vectors (96, 200 ...), element-wise tiles otherwise (66 f32, 130 ...)"""
+    rng = np.random.default_rng(n + batch)
+    a = rng.integers(-30000, 30000, batch * n * n).astype(dt)
+    want = a.reshape(batch, n, n).transpose(0, 2, 1).reshape(-1)
+    d = CudaVec.from_host(a)
+    if batch == 1:
+        cuda.transpose_inplace(d, n)
+    else:
+        cuda.transpose_inplace_batched(d, n * n, n)
+    assert np.array_equal(d.to_host(), want)
