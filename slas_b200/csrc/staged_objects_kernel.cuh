@@ -195,11 +195,13 @@ batched_reduce_staged_kernel(const T *__restrict__ a, const T *__restrict__ b, T
 //     instructions per element, all indices constants;
 //   otherwise the 256 consumers walk the OUTPUT elements of the chunk linearly -- thread t takes elements t, t + 256,
 //     ... and keeps (object, row, column) up to date with additions only -- and gather each from its transposed position
-//     in the stage (consecutive threads write consecutive elements: conflict-free).
-template <typename E, unsigned CLEN, unsigned CROWS, unsigned CCOLS, bool PER_OBJECT>
+//     in the stage (consecutive threads write consecutive elements: conflict-free).  When that gather would walk a
+//     single bank (an input row of a multiple of 16 words) the producer copies row by row into a padded stage
+//     (pitch = rows + 16 bytes: a 4-way conflict instead of a 32-way one).
+template <typename E, unsigned CLEN, unsigned CROWS, unsigned CCOLS, bool PER_OBJECT, bool PADDED = false>
 __global__ void __launch_bounds__(288)
 transpose_staged_kernel(const E *in, E *out, size_t batch, size_t nchunks, unsigned len_arg, unsigned rows_arg,
-                        unsigned columns_arg, unsigned G, unsigned stage_bytes) {
+                        unsigned columns_arg, unsigned G, unsigned stage_bytes, unsigned pitch) {
     constexpr int CONSUMERS = 256, STAGES = 3;
     static_assert(!PER_OBJECT || CLEN != 0, "a thread per object needs the shape at compile time");
     const unsigned len = CLEN ? CLEN : len_arg, rows = CLEN ? CROWS : rows_arg, columns = CLEN ? CCOLS : columns_arg;
@@ -220,10 +222,24 @@ transpose_staged_kernel(const E *in, E *out, size_t batch, size_t nchunks, unsig
                 if (use > 0) mbar_wait_backoff(empty + s, (use - 1) & 1);
                 const size_t first = ch * G;
                 const uint32_t cnt = (uint32_t)(batch - first < (size_t)G ? batch - first : G);
-                // ragged final chunk: whole 16-byte words (the array ends on one: checked by the launcher)
-                const uint32_t bytes = (cnt * len * (uint32_t)sizeof(E) + 15u) & ~15u;
-                mbar_expect_tx(full + s, bytes);
-                bulk_g2s(staged_smem + (size_t)s * stage_bytes, in + first * len, bytes, full + s);
+                if (!PADDED) {
+                    // ragged final chunk: whole 16-byte words (the array ends on one: checked by the launcher)
+                    const uint32_t bytes = (cnt * len * (uint32_t)sizeof(E) + 15u) & ~15u;
+                    mbar_expect_tx(full + s, bytes);
+                    bulk_g2s(staged_smem + (size_t)s * stage_bytes, in + first * len, bytes, full + s);
+                } else {
+                    // padded stage: every input row (rows elements, whole 16-byte words) lands `pitch` elements after
+                    // the previous one, so that the gather below does not walk one bank
+                    const uint32_t row_bytes = rows * (uint32_t)sizeof(E);
+                    mbar_expect_tx(full + s, cnt * columns * row_bytes);
+                    // (one copy per loop iteration: a straight-line run of four or more cp.async.bulk, which is what the
+                    // unrolled loop becomes, faults with "illegal memory access" on this toolchain / part -- reproduced in
+                    // isolation; two or three in a row, as everywhere else in this library, are fine)
+#pragma unroll 1
+                    for (uint32_t r = 0; r < cnt * columns; ++r)
+                        bulk_g2s(staged_smem + (size_t)s * stage_bytes + (size_t)r * pitch * sizeof(E), in + first * len + (size_t)r * rows,
+                                 row_bytes, full + s);
+                }
             }
         }
         return;
@@ -257,7 +273,8 @@ transpose_staged_kernel(const E *in, E *out, size_t batch, size_t nchunks, unsig
             unsigned obj = threadIdx.x / len, o = threadIdx.x % len;
             unsigned orow = o / columns, ocol = o % columns;
             for (unsigned e = threadIdx.x; e < total; e += CONSUMERS) {
-                cst[e] = src[obj * len + ocol * rows + orow];  // buffer[columns*row + column] = a[rows*column + row]
+                // buffer[columns*row + column] = a[rows*column + row]
+                cst[e] = PADDED ? src[(obj * columns + ocol) * pitch + orow] : src[obj * len + ocol * rows + orow];
                 obj += step_obj; o += step_o; orow += step_row; ocol += step_col;
                 if (ocol >= columns) { ocol -= columns; ++orow; }
                 if (o >= len) { o -= len; ++obj; orow -= rows; }

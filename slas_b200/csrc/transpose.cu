@@ -229,7 +229,7 @@ transpose_small_kernel(const E *in, E *out, size_t batch, unsigned len, unsigned
 // of 8- and 16-byte elements the shape is a template constant and a thread moves a whole object (3x3 built in, other
 // shapes specialised by NVRTC at run time, staged_jit.cu) -- see the launcher for the measurements behind the split.
 template <typename E>
-using StagedTransposeKernel = void (*)(const E *, E *, size_t, size_t, unsigned, unsigned, unsigned, unsigned, unsigned);
+using StagedTransposeKernel = void (*)(const E *, E *, size_t, size_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned);
 template <typename E>
 static StagedTransposeKernel<E> staged_transpose_builtin(size_t rows, size_t columns) {
     if constexpr (sizeof(E) == 4 || sizeof(E) == 8) {
@@ -250,8 +250,12 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     // (columns >= 16): the contiguous stage cannot be padded, and 96x96 f32 measured 0.29 that way against 0.82 for the
     // padded tiles of the other kernels (with few columns the same stride is harmless: 16x3 0.93, 48x5 f64 1.00)
     const size_t limit = tunable("transpose_staged_limit") > 0 ? (size_t)tunable("transpose_staged_limit") : 48 * 1024;
+    // ... objects of up to 16 KB take the staged kernel anyway, with a padded stage filled row by row (64x40 f32: 0.47 on the
+    // warp-per-object kernel)
     const size_t stride_words = rows * sizeof(E) / 4;
-    if ((rows * sizeof(E)) % 4 == 0 && stride_words % 16 == 0 && columns >= 16 && tunable("transpose_variant") != 12) return SLAS_OK;
+    const bool one_bank = (rows * sizeof(E)) % 4 == 0 && stride_words % 16 == 0 && columns >= 16 && tunable("transpose_variant") != 12;
+    const bool padded_stage = one_bank && obj_bytes <= 16 * 1024 && tunable("transpose_variant") != 14;
+    if (one_bank && !padded_stage) return SLAS_OK;
     if (len != rows * columns || obj_bytes > limit || batch < 256 || !aligned16(a) || !aligned16(buffer) ||
         tunable("transpose_variant") == 11)
         return SLAS_OK;
@@ -295,7 +299,8 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     // tunable staged_jit: 1 = no NVRTC, 2 = run-time shape only.
     const long jit_mode = tunable("staged_jit");
     const bool banks_ok = sizeof(E) == 4 ? gcd_u((unsigned)len, 32) <= 2 : gcd_u((unsigned)len, 128 / (unsigned)sizeof(E)) <= 2;
-    bool per_object = jit_mode != 2 && sizeof(E) >= 4 && banks_ok && obj_bytes <= (sizeof(E) == 4 ? 120 : 256);
+    bool per_object = jit_mode != 2 && sizeof(E) >= 4 && banks_ok && obj_bytes <= (sizeof(E) == 4 ? 120 : 256) && !padded_stage;
+    const size_t pitch = padded_stage ? rows + 16 / sizeof(E) : rows;
     // the specialised kernel first: without one (no NVRTC, compile failure) the run-time walk keeps its own stage size
     StagedTransposeKernel<E> kern = per_object ? staged_transpose_builtin<E>(rows, columns) : nullptr;
     CUfunction jit_fn = nullptr;
@@ -304,7 +309,7 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     const size_t stage_kb = tunable("transpose_stage_kb") > 0 ? (size_t)tunable("transpose_stage_kb") : (per_object && obj_bytes <= 120 ? 4 : 16);
     size_t G = (stage_kb * 1024 / obj_bytes) / galign * galign;
     if (G < galign) G = galign;
-    const size_t stage_bytes = (G * obj_bytes + 127) / 128 * 128;
+    const size_t stage_bytes = (G * columns * pitch * sizeof(E) + 127) / 128 * 128;  // (== G * obj_bytes without padding)
     const size_t smem = 5 * stage_bytes + 6 * sizeof(uint64_t);
     if (smem > 200 * 1024) return SLAS_OK;
     const size_t nchunks = (batch + G - 1) / G;
@@ -317,17 +322,17 @@ static int launch_transpose_staged(Context *ctx, cudaStream_t st, size_t batch, 
     if (jit_fn) {
         size_t batch_arg = batch, nchunks_arg = nchunks;
         unsigned len_arg = (unsigned)len, rows_arg = (unsigned)rows, cols_arg = (unsigned)columns, g_arg = (unsigned)G,
-                 stage_arg = (unsigned)stage_bytes;
+                 stage_arg = (unsigned)stage_bytes, pitch_arg = (unsigned)pitch;
         void *params[] = {(void *)&a,        (void *)&buffer,   (void *)&batch_arg, (void *)&nchunks_arg, (void *)&len_arg,
-                          (void *)&rows_arg, (void *)&cols_arg, (void *)&g_arg,     (void *)&stage_arg};
+                          (void *)&rows_arg, (void *)&cols_arg, (void *)&g_arg,     (void *)&stage_arg,   (void *)&pitch_arg};
         SLAS_TRY(jit_launch(jit_fn, (unsigned)grid, 288, smem, st, params));
         *handled = true;
         return SLAS_OK;
     }
-    if (!kern) kern = transpose_staged_kernel<E, 0, 0, 0, false>;
+    if (!kern) kern = padded_stage ? transpose_staged_kernel<E, 0, 0, 0, false, true> : transpose_staged_kernel<E, 0, 0, 0, false>;
     SLAS_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)grid, 288, smem, st>>>(a, buffer, batch, nchunks, (unsigned)len, (unsigned)rows, (unsigned)columns, (unsigned)G,
-                                            (unsigned)stage_bytes);
+                                            (unsigned)stage_bytes, (unsigned)pitch);
     SLAS_LAUNCH_CHECK();
     *handled = true;
     return SLAS_OK;

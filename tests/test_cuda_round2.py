@@ -407,7 +407,9 @@ def test_staged_reductions_same_bits_for_every_form_of_the_shape(dt, length, bat
 @pytest.mark.gpu
 @pytest.mark.parametrize("elem", [1, 2, 4, 8, 16])
 @pytest.mark.parametrize("rows,cols,batch", [(3, 3, 70001), (2, 3, 4096), (3, 2, 1001), (5, 5, 3000), (3, 5, 2050), (6, 6, 999), (7, 9, 1024),
-                                             (10, 10, 600), (30, 31, 300), (1, 7, 4096), (7, 1, 4096)])
+                                             (10, 10, 600), (30, 31, 300), (1, 7, 4096), (7, 1, 4096),
+                                             # input rows of a multiple of 16 words: the padded stage, filled row by row
+                                             (64, 40, 300), (32, 16, 1000), (16, 64, 700), (48, 32, 260), (128, 16, 257)])
 def test_staged_transposes_same_bytes_for_every_form_of_the_shape(elem, rows, cols, batch):
     rng = np.random.default_rng(elem * 100 + rows * 10 + cols)
     n = rows * cols
