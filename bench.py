@@ -58,6 +58,8 @@ def parse_args():
     p.add_argument("--no-others", action="store_true", help="skip the secondary configs")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu", action="store_true")
+    p.add_argument("--no-numa-bind", action="store_true",
+                   help="N > 1: do not bind a rank to the CPUs NVML reports as local to its GPU")
     return p.parse_args()
 
 
@@ -257,6 +259,7 @@ def run_cuda(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_local_cpus(local_rank) if (world > 1 and not args.no_numa_bind) else "not bound (one rank)"
     host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -445,6 +448,7 @@ def run_cuda(args):
         # GPU the step's 2 : 1 mix of directions is bound by the down direction -- frac_of_copy_floor is the figure there --
         # and cannot reach the 1 : 1 aggregate: ~0.8.)
         e2e["vs_bare_copies_both_directions"] = e2e["aggregate_gbs_in_step"] / e2e["copy_only"]["aggregate_gbs"]["both_directions_at_once"]
+        e2e["cpu_affinity"] = numa_note
         _lib.call("slas_cuda_free_host", hp[2].value)
         del hC
 
@@ -926,6 +930,27 @@ def run_cuda(args):
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_local_cpus(device_index: int) -> str:
+    """One process per GPU: run the rank -- and with it the first touch of its pinned host buffers and the library's copy
+    threads -- on the CPUs NVML reports as local to the GPU, as `numactl --cpunodebind` would.  With several ranks the
+    host-to-device leg is bound by the host's memory system (bench: e2e.copy_only), and buffers on the far socket halve it."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return f"NVML reports no narrower CPU set than the {len(allowed)} allowed CPUs"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to the {len(cpus)} CPUs local to GPU {device_index} (NVML)"
+    except Exception as e:  # noqa: BLE001 -- a box without NVML topology information: run unbound
+        return f"not bound ({type(e).__name__}: {e})"
 
 
 def main():
