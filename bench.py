@@ -259,7 +259,8 @@ def run_cuda(args):
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa_note = bind_to_gpu_local_cpus(local_rank) if (world > 1 and not args.no_numa_bind) else "not bound (one rank)"
+    numa_note = ("not bound (one rank)" if world == 1 else "not bound (--no-numa-bind)" if args.no_numa_bind
+                 else bind_to_gpu_local_cpus(local_rank))
     host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
