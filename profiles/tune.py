@@ -579,7 +579,26 @@ def g_trmid():
         torch.cuda.empty_cache()
 
 
+def g_lanevsstaged():
+    """vectors of whole 16-byte words up to 256 bytes: a lane per vector with 256-bit accesses (shipped) against the bulk-TMA
+    staged thread-per-vector kernel (bdot_variant 4)"""
+    for length, log2, dt in ((4, 24, np.float32), (8, 24, np.float32), (16, 24, np.float32), (32, 23, np.float32), (64, 22, np.float32),
+                             (4, 24, np.float64), (8, 23, np.float64), (16, 23, np.float64), (32, 22, np.float64)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, x), (_, y), (_, o) = uniform(b * length, dt, 1), uniform(b * length, dt, 2), uniform(b, dt, 3)
+        for v in (0, 4):
+            set_tunable("bdot_variant", v)
+            tag = "lane per vector" if v == 0 else "staged"
+            report(f"batched LEN {length} {np.dtype(dt).name} dot, 2^{log2}, {tag}", timed(lambda: cuda.dot_batched(x, y, o, length)), nbytes=(2.0 * length + 1) * b * es)
+            report(f"batched LEN {length} {np.dtype(dt).name} norm, 2^{log2}, {tag}", timed(lambda: cuda.norm_batched(x, o, length)), nbytes=(length + 1.0) * b * es)
+            report(f"batched LEN {length} {np.dtype(dt).name} normalize, 2^{log2}, {tag}", timed(lambda: cuda.normalize_batched(x, length)), nbytes=2.0 * length * b * es)
+        del x, y, o
+        torch.cuda.empty_cache()
+    set_tunable("bdot_variant", 0)
+
+
 GROUPS = {
+    "lanevsstaged": g_lanevsstaged,
     "trmid": g_trmid,
     "oddsweep4": g_oddsweep4,
     "trsmall": g_trsmall,

@@ -545,9 +545,12 @@ static StagedReduceKernel<T, MODE> staged_reduce_builtin(size_t len) {
     case 5: return batched_reduce_staged_kernel<T, MODE, 5>;
     case 7: return batched_reduce_staged_kernel<T, MODE, 7>;
     }
-    if constexpr (sizeof(T) == 4) {  // (even lengths of 8-byte elements are whole 16-byte words: never staged)
+    if constexpr (sizeof(T) == 4) {  // (even lengths of 8-byte elements are whole 16-byte words: only LEN 2 is staged)
         if (len == 2) return batched_reduce_staged_kernel<T, MODE, 2>;
+        if (len == 4) return batched_reduce_staged_kernel<T, MODE, 4>;
         if (len == 6) return batched_reduce_staged_kernel<T, MODE, 6>;
+    } else {
+        if (len == 2) return batched_reduce_staged_kernel<T, MODE, 2>;
     }
     return nullptr;
 }
@@ -750,7 +753,7 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
     // divides by the bits norm returns), up to 128 bytes for dot (two operands: 256-byte vectors cost it its occupancy;
     // measured, LEN 32 f64: 0.70 against 1.02 for the lanes-per-vector kernel below)
     if (vec && len > 0 && (len * sizeof(T)) % 32 == 0 && len * sizeof(T) <= (MODE == 0 ? 128 : 256) && (uintptr_t)base % 32 == 0 &&
-        (MODE != 0 || (uintptr_t)b % 32 == 0) && tunable("bdot_variant") != 1) {
+        (MODE != 0 || (uintptr_t)b % 32 == 0) && tunable("bdot_variant") != 1 && tunable("bdot_variant") != 4) {
         const unsigned chunks = (unsigned)(len * sizeof(T) / 32);
         size_t blocks = (batch + 255) / 256;
         const size_t lcap = (size_t)ctx->sm_count * 16;
@@ -762,8 +765,10 @@ static int launch_batched_reduce_mode(Context *ctx, cudaStream_t st, size_t batc
         SLAS_LAUNCH_CHECK();
         return SLAS_OK;
     }
-    if (!vec || len < (size_t)N) {
-        // not whole 16-byte words (3-vectors, LEN 5, 30 ...): bulk-TMA staged, a thread per vector
+    if (!vec || len <= (size_t)N || tunable("bdot_variant") == 4) {
+        // not whole 16-byte words (3-vectors, LEN 5, 30 ...), and ONE 16-byte word (4-vectors f32, 2-vectors f64: normalize
+        // 0.84 -> 0.90, norm 0.94 -> 0.99 against the sub-warp kernel; longer power-of-two vectors would walk a single
+        // shared-memory bank there: LEN 16 f32 0.34, profiles/r3r_tune_lanevsstaged.log): bulk-TMA staged, a thread per vector
         bool staged = false;
         SLAS_TRY((launch_batched_reduce_staged<T, MODE>(ctx, st, batch, len, a, b, out, a_mut, &staged)));
         if (staged) return SLAS_OK;
