@@ -597,7 +597,25 @@ def g_lanevsstaged():
     set_tunable("bdot_variant", 0)
 
 
+def g_tinyvsjit():
+    """every dimension in 1..4: a thread per matrix (gemm_tiny, shipped) against whatever the run-time specialisation picks
+    (gemm_tiny_variant 1: register tiles where N and K are whole 16-byte vectors, else scalar register tiles)"""
+    for (m, n, k, dt, log2) in ((2, 2, 2, np.float32, 24), (4, 4, 2, np.float32, 24), (2, 4, 4, np.float32, 24), (4, 1, 4, np.float32, 24),
+                                (4, 4, 4, np.float64, 23), (2, 4, 4, np.float64, 24), (4, 2, 4, np.float64, 24), (2, 2, 2, np.float64, 24),
+                                (3, 3, 3, np.float32, 24), (4, 4, 3, np.float32, 24)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, a), (_, bb), (_, c) = uniform(b * m * k, dt, 1), uniform(b * k * n, dt, 2), uniform(b * m * n, dt, 3)
+        for v in (0, 1):
+            set_tunable("gemm_tiny_variant", v)
+            report(f"gemm {m}x{k} . {k}x{n} {np.dtype(dt).name} batch 2^{log2} [{'thread per matrix' if v == 0 else 'run-time specialised'}]",
+                   timed(lambda: cuda.matrix_mul_batched(a, bb, c, m, n, k)), nbytes=float(b) * (m * k + k * n + m * n) * es)
+        del a, bb, c
+        torch.cuda.empty_cache()
+    set_tunable("gemm_tiny_variant", 0)
+
+
 GROUPS = {
+    "tinyvsjit": g_tinyvsjit,
     "lanevsstaged": g_lanevsstaged,
     "trmid": g_trmid,
     "oddsweep4": g_oddsweep4,

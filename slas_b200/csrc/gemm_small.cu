@@ -203,6 +203,15 @@ using CfgD16t = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 2, true>;
 template <typename T>
 static int launch_other_shapes(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T *b, T *c, size_t m, size_t n,
                                size_t k, int ta, int tb) {
+    // f64 objects of 256 bytes whose N and K are whole 16-byte vectors (2x4 . 4x4, 4x4 . 4x2, 4x2 . 2x4): a thread per
+    // matrix reads power-of-two strided objects through 4- to 8-way shared-memory bank conflicts (0.77-0.80 of HBM peak);
+    // the run-time specialised register-tile kernel splits a matrix over threads that read consecutive vectors (0.85-0.87,
+    // profiles/r3t_tune_tinyvsjit.log).  Without NVRTC the thread-per-matrix kernel below still takes them.
+    if (sizeof(T) == 8 && m <= 4 && n <= 4 && k <= 4 && n % 2 == 0 && k % 2 == 0 && (m * k + k * n + m * n) * sizeof(T) >= 256 &&
+        !(m == 4 && n == 4 && k == 4) && tunable("gemm_tiny_variant") != 2) {
+        const int rj = launch_gemm_jit_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
+        if (rj != SLAS_ERR_UNSUPPORTED) return rj;
+    }
     const int r = launch_gemm_tiny_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
     if (r != SLAS_ERR_UNSUPPORTED) return r;
     const int rj = launch_gemm_jit_batched<T>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
