@@ -614,7 +614,18 @@ def g_tinyvsjit():
     set_tunable("gemm_tiny_variant", 0)
 
 
+def g_gemm4d():
+    """4x4 f64 batched products (the f64 sibling of the headline): stage depth / matrices per stage / bulk C store"""
+    b = 1 << 23
+    (_, a), (_, bb), (_, c) = uniform(b * 16, np.float64, 1), uniform(b * 16, np.float64, 2), uniform(b * 16, np.float64, 3)
+    for v in (0, 1, 2, 3, 4):
+        set_tunable("gemm4d_variant", v)
+        report(f"gemm 4x4 . 4x4 float64 batch 2^23 variant {v}", timed(lambda: cuda.matrix_mul_batched(a, bb, c, 4, 4, 4)), nbytes=float(b) * 48 * 8)
+    set_tunable("gemm4d_variant", 0)
+
+
 GROUPS = {
+    "gemm4d": g_gemm4d,
     "tinyvsjit": g_tinyvsjit,
     "lanevsstaged": g_lanevsstaged,
     "trmid": g_trmid,

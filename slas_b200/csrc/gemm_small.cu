@@ -179,6 +179,10 @@ using CfgS8 = SmallCfg<float, 8, 8, 8, 2, 4, 256, 64, 3, true>;
 using CfgS16 = SmallCfg<float, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgS32 = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 3>;
 using CfgD4 = SmallCfg<double, 4, 4, 4, 1, 4, 256, 128, 4>;
+using CfgD4t = SmallCfg<double, 4, 4, 4, 1, 4, 256, 64, 3, true>;    // bulk-store variants (benchmark knob gemm4d_variant)
+using CfgD4u = SmallCfg<double, 4, 4, 4, 1, 4, 256, 128, 3, true>;
+using CfgD4v = SmallCfg<double, 4, 4, 4, 1, 2, 256, 64, 3, true>;
+using CfgD4w = SmallCfg<double, 4, 4, 4, 1, 4, 256, 64, 4, false>;
 using CfgD8 = SmallCfg<double, 8, 8, 8, 2, 4, 256, 32, 3, true>;
 using CfgD16 = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 3>;
 using CfgD32 = SmallCfg<double, 32, 32, 32, 8, 4, 128, 4, 3>;
@@ -280,7 +284,14 @@ int launch_gemm_small_batched<double>(Context *ctx, cudaStream_t st, size_t batc
         return launch_other_shapes_split<double>(ctx, st, batch, a, b, c, m, n, k, ta, tb);
     }
     switch (m) {
-    case 4: return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
+    case 4:
+        // measured on B200 (2^23 pairs, profiles/r3u_tune_gemm4d.log): 64 pairs per stage, three stages, bulk C store =
+        // 1.08 of the HBM copy peak (three CTAs per SM); 128 per stage with per-warp stores (one CTA per SM) 0.89
+        if (tunable("gemm4d_variant") == 1) return launch_cfg<double, CfgD4>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4d_variant") == 2) return launch_cfg<double, CfgD4u>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4d_variant") == 3) return launch_cfg<double, CfgD4v>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm4d_variant") == 4) return launch_cfg<double, CfgD4w>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<double, CfgD4t>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<double, CfgD8>(ctx, st, batch, a, b, c, ta, tb);
     case 16: return launch_cfg<double, CfgD16>(ctx, st, batch, a, b, c, ta, tb);
     case 64: return launch_cfg<double, CfgD64>(ctx, st, batch, a, b, c, ta, tb);
