@@ -650,8 +650,8 @@ GROUPS = {
     "dgemm": g_dgemm,
     "fused": g_fused,
     "gemm32d": lambda: g_gemm("gemm32d_variant", 32, np.float64, (0, 1)),
-    "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1)),
-    "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2)),
+    "gemm32s": lambda: g_gemm("gemm32s_variant", 32, np.float32, (0, 1, 3, 4, 5, 0)),
+    "gemm16s": lambda: g_gemm("gemm16s_variant", 16, np.float32, (0, 1, 2, 3, 4, 5, 6, 0)),
     "gemm64": lambda: (g_gemm("gemm32s_variant", 64, np.float32, (0,), 18), g_gemm("gemm32d_variant", 64, np.float64, (0,), 17),
                        g_gemm("gemm4s_variant", 8, np.float32, (0,), 22), g_gemm("gemm4s_variant", 8, np.float64, (0,), 22),
                        g_gemm("gemm4s_variant", 4, np.float64, (0,), 24)),

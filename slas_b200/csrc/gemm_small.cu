@@ -197,6 +197,11 @@ using CfgS32b = SmallCfg<float, 32, 32, 32, 8, 8, 128, 8, 3>;
 using CfgS16b = SmallCfg<float, 16, 16, 16, 4, 4, 256, 32, 3>;
 using CfgS16c = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 3>;
 using CfgS16t = SmallCfg<float, 16, 16, 16, 8, 4, 256, 32, 2, true>;
+using CfgS16v4 = SmallCfg<float, 16, 16, 16, 8, 4, 128, 16, 3, true>;   // two CTAs per SM, bulk C store
+using CfgS16v5 = SmallCfg<float, 16, 16, 16, 8, 4, 128, 16, 3, false>;
+using CfgS16v6 = SmallCfg<float, 16, 16, 16, 8, 4, 64, 8, 3, true>;     // four CTAs per SM
+using CfgS32v4 = SmallCfg<float, 32, 32, 32, 8, 4, 128, 4, 3, true>;
+using CfgS32v5 = SmallCfg<float, 32, 32, 32, 8, 4, 128, 4, 3, false>;
 using CfgS32t = SmallCfg<float, 32, 32, 32, 8, 4, 256, 8, 2, true>;
 using CfgD16t = SmallCfg<double, 16, 16, 16, 4, 4, 256, 16, 2, true>;
 
@@ -256,11 +261,16 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
         return launch_cfg<float, CfgS4u>(ctx, st, batch, a, b, c, ta, tb);
     case 8: return launch_cfg<float, CfgS8>(ctx, st, batch, a, b, c, ta, tb);
     case 16:
-        // measured on B200 (profiles/r1b_tune.log): 8x4 tiles, 32 matrices per stage = 0.96 of HBM peak
+        // measured on B200 (2^20 pairs, profiles/r3v_tune_gemm16s.log): 8x4 tiles, 128 consumers, 16 matrices per stage,
+        // bulk C store = TWO CTAs per SM: 1.00 of the HBM copy peak; 256 consumers and 32 per stage (one CTA per SM) 0.96,
+        // the same with per-warp stores 0.96, four CTAs of 64 consumers 0.86
         if (tunable("gemm16s_variant") == 1) return launch_cfg<float, CfgS16b>(ctx, st, batch, a, b, c, ta, tb);
         if (tunable("gemm16s_variant") == 3) return launch_cfg<float, CfgS16t>(ctx, st, batch, a, b, c, ta, tb);
         if (tunable("gemm16s_variant") == 2) return launch_cfg<float, CfgS16>(ctx, st, batch, a, b, c, ta, tb);
-        return launch_cfg<float, CfgS16c>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm16s_variant") == 4) return launch_cfg<float, CfgS16c>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm16s_variant") == 5) return launch_cfg<float, CfgS16v5>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm16s_variant") == 6) return launch_cfg<float, CfgS16v6>(ctx, st, batch, a, b, c, ta, tb);
+        return launch_cfg<float, CfgS16v4>(ctx, st, batch, a, b, c, ta, tb);
     case 64:
         // measured (B200, batch 2^18): 8x4 tiles on 8 consumer warps 39.8 TFLOP/s (0.74 of the FMA-peak
         // microbench), 4x8 38.7, 8x8 tiles on 4 warps 20.7
@@ -270,6 +280,8 @@ int launch_gemm_small_batched<float>(Context *ctx, cudaStream_t st, size_t batch
     case 32:
         if (tunable("gemm32s_variant") == 1) return launch_cfg<float, CfgS32b>(ctx, st, batch, a, b, c, ta, tb);
         if (tunable("gemm32s_variant") == 3) return launch_cfg<float, CfgS32t>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm32s_variant") == 4) return launch_cfg<float, CfgS32v4>(ctx, st, batch, a, b, c, ta, tb);
+        if (tunable("gemm32s_variant") == 5) return launch_cfg<float, CfgS32v5>(ctx, st, batch, a, b, c, ta, tb);
         return launch_cfg<float, CfgS32>(ctx, st, batch, a, b, c, ta, tb);
     }
     return SLAS_ERR_UNSUPPORTED;
