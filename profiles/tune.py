@@ -624,7 +624,24 @@ def g_gemm4d():
     set_tunable("gemm4d_variant", 0)
 
 
+def g_jitbulkc():
+    """run-time specialised register-tile products: per-warp C stores against a bulk C store from a shared tile"""
+    for (m, n, k, dt, log2) in ((12, 12, 12, np.float64, 20), (8, 4, 16, np.float32, 22), (16, 32, 8, np.float32, 20), (6, 6, 6, np.float64, 22),
+                                (20, 20, 20, np.float32, 18), (24, 24, 24, np.float32, 18), (8, 8, 4, np.float32, 22), (2, 4, 4, np.float64, 24),
+                                (12, 12, 12, np.float32, 20), (20, 20, 20, np.float64, 17)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, a), (_, bb), (_, c) = uniform(b * m * k, dt, 1), uniform(b * k * n, dt, 2), uniform(b * m * n, dt, 3)
+        for v in (2, 1, 0):
+            set_tunable("gemm_jit_bulk_c", v)
+            report(f"gemm {m}x{k} . {k}x{n} {np.dtype(dt).name} batch 2^{log2} [{('shipped rule', 'bulk C store', 'per-warp C stores')[v]}]",
+                   timed(lambda: cuda.matrix_mul_batched(a, bb, c, m, n, k)), nbytes=float(b) * (m * k + k * n + m * n) * es)
+        del a, bb, c
+        torch.cuda.empty_cache()
+    set_tunable("gemm_jit_bulk_c", 0)
+
+
 GROUPS = {
+    "jitbulkc": g_jitbulkc,
     "gemm4d": g_gemm4d,
     "tinyvsjit": g_tinyvsjit,
     "lanevsstaged": g_lanevsstaged,

@@ -35,7 +35,7 @@ static Tunable g_tunables[] = {{"transpose_variant", 0}, {"gemm32d_variant", 0},
                                {"gemm16s_variant", 0}, {"gemm4s_variant", 0}, {"gemm_large_variant", 0},
                                {"tc_variant", 0}, {"gemm_tiny_variant", 0}, {"host_slot_mb", 0}, {"gemv_variant", 0}, {"bdot_variant", 0}, {"gemm_jit", 0}, {"bdot_limit", 0}, {"transpose_staged_limit", 0},
                                {"reduce_small", 0}, {"reduce_small_threads", 0}, {"reduce_small_cps", 0}, {"reduce_small_tail", 0},
-                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}, {"host_copy_threads", 0}, {"host_bounce", 0}, {"host_copy_nt", 0}, {"bdot_stage_kb", 0}, {"host_result", 0}, {"normalize_fused", 0}, {"staged_jit", 0}, {"bdot_gcap", 0}, {"transpose_stage_kb", 0}, {"staged_cta_cap", 0}, {"bnorm_cluster", 0}, {"bnorm_cluster_ctas", 0}, {"gemm4d_variant", 0}};
+                               {"reduce_phases", 0}, {"ewise_small", 0}, {"pdl", 0}, {"multi_split_mb", 0}, {"host_copy_threads", 0}, {"host_bounce", 0}, {"host_copy_nt", 0}, {"bdot_stage_kb", 0}, {"host_result", 0}, {"normalize_fused", 0}, {"staged_jit", 0}, {"bdot_gcap", 0}, {"transpose_stage_kb", 0}, {"staged_cta_cap", 0}, {"bnorm_cluster", 0}, {"bnorm_cluster_ctas", 0}, {"gemm4d_variant", 0}, {"gemm_jit_bulk_c", 0}};
 long tunable(const char *name) {
     for (auto &t : g_tunables)
         if (strcmp(t.name, name) == 0) return t.value;

@@ -117,6 +117,19 @@ static bool choose_tiny_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *o
     return false;
 }
 
+// C through a double-buffered shared tile and one bulk store per chunk, or straight from the registers with per-warp
+// 16-byte stores?  Measured both ways (profiles/r3x_tune_jitbulkc.log): the bulk store wins when per-warp stores leave
+// partial lines -- rows that are not whole 128-byte lines in big objects (20x20 f32 0.88 -> 0.95, 24x24 0.85 -> 0.92,
+// 20x20 f64 0.87 -> 0.97) or not whole 32-byte sectors (6x6 f64 0.86 -> 1.01) -- and loses a few per cent where the
+// stores are already whole lines (16x8 . 8x32: 0.94 -> 0.91) or whole tiny objects (8x16 . 16x4: 1.04 -> 0.97).
+// tunable gemm_jit_bulk_c: 1 = always, 2 = never.
+static bool jit_bulk_c_store(size_t elem, size_t m, size_t n) {
+    if (tunable("gemm_jit_bulk_c") == 1) return true;
+    if (tunable("gemm_jit_bulk_c") == 2) return false;
+    const size_t row = n * elem, obj = m * n * elem;
+    return row % 128 != 0 && (obj >= 1536 || (row % 32 != 0 && row > 32));
+}
+
 // The rules of SmallCfg / gemm_small_kernel: K and TN whole 16-byte vectors, TM | M, TN | N, threads per matrix
 // (M/TM)*(N/TN) dividing the consumer count (whole warps, at most 512 threads), a chunk = whole passes, the stage ring within the
 // shared-memory budget.  Among the configurations that fit: big, squarish register tiles (fewer shared-memory loads
@@ -150,8 +163,9 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
                 if (g < mpp) g = mpp;
                 if (g > 256) g = 256 / mpp * mpp;
                 if (g == 0) continue;
+                const bool bulk_c = jit_bulk_c_store(elem, m, n);
                 for (int stages = 3; stages >= 2; --stages) {
-                    const size_t smem = (size_t)stages * g * per_pair + 2 * stages * sizeof(uint64_t);
+                    const size_t smem = (size_t)stages * g * per_pair + (bulk_c ? 2 * g * m * n * elem : 0) + 2 * stages * sizeof(uint64_t);
                     if (smem > 200 * 1024) continue;
                     const size_t per_sm = (size_t)227 * 1024 / (smem + 1024);
                     double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm) + 1e-3 * (double)tn;
@@ -276,9 +290,9 @@ static bool compile_kernel(size_t elem, size_t m, size_t n, size_t k, int ta, in
         snprintf(expr, sizeof(expr), "slas::gemm_rect_kernel<%s, %zu, %zu, %zu, %d, %d, %d>", tname, m, n, k, kern->cfg.tm, kern->cfg.tn,
                  kern->cfg.g);
     else
-        snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, false>, %s, %s>",
+        snprintf(expr, sizeof(expr), "slas::gemm_small_kernel<%s, slas::SmallCfg<%s, %zu, %zu, %zu, %d, %d, %d, %d, %d, %s>, %s, %s>",
                  tname, tname, m, n, k, kern->cfg.tm, kern->cfg.tn, kern->cfg.cons, kern->cfg.g, kern->cfg.stages,
-                 ta ? "true" : "false", tb ? "true" : "false");
+                 jit_bulk_c_store(elem, m, n) ? "true" : "false", ta ? "true" : "false", tb ? "true" : "false");
     return jit_compile(kKernelSource, "gemm_small_jit.cu", expr, kern->cfg.smem, &kern->fn);
 }
 
@@ -296,7 +310,7 @@ int launch_gemm_jit_batched(Context *ctx, cudaStream_t st, size_t batch, const T
         // ... and scalar register tiles for whatever is left (9x9, 10x10 f32, 5x9 ...)
         const bool tiled = choose_cfg(sizeof(T), m, n, k, &cfg);
         const bool tiny = !tiled && (choose_tiny_cfg(sizeof(T), m, n, k, &cfg) || choose_rect_cfg(sizeof(T), m, n, k, &cfg));
-        const JitKey key{ctx->device, (int)sizeof(T), m, n, k, tiny ? 0 : (ta ? 1 : 0), tiny ? 0 : (tb ? 1 : 0)};
+        const JitKey key{ctx->device, (int)sizeof(T) + (jit_bulk_c_store(sizeof(T), m, n) ? 100 : 0), m, n, k, tiny ? 0 : (ta ? 1 : 0), tiny ? 0 : (tb ? 1 : 0)};
         auto it = g_cache.find(key);
         if (it == g_cache.end()) {
             JitKernel fresh;
