@@ -640,7 +640,20 @@ def g_jitbulkc():
     set_tunable("gemm_jit_bulk_c", 0)
 
 
+def g_shortk():
+    """run-time specialised register tiles with K of one or two 16-byte vectors"""
+    for (m, n, k, dt, log2) in ((8, 8, 4, np.float32, 22), (16, 16, 4, np.float32, 20), (8, 16, 8, np.float32, 21), (8, 8, 2, np.float64, 22),
+                                (16, 8, 4, np.float64, 20), (12, 12, 4, np.float32, 21)):
+        b, es = 1 << log2, np.dtype(dt).itemsize
+        (_, a), (_, bb), (_, c) = uniform(b * m * k, dt, 1), uniform(b * k * n, dt, 2), uniform(b * m * n, dt, 3)
+        report(f"gemm {m}x{k} . {k}x{n} {np.dtype(dt).name} batch 2^{log2}", timed(lambda: cuda.matrix_mul_batched(a, bb, c, m, n, k)),
+               nbytes=float(b) * (m * k + k * n + m * n) * es)
+        del a, bb, c
+        torch.cuda.empty_cache()
+
+
 GROUPS = {
+    "shortk": g_shortk,
     "jitbulkc": g_jitbulkc,
     "gemm4d": g_gemm4d,
     "tinyvsjit": g_tinyvsjit,

@@ -169,6 +169,10 @@ static bool choose_cfg(size_t elem, size_t m, size_t n, size_t k, JitCfg *out) {
                     if (smem > 200 * 1024) continue;
                     const size_t per_sm = (size_t)227 * 1024 / (smem + 1024);
                     double score = 1.0 / (1.0 / (double)tn + 1.0 / (double)tm) + 1e-3 * (double)tn;
+                    // K of one or two vectors: nothing to reuse, and a thread that owns most of a matrix reads its rows at
+                    // the matrix stride -- lanes collide in shared memory (8x4 . 4x8 f32 as one thread per matrix: 0.53
+                    // of HBM peak).  Prefer eight or more threads per matrix there, which read consecutive vectors.
+                    if (k <= 2 * kvn && tpm < 8 && (m / 1) * (n / kvn) >= 8) score *= 0.25;
                     if (per_sm < 2) score *= 0.6;
                     if (stages == 2) score *= 0.9;
                     if (cons < 192) score *= 0.95;
