@@ -131,6 +131,7 @@ TARGETS = {
     "odd_normalize": odd_normalize,
     "gemm4_f32": lambda: gemm_batched(4, np.float32, 24),
     "gemm16_f32": lambda: gemm_batched(16, np.float32, 20),
+    "gemm4_f64": lambda: gemm_batched(4, np.float64, 23),
     "gemm32_f32": lambda: gemm_batched(32, np.float32, 20),
     "gemm16_f64": lambda: gemm_batched(16, np.float64, 20),
     "gemm32_f64": lambda: gemm_batched(32, np.float64, 20),
