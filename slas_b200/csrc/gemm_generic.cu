@@ -8,6 +8,8 @@
 //         op(B)[p][j] = b_trans ? b[j*ldb + p] : b[p*ldb + j]
 //   gemv: trait arguments m = underlying width, n = underlying height (src/tensor.rs:428-437);
 //         y = op(A) . x with A stored n rows x m columns, lda = m.
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -217,6 +219,46 @@ gemv_rowlane_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restr
     }
 }
 
+// The same batched y = A x with FULLY COALESCED loads: VPR = row bytes / 16 consecutive lanes share a row (lane q reads
+// 16-byte vector q), so a warp instruction reads 512 consecutive bytes of the row stream instead of one 32-byte sector
+// from each of 32 rows; a butterfly over the VPR lanes adds the partial sums (fixed order) and one more shuffle per step
+// hands row t of the warp's 32-row block to lane t, so y leaves as one coalesced store per block.  All VPR loads of a lane
+// are issued before the first use.
+template <typename T, int VPR>
+__global__ void __launch_bounds__(256)
+gemv_rowgroup_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, size_t rows_total, unsigned n) {
+    constexpr int N = 16 / (int)sizeof(T), RPW = 32 / VPR;  // rows per warp and step
+    using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    const int lane = threadIdx.x & 31, q = lane % VPR, g = lane / VPR;
+    const size_t warps = (size_t)gridDim.x * 8, w0 = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const V *av = reinterpret_cast<const V *>(a);
+    const V *xv = reinterpret_cast<const V *>(x);
+    for (size_t base = w0 * 32; base < rows_total; base += warps * 32) {
+        V ra[VPR], rx[VPR];
+#pragma unroll
+        for (int s = 0; s < VPR; ++s) {
+            size_t row = base + (size_t)s * RPW + g;
+            if (row >= rows_total) row = rows_total - 1;
+            ra[s] = __ldcs(av + row * VPR + q);
+            rx[s] = __ldg(xv + (row / n) * VPR + q);
+        }
+        T mine = T(0);
+#pragma unroll
+        for (int s = 0; s < VPR; ++s) {
+            const T *pa = reinterpret_cast<const T *>(&ra[s]), *px = reinterpret_cast<const T *>(&rx[s]);
+            T acc = T(0);
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc = fma(pa[j], px[j], acc);
+#pragma unroll
+            for (int o = VPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, VPR);
+            // row s * RPW + g' of the block goes to lane s * RPW + g': that lane reads group g' = lane % RPW
+            const T v = __shfl_sync(0xffffffffu, acc, (lane % RPW) * VPR);
+            if (lane / RPW == s) mine = v;
+        }
+        if (base + lane < rows_total) y[base + lane] = mine;
+    }
+}
+
 // One large matrix, y = A x: a warp per row, 128-bit loads, four independent accumulators, x through L1/L2.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -351,6 +393,27 @@ int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T
         constexpr size_t VW = 16 / sizeof(T);
         const bool pow2 = m && n && !(m & (m - 1)) && !(n & (n - 1));
         const size_t xlen = ta ? n : m, ylen = ta ? m : n;
+        // rows of 32 / 64 / 128 bytes: lanes share a row, loads fully coalesced -- 16x16 / 32x32 f32 0.95 / 0.93 -> 1.01 / 1.00 of
+        // HBM peak (profiles/r4a_tune_gemv.log); 256-byte rows would keep 16 vectors of A and of x per lane (0.50-0.53) and stay
+        // on the lane-per-row kernel below (gemv_variant 3 forces it)
+        if (batch > 1 && !ta && lda == m && n > 0 && stride_a == m * n && stride_x == m && stride_y == n && aligned16(a) && aligned16(x) &&
+            tunable("gemv_variant") != 1 && tunable("gemv_variant") != 3) {
+            const size_t rows_total = batch * n;
+            size_t blocks = (rows_total + 255) / 256;
+            const size_t cap = (size_t)ctx->sm_count * 16;
+            if (blocks > cap) blocks = cap;
+            bool done = true;
+            switch (m * sizeof(T)) {
+            case 32: gemv_rowgroup_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
+            case 64: gemv_rowgroup_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
+            case 128: gemv_rowgroup_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
+            default: done = false;
+            }
+            if (done) {
+                SLAS_LAUNCH_CHECK();
+                return SLAS_OK;
+            }
+        }
         if (batch > 1 && !ta && lda == m && (m * sizeof(T)) % 32 == 0 && m * sizeof(T) <= 1024 && n > 0 && stride_a == m * n &&
             stride_x == m && stride_y == n && (uintptr_t)a % 32 == 0 && aligned16(x) && tunable("gemv_variant") != 1) {
             const size_t rows_total = batch * n;
