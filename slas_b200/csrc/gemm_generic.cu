@@ -228,32 +228,36 @@ template <typename T, int VPR>
 __global__ void __launch_bounds__(256)
 gemv_rowgroup_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, size_t rows_total, unsigned n) {
     constexpr int N = 16 / (int)sizeof(T), RPW = 32 / VPR;  // rows per warp and step
+    constexpr int PASS = VPR < 8 ? VPR : 8;                 // steps whose loads are in flight together (8 x 2 vectors per lane)
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     const int lane = threadIdx.x & 31, q = lane % VPR, g = lane / VPR;
     const size_t warps = (size_t)gridDim.x * 8, w0 = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     const V *av = reinterpret_cast<const V *>(a);
     const V *xv = reinterpret_cast<const V *>(x);
     for (size_t base = w0 * 32; base < rows_total; base += warps * 32) {
-        V ra[VPR], rx[VPR];
-#pragma unroll
-        for (int s = 0; s < VPR; ++s) {
-            size_t row = base + (size_t)s * RPW + g;
-            if (row >= rows_total) row = rows_total - 1;
-            ra[s] = __ldcs(av + row * VPR + q);
-            rx[s] = __ldg(xv + (row / n) * VPR + q);
-        }
         T mine = T(0);
 #pragma unroll
-        for (int s = 0; s < VPR; ++s) {
-            const T *pa = reinterpret_cast<const T *>(&ra[s]), *px = reinterpret_cast<const T *>(&rx[s]);
-            T acc = T(0);
+        for (int s0 = 0; s0 < VPR; s0 += PASS) {
+            V ra[PASS], rx[PASS];
 #pragma unroll
-            for (int j = 0; j < N; ++j) acc = fma(pa[j], px[j], acc);
+            for (int s = 0; s < PASS; ++s) {
+                size_t row = base + (size_t)(s0 + s) * RPW + g;
+                if (row >= rows_total) row = rows_total - 1;
+                ra[s] = __ldcs(av + row * VPR + q);
+                rx[s] = __ldg(xv + (row / n) * VPR + q);
+            }
 #pragma unroll
-            for (int o = VPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, VPR);
-            // row s * RPW + g' of the block goes to lane s * RPW + g': that lane reads group g' = lane % RPW
-            const T v = __shfl_sync(0xffffffffu, acc, (lane % RPW) * VPR);
-            if (lane / RPW == s) mine = v;
+            for (int s = 0; s < PASS; ++s) {
+                const T *pa = reinterpret_cast<const T *>(&ra[s]), *px = reinterpret_cast<const T *>(&rx[s]);
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < N; ++j) acc = fma(pa[j], px[j], acc);
+#pragma unroll
+                for (int o = VPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, VPR);
+                // row (s0 + s) * RPW + g' of the block goes to lane (s0 + s) * RPW + g': that lane reads group g' = lane % RPW
+                const T v = __shfl_sync(0xffffffffu, acc, (lane % RPW) * VPR);
+                if (lane / RPW == s0 + s) mine = v;
+            }
         }
         if (base + lane < rows_total) y[base + lane] = mine;
     }
@@ -407,6 +411,10 @@ int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T
             case 32: gemv_rowgroup_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
             case 64: gemv_rowgroup_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
             case 128: gemv_rowgroup_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
+            case 256:
+                if (tunable("gemv_variant") == 4) { gemv_rowgroup_kernel<T, 16><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break; }
+                done = false;
+                break;
             default: done = false;
             }
             if (done) {
