@@ -226,7 +226,7 @@ def g_gemv():
         es = np.dtype(dt).itemsize
         (_, a), (_, x), (_, y) = uniform(b * size * size, dt, 1), uniform(b * size, dt, 2), uniform(b * size, dt, 3)
         for ta in (False, True):
-            for v in ((0, 3, 4) if not ta else (0,)):   # 0 shipped; 3: lane per row; 4: lanes share a row also for 256-byte rows
+            for v in ((0, 3) if not ta else (0,)):   # 0 shipped (lanes share a row); 3: lane per row
                 set_tunable("gemv_variant", v)
                 report(f"gemv {size}x{size} {np.dtype(dt).name} batch 2^{log2} trans={ta} variant {v}",
                        timed(lambda: cuda.matrix_vector_mul_batched(a, x, y, size, size, ta)), nbytes=float(b) * (size * size + 2 * size) * es)

@@ -224,11 +224,14 @@ gemv_rowlane_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restr
 // from each of 32 rows; a butterfly over the VPR lanes adds the partial sums (fixed order) and one more shuffle per step
 // hands row t of the warp's 32-row block to lane t, so y leaves as one coalesced store per block.  All VPR loads of a lane
 // are issued before the first use.
-template <typename T, int VPR>
+// CH = 16-byte vectors per lane and row: a row of VPR * CH vectors is read as CH pieces of VPR consecutive vectors (256-byte
+// rows: 8 lanes x 2 pieces of 128 bytes -- whole lines -- instead of 16 lanes per row, which leaves two rows per warp
+// instruction and measured 0.74-0.80).
+template <typename T, int VPR, int CH = 1>
 __global__ void __launch_bounds__(256)
 gemv_rowgroup_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__restrict__ y, size_t rows_total, unsigned n) {
-    constexpr int N = 16 / (int)sizeof(T), RPW = 32 / VPR;  // rows per warp and step
-    constexpr int PASS = VPR < 8 ? VPR : 8;                 // steps whose loads are in flight together (8 x 2 vectors per lane)
+    constexpr int N = 16 / (int)sizeof(T), RPW = 32 / VPR, STEPS = 32 / RPW;  // rows per warp and step; steps per 32-row block
+    constexpr int PASS = (STEPS * CH <= 8) ? STEPS : 8 / CH;                   // steps whose loads are in flight together
     using V = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
     const int lane = threadIdx.x & 31, q = lane % VPR, g = lane / VPR;
     const size_t warps = (size_t)gridDim.x * 8, w0 = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -237,21 +240,27 @@ gemv_rowgroup_kernel(const T *__restrict__ a, const T *__restrict__ x, T *__rest
     for (size_t base = w0 * 32; base < rows_total; base += warps * 32) {
         T mine = T(0);
 #pragma unroll
-        for (int s0 = 0; s0 < VPR; s0 += PASS) {
-            V ra[PASS], rx[PASS];
+        for (int s0 = 0; s0 < STEPS; s0 += PASS) {
+            V ra[PASS][CH], rx[PASS][CH];
 #pragma unroll
             for (int s = 0; s < PASS; ++s) {
                 size_t row = base + (size_t)(s0 + s) * RPW + g;
                 if (row >= rows_total) row = rows_total - 1;
-                ra[s] = __ldcs(av + row * VPR + q);
-                rx[s] = __ldg(xv + (row / n) * VPR + q);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    ra[s][c] = __ldcs(av + row * (VPR * CH) + c * VPR + q);
+                    rx[s][c] = __ldg(xv + (row / n) * (VPR * CH) + c * VPR + q);
+                }
             }
 #pragma unroll
             for (int s = 0; s < PASS; ++s) {
-                const T *pa = reinterpret_cast<const T *>(&ra[s]), *px = reinterpret_cast<const T *>(&rx[s]);
                 T acc = T(0);
 #pragma unroll
-                for (int j = 0; j < N; ++j) acc = fma(pa[j], px[j], acc);
+                for (int c = 0; c < CH; ++c) {
+                    const T *pa = reinterpret_cast<const T *>(&ra[s][c]), *px = reinterpret_cast<const T *>(&rx[s][c]);
+#pragma unroll
+                    for (int j = 0; j < N; ++j) acc = fma(pa[j], px[j], acc);
+                }
 #pragma unroll
                 for (int o = VPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, VPR);
                 // row (s0 + s) * RPW + g' of the block goes to lane (s0 + s) * RPW + g': that lane reads group g' = lane % RPW
@@ -397,9 +406,9 @@ int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T
         constexpr size_t VW = 16 / sizeof(T);
         const bool pow2 = m && n && !(m & (m - 1)) && !(n & (n - 1));
         const size_t xlen = ta ? n : m, ylen = ta ? m : n;
-        // rows of 32 / 64 / 128 bytes: lanes share a row, loads fully coalesced -- 16x16 / 32x32 f32 0.95 / 0.93 -> 1.01 / 1.00 of
-        // HBM peak (profiles/r4a_tune_gemv.log); 256-byte rows would keep 16 vectors of A and of x per lane (0.50-0.53) and stay
-        // on the lane-per-row kernel below (gemv_variant 3 forces it)
+        // rows of 32 / 64 / 128 / 256 bytes: lanes share a row, loads fully coalesced -- 16x16 / 32x32 / 64x64 f32 0.95 / 0.93 /
+        // 0.89 -> 1.01 / 1.00 / 0.99 of HBM peak, 32x32 f64 0.93 -> 0.95 (profiles/r4a_tune_gemv.log, r4d_tune_gemv.log); 256-byte
+        // rows as 8 lanes x 2 pieces of 128 bytes (16 lanes per row measured 0.74-0.80).  gemv_variant 3: the lane-per-row kernel
         if (batch > 1 && !ta && lda == m && n > 0 && stride_a == m * n && stride_x == m && stride_y == n && aligned16(a) && aligned16(x) &&
             tunable("gemv_variant") != 1 && tunable("gemv_variant") != 3) {
             const size_t rows_total = batch * n;
@@ -411,10 +420,7 @@ int launch_gemv(Context *ctx, cudaStream_t st, size_t batch, const T *a, const T
             case 32: gemv_rowgroup_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
             case 64: gemv_rowgroup_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
             case 128: gemv_rowgroup_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
-            case 256:
-                if (tunable("gemv_variant") == 4) { gemv_rowgroup_kernel<T, 16><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break; }
-                done = false;
-                break;
+            case 256: gemv_rowgroup_kernel<T, 8, 2><<<(unsigned)blocks, 256, 0, st>>>(a, x, y, rows_total, (unsigned)n); break;
             default: done = false;
             }
             if (done) {
