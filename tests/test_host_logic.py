@@ -243,15 +243,12 @@ import sys
 from cuda.bindings import nvrtc
 text = open(sys.argv[1]).read()
 src = text[text.index('R"SLASJIT(') + len('R"SLASJIT('):text.rindex(')SLASJIT"')]
-exprs = ["slas::gemm_small_kernel<float, slas::SmallCfg<float, 8, 4, 16, 1, 4, 256, 32, 3, false>, false, true>",
-         "slas::gemm_small_kernel<double, slas::SmallCfg<double, 12, 12, 12, 3, 6, 256, 32, 2, false>, true, false>",
-         "slas::gemm_tiny_kernel<float, 5, 5, 5, 256>", "slas::gemm_tiny_kernel<double, 3, 7, 5, 128>",
-         "slas::gemm_rect_kernel<float, 9, 9, 9, 3, 3, 28>", "slas::gemm_rect_kernel<double, 40, 40, 40, 5, 2, 1>"]
+exprs = sys.argv[2:]
 for expr in exprs:
     err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"gemm_small_jit.cu", 0, [], [])
     assert err == nvrtc.nvrtcResult.NVRTC_SUCCESS
     nvrtc.nvrtcAddNameExpression(prog, expr.encode())
-    opts = [b"--gpu-architecture=sm_100a", b"--std=c++17"]
+    opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device"]
     err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
     _, n = nvrtc.nvrtcGetProgramLogSize(prog)
     log = b" " * n
@@ -265,19 +262,34 @@ print("ok", len(exprs))
 
 
 def test_run_time_specialised_kernel_text_compiles_for_sm_100a():
-    """gemm_jit.cu hands NVRTC the text of async.cuh + gemm_small_kernel.cuh + gemm_tiny_kernel.cuh (embedded by
-    embed_jit_source.py at build time).  nvcc never sees gemm_rect_kernel and only some instantiations of the other two,
-    so one specialisation of each is compiled here (NVRTC needs no GPU) -- in a child process: importing the CUDA Python
+    """gemm_jit.cu and staged_jit.cu hand NVRTC kernel headers embedded as text by embed_jit_source.py at build time.  nvcc
+    never sees gemm_rect_kernel and only some instantiations of the others, and a host include slipping into one of those
+    headers would not break the build -- only silently send such shapes to the slower run-time-shape kernels on the GPU
+    box.  So specialisations of each are compiled here (NVRTC needs no GPU) -- in a child process: importing the CUDA Python
     bindings into this one breaks a later `import torch`."""
     import importlib.util
     import subprocess
     import sys
     if importlib.util.find_spec("cuda") is None or importlib.util.find_spec("cuda.bindings") is None:
         pytest.skip("cuda-python is not installed")
-    inc = os.path.join(ROOT, "slas_b200", "lib", "obj", "gemm_small_jit_src.inc")
-    assert os.path.exists(inc), "build the library first (__graft_entry__.build())"
-    r = subprocess.run([sys.executable, "-c", _NVRTC_CHECK, inc], capture_output=True, text=True, timeout=300)
-    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+    cases = {
+        "gemm_small_jit_src.inc": [
+            "slas::gemm_small_kernel<float, slas::SmallCfg<float, 8, 4, 16, 1, 4, 256, 32, 3, false>, false, true>",
+            "slas::gemm_small_kernel<double, slas::SmallCfg<double, 12, 12, 12, 3, 6, 256, 32, 2, false>, true, false>",
+            "slas::gemm_small_kernel<float, slas::SmallCfg<float, 20, 20, 20, 5, 4, 160, 16, 3, true>, false, false>",
+            "slas::gemm_tiny_kernel<float, 5, 5, 5, 256>", "slas::gemm_tiny_kernel<double, 3, 7, 5, 128>",
+            "slas::gemm_rect_kernel<float, 9, 9, 9, 3, 3, 28>", "slas::gemm_rect_kernel<double, 40, 40, 40, 5, 2, 1>"],
+        # staged_jit.cu: async.cuh + divby.cuh + staged_objects_kernel.cuh (short-vector reductions, small transposes)
+        "staged_jit_src.inc": [
+            "slas::batched_reduce_staged_kernel<float, 2, 30u>", "slas::batched_reduce_staged_kernel<double, 0, 9u>",
+            "slas::batched_reduce_staged_kernel<float, 1, 127u>",
+            "slas::transpose_staged_kernel<uint64_t, 15u, 5u, 3u, true>", "slas::transpose_staged_kernel<uint4, 6u, 2u, 3u, true>"],
+    }
+    for name, exprs in cases.items():
+        inc = os.path.join(ROOT, "slas_b200", "lib", "obj", name)
+        assert os.path.exists(inc), "build the library first (__graft_entry__.build())"
+        r = subprocess.run([sys.executable, "-c", _NVRTC_CHECK, inc] + exprs, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and r.stdout.startswith("ok"), name + "\n" + r.stdout + r.stderr
 
 
 def test_c99_program_links_and_runs(tmp_path):
